@@ -1,0 +1,226 @@
+/* lsspg.h -- C ABI of the B200-native LSSP solve-loop library (liblsspg.so).
+ *
+ * This is the drop-in boundary for the hot path of huiscliu/lssp: CSR SpMV and
+ * residual, BLAS-1, preconditioner application and the Krylov drivers.  Plain
+ * pointers and sizes only; no C++ or torch types.  The C++ facade in
+ * include/lssp/ (signature-identical to the reference's lssp.h / mvops.h /
+ * vector.h / solver-*.h / pc-*.h) and the Python host mirror (lssp_b200/) both
+ * sit on top of exactly these entry points.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     lsspg_last_error() gives the message (CUDA error string or argument
+ *     check).  The C++ facade maps a failure to lssp_error(1, ...) which
+ *     prints and exit()s, as the reference does (src/utils.cxx:114-135).
+ *   - "h" pointers are host memory, "d" pointers are device memory obtained
+ *     from lsspg_malloc() on the same context.
+ *   - fp64 values, int32 indices, as in the reference (include/type-defs.h:15-24).
+ *   - There is NO CPU fallback: without a CUDA device lsspg_ctx_create fails.
+ *
+ * Each entry point cites the reference interface (file:line under
+ * /root/reference) that it replaces.
+ */
+#ifndef LSSPG_H
+#define LSSPG_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsspg_ctx lsspg_ctx;   /* one device, one stream, reduction scratch        */
+typedef struct lsspg_csr lsspg_csr;   /* device-resident CSR matrix + SpMV row-tile schedule */
+typedef struct lsspg_tri lsspg_tri;   /* device-resident triangular factor, level-ordered  */
+typedef struct lsspg_pc  lsspg_pc;    /* preconditioner application object                 */
+
+const char *lsspg_last_error(void);
+const char *lsspg_version(void);
+
+/* ---- context / memory ---------------------------------------------------- */
+int lsspg_ctx_create(int device, lsspg_ctx **out);
+int lsspg_ctx_destroy(lsspg_ctx *ctx);
+int lsspg_sync(lsspg_ctx *ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on */
+void *lsspg_ctx_stream(lsspg_ctx *ctx);
+/* CUDA-event timer on that stream (slot 0..3): milliseconds between start and stop */
+int lsspg_timer_start(lsspg_ctx *ctx, int slot);
+int lsspg_timer_stop(lsspg_ctx *ctx, int slot, double *ms);
+/* number of kernels this context has launched so far (bench.py: gpu_launches) */
+long long lsspg_ctx_launches(lsspg_ctx *ctx);
+/* options: see LSSPG_OPT_* */
+int lsspg_ctx_set_option(lsspg_ctx *ctx, int option, int value);
+
+#define LSSPG_OPT_SPMV_KERNEL   1   /* 0 auto, 1 stream (LDG staging), 2 stream (bulk-copy pipeline), 3 vector only */
+#define LSSPG_OPT_SPMV_EXACT    2   /* 1: never use the shuffle-reduced long-row path (bit-exact always) */
+#define LSSPG_OPT_CHECK_EVERY   3   /* Krylov drivers: residual read-back every k iterations (default 1) */
+
+int lsspg_malloc(lsspg_ctx *ctx, size_t bytes, void **dptr);
+int lsspg_free(lsspg_ctx *ctx, void *dptr);
+int lsspg_h2d(lsspg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int lsspg_d2h(lsspg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int lsspg_memset_zero(lsspg_ctx *ctx, void *dptr, size_t bytes);
+/* pinned host staging memory (for the host-buffer entry points and bench.py) */
+int lsspg_host_alloc(size_t bytes, void **hptr);
+int lsspg_host_free(void *hptr);
+
+/* ---- CSR matrix (replaces lssp_mat_csr, include/type-defs.h:15-24) -------- */
+/* Upload a host CSR matrix (copied; the caller keeps its arrays) and build the
+ * row-tile schedule used by the SpMV kernels.  hAp == NULL gives the
+ * reference's "zero matrix" (src/mvops.cxx:33-38). */
+int lsspg_csr_upload(lsspg_ctx *ctx, int num_rows, int num_cols, const int *hAp,
+                     const int *hAj, const double *hAx, lsspg_csr **out);
+int lsspg_csr_destroy(lsspg_ctx *ctx, lsspg_csr *A);
+int lsspg_csr_dims(const lsspg_csr *A, int *num_rows, int *num_cols, int *num_nnzs);
+/* schedule introspection for tests: number of row tiles and how many of them
+ * take the row-sequential (bit-exact) path */
+int lsspg_csr_schedule_info(const lsspg_csr *A, int *num_tiles, int *num_stream_tiles,
+                            int *max_tile_nnz);
+/* algorithmic bytes of one y = A x: 12 nnz + 4 (n+1) + 16 n */
+double lsspg_csr_spmv_bytes(const lsspg_csr *A);
+
+/* ---- mvops (replaces include/mvops.h:8-19, src/mvops.cxx) ------------------ */
+#define LSSPG_MV_MXY      0   /* z = A x                  lssp_mv_mxy      src/mvops.cxx:118-150 */
+#define LSSPG_MV_AMXY     1   /* z = (A x) * a            lssp_mv_amxy     src/mvops.cxx:81-115  */
+#define LSSPG_MV_AMXPBY   2   /* z = (A x) * a + y * b    lssp_mv_amxpby   src/mvops.cxx:5-39  (reference: in place, z == y) */
+#define LSSPG_MV_AMXPBYZ  3   /* z = y * b + a * (A x)    lssp_mv_amxpbyz  src/mvops.cxx:42-78   */
+/* device-resident operands */
+int lsspg_mv(lsspg_ctx *ctx, int kind, const lsspg_csr *A, double alpha, const double *dx,
+             double beta, const double *dy, double *dz);
+/* host operands (the reference-facing call: lssp_vec lives in host memory);
+ * copies x (and y) up, runs the kernel, copies z back */
+int lsspg_mv_host(lsspg_ctx *ctx, int kind, const lsspg_csr *A, double alpha, const double *hx,
+                  double beta, const double *hy, double *hz);
+
+/* ---- vector (replaces include/vector.h:7-40, src/vector.cxx) --------------- */
+int lsspg_vec_set(lsspg_ctx *ctx, int n, double *dx, double val);                       /* :31-38  */
+int lsspg_vec_copy(lsspg_ctx *ctx, int n, double *ddst, const double *dsrc);            /* :74-84  */
+int lsspg_vec_axy(lsspg_ctx *ctx, int n, double a, const double *dx, double *dy);       /* :86-96   y = x*a       */
+int lsspg_vec_axpby(lsspg_ctx *ctx, int n, double a, const double *dx, double b, double *dy);  /* :98-108  y = y*b + x*a */
+int lsspg_vec_axpbyz(lsspg_ctx *ctx, int n, double a, const double *dx, double b,
+                     const double *dy, double *dz);                                     /* :110-121 z = y*b + x*a */
+int lsspg_vec_scale(lsspg_ctx *ctx, int n, double *dx, double a);                       /* :141-146 */
+int lsspg_vec_dot(lsspg_ctx *ctx, int n, const double *dx, const double *dy, double *h_out);   /* :123-133 */
+int lsspg_vec_norm(lsspg_ctx *ctx, int n, const double *dx, double *h_out);             /* :135-138 */
+/* k dot products x_i . y in one pass over y (k <= 8); results to h_out[0..k) */
+int lsspg_vec_multidot(lsspg_ctx *ctx, int n, int k, const double *const *dxs, const double *dy,
+                       double *h_out);
+
+/* ---- sparse triangular solves (replaces include/solver-tri.h:8-12) -------- */
+/* Analyse a host triangular factor stored as the reference stores it
+ * (lower: diagonal LAST in each row, src/solver-tri.cxx:4-24; upper: diagonal
+ * FIRST, off-diagonals applied in DESCENDING storage order, :26-46), compute
+ * the dependency levels, and upload it in level order (sliced-ELL, 32-row
+ * slices).  The block-ILU factors use the same layout (src/pc-biluk.cxx:37-59). */
+#define LSSPG_TRI_LOWER 0
+#define LSSPG_TRI_UPPER 1
+int lsspg_tri_analyse(lsspg_ctx *ctx, int which, int n, const int *hTp,
+                      const int *hTj, const double *hTx, lsspg_tri **out);
+int lsspg_tri_destroy(lsspg_ctx *ctx, lsspg_tri *T);
+int lsspg_tri_info(const lsspg_tri *T, int *num_levels, int *num_slices, long long *padded_nnz);
+/* x = T^-1 rhs (device operands; x and rhs must not alias) */
+int lsspg_tri_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs);
+/* host-side schedule for tests: level of every row (length n) */
+int lsspg_tri_levels_host(int which, int n, const int *hTp, const int *hTj,
+                          int *h_level, int *num_levels);
+
+/* Layout self-check for the CPU test-suite: builds the level-ordered sliced-ELL
+ * image on the host and walks it slice by slice in ticket order.  NOT a
+ * fallback: no driver, preconditioner or facade function ever calls it. */
+int lsspg_debug_tri_walk_layout_host(int which, int n, const int *hTp, const int *hTj,
+                                     const double *hTx, double *hx, const double *hrhs,
+                                     int *num_slices, long long *padded_nnz);
+
+/* ---- host-side incomplete factorisations (setup; replaces src/pc-iluk.cxx,
+ *      src/pc-ilut.cxx incl. lssp_mat_adjust_zero_diag / get_block_diag) ----- */
+typedef struct lsspg_factors lsspg_factors;   /* host L and U in the reference's layout */
+#define LSSPG_ILUK 0
+#define LSSPG_ILUT 1
+/* blk_size <= 0 or >= n: one global factorisation (what the reference always
+ * does, src/pc-iluk.cxx:574); smaller: block-Jacobi with uniform blocks
+ * (the reference's blocked driver, src/pc-iluk.cxx:411-552). */
+int lsspg_ilu_factor(int kind, int n, const int *hAp, const int *hAj, const double *hAx,
+                     int level, int p, double tol, int blk_size, lsspg_factors **out);
+int lsspg_factors_sizes(const lsspg_factors *F, int *n, int *nnzL, int *nnzU);
+int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int *Up, int *Uj,
+                      double *Ux);
+int lsspg_factors_destroy(lsspg_factors *F);
+
+/* ---- preconditioner application (replaces LSSP_PC.solve,
+ *      include/type-defs.h:104,144) ------------------------------------------ */
+#define LSSPG_PC_NON   0   /* x = rhs                          src/pc.cxx:67-70            */
+#define LSSPG_PC_ILU   1   /* x = U^-1 L^-1 rhs                src/solver-tri.cxx:48-60    */
+#define LSSPG_PC_BILU  2   /* x = U^-1 D L^-1 rhs              src/pc-biluk.cxx:22-60      */
+#define LSSPG_PC_AMG   3   /* one SX-AMG-style V-cycle from x  src/pc-sxamg.cxx:42-73      */
+int lsspg_pc_create_non(lsspg_ctx *ctx, int n, lsspg_pc **out);
+/* takes host L/U in the reference layout (as produced by lsspg_ilu_factor) */
+int lsspg_pc_create_ilu(lsspg_ctx *ctx, int n, const int *Lp, const int *Lj, const double *Lx,
+                        const int *Up, const int *Uj, const double *Ux, lsspg_pc **out);
+int lsspg_pc_create_bilu(lsspg_ctx *ctx, int n, const int *Lp, const int *Lj, const double *Lx,
+                         const int *Dp, const int *Dj, const double *Dx, const int *Up,
+                         const int *Uj, const double *Ux, lsspg_pc **out);
+int lsspg_pc_destroy(lsspg_ctx *ctx, lsspg_pc *pc);
+int lsspg_pc_kind(const lsspg_pc *pc);
+int lsspg_pc_info(const lsspg_pc *pc, int *levels_L, int *levels_U, long long *padded_L,
+                  long long *padded_U);
+/* algorithmic bytes of one application */
+double lsspg_pc_bytes(const lsspg_pc *pc);
+int lsspg_pc_apply(lsspg_ctx *ctx, lsspg_pc *pc, double *dx, const double *drhs);
+int lsspg_pc_apply_host(lsspg_ctx *ctx, lsspg_pc *pc, double *hx, const double *hrhs);
+
+/* ---- Krylov drivers (replace int lssp_solver_<m>(LSSP_SOLVER&, LSSP_PC&),
+ *      src/solver-*.cxx; numbering = LSSP_SOLVER_TYPE with every USE_* = 0,
+ *      include/type-defs.h:156-174) ------------------------------------------ */
+#define LSSPG_GMRES      0
+#define LSSPG_LGMRES     1
+#define LSSPG_RGMRES     2
+#define LSSPG_RLGMRES    3
+#define LSSPG_BICGSTAB   4
+#define LSSPG_BICGSTABL  5
+#define LSSPG_BICGSAFE   6
+#define LSSPG_CG         7
+#define LSSPG_CGS        8
+#define LSSPG_GPBICG     9
+#define LSSPG_CR        10
+#define LSSPG_CRS       11
+#define LSSPG_BICRSTAB  12
+#define LSSPG_BICRSAFE  13
+#define LSSPG_GPBICR    14
+#define LSSPG_QMRCGSTAB 15
+#define LSSPG_TFQMR     16
+#define LSSPG_ORTHOMIN  17
+#define LSSPG_IDRS      18
+
+typedef struct lsspg_solver_opts {
+    double tol_rel, tol_abs, tol_rb;   /* LSSP_SOLVER.tol_rel/abs/rb, include/type-defs.h:237-239 */
+    int maxit, restart, aug_k, bgsl, idrs;
+    int verb;                          /* >=1: per-iteration lines in the reference's format */
+    int hist_len;                      /* capacity of hist (0: none) */
+    double *hist;                      /* host: ||r|| after each iteration, full precision */
+} lsspg_solver_opts;
+
+typedef struct lsspg_solve_info {
+    int nits;              /* return value of the reference driver                 */
+    double residual;       /* LSSP_SOLVER.residual                                  */
+    int hist_used;
+    double solve_ms;       /* device time of the solve loop (CUDA events)           */
+    long long launches;    /* kernels launched by this solve                        */
+    int breakdown;         /* 1 when a breakdown branch of the reference was taken  */
+} lsspg_solve_info;
+
+int lsspg_solver_opts_default(lsspg_solver_opts *o);   /* src/lssp.cxx:5-14 defaults */
+int lsspg_solver_supported(int solver);
+/* device-resident b and x (x: initial guess in, solution out) */
+int lsspg_krylov_solve(lsspg_ctx *ctx, int solver, const lsspg_csr *A, lsspg_pc *pc,
+                       const double *db, double *dx, const lsspg_solver_opts *opts,
+                       lsspg_solve_info *info);
+/* host b and x, as the reference's lssp_solver_solve sees them (src/lssp.cxx:250):
+ * uploads b and x, solves, downloads x */
+int lsspg_krylov_solve_host(lsspg_ctx *ctx, int solver, const lsspg_csr *A, lsspg_pc *pc,
+                            const double *hb, double *hx, const lsspg_solver_opts *opts,
+                            lsspg_solve_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSSPG_H */

@@ -1,0 +1,407 @@
+"""Python host mirror of the LSSP interface for the solve-loop hot path.
+
+Thin object layer over the C ABI (include/lsspg.h).  Names follow the reference
+(`lssp_mv_mxy`, `lssp_vec_dot`, `lssp_pc_ilu_solve`, `lssp_solver_solve` ...;
+reference include/mvops.h, include/vector.h, include/solver-tri.h,
+include/lssp.h) so parity tests read like calls into the reference.  All
+arithmetic happens in the CUDA kernels behind the C ABI; nothing here computes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import SolveInfo, SolverOpts, check, lib
+
+SOLVERS = {"gmres": 0, "lgmres": 1, "rgmres": 2, "rlgmres": 3, "bicgstab": 4, "bicgstabl": 5,
+           "bicgsafe": 6, "cg": 7, "cgs": 8, "gpbicg": 9, "cr": 10, "crs": 11, "bicrstab": 12,
+           "bicrsafe": 13, "gpbicr": 14, "qmrcgstab": 15, "tfqmr": 16, "orthomin": 17, "idrs": 18}
+MV_MXY, MV_AMXY, MV_AMXPBY, MV_AMXPBYZ = 0, 1, 2, 3
+OPT_SPMV_KERNEL, OPT_SPMV_EXACT, OPT_CHECK_EVERY = 1, 2, 3
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One device + one stream (lsspg_ctx)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().lsspg_ctx_create(int(device), C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().lsspg_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(lib().lsspg_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib().lsspg_ctx_launches(self.h)
+
+    @property
+    def stream(self):
+        return lib().lsspg_ctx_stream(self.h)
+
+    def set_option(self, opt, val):
+        check(lib().lsspg_ctx_set_option(self.h, int(opt), int(val)))
+
+    def empty(self, n):
+        return DVec(self, n)
+
+    def zeros(self, n):
+        v = DVec(self, n)
+        check(lib().lsspg_memset_zero(self.h, v.ptr, C.c_size_t(8 * n)))
+        return v
+
+    def upload(self, a):
+        a = _f64(a)
+        v = DVec(self, len(a))
+        v.set(a)
+        return v
+
+
+class DVec:
+    """Device vector of n doubles (the device image of an lssp_vec)."""
+
+    def __init__(self, ctx, n):
+        self.ctx, self.n = ctx, int(n)
+        self.ptr = C.c_void_p()
+        check(lib().lsspg_malloc(ctx.h, C.c_size_t(8 * max(self.n, 1)), C.byref(self.ptr)))
+
+    def set(self, a):
+        a = _f64(a)
+        assert len(a) == self.n
+        check(lib().lsspg_h2d(self.ctx.h, self.ptr, _p(a), C.c_size_t(8 * self.n)))
+
+    def get(self):
+        out = np.empty(self.n)
+        check(lib().lsspg_d2h(self.ctx.h, _p(out), self.ptr, C.c_size_t(8 * self.n)))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().lsspg_free(self.ctx.h, self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Csr:
+    """Device-resident CSR matrix (the device image of an lssp_mat_csr)."""
+
+    def __init__(self, ctx, A, num_cols=None):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        if A[0] is None:  # the reference's zero matrix: Ap == NULL
+            n = int(A[1])
+            self.n, self.nnz = n, 0
+            check(lib().lsspg_csr_upload(ctx.h, n, n, None, None, None, C.byref(self.h)))
+            return
+        Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
+        self.n = len(Ap) - 1
+        self.nnz = int(Ap[-1])
+        check(lib().lsspg_csr_upload(ctx.h, self.n, self.n if num_cols is None else num_cols,
+                                     _p(Ap), _p(Aj), _p(Ax), C.byref(self.h)))
+
+    @property
+    def spmv_bytes(self):
+        return lib().lsspg_csr_spmv_bytes(self.h)
+
+    def schedule_info(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(lib().lsspg_csr_schedule_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(num_tiles=a.value, num_stream_tiles=b.value, max_tile_nnz=c.value)
+
+    def mv(self, kind, x, z, alpha=1.0, beta=0.0, y=None):
+        check(lib().lsspg_mv(self.ctx.h, kind, self.h, C.c_double(alpha), x.ptr, C.c_double(beta),
+                             y.ptr if y is not None else None, z.ptr))
+
+    def mv_host(self, kind, x, alpha=1.0, beta=0.0, y=None):
+        x = _f64(x)
+        y = None if y is None else _f64(y)
+        z = np.empty(self.n)
+        check(lib().lsspg_mv_host(self.ctx.h, kind, self.h, C.c_double(alpha), _p(x), C.c_double(beta),
+                                  _p(y), _p(z)))
+        return z
+
+    def free(self):
+        if self.h:
+            lib().lsspg_csr_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---- reference-named entry points (host vectors in, host vectors out) ------------
+def lssp_mv_mxy(A, x):
+    """y = A x   (reference src/mvops.cxx:118-150)"""
+    return A.mv_host(MV_MXY, x)
+
+
+def lssp_mv_amxy(a, A, x):
+    """y = a A x   (reference src/mvops.cxx:81-115)"""
+    return A.mv_host(MV_AMXY, x, alpha=a)
+
+
+def lssp_mv_amxpby(alpha, A, x, beta, y):
+    """y = beta y + alpha A x   (reference src/mvops.cxx:5-39); returns the new y"""
+    return A.mv_host(MV_AMXPBY, x, alpha=alpha, beta=beta, y=y)
+
+
+def lssp_mv_amxpbyz(alpha, A, x, beta, y):
+    """z = beta y + alpha A x   (reference src/mvops.cxx:42-78)"""
+    return A.mv_host(MV_AMXPBYZ, x, alpha=alpha, beta=beta, y=y)
+
+
+def lssp_vec_dot(ctx, x, y):
+    out = C.c_double()
+    check(lib().lsspg_vec_dot(ctx.h, x.n, x.ptr, y.ptr, C.byref(out)))
+    return out.value
+
+
+def lssp_vec_norm(ctx, x):
+    out = C.c_double()
+    check(lib().lsspg_vec_norm(ctx.h, x.n, x.ptr, C.byref(out)))
+    return out.value
+
+
+def lssp_vec_multidot(ctx, xs, y):
+    k = len(xs)
+    arr = (C.c_void_p * k)(*[v.ptr.value for v in xs])
+    out = (C.c_double * k)()
+    check(lib().lsspg_vec_multidot(ctx.h, y.n, k, arr, y.ptr, out))
+    return np.array(out[:])
+
+
+def lssp_vec_set_value(ctx, x, val):
+    check(lib().lsspg_vec_set(ctx.h, x.n, x.ptr, C.c_double(val)))
+
+
+def lssp_vec_copy(ctx, dst, src):
+    check(lib().lsspg_vec_copy(ctx.h, dst.n, dst.ptr, src.ptr))
+
+
+def lssp_vec_axy(ctx, a, x, y):
+    check(lib().lsspg_vec_axy(ctx.h, x.n, C.c_double(a), x.ptr, y.ptr))
+
+
+def lssp_vec_axpby(ctx, a, x, b, y):
+    check(lib().lsspg_vec_axpby(ctx.h, x.n, C.c_double(a), x.ptr, C.c_double(b), y.ptr))
+
+
+def lssp_vec_axpbyz(ctx, a, x, b, y, z):
+    check(lib().lsspg_vec_axpbyz(ctx.h, x.n, C.c_double(a), x.ptr, C.c_double(b), y.ptr, z.ptr))
+
+
+def lssp_vec_scale(ctx, x, a):
+    check(lib().lsspg_vec_scale(ctx.h, x.n, x.ptr, C.c_double(a)))
+
+
+# ---- triangular factors / preconditioners ----------------------------------------------
+def tri_levels(which, T):
+    """Host-side dependency levels of a triangular factor (0 lower / 1 upper)."""
+    Tp, Tj = _i32(T[0]), _i32(T[1])
+    n = len(Tp) - 1
+    lev = np.empty(n, np.int32)
+    nl = C.c_int()
+    check(lib().lsspg_tri_levels_host(which, n, _p(Tp), _p(Tj), _p(lev), C.byref(nl)))
+    return lev, nl.value
+
+
+def tri_walk_layout_host(which, T, rhs):
+    """Layout self-check (tests only): walk the level-ordered sliced-ELL image on the host."""
+    Tp, Tj, Tx = _i32(T[0]), _i32(T[1]), _f64(T[2])
+    n = len(Tp) - 1
+    x = np.zeros(n)
+    ns, pad = C.c_int(), C.c_longlong()
+    check(lib().lsspg_debug_tri_walk_layout_host(which, n, _p(Tp), _p(Tj), _p(Tx), _p(x), _p(_f64(rhs)),
+                                                 C.byref(ns), C.byref(pad)))
+    return x, ns.value, pad.value
+
+
+class Tri:
+    """Device-resident triangular factor in level order (lsspg_tri)."""
+
+    def __init__(self, ctx, which, T):
+        self.ctx = ctx
+        Tp, Tj, Tx = _i32(T[0]), _i32(T[1]), _f64(T[2])
+        self.n = len(Tp) - 1
+        self.h = C.c_void_p()
+        check(lib().lsspg_tri_analyse(ctx.h, which, self.n, _p(Tp), _p(Tj), _p(Tx), C.byref(self.h)))
+
+    def info(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_longlong()
+        check(lib().lsspg_tri_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(num_levels=a.value, num_slices=b.value, padded_nnz=c.value)
+
+    def solve(self, x, rhs):
+        check(lib().lsspg_tri_solve(self.ctx.h, self.h, x.ptr, rhs.ptr))
+
+    def free(self):
+        if self.h:
+            lib().lsspg_tri_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def ilu_factor(A, kind="iluk", level=0, p=-1, tol=1e-3, blk_size=0):
+    """Host-side ILU(k) / ILUT set-up (reference src/pc-iluk.cxx, src/pc-ilut.cxx).
+    Returns (L, U) CSR triples in the reference's layout."""
+    Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
+    n = len(Ap) - 1
+    h = C.c_void_p()
+    check(lib().lsspg_ilu_factor(0 if kind == "iluk" else 1, n, _p(Ap), _p(Aj), _p(Ax), int(level), int(p),
+                                 C.c_double(tol), int(blk_size), C.byref(h)))
+    nn, nl, nu = C.c_int(), C.c_int(), C.c_int()
+    lib().lsspg_factors_sizes(h, C.byref(nn), C.byref(nl), C.byref(nu))
+    Lp, Lj, Lx = np.empty(n + 1, np.int32), np.empty(nl.value, np.int32), np.empty(nl.value)
+    Up, Uj, Ux = np.empty(n + 1, np.int32), np.empty(nu.value, np.int32), np.empty(nu.value)
+    lib().lsspg_factors_get(h, _p(Lp), _p(Lj), _p(Lx), _p(Up), _p(Uj), _p(Ux))
+    lib().lsspg_factors_destroy(h)
+    return (Lp, Lj, Lx), (Up, Uj, Ux)
+
+
+class Preconditioner:
+    """Device-side preconditioner application (the `pc.solve` seam, reference
+    include/type-defs.h:104,144)."""
+
+    def __init__(self, ctx, kind, n, L=None, U=None, D=None):
+        self.ctx, self.kind, self.n = ctx, kind, n
+        self.h = C.c_void_p()
+        if kind == "non":
+            check(lib().lsspg_pc_create_non(ctx.h, n, C.byref(self.h)))
+        elif kind == "ilu":
+            L = (_i32(L[0]), _i32(L[1]), _f64(L[2]))
+            U = (_i32(U[0]), _i32(U[1]), _f64(U[2]))
+            check(lib().lsspg_pc_create_ilu(ctx.h, n, _p(L[0]), _p(L[1]), _p(L[2]), _p(U[0]), _p(U[1]),
+                                            _p(U[2]), C.byref(self.h)))
+        elif kind == "bilu":
+            L = (_i32(L[0]), _i32(L[1]), _f64(L[2]))
+            U = (_i32(U[0]), _i32(U[1]), _f64(U[2]))
+            D = (_i32(D[0]), _i32(D[1]), _f64(D[2]))
+            check(lib().lsspg_pc_create_bilu(ctx.h, n, _p(L[0]), _p(L[1]), _p(L[2]), _p(D[0]), _p(D[1]),
+                                             _p(D[2]), _p(U[0]), _p(U[1]), _p(U[2]), C.byref(self.h)))
+        else:
+            raise ValueError(kind)
+
+    @classmethod
+    def non(cls, ctx, n):
+        return cls(ctx, "non", n)
+
+    @classmethod
+    def iluk(cls, ctx, A, level=1, blk_size=0):
+        """lssp_pc_iluk_assemble (reference src/pc-iluk.cxx:566-581); default level 1 (src/pc.cxx:3)"""
+        L, U = ilu_factor(A, "iluk", level=level, blk_size=blk_size)
+        return cls(ctx, "ilu", len(L[0]) - 1, L, U)
+
+    @classmethod
+    def ilut(cls, ctx, A, p=-1, tol=1e-3, blk_size=0):
+        """lssp_pc_ilut_assemble (reference src/pc-ilut.cxx:429-456)"""
+        L, U = ilu_factor(A, "ilut", p=p, tol=tol, blk_size=blk_size)
+        return cls(ctx, "ilu", len(L[0]) - 1, L, U)
+
+    @property
+    def bytes(self):
+        return lib().lsspg_pc_bytes(self.h)
+
+    def info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_longlong(), C.c_longlong()
+        check(lib().lsspg_pc_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(levels_L=a.value, levels_U=b.value, padded_L=c.value, padded_U=d.value)
+
+    def apply(self, x, rhs):
+        """pc.solve(&pc, x, rhs) on device vectors"""
+        check(lib().lsspg_pc_apply(self.ctx.h, self.h, x.ptr, rhs.ptr))
+
+    def apply_host(self, rhs, x0=None):
+        """pc.solve(&pc, x, rhs) on host vectors (x0: incoming contents of x)"""
+        rhs = _f64(rhs)
+        x = np.zeros(self.n) if x0 is None else np.array(x0, dtype=np.float64)
+        check(lib().lsspg_pc_apply_host(self.ctx.h, self.h, _p(x), _p(rhs)))
+        return x
+
+    def free(self):
+        if self.h:
+            lib().lsspg_pc_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def solver_supported(name):
+    return bool(lib().lsspg_solver_supported(SOLVERS[name]))
+
+
+def _opts(hist, **kw):
+    o = SolverOpts()
+    check(lib().lsspg_solver_opts_default(C.byref(o)))
+    names = dict(rtol="tol_rel", atol="tol_abs", rbtol="tol_rb", maxit="maxit", restart="restart",
+                 augk="aug_k", bgsl="bgsl", idrs="idrs", verb="verb")
+    for k, v in kw.items():
+        setattr(o, names[k], v)
+    if hist is not None:
+        o.hist_len = len(hist)
+        o.hist = hist.ctypes.data_as(C.POINTER(C.c_double))
+    return o
+
+
+def lssp_solver_solve(ctx, solver, A, pc, b, x, nhist=0, **kw):
+    """lssp_solver_solve (reference src/lssp.cxx:250-414) with HOST b / x, as a
+    caller of the reference sees it: x is the initial guess on entry and is
+    overwritten with the solution.  Returns dict(nits, residual, hist, ...)."""
+    b = _f64(b)
+    assert isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous
+    hist = np.zeros(nhist) if nhist else None
+    o = _opts(hist, **kw)
+    info = SolveInfo()
+    check(lib().lsspg_krylov_solve_host(ctx.h, SOLVERS[solver], A.h, pc.h, _p(b), _p(x), C.byref(o),
+                                        C.byref(info)))
+    return dict(nits=info.nits, residual=info.residual, x=x, solve_ms=info.solve_ms,
+                launches=info.launches, breakdown=info.breakdown,
+                hist=None if hist is None else hist[:info.hist_used])
+
+
+def solve_device(ctx, solver, A, pc, b, x, nhist=0, **kw):
+    """Same solve with device-resident b / x (DVec)."""
+    hist = np.zeros(nhist) if nhist else None
+    o = _opts(hist, **kw)
+    info = SolveInfo()
+    check(lib().lsspg_krylov_solve(ctx.h, SOLVERS[solver], A.h, pc.h, b.ptr, x.ptr, C.byref(o), C.byref(info)))
+    return dict(nits=info.nits, residual=info.residual, solve_ms=info.solve_ms, launches=info.launches,
+                breakdown=info.breakdown, hist=None if hist is None else hist[:info.hist_used])

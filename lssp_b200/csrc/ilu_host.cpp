@@ -1,0 +1,454 @@
+// ilu_host.cpp -- host-side incomplete factorisations that feed L and U to the
+// GPU triangular solves.  Setup code ("apply on GPU,
+// setup on host in phase 1"), written fresh but arithmetically identical to the
+// reference so that the factors -- and therefore every preconditioned iteration
+// -- match bit for bit:
+//   * missing-diagonal repair            (reference src/matrix-utils.cxx:483-587)
+//   * uniform block-diagonal extraction  (src/matrix-utils.cxx:589-698) -- this is
+//     also the definition of the block-Jacobi preconditioner used when the
+//     matrix is row-sharded across GPUs
+//   * ILU(k): level-of-fill symbolic phase with the reference's level-RAISING
+//     rule (src/pc-iluk.cxx:22-135, esp. :84-86,:101), IKJ numeric phase with
+//     its pivot repair (src/pc-iluk.cxx:347-409), L/U split with the unit
+//     diagonal appended to L (src/pc-iluk.cxx:497-532)
+//   * ILUT(p, tau): row-wise dual-threshold factorisation including the
+//     quick-select ordering of the kept entries (src/pc-ilut.cxx:7-286) and the
+//     same L/U split (src/pc-ilut.cxx:375-402).
+// No FMA: built with -ffp-contract=off.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <numeric>
+#include <vector>
+#include "../../include/lsspg.h"
+
+namespace lsspg {
+void set_error(const char *fmt, ...);
+}
+
+namespace {
+
+constexpr double kPivotTol = 1e-10;   // mat_zero_diag_tol,   reference src/pc.cxx:7
+constexpr double kPivotValue = 1e-3;  // mat_zero_diag_value, reference src/pc.cxx:6
+
+struct Csr {
+    int n = 0;
+    std::vector<int> p, j;
+    std::vector<double> x;
+    int nnz() const { return p.empty() ? 0 : p[n]; }
+};
+
+// rows sorted by ascending column (what lssp_solver_assemble guarantees, src/lssp.cxx:173)
+void sort_rows(Csr &A)
+{
+    std::vector<int> idx;
+    std::vector<int> tj;
+    std::vector<double> tx;
+    for (int i = 0; i < A.n; i++) {
+        const int b = A.p[i], e = A.p[i + 1];
+        if (std::is_sorted(A.j.begin() + b, A.j.begin() + e)) continue;
+        idx.resize(e - b);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int c) { return A.j[b + a] < A.j[b + c]; });
+        tj.assign(A.j.begin() + b, A.j.begin() + e);
+        tx.assign(A.x.begin() + b, A.x.begin() + e);
+        for (int k = 0; k < e - b; k++) {
+            A.j[b + k] = tj[idx[k]];
+            A.x[b + k] = tx[idx[k]];
+        }
+    }
+}
+
+// A row without a stored diagonal receives (i, tol), slid into sorted position.
+Csr with_diagonal(const Csr &A, double tol)
+{
+    Csr M;
+    M.n = A.n;
+    M.p.assign(A.n + 1, 0);
+    std::vector<char> has(A.n, 0);
+    for (int i = 0; i < A.n; i++) {
+        for (int k = A.p[i]; k < A.p[i + 1]; k++)
+            if (A.j[k] == i) has[i] = 1;
+        M.p[i + 1] = M.p[i] + (A.p[i + 1] - A.p[i]) + (has[i] ? 0 : 1);
+    }
+    M.j.resize(M.p[A.n]);
+    M.x.resize(M.p[A.n]);
+    for (int i = 0; i < A.n; i++) {
+        int o = M.p[i];
+        for (int k = A.p[i]; k < A.p[i + 1]; k++, o++) {
+            M.j[o] = A.j[k];
+            M.x[o] = A.x[k];
+        }
+        if (!has[i]) {
+            M.j[o] = i;
+            M.x[o] = 1 * tol;
+            // slide towards the front while the left neighbour has a larger column
+            for (int q = o; q > M.p[i] && M.j[q - 1] > M.j[q]; q--) {
+                std::swap(M.j[q - 1], M.j[q]);
+                std::swap(M.x[q - 1], M.x[q]);
+            }
+        }
+    }
+    return M;
+}
+
+// Entries outside the row's own block are discarded; a row left empty becomes a unit row.
+Csr block_diagonal(const Csr &A, int bs)
+{
+    if (bs >= A.n) return A;
+    Csr M;
+    M.n = A.n;
+    M.p.assign(A.n + 1, 0);
+    M.j.reserve(A.j.size());
+    M.x.reserve(A.x.size());
+    for (int i = 0; i < A.n; i++) {
+        const int lo = (i / bs) * bs, hi = std::min(A.n, lo + bs);
+        int kept = 0;
+        for (int k = A.p[i]; k < A.p[i + 1]; k++) {
+            if (A.j[k] >= lo && A.j[k] < hi) {
+                M.j.push_back(A.j[k]);
+                M.x.push_back(A.x[k]);
+                kept++;
+            }
+        }
+        if (kept == 0) {
+            M.j.push_back(i);
+            M.x.push_back(1.0);
+        }
+        M.p[i + 1] = (int)M.j.size();
+    }
+    return M;
+}
+
+// ---- ILU(k) symbolic ----------------------------------------------------------
+// Returns A's values scattered into the level-<=`level` fill pattern (zeros on
+// fill), columns sorted.  Level rule: a candidate reached through pivot k gets
+// lev(i,k) + lev(k,c) + 1; candidates above `level` are ignored; an entry that
+// is ALREADY in the row has its level RAISED to the candidate's when that is
+// larger (the reference's non-textbook rule).
+Csr iluk_pattern(const Csr &A, int level)
+{
+    const int n = A.n;
+    std::vector<std::vector<int>> ucol(n), ulev(n);   // strict upper part of every finished row
+    std::vector<int> where(n, -1);                    // column -> index in the row's work lists
+    std::vector<int> lc, ll, uc, ul;                  // lower cols/levels, upper cols/levels of row i
+    Csr M;
+    M.n = n;
+    M.p.assign(n + 1, 0);
+    std::vector<double> dense(n, 0.0);
+    for (int i = 0; i < n; i++) {
+        lc.clear(); ll.clear(); uc.clear(); ul.clear();
+        for (int k = A.p[i]; k < A.p[i + 1]; k++) {
+            const int c = A.j[k];
+            if (c < i) { where[c] = (int)lc.size(); lc.push_back(c); ll.push_back(0); }
+            else if (c > i) { where[c] = n + (int)uc.size(); uc.push_back(c); ul.push_back(0); }
+        }
+        for (size_t t = 0; t < lc.size(); t++) {
+            // next pivot = smallest not-yet-used lower column (fill may have appended more)
+            size_t m = t;
+            for (size_t q = t + 1; q < lc.size(); q++)
+                if (lc[q] < lc[m]) m = q;
+            if (m != t) {
+                std::swap(lc[t], lc[m]);
+                std::swap(ll[t], ll[m]);
+                where[lc[t]] = (int)t;
+                where[lc[m]] = (int)m;
+            }
+            const int piv = lc[t];
+            for (size_t q = 0; q < ucol[piv].size(); q++) {
+                const int c = ucol[piv][q];
+                const int cand = ulev[piv][q] + ll[t] + 1;
+                if (cand > level) continue;
+                const int w = where[c];
+                if (w < 0) {
+                    if (c < i) { where[c] = (int)lc.size(); lc.push_back(c); ll.push_back(cand); }
+                    else if (c > i) { where[c] = n + (int)uc.size(); uc.push_back(c); ul.push_back(cand); }
+                }
+                else if (w >= n) { if (ul[w - n] < cand) ul[w - n] = cand; }
+                else { if (ll[w] < cand) ll[w] = cand; }
+            }
+        }
+        for (int c : lc) where[c] = -1;
+        for (int c : uc) where[c] = -1;
+        ucol[i] = uc;
+        ulev[i] = ul;
+        // emit the row: sorted pattern, A's values where present, 0 on fill
+        for (int k = A.p[i]; k < A.p[i + 1]; k++) dense[A.j[k]] = A.x[k];
+        std::vector<int> cols(lc);
+        cols.push_back(i);
+        cols.insert(cols.end(), uc.begin(), uc.end());
+        std::sort(cols.begin(), cols.end());
+        for (int c : cols) {
+            M.j.push_back(c);
+            M.x.push_back(dense[c]);
+        }
+        for (int k = A.p[i]; k < A.p[i + 1]; k++) dense[A.j[k]] = 0.0;
+        M.p[i + 1] = (int)M.j.size();
+    }
+    return M;
+}
+
+inline double repaired_pivot_signed(double d)
+{
+    if (fabs(d) < kPivotTol) return d > 0 ? kPivotValue : -kPivotValue;
+    return d;
+}
+
+// ---- ILU(0) numeric, in place on rows [r0, r1) of M (columns are global and
+// confined to the block; sorted).  IKJ variant.
+void ilu0_block(Csr &M, int r0, int r1, std::vector<double> &wk, std::vector<double> &inv)
+{
+    const int *P = M.p.data();
+    int *C = M.j.data();
+    double *X = M.x.data();
+    // first row of the block: its leading entry is taken as the pivot; the
+    // repaired value only enters the inverse, the stored entry is left alone
+    inv[r0] = 1. / repaired_pivot_signed(X[P[r0]]);
+    for (int i = r0 + 1; i < r1; i++) {
+        const int e = P[i + 1];
+        int k = P[i];
+        for (; C[k] < i; k++) {
+            const int pr = C[k];
+            for (int q = P[pr]; q < P[pr + 1]; q++) wk[C[q]] = X[q];
+            const double a_ik = X[k] = X[k] * inv[pr];
+            for (int q = k + 1; q < e; q++)
+                if (wk[C[q]] != 0.) X[q] = X[q] - a_ik * wk[C[q]];
+            for (int q = P[pr]; q < P[pr + 1]; q++) wk[C[q]] = 0;
+        }
+        double d = kPivotValue;
+        if (C[k] == i) {
+            if (fabs(X[k]) < kPivotTol) X[k] = kPivotValue;
+            d = X[k];
+        }
+        inv[i] = 1. / d;
+    }
+}
+
+struct Factors {
+    int n = 0;
+    Csr L, U;
+};
+
+// rows of the factored matrix F -> L (strict lower + unit diagonal LAST) and U (diagonal FIRST + strict upper)
+void split_row(const int *cj, const double *cx, int len, int row, Csr &L, Csr &U)
+{
+    for (int k = 0; k < len; k++) {
+        if (cj[k] < row) { L.j.push_back(cj[k]); L.x.push_back(cx[k]); }
+        else if (cj[k] == row) {
+            L.j.push_back(row); L.x.push_back(1);
+            U.j.push_back(row); U.x.push_back(cx[k]);
+        }
+        else { U.j.push_back(cj[k]); U.x.push_back(cx[k]); }
+    }
+    L.p.push_back((int)L.j.size());
+    U.p.push_back((int)U.j.size());
+}
+
+Factors factor_iluk(const Csr &A, int level, int bs)
+{
+    Csr M = (level > 0) ? block_diagonal(iluk_pattern(A, level), bs) : block_diagonal(A, bs);
+    const int n = A.n;
+    std::vector<double> wk(n, 0.0), inv(n, 0.0);
+    for (int r0 = 0; r0 < n; r0 += bs) ilu0_block(M, r0, std::min(n, r0 + bs), wk, inv);
+    Factors F;
+    F.n = n;
+    F.L.n = F.U.n = n;
+    F.L.p.push_back(0);
+    F.U.p.push_back(0);
+    for (int i = 0; i < n; i++) split_row(&M.j[M.p[i]], &M.x[M.p[i]], M.p[i + 1] - M.p[i], i, F.L, F.U);
+    return F;
+}
+
+// ---- ILUT ---------------------------------------------------------------------
+// Partial ordering: afterwards the `ncut` entries of largest magnitude occupy
+// a[0..ncut).  The exact sequence of exchanges is part of the contract because
+// the kept entries are stored -- and later summed by the triangular solves -- in
+// the order this leaves them.
+void select_largest(double *a, int *ind, int n, int ncut)
+{
+    int lo = 0, hi = n - 1;
+    if (ncut < lo || ncut >= hi) return;
+    for (;;) {
+        int mid = lo;
+        const double key = fabs(a[mid]);
+        for (int q = lo + 1; q <= hi; q++) {
+            if (fabs(a[q]) > key) {
+                ++mid;
+                std::swap(a[mid], a[q]);
+                std::swap(ind[mid], ind[q]);
+            }
+        }
+        std::swap(a[mid], a[lo]);
+        std::swap(ind[mid], ind[lo]);
+        if (mid == ncut) return;
+        if (mid > ncut) hi = mid - 1;
+        else lo = mid + 1;
+    }
+}
+
+// One block: rows [r0, r1) of B (block-diagonal, global sorted columns).  Emits the
+// factored rows straight into L/U.
+void ilut_block(const Csr &B, int r0, int r1, double tau, int p, Csr &L, Csr &U)
+{
+    const int m = r1 - r0;
+    // local factored matrix of the block, rows stored [kept lower | diagonal | kept upper], local columns
+    std::vector<int> fp(1, 0), fj;
+    std::vector<double> fx;
+    std::vector<double> w(2 * (size_t)m + 2), diag(m);
+    std::vector<int> jw(2 * (size_t)m + 2), jr(m, -1);
+    std::vector<int> gcol;
+    auto emit = [&](int li) {
+        const int b = fp[li], e = fp[li + 1];
+        gcol.resize(e - b);
+        for (int k = b; k < e; k++) gcol[k - b] = fj[k] + r0;
+        split_row(gcol.data(), &fx[b], e - b, r0 + li, L, U);
+    };
+    // first row: copied verbatim; its leading entry is the pivot
+    for (int k = B.p[r0]; k < B.p[r0 + 1]; k++) {
+        fj.push_back(B.j[k] - r0);
+        fx.push_back(B.x[k]);
+    }
+    fp.push_back((int)fj.size());
+    diag[0] = repaired_pivot_signed(B.x[B.p[r0]]);
+    emit(0);
+    for (int i = 1; i < m; i++) {
+        const int b = B.p[r0 + i], e = B.p[r0 + i + 1];
+        double norm = 0.0;
+        for (int k = b; k < e; k++) norm += fabs(B.x[k]);
+        norm /= (double)(e - b);
+        const double drop = tau * norm;
+        // work row: lower part at [0, nl), diagonal at i, upper part at (i, i + nu]
+        int nl = 0, nu = 0;
+        jw[i] = i;
+        w[i] = 0.0;
+        jr[i] = i;
+        for (int k = b; k < e; k++) {
+            const int c = B.j[k] - r0;
+            if (c < i) { jr[c] = nl; jw[nl] = c; w[nl] = B.x[k]; nl++; }
+            else if (c == i) w[i] = B.x[k];
+            else { nu++; jr[c] = i + nu; jw[i + nu] = c; w[i + nu] = B.x[k]; }
+        }
+        for (int t = 0; t < nl; t++) {
+            int piv = jw[t], at = t;
+            for (int q = t + 1; q < nl; q++)
+                if (jw[q] < piv) { piv = jw[q]; at = q; }
+            if (at != t) {
+                const int c = jw[t];
+                jw[t] = jw[at];
+                jw[at] = c;
+                jr[piv] = t;
+                jr[c] = at;
+                std::swap(w[t], w[at]);
+            }
+            jr[piv] = -1;
+            const double a_ik = w[t] = w[t] / diag[piv];
+            for (int q = fp[piv]; q < fp[piv + 1]; q++) {
+                const int c = fj[q];
+                if (c <= piv) continue;
+                const int at2 = jr[c];
+                const double mx = -a_ik * fx[q];
+                if (at2 == -1 && fabs(mx) < drop) continue;   // only NEW fill is dropped
+                if (at2 != -1) w[at2] += mx;
+                else if (c < i) { jw[nl] = c; jr[c] = nl; w[nl] = mx; nl++; }
+                else { nu++; jw[i + nu] = c; jr[c] = i + nu; w[i + nu] = mx; }
+            }
+        }
+        diag[i] = w[i];
+        jr[i] = -1;
+        for (int q = 0; q < nl; q++) jr[jw[q]] = -1;
+        for (int q = 1; q <= nu; q++) jr[jw[i + q]] = -1;
+        diag[i] = repaired_pivot_signed(diag[i]);
+        int keep = std::min(nl, p);
+        select_largest(w.data(), jw.data(), nl, keep);
+        for (int q = 0; q < keep; q++) { fj.push_back(jw[q]); fx.push_back(w[q]); }
+        fj.push_back(i);
+        fx.push_back(diag[i]);
+        keep = std::min(nu, p);
+        select_largest(w.data() + i + 1, jw.data() + i + 1, nu, keep);
+        for (int q = 0; q < keep; q++) { fj.push_back(jw[i + 1 + q]); fx.push_back(w[i + 1 + q]); }
+        fp.push_back((int)fj.size());
+        emit(i);
+    }
+}
+
+Factors factor_ilut(const Csr &A, double tau, int p, int bs)
+{
+    Csr B = block_diagonal(A, bs);
+    Factors F;
+    F.n = A.n;
+    F.L.n = F.U.n = A.n;
+    F.L.p.push_back(0);
+    F.U.p.push_back(0);
+    for (int r0 = 0; r0 < A.n; r0 += bs) ilut_block(B, r0, std::min(A.n, r0 + bs), tau, p, F.L, F.U);
+    return F;
+}
+
+}  // namespace
+
+struct lsspg_factors {
+    Factors f;
+};
+
+extern "C" {
+
+int lsspg_ilu_factor(int kind, int n, const int *hAp, const int *hAj, const double *hAx, int level, int p,
+                     double tol, int blk_size, lsspg_factors **out)
+{
+    if (!out || !hAp || !hAj || !hAx || n <= 0) {
+        lsspg::set_error("lsspg_ilu_factor: bad argument");
+        return 1;
+    }
+    if (kind != LSSPG_ILUK && kind != LSSPG_ILUT) {
+        lsspg::set_error("lsspg_ilu_factor: unknown kind %d", kind);
+        return 1;
+    }
+    Csr A;
+    A.n = n;
+    A.p.assign(hAp, hAp + n + 1);
+    A.j.assign(hAj, hAj + hAp[n]);
+    A.x.assign(hAx, hAx + hAp[n]);
+    sort_rows(A);
+    const int nnz = A.nnz();
+    Csr Ad = with_diagonal(A, kPivotTol);   // reference src/pc-iluk.cxx:573, src/pc-ilut.cxx:448
+    const int bs = (blk_size <= 0 || blk_size > n) ? n : blk_size;
+    lsspg_factors *F = new lsspg_factors();
+    if (kind == LSSPG_ILUK) {
+        if (level < 0) level = 0;               // reference src/pc-iluk.cxx:286-290
+        F->f = factor_iluk(Ad, level, bs);
+    }
+    else {
+        if (p <= 0) p = (nnz + n - 1) / n;      // reference src/pc-ilut.cxx:436-438
+        if (tol < 0) tol = 1e-3;                // reference src/pc-ilut.cxx:440-442, src/pc.cxx:4
+        F->f = factor_ilut(Ad, tol, p, bs);
+    }
+    *out = F;
+    return 0;
+}
+
+int lsspg_factors_sizes(const lsspg_factors *F, int *n, int *nnzL, int *nnzU)
+{
+    if (n) *n = F->f.n;
+    if (nnzL) *nnzL = F->f.L.nnz();
+    if (nnzU) *nnzU = F->f.U.nnz();
+    return 0;
+}
+
+int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int *Up, int *Uj, double *Ux)
+{
+    const Csr &L = F->f.L, &U = F->f.U;
+    memcpy(Lp, L.p.data(), sizeof(int) * L.p.size());
+    memcpy(Lj, L.j.data(), sizeof(int) * L.j.size());
+    memcpy(Lx, L.x.data(), sizeof(double) * L.x.size());
+    memcpy(Up, U.p.data(), sizeof(int) * U.p.size());
+    memcpy(Uj, U.j.data(), sizeof(int) * U.j.size());
+    memcpy(Ux, U.x.data(), sizeof(double) * U.x.size());
+    return 0;
+}
+
+int lsspg_factors_destroy(lsspg_factors *F)
+{
+    delete F;
+    return 0;
+}
+
+}  // extern "C"

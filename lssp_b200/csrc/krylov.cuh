@@ -1,0 +1,74 @@
+// krylov.cuh -- shared scaffolding of the Krylov drivers.
+#pragma once
+#include <math.h>
+#include <vector>
+#include "blas1.cuh"
+#include "pc.cuh"
+#include "spmv.cuh"
+
+namespace lsspg {
+
+// reference defaults, src/lssp.cxx:5-14
+constexpr int kDefRestart = 50, kDefAugK = 3, kDefBgsl = 4, kDefIdrs = 4, kDefMaxit = 1000;
+constexpr double kDefAtol = 1e-7, kDefRtol = 1e-7, kDefRb = 1e-7, kBreakdown = 1e-40;
+
+// Work-vector arena of one solve: device vectors of n doubles, zero-initialised
+// (the reference mallocs without zeroing; drivers that read before writing are
+// compared against the zero-initialising oracle build).
+struct Workspace {
+    lsspg_ctx *ctx;
+    int n;
+    std::vector<double *> ptrs;
+    Workspace(lsspg_ctx *c, int n_) : ctx(c), n(n_) {}
+    ~Workspace()
+    {
+        cudaStreamSynchronize(ctx->stream);
+        for (double *p : ptrs) cudaFree(p);
+    }
+    double *vec()
+    {
+        double *p = nullptr;
+        if (cudaMalloc(&p, sizeof(double) * (size_t)(n > 0 ? n : 1) + 64) != cudaSuccess) return nullptr;
+        cudaMemsetAsync(p, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream);
+        ptrs.push_back(p);
+        return p;
+    }
+};
+
+struct KrylovArgs {
+    lsspg_ctx *ctx;
+    const lsspg_csr *A;
+    lsspg_pc *pc;
+    const double *b;
+    double *x;
+    int n;
+    // resolved options
+    double tol_abs, tol_rel, tol_rb;
+    int maxit, restart, aug_k, bgsl, idrs, verb;
+    double *hist;
+    int hist_len;
+    lsspg_solve_info *info;
+};
+
+// tol = max(rtol*||r0||, atol, rbtol*||b||)  (e.g. src/solver-cg.cxx:56-70)
+inline double stop_tolerance(const KrylovArgs &k, double res0, double bnorm)
+{
+    double tol = k.tol_rel * res0;
+    const double tol_rb = k.tol_rb * bnorm;
+    if (tol < k.tol_abs) tol = k.tol_abs;
+    if (tol < tol_rb) tol = tol_rb;
+    return tol;
+}
+
+inline void record(const KrylovArgs &k, int it, double res)
+{
+    if (k.hist && it < k.hist_len) {
+        k.hist[it] = res;
+        if (k.info->hist_used < it + 1) k.info->hist_used = it + 1;
+    }
+}
+
+int krylov_cg(KrylovArgs &k);
+int krylov_bicgstab(KrylovArgs &k);
+
+}  // namespace lsspg

@@ -1,0 +1,22 @@
+// pc.cuh -- preconditioner application object.
+#pragma once
+#include "common.cuh"
+
+struct lsspg_tri;
+struct lsspg_csr;
+
+struct lsspg_pc {
+    int kind = 0;
+    int n = 0;
+    lsspg_tri *L = nullptr;
+    lsspg_tri *U = nullptr;
+    lsspg_csr *D = nullptr;     // block-ILU: block-diagonal of inverted pivot blocks
+    double *cache = nullptr;    // n doubles (ILU) / 2n doubles (block-ILU), as pc.cache in the reference
+    double bytes = 0.0;         // algorithmic bytes of one application
+};
+
+namespace lsspg {
+// x = M^-1 rhs.  `guarded`: every kernel of the application is skipped when the
+// device stop flag is set (used inside the Krylov drivers).
+int pc_apply(lsspg_ctx *ctx, lsspg_pc *pc, double *dx, const double *drhs, bool guarded);
+}  // namespace lsspg

@@ -1,0 +1,396 @@
+// spmv.cu -- CSR SpMV / residual kernels for sm_100a (replaces src/mvops.cxx).
+//
+// Layout in HBM: plain CSR (Ap int32[n+1], Aj int32[nnz], Ax fp64[nnz]), padded
+// so that 16-byte vector loads may start at the previous multiple of 4 elements.
+// At upload the rows are cut into contiguous ROW TILES:
+//   STREAM tile : <= 256 rows and <= 2048 nnz, every row short (<= 64 nnz).
+//                 The CTA copies the tile's contiguous val/col segment into
+//                 shared memory with coalesced 128-bit loads, then one thread
+//                 per row adds its products SEQUENTIALLY in storage order:
+//                 bit-identical to the reference loop (src/mvops.cxx:130-132).
+//   WARP tile   : <= 8 consecutive long rows, one warp per row, lanes stride the
+//                 row and a shuffle tree adds the lane sums (<= 1e-14 relative).
+//   SERIAL tile : long rows in LSSPG_OPT_SPMV_EXACT mode, one thread per row
+//                 straight from global memory (bit-exact, slow; opt-in).
+// Algorithmic bytes per launch: 12 nnz + 4 (n+1) + 16 n (+ 8 n when y is read).
+// x is gathered through L1/L2 (read-only path); val/col/Ap/y/z cross HBM once.
+#include <algorithm>
+#include "spmv.cuh"
+
+namespace lsspg {
+
+__device__ __forceinline__ double2 ld_stream_f2(const double2 *p)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int4 ld_stream_i4(const int4 *p)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <int KIND>
+__device__ __forceinline__ double epilogue(double sum, double alpha, double beta, const double *y, int r)
+{
+    // operand order exactly as the reference
+    if (KIND == LSSPG_MV_MXY) return sum;
+    if (KIND == LSSPG_MV_AMXY) return sum * alpha;                     // src/mvops.cxx:99
+    if (KIND == LSSPG_MV_AMXPBY) return sum * alpha + y[r] * beta;     // src/mvops.cxx:23
+    return y[r] * beta + alpha * sum;                                  // src/mvops.cxx:61
+}
+
+struct SpmvArgs {
+    const int *Ap;
+    const int *Aj;
+    const double *Ax;
+    const int *tile_row;
+    const unsigned char *tile_kind;
+    int num_tiles;
+    int cap;  // smem capacity in nnz (multiple of 4)
+    const double *x;
+    const double *y;
+    double *z;
+    Coef alpha, beta;
+    const double *w0, *w1;
+    double *scal;
+    int *flags;
+    double *partials;
+    unsigned int *ticket;
+    int out_slot;
+    const int *stop;
+    FinProg fin;
+};
+
+template <int KIND, int NDOT>
+__global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sval = reinterpret_cast<double *>(smem_raw);
+    int *scol = reinterpret_cast<int *>(sval + a.cap + 8);
+    int *sap = scol + a.cap + 8;
+
+    if (a.stop && *a.stop) return;
+    const int tid = threadIdx.x;
+    const double alpha = coef_get(a.alpha, a.scal);
+    const double beta = coef_get(a.beta, a.scal);
+    const double *__restrict__ x = a.x;
+    double acc[NDOT > 0 ? NDOT : 1];
+#pragma unroll
+    for (int k = 0; k < (NDOT > 0 ? NDOT : 1); k++) acc[k] = 0.0;
+
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int r0 = a.tile_row[tile];
+        const int nr = a.tile_row[tile + 1] - r0;
+        const int kind = a.tile_kind[tile];
+        if (kind == TILE_STREAM) {
+            for (int i = tid; i <= nr; i += kBlock) sap[i] = a.Ap[r0 + i];
+            __syncthreads();
+            const int e0 = sap[0], e1 = sap[nr];
+            const int a0 = e0 & ~3;
+            const int nvec = (e1 - a0 + 3) >> 2;  // groups of 4 elements
+            const double2 *gv = reinterpret_cast<const double2 *>(a.Ax + a0);
+            const int4 *gc = reinterpret_cast<const int4 *>(a.Aj + a0);
+            double2 *sv = reinterpret_cast<double2 *>(sval);
+            int4 *sc = reinterpret_cast<int4 *>(scol);
+#pragma unroll 4
+            for (int i = tid; i < 2 * nvec; i += kBlock) sv[i] = ld_stream_f2(gv + i);
+#pragma unroll 2
+            for (int i = tid; i < nvec; i += kBlock) sc[i] = ld_stream_i4(gc + i);
+            __syncthreads();
+            for (int r = tid; r < nr; r += kBlock) {
+                int k = sap[r] - a0;
+                const int k1 = sap[r + 1] - a0;
+                double sum = 0.0;
+                for (; k + 4 <= k1; k += 4) {
+                    const double x0 = __ldg(x + scol[k]), x1 = __ldg(x + scol[k + 1]);
+                    const double x2 = __ldg(x + scol[k + 2]), x3 = __ldg(x + scol[k + 3]);
+                    const double p0 = x0 * sval[k], p1 = x1 * sval[k + 1];
+                    const double p2 = x2 * sval[k + 2], p3 = x3 * sval[k + 3];
+                    sum += p0; sum += p1; sum += p2; sum += p3;
+                }
+                for (; k < k1; k++) sum += __ldg(x + scol[k]) * sval[k];
+                const double out = epilogue<KIND>(sum, alpha, beta, a.y, r0 + r);
+                a.z[r0 + r] = out;
+                if (NDOT >= 1) acc[0] += out * (a.w0 ? a.w0[r0 + r] : out);
+                if (NDOT >= 2) acc[NDOT >= 2 ? 1 : 0] += out * (a.w1 ? a.w1[r0 + r] : out);
+            }
+            __syncthreads();
+        }
+        else if (kind == TILE_WARP) {
+            const int w = tid >> 5, lane = tid & 31;
+            if (w < nr) {
+                const int r = r0 + w;
+                const int e0 = a.Ap[r], e1 = a.Ap[r + 1];
+                double s = 0.0;
+                for (int k = e0 + lane; k < e1; k += 32) s += __ldg(x + a.Aj[k]) * a.Ax[k];
+                s = warp_sum(s);
+                if (lane == 0) {
+                    const double out = epilogue<KIND>(s, alpha, beta, a.y, r);
+                    a.z[r] = out;
+                    if (NDOT >= 1) acc[0] += out * (a.w0 ? a.w0[r] : out);
+                    if (NDOT >= 2) acc[NDOT >= 2 ? 1 : 0] += out * (a.w1 ? a.w1[r] : out);
+                }
+            }
+        }
+        else {  // TILE_SERIAL
+            for (int rr = tid; rr < nr; rr += kBlock) {
+                const int r = r0 + rr;
+                const int e1 = a.Ap[r + 1];
+                double sum = 0.0;
+                for (int k = a.Ap[r]; k < e1; k++) sum += __ldg(x + a.Aj[k]) * a.Ax[k];
+                const double out = epilogue<KIND>(sum, alpha, beta, a.y, r);
+                a.z[r] = out;
+                if (NDOT >= 1) acc[0] += out * (a.w0 ? a.w0[r] : out);
+                if (NDOT >= 2) acc[NDOT >= 2 ? 1 : 0] += out * (a.w1 ? a.w1[r] : out);
+            }
+        }
+    }
+    if (NDOT > 0) {
+        double *scal = a.scal;
+        int *flags = a.flags;
+        const int slot = a.out_slot;
+        const FinProg &fin = a.fin;
+        grid_sum<(NDOT > 0 ? NDOT : 1)>(acc, a.partials, a.ticket, [&](double(&s)[NDOT > 0 ? NDOT : 1]) {
+#pragma unroll
+            for (int k = 0; k < NDOT; k++) scal[slot + k] = s[k];
+            fin_run(fin, scal, flags);
+        });
+    }
+}
+
+// zero matrix: z = epilogue(0)
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) spmv_zero_kernel(int n, Coef ca, Coef cb, const double *scal,
+                                                            const double *y, double *z)
+{
+    const double alpha = coef_get(ca, scal), beta = coef_get(cb, scal);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        // reference zero-matrix branches: mxy/amxy write 0 (src/mvops.cxx:110-114,145-149),
+        // amxpby / amxpbyz scale y by beta (src/mvops.cxx:33-38, :72-76)
+        if (KIND == LSSPG_MV_MXY || KIND == LSSPG_MV_AMXY) z[i] = 0.0;
+        else z[i] = y[i] * beta;
+    }
+    (void)alpha;
+}
+
+template <int KIND>
+static int launch_kind(lsspg_ctx *ctx, const lsspg_csr *A, const SpmvArgs &args, int ndot, int grid, size_t smem)
+{
+    switch (ndot) {
+        case 0: LSSPG_LAUNCH(ctx, (spmv_tiles_kernel<KIND, 0>), grid, kBlock, smem, args); break;
+        case 1: LSSPG_LAUNCH(ctx, (spmv_tiles_kernel<KIND, 1>), grid, kBlock, smem, args); break;
+        default: LSSPG_LAUNCH(ctx, (spmv_tiles_kernel<KIND, 2>), grid, kBlock, smem, args); break;
+    }
+    (void)A;
+    return 0;
+}
+
+int spmv_launch(lsspg_ctx *ctx, int kind, const lsspg_csr *A, Coef alpha, const double *dx, Coef beta,
+                const double *dy, double *dz, const SpmvDots *dots, bool guarded)
+{
+    LSSPG_CHECK(A && dx && dz, "spmv: NULL operand");
+    LSSPG_CHECK(kind >= 0 && kind <= 3, "spmv: bad kind %d", kind);
+    LSSPG_CHECK(kind < 2 || dy != nullptr, "spmv: y required for kind %d", kind);
+    LSSPG_CHECK(dx != dz, "spmv: x and z must not alias");
+    const int n = A->num_rows;
+    if (n == 0) return 0;
+    if (A->zero) {
+        LSSPG_CHECK(!dots || dots->ndot == 0, "spmv: fused dots are not supported on the zero matrix");
+        const int grid = stream_grid(ctx, n, kBlock);
+        switch (kind) {
+            case 0: LSSPG_LAUNCH(ctx, spmv_zero_kernel<0>, grid, kBlock, 0, n, alpha, beta, ctx->d_scal, dy, dz); break;
+            case 1: LSSPG_LAUNCH(ctx, spmv_zero_kernel<1>, grid, kBlock, 0, n, alpha, beta, ctx->d_scal, dy, dz); break;
+            case 2: LSSPG_LAUNCH(ctx, spmv_zero_kernel<2>, grid, kBlock, 0, n, alpha, beta, ctx->d_scal, dy, dz); break;
+            default: LSSPG_LAUNCH(ctx, spmv_zero_kernel<3>, grid, kBlock, 0, n, alpha, beta, ctx->d_scal, dy, dz); break;
+        }
+        return 0;
+    }
+    SpmvArgs args;
+    args.Ap = A->dAp; args.Aj = A->dAj; args.Ax = A->dAx;
+    args.tile_row = A->d_tile_row; args.tile_kind = A->d_tile_kind;
+    args.num_tiles = A->num_tiles;
+    args.cap = (A->max_tile_nnz + 3) & ~3;
+    args.x = dx; args.y = dy; args.z = dz;
+    args.alpha = alpha; args.beta = beta;
+    args.w0 = dots ? dots->w[0] : nullptr;
+    args.w1 = dots ? dots->w[1] : nullptr;
+    args.scal = ctx->d_scal; args.flags = ctx->d_flags;
+    args.partials = ctx->d_partials; args.ticket = ctx->d_ticket;
+    args.out_slot = dots ? dots->out_slot : 0;
+    args.stop = guarded ? ctx->d_flags : nullptr;  // FLAG_STOP == 0
+    if (dots) args.fin = dots->fin;
+    const int ndot = dots ? dots->ndot : 0;
+    LSSPG_CHECK(ndot >= 0 && ndot <= 2, "spmv: ndot %d out of range", ndot);
+    const size_t smem = (size_t)(args.cap + 8) * (sizeof(double) + sizeof(int)) + (kTileRows + 1) * sizeof(int);
+    // resident CTAs per SM: limited by threads (2048/256 = 8) and shared memory
+    int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    int grid = std::min(A->num_tiles, ctx->num_sms * per_sm);
+    if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+    switch (kind) {
+        case 0: return launch_kind<0>(ctx, A, args, ndot, grid, smem);
+        case 1: return launch_kind<1>(ctx, A, args, ndot, grid, smem);
+        case 2: return launch_kind<2>(ctx, A, args, ndot, grid, smem);
+        default: return launch_kind<3>(ctx, A, args, ndot, grid, smem);
+    }
+}
+
+// Host-side row-tile partition (O(n)); see the header comment for the rules.
+static void build_tiles(int n, const int *Ap, bool exact, std::vector<int> &rows, std::vector<unsigned char> &kinds,
+                        int &max_nnz, int &nstream)
+{
+    rows.clear();
+    kinds.clear();
+    max_nnz = 0;
+    nstream = 0;
+    auto len = [&](int i) { return Ap[i + 1] - Ap[i]; };
+    auto is_long = [&](int i) { return exact ? len(i) > kTileNnzCap : len(i) > kLongRow; };
+    int i = 0;
+    while (i < n) {
+        int j = i;
+        if (is_long(i)) {
+            const int lim = exact ? kTileRows : kWarpRowsPerTile;
+            while (j < n && j - i < lim && is_long(j)) j++;
+            kinds.push_back(exact ? TILE_SERIAL : TILE_WARP);
+        }
+        else {
+            int cnt = 0;
+            while (j < n && j - i < kTileRows && !is_long(j) && cnt + len(j) <= kTileNnzCap) {
+                cnt += len(j);
+                j++;
+            }
+            // the tile is loaded from the previous multiple of 4 elements
+            const int span = (Ap[j] - (Ap[i] & ~3) + 3) & ~3;
+            max_nnz = std::max(max_nnz, span);
+            kinds.push_back(TILE_STREAM);
+            nstream++;
+        }
+        rows.push_back(i);
+        i = j;
+    }
+    rows.push_back(n);
+}
+
+}  // namespace lsspg
+
+using namespace lsspg;
+
+extern "C" {
+
+int lsspg_csr_upload(lsspg_ctx *ctx, int num_rows, int num_cols, const int *hAp, const int *hAj, const double *hAx,
+                     lsspg_csr **out)
+{
+    LSSPG_CHECK(ctx && out, "lsspg_csr_upload: NULL argument");
+    LSSPG_CHECK(num_rows >= 0 && num_cols >= 0, "lsspg_csr_upload: negative dimension");
+    LSSPG_CUDA(cudaSetDevice(ctx->device));
+    lsspg_csr *A = new lsspg_csr();
+    A->num_rows = num_rows;
+    A->num_cols = num_cols;
+    if (hAp == nullptr) {
+        A->zero = true;
+        *out = A;
+        return 0;
+    }
+    const int nnz = hAp[num_rows];
+    LSSPG_CHECK(nnz >= 0 && hAp[0] == 0, "lsspg_csr_upload: malformed Ap");
+    LSSPG_CHECK(nnz == 0 || (hAj && hAx), "lsspg_csr_upload: NULL Aj/Ax");
+    A->num_nnzs = nnz;
+    std::vector<int> rows;
+    std::vector<unsigned char> kinds;
+    build_tiles(num_rows, hAp, ctx->opt_spmv_exact != 0, rows, kinds, A->max_tile_nnz, A->num_stream_tiles);
+    A->num_tiles = (int)kinds.size();
+    LSSPG_CUDA(cudaMalloc(&A->dAp, sizeof(int) * ((size_t)num_rows + 1)));
+    LSSPG_CUDA(cudaMalloc(&A->dAj, sizeof(int) * ((size_t)nnz + 16)));
+    LSSPG_CUDA(cudaMalloc(&A->dAx, sizeof(double) * ((size_t)nnz + 16)));
+    LSSPG_CUDA(cudaMemsetAsync(A->dAj + nnz, 0, sizeof(int) * 16, ctx->stream));
+    LSSPG_CUDA(cudaMemsetAsync(A->dAx + nnz, 0, sizeof(double) * 16, ctx->stream));
+    LSSPG_CUDA(cudaMalloc(&A->d_tile_row, sizeof(int) * rows.size()));
+    LSSPG_CUDA(cudaMalloc(&A->d_tile_kind, std::max<size_t>(kinds.size(), 1)));
+    LSSPG_CUDA(cudaMemcpyAsync(A->dAp, hAp, sizeof(int) * ((size_t)num_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        LSSPG_CUDA(cudaMemcpyAsync(A->dAj, hAj, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+        LSSPG_CUDA(cudaMemcpyAsync(A->dAx, hAx, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LSSPG_CUDA(cudaMemcpyAsync(A->d_tile_row, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!kinds.empty())
+        LSSPG_CUDA(cudaMemcpyAsync(A->d_tile_kind, kinds.data(), kinds.size(), cudaMemcpyHostToDevice, ctx->stream));
+    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    // opt in to the shared-memory footprint of the stream kernel once per process
+    static bool attr_done = false;
+    if (!attr_done) {
+        const int maxsmem = 200 * 1024;
+#define SET_ATTR(K, D) cudaFuncSetAttribute(spmv_tiles_kernel<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem)
+        SET_ATTR(0, 0); SET_ATTR(0, 1); SET_ATTR(0, 2); SET_ATTR(1, 0); SET_ATTR(1, 1); SET_ATTR(1, 2);
+        SET_ATTR(2, 0); SET_ATTR(2, 1); SET_ATTR(2, 2); SET_ATTR(3, 0); SET_ATTR(3, 1); SET_ATTR(3, 2);
+#undef SET_ATTR
+        attr_done = true;
+    }
+    *out = A;
+    return 0;
+}
+
+int lsspg_csr_destroy(lsspg_ctx *ctx, lsspg_csr *A)
+{
+    if (!A) return 0;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(A->dAp);
+    cudaFree(A->dAj);
+    cudaFree(A->dAx);
+    cudaFree(A->d_tile_row);
+    cudaFree(A->d_tile_kind);
+    delete A;
+    return 0;
+}
+
+int lsspg_csr_dims(const lsspg_csr *A, int *num_rows, int *num_cols, int *num_nnzs)
+{
+    if (num_rows) *num_rows = A->num_rows;
+    if (num_cols) *num_cols = A->num_cols;
+    if (num_nnzs) *num_nnzs = A->num_nnzs;
+    return 0;
+}
+
+int lsspg_csr_schedule_info(const lsspg_csr *A, int *num_tiles, int *num_stream_tiles, int *max_tile_nnz)
+{
+    if (num_tiles) *num_tiles = A->num_tiles;
+    if (num_stream_tiles) *num_stream_tiles = A->num_stream_tiles;
+    if (max_tile_nnz) *max_tile_nnz = A->max_tile_nnz;
+    return 0;
+}
+
+double lsspg_csr_spmv_bytes(const lsspg_csr *A)
+{
+    return 12.0 * A->num_nnzs + 4.0 * (A->num_rows + 1.0) + 16.0 * A->num_rows;
+}
+
+int lsspg_mv(lsspg_ctx *ctx, int kind, const lsspg_csr *A, double alpha, const double *dx, double beta,
+             const double *dy, double *dz)
+{
+    return spmv_launch(ctx, kind, A, coef_imm(alpha), dx, coef_imm(beta), dy, dz, nullptr);
+}
+
+int lsspg_mv_host(lsspg_ctx *ctx, int kind, const lsspg_csr *A, double alpha, const double *hx, double beta,
+                  const double *hy, double *hz)
+{
+    LSSPG_CHECK(A && hx && hz, "lsspg_mv_host: NULL operand");
+    const size_t nr = A->num_rows, nc = A->num_cols;
+    LSSPG_TRY(ensure_stage(ctx, std::max(nr, nc)));
+    double *dx = ctx->stage[0], *dy = ctx->stage[1], *dz = ctx->stage[2];
+    LSSPG_CUDA(cudaMemcpyAsync(dx, hx, nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (kind >= 2) {
+        LSSPG_CHECK(hy != nullptr, "lsspg_mv_host: y required");
+        LSSPG_CUDA(cudaMemcpyAsync(dy, hy, nr * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LSSPG_TRY(lsspg_mv(ctx, kind, A, alpha, dx, beta, dy, dz));
+    LSSPG_CUDA(cudaMemcpyAsync(hz, dz, nr * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// tri.cuh -- level-scheduled sparse triangular solves (K5/K6 of SURVEY.md 2.2).
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace lsspg {
+
+// Host image of one triangular factor in level order, sliced-ELL with 32-row
+// slices (one slice = one warp-ticket).  Slot s*32+lane holds row perm[slot]
+// (-1: empty).  Slice s owns columns [slice_ptr[s], slice_ptr[s+1]) of width-32
+// panels: entry k of the row in `lane` sits at (slice_ptr[s] + k) * 32 + lane,
+// in APPLICATION order (lower: ascending storage order; upper: descending
+// storage order, as src/solver-tri.cxx:17-19 / :39-41).  col < 0 marks padding.
+struct TriHost {
+    int n = 0, which = 0;
+    int num_levels = 0, num_slices = 0;
+    long long padded_nnz = 0, offdiag_nnz = 0;
+    std::vector<int> level;      // [n]
+    std::vector<int> perm;       // [num_slices*32]
+    std::vector<double> diag;    // [num_slices*32] divisor of the row
+    std::vector<int> slice_ptr;  // [num_slices+1]
+    std::vector<int> col;        // [padded_nnz]
+    std::vector<double> val;     // [padded_nnz]
+};
+
+// returns 0 on success; levels only when want_layout == false
+int tri_build_host(int which, int n, const int *Tp, const int *Tj, const double *Tx, bool want_layout, TriHost &H);
+
+}  // namespace lsspg
+
+struct lsspg_tri {
+    int n = 0, which = 0;
+    int num_levels = 0, num_slices = 0;
+    long long padded_nnz = 0, offdiag_nnz = 0;
+    int *d_perm = nullptr;
+    double *d_diag = nullptr;
+    int *d_slice_ptr = nullptr;
+    int *d_col = nullptr;
+    double *d_val = nullptr;
+    unsigned int *d_counter = nullptr;
+};
+
+namespace lsspg {
+// x = T^-1 rhs; `guarded`: skip when ctx->d_flags[FLAG_STOP] is set
+int tri_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded);
+}  // namespace lsspg

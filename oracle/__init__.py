@@ -173,8 +173,7 @@ class Port:
 
     def __init__(self):
         self.path = os.path.join(HERE, "liboracle.so")
-        if not os.path.exists(self.path):
-            build(port=True, ref=False)
+        build(port=True, ref=False)   # make: a no-op when liboracle.so is up to date
         L = self.lib = C.CDLL(self.path)
         L.orc_dot.restype = C.c_double
         L.orc_norm.restype = C.c_double

@@ -88,26 +88,18 @@ void orc_ilu_apply(int n, const int *Lp, const int *Lj, const double *Lx, const 
     orc_tri_upper(n, Up, Uj, Ux, x, cache);
 }
 
-/* block-ILU apply: y = L^-1 rhs (unit diag, strictly-lower rows), z = D y (SpMV),
- * x = U^-1 z (unit diag, strictly-upper rows, ASCENDING order):
+/* block-ILU apply: y = L^-1 rhs, z = D y (SpMV with the block-diagonal of
+ * inverted pivot blocks), x = U^-1 z; L/U stored like the ILU factors (diag
+ * last / diag first, upper applied in descending order):
  * src/pc-biluk.cxx:22-60.  cache holds 2n doubles. */
 void orc_bilu_apply(int n, const int *Lp, const int *Lj, const double *Lx, const int *Dp,
                     const int *Dj, const double *Dx, const int *Up, const int *Uj,
                     const double *Ux, double *x, const double *rhs, double *cache)
 {
     double *y = cache, *z = cache + n;
-    int i, j;
-    for (i = 0; i < n; i++) {
-        double r = rhs[i];
-        for (j = Lp[i]; j < Lp[i + 1]; j++) r -= Lx[j] * y[Lj[j]];
-        y[i] = r;
-    }
+    orc_tri_lower(n, Lp, Lj, Lx, y, rhs);
     orc_mv(0, n, Dp, Dj, Dx, 1., y, 0., NULL, z);
-    for (i = n - 1; i >= 0; i--) {
-        double r = z[i];
-        for (j = Up[i]; j < Up[i + 1]; j++) r -= Ux[j] * x[Uj[j]];
-        x[i] = r;
-    }
+    orc_tri_upper(n, Up, Uj, Ux, x, z);
 }
 
 /* ------------------------------------------------------ Krylov drivers --- */

@@ -202,3 +202,93 @@ int ref_solve(int solver_type, int pc_type, int n, int *Ap, int *Aj, double *Ax,
 }
 
 } /* extern "C" */
+
+/* ---- persistent solver (bench.py reference arm: time lssp_solver_solve only) ---- */
+extern "C" {
+
+typedef struct ref_session_ {
+    LSSP_SOLVER s;
+    LSSP_PC pc;
+    lssp_vec x, b;
+    int n;
+} ref_session;
+
+/* create + assemble once (src/lssp.cxx:16-189); the matrix is deep-copied by the reference */
+void *ref_session_create(int solver_type, int pc_type, int n, int *Ap, int *Aj, double *Ax,
+                         const ref_params *prm, double *assemble_seconds)
+{
+    ref_session *h = (ref_session *)calloc(1, sizeof(ref_session));
+    lssp_mat_csr A = view_csr(n, Ap, Aj, Ax);
+    double t0;
+    lssp_verbosity = prm->verb;
+    h->n = n;
+    h->x = lssp_vec_create(n);
+    h->b = lssp_vec_create(n);
+    lssp_solver_create(h->s, (LSSP_SOLVER_TYPE)solver_type, h->pc, (LSSP_PC_TYPE)pc_type);
+    lssp_solver_set_rtol(h->s, prm->rtol);
+    lssp_solver_set_atol(h->s, prm->atol);
+    lssp_solver_set_rbtol(h->s, prm->rbtol);
+    lssp_solver_set_maxit(h->s, prm->maxit);
+    lssp_solver_set_restart(h->s, prm->restart);
+    lssp_solver_set_augk(h->s, prm->augk);
+    lssp_solver_set_bgsl(h->s, prm->bgsl);
+    lssp_solver_set_idrs(h->s, prm->idrs);
+    lssp_pc_iluk_set_level(h->pc, prm->iluk_level);
+    lssp_pc_ilut_set_p(h->pc, prm->ilut_p);
+    if (prm->ilut_tol >= 0) lssp_pc_ilut_set_drop_tol(h->pc, prm->ilut_tol);
+    t0 = lssp_get_time();
+    lssp_solver_assemble(h->s, A, h->x, h->b, h->pc);
+    if (assemble_seconds) *assemble_seconds = lssp_get_time() - t0;
+    return h;
+}
+
+/* one lssp_solver_solve from the given x0 with the given maxit; returns nits */
+int ref_session_solve(void *hh, const double *b, double *x, int maxit, double *residual, double *seconds)
+{
+    ref_session *h = (ref_session *)hh;
+    double t0;
+    int nits;
+    memcpy(h->b.d, b, sizeof(double) * h->n);
+    memcpy(h->x.d, x, sizeof(double) * h->n);
+    lssp_solver_set_maxit(h->s, maxit);
+    t0 = lssp_get_time();
+    nits = lssp_solver_solve(h->s, h->pc);
+    if (seconds) *seconds = lssp_get_time() - t0;
+    memcpy(x, h->x.d, sizeof(double) * h->n);
+    if (residual) *residual = h->s.residual;
+    return nits;
+}
+
+/* one reference SpMV / ILU application on the session's own copies (micro-timings) */
+double ref_session_time_mxy(void *hh, int reps)
+{
+    ref_session *h = (ref_session *)hh;
+    lssp_vec y = lssp_vec_create(h->n);
+    double t0 = lssp_get_time();
+    for (int r = 0; r < reps; r++) lssp_mv_mxy(h->s.A, h->b, y);
+    t0 = lssp_get_time() - t0;
+    lssp_vec_destroy(y);
+    return t0 / reps;
+}
+
+double ref_session_time_pc(void *hh, int reps)
+{
+    ref_session *h = (ref_session *)hh;
+    lssp_vec y = lssp_vec_create(h->n);
+    double t0 = lssp_get_time();
+    for (int r = 0; r < reps; r++) h->pc.solve(&h->pc, y, h->b);
+    t0 = lssp_get_time() - t0;
+    lssp_vec_destroy(y);
+    return t0 / reps;
+}
+
+void ref_session_destroy(void *hh)
+{
+    ref_session *h = (ref_session *)hh;
+    lssp_solver_destroy(h->s, h->pc);
+    lssp_vec_destroy(h->x);
+    lssp_vec_destroy(h->b);
+    free(h);
+}
+
+} /* extern "C" */
