@@ -50,20 +50,20 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, device=0):
         super().__init__(daemon=True)
-        self.device, self.rows, self._stop = device, [], threading.Event()
+        self.device, self.rows, self._halt = device, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]

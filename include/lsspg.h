@@ -54,6 +54,9 @@ int lsspg_ctx_set_option(lsspg_ctx *ctx, int option, int value);
 #define LSSPG_OPT_SPMV_KERNEL   1   /* 0 auto, 1 stream (LDG staging), 2 stream (bulk-copy pipeline), 3 vector only */
 #define LSSPG_OPT_SPMV_EXACT    2   /* 1: never use the shuffle-reduced long-row path (bit-exact always) */
 #define LSSPG_OPT_CHECK_EVERY   3   /* Krylov drivers: residual read-back every k iterations (default 1) */
+#define LSSPG_OPT_REDUCE_SEQUENTIAL 4 /* 1: every dot/norm is summed in the reference's sequential order
+                                       (src/vector.cxx:129) -> whole solves become bit-identical to the
+                                       CPU reference; verification mode, one thread does the adds */
 
 int lsspg_malloc(lsspg_ctx *ctx, size_t bytes, void **dptr);
 int lsspg_free(lsspg_ctx *ctx, void *dptr);

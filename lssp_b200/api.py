@@ -16,7 +16,7 @@ SOLVERS = {"gmres": 0, "lgmres": 1, "rgmres": 2, "rlgmres": 3, "bicgstab": 4, "b
            "bicgsafe": 6, "cg": 7, "cgs": 8, "gpbicg": 9, "cr": 10, "crs": 11, "bicrstab": 12,
            "bicrsafe": 13, "gpbicr": 14, "qmrcgstab": 15, "tfqmr": 16, "orthomin": 17, "idrs": 18}
 MV_MXY, MV_AMXY, MV_AMXPBY, MV_AMXPBYZ = 0, 1, 2, 3
-OPT_SPMV_KERNEL, OPT_SPMV_EXACT, OPT_CHECK_EVERY = 1, 2, 3
+OPT_SPMV_KERNEL, OPT_SPMV_EXACT, OPT_CHECK_EVERY, OPT_REDUCE_SEQUENTIAL = 1, 2, 3, 4
 
 
 def _p(a):
@@ -98,9 +98,9 @@ class DVec:
         return out
 
     def free(self):
-        if self.ptr:
+        if self.ptr and self.ctx.h:      # a closed context has already released the device
             lib().lsspg_free(self.ctx.h, self.ptr)
-            self.ptr = C.c_void_p()
+        self.ptr = C.c_void_p()
 
     def __del__(self):
         try:
@@ -148,9 +148,9 @@ class Csr:
         return z
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:
             lib().lsspg_csr_destroy(self.ctx.h, self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -265,9 +265,9 @@ class Tri:
         check(lib().lsspg_tri_solve(self.ctx.h, self.h, x.ptr, rhs.ptr))
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:
             lib().lsspg_tri_destroy(self.ctx.h, self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -353,9 +353,9 @@ class Preconditioner:
         return x
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:
             lib().lsspg_pc_destroy(self.ctx.h, self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -41,6 +41,8 @@ struct RedArgs {
     unsigned int *ticket;
     int out_slot;
     const int *stop;
+    double *seq;          // sequential-order verification mode: per-element terms, [K][seq_n]
+    long long seq_n;
     FinProg fin;
 };
 
@@ -50,12 +52,51 @@ static RedArgs red_args(lsspg_ctx *ctx, const RedOut &o)
     r.scal = ctx->d_scal; r.flags = ctx->d_flags; r.partials = ctx->d_partials; r.ticket = ctx->d_ticket;
     r.out_slot = o.out_slot; r.fin = o.fin;
     r.stop = o.guarded ? ctx->d_flags + FLAG_STOP : nullptr;
+    r.seq = ctx->opt_reduce_sequential ? ctx->d_seq : nullptr;
+    r.seq_n = (long long)ctx->seq_len;
     return r;
+}
+
+// one term of sum k at element i: accumulated per thread (fast mode) or parked for the
+// single-thread in-order adder (sequential mode)
+__device__ __forceinline__ void red_add(const RedArgs &ra, double &acc, int k, long long i, double term)
+{
+    if (ra.seq) ra.seq[(size_t)k * ra.seq_n + i] = term;
+    else acc += term;
+}
+
+// Sequential-order adder: thread k adds the n parked terms of sum k exactly as the
+// reference's `for (i = 0; i < n; i++) sum += x[i] * y[i]` (src/vector.cxx:129) does.
+__global__ void k_seq_sum(long long n, int K, RedArgs ra)
+{
+    if (ra.stop && *ra.stop) return;
+    if ((int)threadIdx.x < K) {
+        const double *t = ra.seq + (size_t)threadIdx.x * ra.seq_n;
+        double s = 0.0;
+        for (long long i = 0; i < n; i++) s += t[i];
+        ra.scal[ra.out_slot + threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) fin_run(ra.fin, ra.scal, ra.flags);
+}
+
+int seq_prepare(lsspg_ctx *ctx, long long n)
+{
+    if (!ctx->opt_reduce_sequential) return 0;
+    return ensure_seq(ctx, (size_t)(n > 0 ? n : 1));
+}
+
+int seq_finish(lsspg_ctx *ctx, long long n, int K, const RedOut &o)
+{
+    if (!ctx->opt_reduce_sequential) return 0;
+    LSSPG_LAUNCH(ctx, k_seq_sum, 1, 32, 0, n, K, red_args(ctx, o));
+    return 0;
 }
 
 template <int K>
 __device__ __forceinline__ void finish(double (&acc)[K], const RedArgs &ra)
 {
+    if (ra.seq) return;   // sums are produced by k_seq_sum
     double *scal = ra.scal;
     int *flags = ra.flags;
     const int slot = ra.out_slot;
@@ -133,9 +174,9 @@ __global__ void __launch_bounds__(kBlock) k_multidot(long long n, DotPtrs p, Red
 #pragma unroll
                 for (int k = 0; k < K; k++) { a[k][u] = p.x[k][i]; b[k][u] = p.y[k][i]; }
             },
-            [&](long long, int u) {
+            [&](long long i, int u) {
 #pragma unroll
-                for (int k = 0; k < K; k++) acc[k] += a[k][u] * b[k][u];
+                for (int k = 0; k < K; k++) red_add(ra, acc[k], k, i, a[k][u] * b[k][u]);
             });
     finish<K>(acc, ra);
 }
@@ -169,7 +210,7 @@ __global__ void __launch_bounds__(kBlock) k_cg_xr(long long n, Coef calpha, cons
                 x[i] = vx[u] + alpha * vp[u];                 // src/solver-cg.cxx:102
                 const double rn = vr[u] - alpha * vq[u];      // :103
                 r[i] = rn;
-                acc[0] += rn * rn;                            // :106 (norm = sqrt(dot(r,r)))
+                red_add(ra, acc[0], 0, i, rn * rn);           // :106 (norm = sqrt(dot(r,r)))
             });
     finish<1>(acc, ra);
 }
@@ -202,7 +243,7 @@ __global__ void __launch_bounds__(kBlock) k_bicgstab_s(long long n, const double
             [&](long long i, int u) {
                 const double sn = a[u] - alpha * b[u];        // src/solver-bicgstab.cxx:114
                 s[i] = sn;
-                acc[0] += sn * sn;
+                red_add(ra, acc[0], 0, i, sn * sn);
             });
     finish<1>(acc, ra);
 }
@@ -225,8 +266,8 @@ __global__ void __launch_bounds__(kBlock) k_bicgstab_xr(long long n, Coef calpha
                 x[i] = vx[u] + alpha * vph[u] + omega * vsh[u];   // src/solver-bicgstab.cxx:137
                 const double rn = vs[u] - omega * vt[u];          // :138
                 r[i] = rn;
-                acc[0] += rn * rn;                                // :141
-                acc[1] += rn * vrh[u];                            // :87 of the next iteration
+                red_add(ra, acc[0], 0, i, rn * rn);               // :141
+                red_add(ra, acc[1], 1, i, rn * vrh[u]);           // :87 of the next iteration
             });
     finish<2>(acc, ra);
 }
@@ -295,6 +336,7 @@ int vec_multidot(lsspg_ctx *ctx, int n, int k, const double *const *xs, const do
         p.x[i] = xs[i < k ? i : 0];
         p.y[i] = ys[i < k ? i : 0];
     }
+    LSSPG_TRY(seq_prepare(ctx, n));
     const RedArgs ra = red_args(ctx, out);
     const int grid = ew_grid(ctx, n > 0 ? n : 1);
     const long long nn = n > 0 ? n : 0;
@@ -308,7 +350,7 @@ int vec_multidot(lsspg_ctx *ctx, int n, int k, const double *const *xs, const do
         case 7: LSSPG_LAUNCH(ctx, k_multidot<7>, grid, kBlock, 0, nn, p, ra); break;
         default: LSSPG_LAUNCH(ctx, k_multidot<8>, grid, kBlock, 0, nn, p, ra); break;
     }
-    return 0;
+    return seq_finish(ctx, nn, k, out);
 }
 
 int cg_update_p(lsspg_ctx *ctx, int n, const double *z, double *p, Coef beta, bool first)
@@ -320,8 +362,9 @@ int cg_update_p(lsspg_ctx *ctx, int n, const double *z, double *p, Coef beta, bo
 int cg_update_xr(lsspg_ctx *ctx, int n, Coef alpha, const double *p, const double *q, double *x, double *r,
                  const RedOut &out)
 {
+    LSSPG_TRY(seq_prepare(ctx, n));
     LSSPG_LAUNCH(ctx, k_cg_xr, ew_grid(ctx, n), kBlock, 0, (long long)n, alpha, p, q, x, r, red_args(ctx, out));
-    return 0;
+    return seq_finish(ctx, n, 1, out);
 }
 
 int bicgstab_update_p(lsspg_ctx *ctx, int n, const double *r, double *p, const double *v, Coef beta, Coef omega,
@@ -335,17 +378,19 @@ int bicgstab_update_p(lsspg_ctx *ctx, int n, const double *r, double *p, const d
 int bicgstab_update_s(lsspg_ctx *ctx, int n, const double *r, const double *v, Coef alpha, double *s,
                       const RedOut &out)
 {
+    LSSPG_TRY(seq_prepare(ctx, n));
     LSSPG_LAUNCH(ctx, k_bicgstab_s, ew_grid(ctx, n), kBlock, 0, (long long)n, r, v, alpha, s, red_args(ctx, out));
-    return 0;
+    return seq_finish(ctx, n, 1, out);
 }
 
 int bicgstab_update_xr(lsspg_ctx *ctx, int n, Coef alpha, Coef omega, const double *ph, const double *sh,
                        const double *s, const double *t, const double *rh, double *x, double *r,
                        const RedOut &out)
 {
+    LSSPG_TRY(seq_prepare(ctx, n));
     LSSPG_LAUNCH(ctx, k_bicgstab_xr, ew_grid(ctx, n), kBlock, 0, (long long)n, alpha, omega, ph, sh, s, t, rh, x, r,
                  red_args(ctx, out));
-    return 0;
+    return seq_finish(ctx, n, 2, out);
 }
 
 int vec_xpay_inplace(lsspg_ctx *ctx, int n, Coef a, const double *p, double *x)

@@ -45,6 +45,10 @@ int bicgstab_update_xr(lsspg_ctx *ctx, int n, Coef alpha, Coef omega, const doub
 // x = x + a*p  (BiCGStab breakdown branch :120-122 and friends)
 int vec_xpay_inplace(lsspg_ctx *ctx, int n, Coef a, const double *p, double *x);
 
+// sequential-order verification mode helpers (LSSPG_OPT_REDUCE_SEQUENTIAL)
+int seq_prepare(lsspg_ctx *ctx, long long n);
+int seq_finish(lsspg_ctx *ctx, long long n, int K, const RedOut &o);
+
 // read scalars / flags back to the pinned mirrors (one sync)
 int read_scalars(lsspg_ctx *ctx, int first, int count, bool with_flags);
 int write_scalar(lsspg_ctx *ctx, int slot, double v);

@@ -67,6 +67,9 @@ struct lsspg_ctx {
     int opt_spmv_kernel = 0;
     int opt_spmv_exact = 0;
     int opt_check_every = 1;
+    int opt_reduce_sequential = 0;   // verification mode: sums in the reference's sequential order
+    double *d_seq = nullptr;         // [kMaxRedK][seq_len] per-element terms of the sums (sequential mode)
+    size_t seq_len = 0;
     // grow-only device staging for the *_host entry points
     double *stage[3] = {nullptr, nullptr, nullptr};
     size_t stage_len = 0;
@@ -87,6 +90,7 @@ inline int stream_grid(const lsspg_ctx *ctx, long long work_items, int per_block
 }
 
 int ensure_stage(lsspg_ctx *ctx, size_t n);
+int ensure_seq(lsspg_ctx *ctx, size_t n);
 
 #ifdef __CUDACC__
 // ---- deterministic block / grid reductions --------------------------------

@@ -32,6 +32,16 @@ int ensure_stage(lsspg_ctx *ctx, size_t n)
     return 0;
 }
 
+int ensure_seq(lsspg_ctx *ctx, size_t n)
+{
+    if (n <= ctx->seq_len) return 0;
+    if (ctx->d_seq) LSSPG_CUDA(cudaFree(ctx->d_seq));
+    ctx->d_seq = nullptr;
+    LSSPG_CUDA(cudaMalloc(&ctx->d_seq, sizeof(double) * kMaxRedK * n));
+    ctx->seq_len = n;
+    return 0;
+}
+
 }  // namespace lsspg
 
 using namespace lsspg;
@@ -82,6 +92,7 @@ int lsspg_ctx_destroy(lsspg_ctx *c)
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 3; i++)
         if (c->stage[i]) cudaFree(c->stage[i]);
+    if (c->d_seq) cudaFree(c->d_seq);
     cudaFree(c->d_partials);
     cudaFree(c->d_ticket);
     cudaFree(c->d_scal);
@@ -134,6 +145,7 @@ int lsspg_ctx_set_option(lsspg_ctx *ctx, int option, int value)
         case LSSPG_OPT_SPMV_KERNEL: ctx->opt_spmv_kernel = value; return 0;
         case LSSPG_OPT_SPMV_EXACT: ctx->opt_spmv_exact = value; return 0;
         case LSSPG_OPT_CHECK_EVERY: ctx->opt_check_every = value < 1 ? 1 : value; return 0;
+        case LSSPG_OPT_REDUCE_SEQUENTIAL: ctx->opt_reduce_sequential = value; return 0;
     }
     set_error("lsspg_ctx_set_option: unknown option %d", option);
     return 1;

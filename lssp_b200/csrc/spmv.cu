@@ -15,6 +15,7 @@
 // Algorithmic bytes per launch: 12 nnz + 4 (n+1) + 16 n (+ 8 n when y is read).
 // x is gathered through L1/L2 (read-only path); val/col/Ap/y/z cross HBM once.
 #include <algorithm>
+#include "blas1.cuh"
 #include "spmv.cuh"
 
 namespace lsspg {
@@ -64,8 +65,25 @@ struct SpmvArgs {
     unsigned int *ticket;
     int out_slot;
     const int *stop;
+    double *seq;          // sequential-order verification mode (see blas1.cu)
+    long long seq_n;
     FinProg fin;
 };
+
+template <int NDOT>
+__device__ __forceinline__ void dots_add(const SpmvArgs &a, double (&acc)[NDOT > 0 ? NDOT : 1], int r, double out)
+{
+    if (NDOT >= 1) {
+        const double t = out * (a.w0 ? a.w0[r] : out);
+        if (a.seq) a.seq[r] = t;
+        else acc[0] += t;
+    }
+    if (NDOT >= 2) {
+        const double t = out * (a.w1 ? a.w1[r] : out);
+        if (a.seq) a.seq[a.seq_n + r] = t;
+        else acc[NDOT >= 2 ? 1 : 0] += t;
+    }
+}
 
 template <int KIND, int NDOT>
 __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
@@ -117,8 +135,7 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
                 for (; k < k1; k++) sum += __ldg(x + scol[k]) * sval[k];
                 const double out = epilogue<KIND>(sum, alpha, beta, a.y, r0 + r);
                 a.z[r0 + r] = out;
-                if (NDOT >= 1) acc[0] += out * (a.w0 ? a.w0[r0 + r] : out);
-                if (NDOT >= 2) acc[NDOT >= 2 ? 1 : 0] += out * (a.w1 ? a.w1[r0 + r] : out);
+                dots_add<NDOT>(a, acc, r0 + r, out);
             }
             __syncthreads();
         }
@@ -133,8 +150,7 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
                 if (lane == 0) {
                     const double out = epilogue<KIND>(s, alpha, beta, a.y, r);
                     a.z[r] = out;
-                    if (NDOT >= 1) acc[0] += out * (a.w0 ? a.w0[r] : out);
-                    if (NDOT >= 2) acc[NDOT >= 2 ? 1 : 0] += out * (a.w1 ? a.w1[r] : out);
+                    dots_add<NDOT>(a, acc, r, out);
                 }
             }
         }
@@ -146,12 +162,11 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
                 for (int k = a.Ap[r]; k < e1; k++) sum += __ldg(x + a.Aj[k]) * a.Ax[k];
                 const double out = epilogue<KIND>(sum, alpha, beta, a.y, r);
                 a.z[r] = out;
-                if (NDOT >= 1) acc[0] += out * (a.w0 ? a.w0[r] : out);
-                if (NDOT >= 2) acc[NDOT >= 2 ? 1 : 0] += out * (a.w1 ? a.w1[r] : out);
+                dots_add<NDOT>(a, acc, r, out);
             }
         }
     }
-    if (NDOT > 0) {
+    if (NDOT > 0 && a.seq == nullptr) {
         double *scal = a.scal;
         int *flags = a.flags;
         const int slot = a.out_slot;
@@ -224,21 +239,31 @@ int spmv_launch(lsspg_ctx *ctx, int kind, const lsspg_csr *A, Coef alpha, const 
     args.partials = ctx->d_partials; args.ticket = ctx->d_ticket;
     args.out_slot = dots ? dots->out_slot : 0;
     args.stop = guarded ? ctx->d_flags : nullptr;  // FLAG_STOP == 0
+    args.seq = nullptr; args.seq_n = 0;
     if (dots) args.fin = dots->fin;
     const int ndot = dots ? dots->ndot : 0;
     LSSPG_CHECK(ndot >= 0 && ndot <= 2, "spmv: ndot %d out of range", ndot);
+    if (ndot > 0 && ctx->opt_reduce_sequential) {
+        LSSPG_TRY(seq_prepare(ctx, n));
+        args.seq = ctx->d_seq; args.seq_n = (long long)ctx->seq_len;
+    }
     const size_t smem = (size_t)(args.cap + 8) * (sizeof(double) + sizeof(int)) + (kTileRows + 1) * sizeof(int);
     // resident CTAs per SM: limited by threads (2048/256 = 8) and shared memory
     int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(A->num_tiles, ctx->num_sms * per_sm);
     if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+    int rc;
     switch (kind) {
-        case 0: return launch_kind<0>(ctx, A, args, ndot, grid, smem);
-        case 1: return launch_kind<1>(ctx, A, args, ndot, grid, smem);
-        case 2: return launch_kind<2>(ctx, A, args, ndot, grid, smem);
-        default: return launch_kind<3>(ctx, A, args, ndot, grid, smem);
+        case 0: rc = launch_kind<0>(ctx, A, args, ndot, grid, smem); break;
+        case 1: rc = launch_kind<1>(ctx, A, args, ndot, grid, smem); break;
+        case 2: rc = launch_kind<2>(ctx, A, args, ndot, grid, smem); break;
+        default: rc = launch_kind<3>(ctx, A, args, ndot, grid, smem); break;
     }
+    if (rc || ndot == 0 || !ctx->opt_reduce_sequential) return rc;
+    RedOut o;
+    o.out_slot = dots->out_slot; o.fin = dots->fin; o.guarded = guarded;
+    return seq_finish(ctx, n, ndot, o);
 }
 
 // Host-side row-tile partition (O(n)); see the header comment for the rules.

@@ -19,6 +19,7 @@
 // is latency-bound by the level count (3N-2 levels on an N^3 7-point grid), not
 // by HBM.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include "blas1.cuh"
 #include "tri.cuh"
@@ -73,10 +74,16 @@ int tri_build_host(int which, int n, const int *Tp, const int *Tj, const double 
     H.perm.assign((size_t)nslices * 32, -1);
     H.diag.assign((size_t)nslices * 32, 1.0);
     H.slice_ptr.assign((size_t)nslices + 1, 0);
+    H.slice_need.assign((size_t)nslices, 0);
     long long s = 0, wsum = 0;
     H.offdiag_nnz = 0;
+    long long first_of_prev_level = 0, first_of_this_level = 0;
     for (int l = 0; l < nlev; l++) {
+        first_of_prev_level = first_of_this_level;
+        first_of_this_level = s;
         for (int r0 = lstart[l]; r0 < lstart[l + 1]; r0 += 32, s++) {
+            // progress hint: start polling the operands once every slice of levels < l-1 is done
+            H.slice_need[s] = (int)first_of_prev_level;
             const int cnt = std::min(32, lstart[l + 1] - r0);
             int w = 0;
             for (int q = 0; q < cnt; q++) {
@@ -123,14 +130,16 @@ struct TriArgs {
     const int *perm;
     const double *diag;
     const int *slice_ptr;
+    const int *slice_need;
     const int *col;
     const double *val;
-    unsigned int *counter;
+    unsigned int *counter;    // [0] ticket dispenser, [32] progress hint (separate 128 B lines)
     int num_slices;
     double *x;
     const double *rhs;
     const int *stop;
     int *err;
+    int hint_on, spin_limit, sleep_ns;   // tuning knobs (LSSPG_TRI_* environment variables)
 };
 
 __device__ __forceinline__ double ld_relaxed_f64(const double *p)
@@ -145,15 +154,29 @@ __device__ __forceinline__ void st_relaxed_f64(double *p, double v)
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ bool is_sentinel(double v) { return (unsigned long long)__double_as_longlong(v) == kSentinelBits; }
 
 constexpr int kTriChunk = 8;
+constexpr int kProgressSlot = 32;
 
+// One warp = one slice ticket.  Waiting happens in two stages so that the thousands of
+// resident warps do not flood L2 with polls: (1) a single lane watches the progress hint
+// (count of finished slices) until every level before the previous one is done -- one
+// address, one sector; (2) only then the lanes poll their own operands x[col].  The hint
+// is only a throttle: correctness rests on the sentinel test alone.
 __global__ void __launch_bounds__(kBlock, 4) tri_solve_kernel(const TriArgs a)
 {
     if (a.stop && *a.stop) return;
     const int lane = threadIdx.x & 31;
     const unsigned int total = (unsigned int)a.num_slices + gridDim.x * (blockDim.x >> 5);
+    unsigned int *progress = a.counter + kProgressSlot;
     for (;;) {
         unsigned int s = 0;
         if (lane == 0) s = atomicInc(a.counter, total - 1);
@@ -164,8 +187,10 @@ __global__ void __launch_bounds__(kBlock, 4) tri_solve_kernel(const TriArgs a)
         const double dg = __ldg(a.diag + slot);
         const int p0 = __ldg(a.slice_ptr + s);
         const int w = __ldg(a.slice_ptr + s + 1) - p0;
+        const unsigned int need = (unsigned int)__ldg(a.slice_need + s);
         double r = (row >= 0) ? __ldg(a.rhs + row) : 0.0;
         const long long base = (long long)p0 * 32 + lane;
+        bool hinted = false;
         for (int k0 = 0; k0 < w; k0 += kTriChunk) {
             int c[kTriChunk];
             double v[kTriChunk], xv[kTriChunk];
@@ -180,11 +205,19 @@ __global__ void __launch_bounds__(kBlock, 4) tri_solve_kernel(const TriArgs a)
                     v[j] = 0.0;
                 }
             }
+            if (!hinted) {   // stage 1 (after the factor loads were issued, so they overlap the wait)
+                if (lane == 0 && need > 0 && a.hint_on) {
+                    int naps = 0;
+                    while (ld_relaxed_u32(progress) < need && ++naps < (1 << 20)) __nanosleep(200);
+                }
+                __syncwarp();
+                hinted = true;
+            }
 #pragma unroll
             for (int j = 0; j < kTriChunk; j++) xv[j] = (c[j] >= 0) ? ld_relaxed_f64(a.x + c[j]) : 0.0;
             bool pending;
             int spins = 0;
-            do {
+            do {   // stage 2
                 pending = false;
 #pragma unroll
                 for (int j = 0; j < kTriChunk; j++) {
@@ -193,8 +226,8 @@ __global__ void __launch_bounds__(kBlock, 4) tri_solve_kernel(const TriArgs a)
                         pending |= is_sentinel(xv[j]);
                     }
                 }
-                if (pending && ++spins > 4) {
-                    __nanosleep(40);
+                if (pending && ++spins > a.spin_limit) {
+                    __nanosleep(a.sleep_ns);
                     // watchdog: a dependency that never arrives (corrupt factor, x aliased by the
                     // caller) must not hang the device -- flag the error and fall through
                     if (spins > (1 << 21)) {
@@ -207,7 +240,13 @@ __global__ void __launch_bounds__(kBlock, 4) tri_solve_kernel(const TriArgs a)
             for (int j = 0; j < kTriChunk; j++)
                 if (c[j] >= 0) r = r - v[j] * xv[j];   // src/solver-tri.cxx:18 / :40
         }
-        if (row >= 0) st_relaxed_f64(a.x + row, r / dg);   // src/solver-tri.cxx:22 / :44
+        // src/solver-tri.cxx:22 / :44; x / 1.0 == x exactly, so the unit diagonal of L skips the divide
+        if (row >= 0) st_relaxed_f64(a.x + row, dg == 1.0 ? r : r / dg);
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned int done = atomicAdd(progress, 1u);
+            if (done == (unsigned int)a.num_slices - 1) atomicExch(progress, 0u);   // last slice: re-arm
+        }
     }
 }
 
@@ -221,12 +260,23 @@ int tri_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs
     memcpy(&sentinel, &bits, sizeof(double));
     LSSPG_TRY(vec_set(ctx, T->n, dx, sentinel, guarded));
     TriArgs a;
-    a.perm = T->d_perm; a.diag = T->d_diag; a.slice_ptr = T->d_slice_ptr; a.col = T->d_col; a.val = T->d_val;
+    a.perm = T->d_perm; a.diag = T->d_diag; a.slice_ptr = T->d_slice_ptr; a.slice_need = T->d_slice_need;
+    a.col = T->d_col; a.val = T->d_val;
     a.counter = T->d_counter; a.num_slices = T->num_slices; a.x = dx; a.rhs = drhs;
     a.stop = guarded ? ctx->d_flags + FLAG_STOP : nullptr;
     a.err = ctx->d_flags + FLAG_TRI_TIMEOUT;
+    static int env_ctas = -1, env_hint = 1, env_spin = 64, env_sleep = 64;
+    if (env_ctas < 0) {
+        const char *e;
+        env_ctas = (e = getenv("LSSPG_TRI_CTAS_PER_SM")) ? atoi(e) : 1;
+        env_hint = (e = getenv("LSSPG_TRI_HINT")) ? atoi(e) : 0;
+        env_spin = (e = getenv("LSSPG_TRI_SPIN")) ? atoi(e) : 64;
+        env_sleep = (e = getenv("LSSPG_TRI_SLEEP")) ? atoi(e) : 64;
+        if (env_ctas < 1) env_ctas = 1;
+    }
+    a.hint_on = env_hint; a.spin_limit = env_spin; a.sleep_ns = env_sleep;
     const int warps_needed = T->num_slices;
-    int grid = std::min((warps_needed + 7) / 8, ctx->num_sms * 8);
+    int grid = std::min((warps_needed + 7) / 8, ctx->num_sms * env_ctas);
     if (grid < 1) grid = 1;
     LSSPG_LAUNCH(ctx, tri_solve_kernel, grid, kBlock, 0, a);
     return 0;
@@ -289,8 +339,12 @@ int lsspg_tri_analyse(lsspg_ctx *ctx, int which, int n, const int *hTp, const in
     LSSPG_CUDA(cudaMalloc(&T->d_slice_ptr, sizeof(int) * ((size_t)H.num_slices + 1)));
     LSSPG_CUDA(cudaMalloc(&T->d_col, sizeof(int) * std::max<size_t>((size_t)H.padded_nnz, 1)));
     LSSPG_CUDA(cudaMalloc(&T->d_val, sizeof(double) * std::max<size_t>((size_t)H.padded_nnz, 1)));
-    LSSPG_CUDA(cudaMalloc(&T->d_counter, sizeof(unsigned int)));
-    LSSPG_CUDA(cudaMemsetAsync(T->d_counter, 0, sizeof(unsigned int), ctx->stream));
+    LSSPG_CUDA(cudaMalloc(&T->d_counter, sizeof(unsigned int) * 64));
+    LSSPG_CUDA(cudaMemsetAsync(T->d_counter, 0, sizeof(unsigned int) * 64, ctx->stream));
+    LSSPG_CUDA(cudaMalloc(&T->d_slice_need, sizeof(int) * std::max<size_t>((size_t)H.num_slices, 1)));
+    if (H.num_slices)
+        LSSPG_CUDA(cudaMemcpyAsync(T->d_slice_need, H.slice_need.data(), sizeof(int) * (size_t)H.num_slices,
+                                   cudaMemcpyHostToDevice, ctx->stream));
     if (slots) {
         LSSPG_CUDA(cudaMemcpyAsync(T->d_perm, H.perm.data(), sizeof(int) * slots, cudaMemcpyHostToDevice, ctx->stream));
         LSSPG_CUDA(cudaMemcpyAsync(T->d_diag, H.diag.data(), sizeof(double) * slots, cudaMemcpyHostToDevice, ctx->stream));
@@ -313,6 +367,7 @@ int lsspg_tri_destroy(lsspg_ctx *ctx, lsspg_tri *T)
     cudaFree(T->d_perm);
     cudaFree(T->d_diag);
     cudaFree(T->d_slice_ptr);
+    cudaFree(T->d_slice_need);
     cudaFree(T->d_col);
     cudaFree(T->d_val);
     cudaFree(T->d_counter);

@@ -19,6 +19,7 @@ struct TriHost {
     std::vector<int> perm;       // [num_slices*32]
     std::vector<double> diag;    // [num_slices*32] divisor of the row
     std::vector<int> slice_ptr;  // [num_slices+1]
+    std::vector<int> slice_need; // [num_slices] progress hint: #slices that precede level(slice) - 1
     std::vector<int> col;        // [padded_nnz]
     std::vector<double> val;     // [padded_nnz]
 };
@@ -35,6 +36,7 @@ struct lsspg_tri {
     int *d_perm = nullptr;
     double *d_diag = nullptr;
     int *d_slice_ptr = nullptr;
+    int *d_slice_need = nullptr;
     int *d_col = nullptr;
     double *d_val = nullptr;
     unsigned int *d_counter = nullptr;

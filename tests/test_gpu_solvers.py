@@ -10,11 +10,46 @@ import pytest
 
 from lssp_b200 import api
 from lssp_b200 import generators as g
-from util import matrix, relerr
+from util import matrix, relerr, tvec
 
 pytestmark = pytest.mark.gpu
 
 HIST_RTOL = 1e-10
+
+
+def assert_history_close(got, want, chaotic=False):
+    """Fast (tree-reduction) mode.  Every element-wise operation, the SpMV and the triangular
+    sweeps are bit-identical to the reference; the only difference is the summation order of
+    the dot products (fixed tree here, sequential there), a relative perturbation of ~1e-16
+    per scalar.  Krylov recurrences amplify such a perturbation by ||r_0||/||r_k||, so the bar
+    is 1e-10 relative per entry while the residual is within 1e-3 of its start, and 1e-12 of
+    ||r_0|| for every entry.  test_sequential_reduction_mode_is_bit_identical removes the
+    summation-order difference and demands equality."""
+    err = np.abs(got - want)
+    head = want >= 1e-3 * want[0]
+    if chaotic:
+        # unpreconditioned BiCGStab: the perturbation grows much faster (non-normal operator,
+        # non-monotone residuals); 1e-10 holds for the first iterations only
+        # (on the power-law matrix a near-breakdown spike at iteration 13 turns 1e-15 into 5e-2)
+        head[8:] = False
+    assert np.max(err[head] / want[head]) <= HIST_RTOL, np.max(err[head] / want[head])
+    assert np.max(err) <= 1e-12 * want[0] or chaotic, np.max(err) / want[0]
+
+
+def nits_close(solver, pc, got, want):
+    """+-1 for the monotone / preconditioned cases.  BiCGStab's count is sensitive to the last bit
+    of its dot products (the reference's own count moves when it is compiled with different
+    flags): 5 % when preconditioned, 15 % when not.  Exact equality is demanded in
+    sequential-reduction mode."""
+    if solver != "bicgstab":
+        return abs(got - want) <= 1
+    return abs(got - want) <= max(1, int(np.ceil((0.15 if pc == "non" else 0.05) * want)))
+
+
+def rhs_for(mname, n):
+    """b = 1 as in example/exam.cxx:92-95, except on the power-law matrix whose row sums are 1
+    (b = 1 would make x = 1 the exact answer after one step)."""
+    return tvec(n) + 1.5 if mname.startswith("powerlaw") else np.ones(n)
 
 
 def make_pc(ctx, A, pc, kw):
@@ -32,7 +67,7 @@ def run(ctx, mname, solver, pc, kw, nhist=20, **opts):
     dA = api.Csr(ctx, A)
     P = make_pc(ctx, A, pc, kw)
     x = np.zeros(n)
-    r = api.lssp_solver_solve(ctx, solver, dA, P, np.ones(n), x, nhist=nhist, maxit=3000, **opts)
+    r = api.lssp_solver_solve(ctx, solver, dA, P, rhs_for(mname, n), x, nhist=nhist, maxit=3000, **opts)
     return A, r
 
 
@@ -53,17 +88,19 @@ def test_history_and_iteration_count_match_reference(ctx, golden, m, s, pc, kw):
     key = key_of(m, s, pc, kw)
     e, h = golden["solves"][key], golden["histories"][key]
     A, r = run(ctx, m, s, pc, kw)
-    assert abs(r["nits"] - e["nits"]) <= 1, (r["nits"], e["nits"])
+    assert nits_close(s, pc, r["nits"], e["nits"]), (r["nits"], e["nits"])
     k = min(len(h), len(r["hist"]))
     assert k >= min(len(h), 10)
     got, want = np.array(r["hist"][:k]), np.array(h[:k])
-    assert np.max(np.abs(got - want) / want) <= HIST_RTOL, np.max(np.abs(got - want) / want)
-    # the answer itself: independent verification residual ||b - A x|| as in example/exam.cxx:114-116
-    n = len(A[0]) - 1
-    dA = api.Csr(ctx, A)
-    res = np.linalg.norm(api.lssp_mv_amxpbyz(-1.0, dA, r["x"], 1.0, np.ones(n)))
-    assert res <= 1.0001e-7 * np.sqrt(n) * 1.5
-    assert abs(np.linalg.norm(r["x"]) - e["xnorm"]) <= 1e-6 * e["xnorm"]
+    assert_history_close(got, want, chaotic=(s == "bicgstab" and pc == "non"))
+    if e["nits"] < 3000:   # (CG on the nonsymmetric operator does not converge in the reference either)
+        # the answer itself: independent verification residual ||b - A x|| as in example/exam.cxx:114-116
+        n = len(A[0]) - 1
+        dA = api.Csr(ctx, A)
+        b = rhs_for(m, n)
+        res = np.linalg.norm(api.lssp_mv_amxpbyz(-1.0, dA, r["x"], 1.0, b))
+        assert res <= 1.0001e-7 * np.linalg.norm(b) * 1.5
+        assert abs(np.linalg.norm(r["x"]) - e["xnorm"]) <= 1e-6 * e["xnorm"]
 
 
 @pytest.mark.parametrize("pc,kw", [("non", {}), ("iluk0", dict(iluk_level=0)), ("iluk1", dict(iluk_level=1)), ("ilut", {})])
@@ -77,9 +114,25 @@ def test_appendix_a1_table(ctx, golden, s, pc, kw):
         assert r["nits"] == 3000 and e["nits"] == 3000
         return
     A, r = run(ctx, "lap2d_100", s, "non" if pc == "non" else pc[:4], kw)
-    assert abs(r["nits"] - e["nits"]) <= 1
-    if r["nits"] == e["nits"]:
+    assert nits_close(s, pc, r["nits"], e["nits"]), (r["nits"], e["nits"])
+    if r["nits"] == e["nits"] and s == "cg":
         assert abs(r["residual"] - e["residual"]) <= 1e-6 * e["residual"] + 1e-12
+
+
+@pytest.mark.parametrize("pc,kw", [("non", {}), ("iluk0", dict(iluk_level=0)), ("iluk1", dict(iluk_level=1)), ("ilut", {})])
+@pytest.mark.parametrize("s", ["cg", "bicgstab"])
+def test_appendix_a1_table_sequential_mode_exact(golden, s, pc, kw):
+    """The same table with dot products summed in the reference's order: every row must
+    reproduce the reference's iteration count AND final residual exactly."""
+    if s == "cg" and pc == "ilut":
+        pytest.skip("3000 iterations of a single-thread adder; covered by the fast-mode test")
+    c = api.Context(0)
+    c.set_option(api.OPT_REDUCE_SEQUENTIAL, 1)
+    e = golden["solves"]["lap2d_100/%s/%s" % (s, pc)]
+    A, r = run(c, "lap2d_100", s, "non" if pc == "non" else pc[:4], kw, nhist=0)
+    assert r["nits"] == e["nits"] and r["residual"] == e["residual"]
+    assert abs(np.linalg.norm(r["x"]) - e["xnorm"]) <= 1e-14 * e["xnorm"]
+    c.close()
 
 
 @pytest.mark.parametrize("s", ["cg", "bicgstab"])
@@ -101,10 +154,28 @@ def test_live_checker_history(ctx, checker, s):
     else:
         want = checker.solve(s, A, b, x0=x0, LU=(L, U), maxit=500, nhist=12)
         hist = want["hist"]
-    assert abs(r["nits"] - want["nits"]) <= 1
+    assert nits_close(s, "iluk", r["nits"], want["nits"])
     k = min(len(hist), len(r["hist"]))
-    assert np.max(np.abs(r["hist"][:k] - hist[:k]) / hist[:k]) <= HIST_RTOL
+    assert_history_close(r["hist"][:k], hist[:k])
     assert relerr(r["x"], want["x"]) <= 1e-8
+
+
+@pytest.mark.parametrize("m,s,pc,kw", CASES)
+def test_sequential_reduction_mode_is_bit_identical(golden, m, s, pc, kw):
+    """LSSPG_OPT_REDUCE_SEQUENTIAL: dot products summed in the reference's own order.  Then
+    nothing differs from the CPU arithmetic any more, and the iteration count, the final
+    residual and the whole residual history must EQUAL the reference's, bit for bit."""
+    c = api.Context(0)
+    c.set_option(api.OPT_REDUCE_SEQUENTIAL, 1)
+    c.set_option(api.OPT_SPMV_EXACT, 1)      # long (power-law) rows on the row-sequential path as well
+    key = key_of(m, s, pc, kw)
+    e, h = golden["solves"][key], golden["histories"][key]
+    A, r = run(c, m, s, pc, kw)
+    assert r["nits"] == e["nits"]
+    assert r["residual"] == e["residual"]
+    assert list(r["hist"][:len(h)]) == h
+    assert abs(np.linalg.norm(r["x"]) - e["xnorm"]) <= 1e-14 * e["xnorm"]
+    c.close()
 
 
 def test_check_every_batches_do_not_change_results(golden):
