@@ -134,6 +134,14 @@ int lsspg_debug_tri_walk_layout_host(int which, int n, const int *hTp, const int
                                      const double *hTx, double *hx, const double *hrhs,
                                      int *num_slices, long long *padded_nnz);
 
+int lsspg_debug_tri_walk_tiled_host(int which, int n, const int *hTp, const int *hTj,
+                                    const double *hTx, double *hx, const double *hrhs,
+                                    int *applicable, int *info /* [8]: boxes, box levels, max rows
+                                    per box, row levels, grid nx ny nz, box edge */);
+/* schedule of a device-resident factor: tiled != 0 when the box schedule is in use */
+int lsspg_tri_schedule(const lsspg_tri *T, int *tiled, int *num_tiles, int *num_tile_levels,
+                       int *max_tile_rows);
+
 /* ---- host-side incomplete factorisations (setup; replaces src/pc-iluk.cxx,
  *      src/pc-ilut.cxx incl. lssp_mat_adjust_zero_diag / get_block_diag) ----- */
 typedef struct lsspg_factors lsspg_factors;   /* host L and U in the reference's layout */

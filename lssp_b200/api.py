@@ -246,6 +246,21 @@ def tri_walk_layout_host(which, T, rhs):
     return x, ns.value, pad.value
 
 
+def tri_walk_tiled_host(which, T, rhs):
+    """Layout self-check (tests only) of the box schedule used for structured-grid factors.
+    Returns (x, info) or (None, None) when the factor has no box schedule."""
+    Tp, Tj, Tx = _i32(T[0]), _i32(T[1]), _f64(T[2])
+    n = len(Tp) - 1
+    x = np.zeros(n)
+    ok, info = C.c_int(), (C.c_int * 8)()
+    check(lib().lsspg_debug_tri_walk_tiled_host(which, n, _p(Tp), _p(Tj), _p(Tx), _p(x), _p(_f64(rhs)),
+                                                C.byref(ok), info))
+    if not ok.value:
+        return None, None
+    keys = ("boxes", "box_levels", "max_box_rows", "row_levels", "nx", "ny", "nz", "box_edge")
+    return x, dict(zip(keys, list(info)))
+
+
 class Tri:
     """Device-resident triangular factor in level order (lsspg_tri)."""
 
@@ -260,6 +275,11 @@ class Tri:
         a, b, c = C.c_int(), C.c_int(), C.c_longlong()
         check(lib().lsspg_tri_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(num_levels=a.value, num_slices=b.value, padded_nnz=c.value)
+
+    def schedule(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().lsspg_tri_schedule(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(tiled=bool(a.value), boxes=b.value, box_levels=c.value, max_box_rows=d.value)
 
     def solve(self, x, rhs):
         check(lib().lsspg_tri_solve(self.ctx.h, self.h, x.ptr, rhs.ptr))

@@ -92,6 +92,7 @@ int lsspg_ctx_destroy(lsspg_ctx *c)
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 3; i++)
         if (c->stage[i]) cudaFree(c->stage[i]);
+    for (auto &pr : c->pool) cudaFree(pr.first);
     if (c->d_seq) cudaFree(c->d_seq);
     cudaFree(c->d_partials);
     cudaFree(c->d_ticket);

@@ -20,17 +20,32 @@ struct Workspace {
     int n;
     std::vector<double *> ptrs;
     Workspace(lsspg_ctx *c, int n_) : ctx(c), n(n_) {}
+    std::vector<size_t> sizes;
     ~Workspace()
     {
         cudaStreamSynchronize(ctx->stream);
-        for (double *p : ptrs) cudaFree(p);
+        for (size_t i = 0; i < ptrs.size(); i++) ctx->pool.push_back(std::make_pair(ptrs[i], sizes[i]));
     }
     double *vec()
     {
+        const size_t bytes = sizeof(double) * (size_t)(n > 0 ? n : 1);
         double *p = nullptr;
-        if (cudaMalloc(&p, sizeof(double) * (size_t)(n > 0 ? n : 1) + 64) != cudaSuccess) return nullptr;
-        cudaMemsetAsync(p, 0, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream);
+        size_t got = 0;
+        for (size_t i = 0; i < ctx->pool.size(); i++) {
+            if (ctx->pool[i].second >= bytes && ctx->pool[i].second <= 2 * bytes) {
+                p = ctx->pool[i].first;
+                got = ctx->pool[i].second;
+                ctx->pool.erase(ctx->pool.begin() + i);
+                break;
+            }
+        }
+        if (!p) {
+            if (cudaMalloc(&p, bytes + 64) != cudaSuccess) return nullptr;
+            got = bytes;
+        }
+        cudaMemsetAsync(p, 0, bytes, ctx->stream);
         ptrs.push_back(p);
+        sizes.push_back(got);
         return p;
     }
 };

@@ -40,9 +40,37 @@ struct lsspg_tri {
     int *d_col = nullptr;
     double *d_val = nullptr;
     unsigned int *d_counter = nullptr;
+    // tile schedule (tri_tiled.cu), used instead of the slice schedule when the factor comes
+    // from a structured grid; all arrays in tile-major row order
+    bool tiled = false;
+    int num_tiles = 0, max_tile_rows = 0, num_tile_levels = 0, tile_dims[3] = {0, 0, 0}, grid_dims[3] = {0, 0, 0};
+    unsigned char *t_blob = nullptr;   // packed boxes (see tri_tiled.cu)
+    void *t_desc = nullptr;            // BoxDesc[num_tiles], ticket order
+    int blob_cap = 0;                  // largest blob (bytes)
+    int max_ext = 0;                   // most operands a box reads from other boxes
+    bool box_flags = false;            // acyclic box graph: wait on per-box completion flags
+    unsigned int *t_flags = nullptr;   // [num_tiles] epoch of the last sweep that finished the box
+    unsigned int epoch = 0;
 };
 
 namespace lsspg {
+
+// Host image of the tile schedule.
+struct TiledHost {
+    int n = 0, which = 0, num_tiles = 0, max_tile_rows = 0, num_tile_levels = 0, num_levels = 0;
+    int tile_dims[3] = {0, 0, 0}, grid_dims[3] = {0, 0, 0};
+    long long offdiag_nnz = 0;
+    std::vector<int> perm, ptr, col, tile_ptr, lev_off, lev_ptr;
+    bool acyclic = false;              // box graph has no cycles: boxes may wait for whole predecessor boxes
+    std::vector<int> pred_ptr, pred;   // per box (ticket order): tickets of the boxes it reads from
+    std::vector<double> diag, val;
+};
+// returns 0 when a tile schedule was built, 2 when the factor is not a structured-grid factor
+// (caller falls back to the slice schedule), 1 on error
+int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const double *Tx, TiledHost &H);
+int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T);
+void tri_tiled_free(lsspg_tri *T);
+int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded);
 // x = T^-1 rhs; `guarded`: skip when ctx->d_flags[FLAG_STOP] is set
 int tri_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded);
 }  // namespace lsspg

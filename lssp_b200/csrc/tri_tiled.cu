@@ -1,0 +1,890 @@
+// tri_tiled.cu -- tile-scheduled sparse triangular solve for structured-grid factors.
+//
+// The slice schedule of tri.cu pays one trip through L2 (~1-2 us) per dependency level;
+// an ILU(0) factor of an N^3 7-point grid has 3N-2 levels, so its sweep is bound by that
+// latency.  When the factor's off-diagonal offsets reveal a lattice (1, nx, nx*ny), rows are
+// grouped into small boxes (8x8x8 by default).  One warp owns one box: dependencies INSIDE
+// the box are served from the warp's shared-memory copy of x after a __syncwarp() (~100
+// cycles per local level), only dependencies on OTHER boxes are polled in global memory
+// with the sentinel protocol of tri.cu.  Seven of eight hops of the critical path thereby
+// stay on chip.  Boxes are drawn as tickets in a topological order of the box graph (which
+// is verified to be acyclic on the host), so the no-deadlock argument of tri.cu carries over.
+//
+// Arithmetic is untouched: every row still subtracts its products sequentially in the
+// reference's order and divides by its stored diagonal -> bit-identical results
+// (reference src/solver-tri.cxx:13-23, :35-45).
+//
+// HBM layout: the factor is stored in box-major row order as plain CSR (ptr/col/val) with
+// perm/diag per slot; a box's rows are contiguous, so every sector is consumed completely
+// while the box is resident.  Algorithmic bytes per sweep: 12 nnz(T) + 20 n.
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <numeric>
+#include "blas1.cuh"
+#include "tri.cuh"
+
+namespace lsspg {
+
+constexpr unsigned long long kSentinelBitsT = 0xFFF8DEADBEEF0001ull;   // same value as tri.cu
+constexpr int kMaxTileRows = 1024;
+
+static bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3])
+{
+    std::map<long long, long long> hist;
+    for (int i = 0; i < n; i++) {
+        for (int k = Tp[i]; k < Tp[i + 1]; k++) {
+            const long long d = llabs((long long)Tj[k] - i);
+            if (d == 0) continue;
+            hist[d]++;
+            if (hist.size() > 16) return false;   // stencil factors have a handful of offsets
+        }
+    }
+    if (hist.size() < 2 || hist.begin()->first != 1) return false;
+    const long long s3 = hist.rbegin()->first;
+    if (s3 <= 1 || n % s3 != 0) return false;
+    if (hist[1] < n / 2 || hist[s3] < n / 4) return false;
+    long long s2 = 0, best = 0;
+    for (auto &kv : hist) {
+        if (kv.first > 1 && kv.first < s3 && s3 % kv.first == 0 && kv.second > best) {
+            s2 = kv.first;
+            best = kv.second;
+        }
+    }
+    if (s2 && best >= n / 4) {
+        dims[0] = (int)s2; dims[1] = (int)(s3 / s2); dims[2] = (int)(n / s3);
+    }
+    else {
+        dims[0] = (int)s3; dims[1] = (int)(n / s3); dims[2] = 1;
+    }
+    return (long long)dims[0] * dims[1] * dims[2] == n;
+}
+
+int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const double *Tx, TiledHost &H)
+{
+    const bool lower = (which == LSSPG_TRI_LOWER);
+    int g[3];
+    if (n < 4096 || !detect_lattice(n, Tp, Tj, g)) return 2;
+    int t[3] = {8, 8, 8};
+    if (g[2] == 1) { t[0] = 16; t[1] = 16; t[2] = 1; }
+    if (const char *e = getenv("LSSPG_TRI_TILE")) {
+        int a, b, c;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { t[0] = a; t[1] = b; t[2] = c; }
+    }
+    if ((long long)t[0] * t[1] * t[2] > kMaxTileRows) return 2;
+    const int nt[3] = {(g[0] + t[0] - 1) / t[0], (g[1] + t[1] - 1) / t[1], (g[2] + t[2] - 1) / t[2]};
+    const int ntiles = nt[0] * nt[1] * nt[2];
+    std::vector<int> tile_of(n);
+    for (int i = 0; i < n; i++) {
+        const int x = i % g[0], y = (i / g[0]) % g[1], z = i / (g[0] * g[1]);
+        tile_of[i] = ((z / t[2]) * nt[1] + (y / t[1])) * nt[0] + (x / t[0]);
+    }
+    // validate the triangle and compute the dependency level of every row, in solve order.  Rows of
+    // a box are later grouped by this GLOBAL level: the unfinished row of smallest level anywhere is
+    // then always inside its box's current group with all operands produced, so level barriers inside
+    // boxes can never deadlock boxes that depend on each other.
+    std::vector<int> gl(n, 0);
+    std::vector<long long> edges;   // box dependency edges: from * ntiles + to
+    int nlev_global = 0;
+    for (int q = 0; q < n; q++) {
+        const int i = lower ? q : n - 1 - q;
+        const int b = Tp[i], e = Tp[i + 1];
+        if (e <= b) return 2;
+        const int dpos = lower ? e - 1 : b;
+        if (Tj[dpos] != i) return 2;
+        int gg = 0;
+        for (int k = b; k < e; k++) {
+            if (k == dpos) continue;
+            const int c = Tj[k];
+            if (lower ? !(c >= 0 && c < i) : !(c > i && c < n)) return 2;
+            gg = std::max(gg, gl[c] + 1);
+            if (tile_of[c] != tile_of[i]) edges.push_back((long long)tile_of[c] * ntiles + tile_of[i]);
+        }
+        gl[i] = gg;
+        nlev_global = std::max(nlev_global, gg + 1);
+    }
+    std::sort(edges.begin(), edges.end());
+    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    // Box graph (producer box -> consumer box).  It may contain cycles (e.g. ILU(1) fill couples
+    // x-neighbouring boxes both ways): boxes of one strongly connected component must simply be in
+    // flight together, which the ticket order guarantees as long as a component is smaller than
+    // the number of resident warps.  Tarjan (iterative) emits components consumers-first.
+    std::vector<int> estart(ntiles + 1, 0);
+    for (long long ed : edges) estart[ed / ntiles + 1]++;
+    for (int k = 0; k < ntiles; k++) estart[k + 1] += estart[k];
+    std::vector<int> idx(ntiles, -1), low(ntiles, 0), comp(ntiles, -1), stk, cu, ce;
+    std::vector<char> onstk(ntiles, 0);
+    int counter = 0, ncomp = 0, max_scc = 0;
+    for (int root = 0; root < ntiles; root++) {
+        if (idx[root] >= 0) continue;
+        idx[root] = low[root] = counter++;
+        stk.push_back(root); onstk[root] = 1;
+        cu.push_back(root); ce.push_back(estart[root]);
+        while (!cu.empty()) {
+            const int u = cu.back();
+            if (ce.back() < estart[u + 1]) {
+                const int v = (int)(edges[ce.back()++] % ntiles);
+                if (idx[v] < 0) {
+                    idx[v] = low[v] = counter++;
+                    stk.push_back(v); onstk[v] = 1;
+                    cu.push_back(v); ce.push_back(estart[v]);
+                }
+                else if (onstk[v]) low[u] = std::min(low[u], idx[v]);
+            }
+            else {
+                if (low[u] == idx[u]) {
+                    int size = 0, w;
+                    do { w = stk.back(); stk.pop_back(); onstk[w] = 0; comp[w] = ncomp; size++; } while (w != u);
+                    max_scc = std::max(max_scc, size);
+                    ncomp++;
+                }
+                cu.pop_back(); ce.pop_back();
+                if (!cu.empty()) low[cu.back()] = std::min(low[cu.back()], low[u]);
+            }
+        }
+    }
+    if (max_scc > 128) return 2;
+    // Boxes that depend on each other both ways (ILU(1)/(2) fill) can only be run with per-operand
+    // polling, which measured slower than the slice schedule; opt-in for experiments.
+    if (max_scc > 1 && !(getenv("LSSPG_TRI_TILED_CYCLIC") && atoi(getenv("LSSPG_TRI_TILED_CYCLIC")) != 0)) return 2;
+    // producers-first rank of every component and its longest-path level in the condensation
+    std::vector<int> rank_of(ntiles), tlc(ncomp, 0), byrank(ntiles), rstart(ncomp + 1, 0);
+    for (int k = 0; k < ntiles; k++) { rank_of[k] = ncomp - 1 - comp[k]; rstart[rank_of[k] + 1]++; }
+    for (int r = 0; r < ncomp; r++) rstart[r + 1] += rstart[r];
+    {
+        std::vector<int> pos(rstart.begin(), rstart.end() - 1);
+        for (int k = 0; k < ntiles; k++) byrank[pos[rank_of[k]]++] = k;
+    }
+    for (int q = 0; q < ntiles; q++) {
+        const int u = byrank[q];
+        for (int k = estart[u]; k < estart[u + 1]; k++) {
+            const int v = (int)(edges[k] % ntiles);
+            if (rank_of[v] != rank_of[u]) tlc[rank_of[v]] = std::max(tlc[rank_of[v]], tlc[rank_of[u]] + 1);
+        }
+    }
+    std::vector<int> tl(ntiles);
+    for (int k = 0; k < ntiles; k++) tl[k] = tlc[rank_of[k]];
+    // ticket order of the boxes: by component level, then component, then id (components stay contiguous)
+    std::vector<int> torder(ntiles);
+    std::iota(torder.begin(), torder.end(), 0);
+    std::stable_sort(torder.begin(), torder.end(), [&](int a, int b) {
+        return tl[a] != tl[b] ? tl[a] < tl[b] : rank_of[a] < rank_of[b];
+    });
+    std::vector<int> ticket_of(ntiles);
+    for (int k = 0; k < ntiles; k++) ticket_of[torder[k]] = k;
+    // slots: rows sorted by (ticket of box, local level, row)
+    std::vector<int> order(n);
+    {
+        std::vector<int> start(ntiles + 1, 0);
+        for (int i = 0; i < n; i++) start[ticket_of[tile_of[i]] + 1]++;
+        for (int k = 0; k < ntiles; k++) start[k + 1] += start[k];
+        std::vector<int> pos(start.begin(), start.end() - 1);
+        for (int i = 0; i < n; i++) order[pos[ticket_of[tile_of[i]]]++] = i;   // bucket by box, rows ascending
+        for (int k = 0; k < ntiles; k++)
+            std::stable_sort(order.begin() + start[k], order.begin() + start[k + 1],
+                             [&](int a, int b) { return gl[a] < gl[b]; });
+    }
+    std::vector<int> slot_of(n);
+    for (int s = 0; s < n; s++) slot_of[order[s]] = s;
+    H.n = n; H.which = which; H.num_tiles = ntiles; H.num_levels = nlev_global;
+    H.num_tile_levels = ntiles ? *std::max_element(tl.begin(), tl.end()) + 1 : 0;
+    H.acyclic = (max_scc <= 1);
+    {   // predecessor boxes of every box, as tickets
+        H.pred_ptr.assign(ntiles + 1, 0);
+        for (long long ed : edges) H.pred_ptr[ticket_of[ed % ntiles] + 1]++;
+        for (int k = 0; k < ntiles; k++) H.pred_ptr[k + 1] += H.pred_ptr[k];
+        H.pred.resize(edges.size());
+        std::vector<int> pos(H.pred_ptr.begin(), H.pred_ptr.end() - 1);
+        for (long long ed : edges) H.pred[pos[ticket_of[ed % ntiles]]++] = ticket_of[ed / ntiles];
+    }
+    for (int k = 0; k < 3; k++) { H.tile_dims[k] = t[k]; H.grid_dims[k] = g[k]; }
+    H.perm = order;
+    H.diag.resize(n);
+    H.ptr.assign(n + 1, 0);
+    H.tile_ptr.assign(ntiles + 1, 0);
+    H.lev_off.assign(ntiles + 1, 0);
+    H.lev_ptr.clear();
+    H.offdiag_nnz = (long long)Tp[n] - n;
+    H.col.resize((size_t)H.offdiag_nnz);
+    H.val.resize((size_t)H.offdiag_nnz);
+    H.max_tile_rows = 0;
+    int s = 0, ent = 0;
+    for (int k = 0; k < ntiles; k++) {
+        const int s0 = s;
+        H.tile_ptr[k] = s0;
+        H.lev_off[k] = (int)H.lev_ptr.size();
+        int cur = -1;
+        while (s < n && ticket_of[tile_of[order[s]]] == k) {
+            const int i = order[s];
+            if (gl[i] != cur) { H.lev_ptr.push_back(s); cur = gl[i]; }
+            const int b = Tp[i], e = Tp[i + 1];
+            H.ptr[s] = ent;
+            H.diag[s] = lower ? Tx[e - 1] : Tx[b];
+            // application order: lower ascending storage order, upper descending
+            for (int q = 0; q < e - b - 1; q++) {
+                const int kk = lower ? b + q : e - 1 - q;
+                const int c = Tj[kk];
+                H.col[ent] = (tile_of[c] == tile_of[i]) ? -(slot_of[c] - s0 + 1) : c;
+                H.val[ent] = Tx[kk];
+                ent++;
+            }
+            s++;
+        }
+        H.lev_ptr.push_back(s);
+        H.max_tile_rows = std::max(H.max_tile_rows, s - s0);
+    }
+    H.tile_ptr[ntiles] = n;
+    H.lev_off[ntiles] = (int)H.lev_ptr.size();
+    H.ptr[n] = ent;
+    if (s != n || H.max_tile_rows > kMaxTileRows) return 2;
+    return 0;
+}
+
+// ---- device side ---------------------------------------------------------------------
+// Every box is packed into one 16-byte aligned blob
+//   [lev: nlev+1 int][ptr: nrows+1 int][perm: nrows int][ext: next int][pred: npred int][diag: nrows f64][col: nent int][val: nent f64]
+// (sections padded to 16 B; lev/ptr are box-relative; col < 0: -(slot in box + 1), col >= 0: index
+// into ext, the list of rows of OTHER boxes this box reads) so that a single bulk async copy
+// (cp.async.bulk, completion on an mbarrier) brings the whole box into shared memory.
+struct BoxDesc {
+    long long off;   // byte offset of the blob
+    int bytes;       // blob size (multiple of 16)
+    int nrows, nent, nlev, next, npred;
+};
+
+static inline size_t pad16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+struct BoxLayout {
+    size_t lev, ptr, perm, ext, pred, diag, col, val, total;
+};
+
+__host__ __device__ inline BoxLayout box_layout(int nrows, int nent, int nlev, int next, int npred)
+{
+    BoxLayout L;
+    size_t o = 0;
+    L.lev = o;  o += (((size_t)(nlev + 1) * 4) + 15) & ~(size_t)15;
+    L.ptr = o;  o += (((size_t)(nrows + 1) * 4) + 15) & ~(size_t)15;
+    L.perm = o; o += (((size_t)nrows * 4) + 15) & ~(size_t)15;
+    L.ext = o;  o += (((size_t)next * 4) + 15) & ~(size_t)15;
+    L.pred = o; o += (((size_t)npred * 4) + 15) & ~(size_t)15;
+    L.diag = o; o += (((size_t)nrows * 8) + 15) & ~(size_t)15;
+    L.col = o;  o += (((size_t)nent * 4) + 15) & ~(size_t)15;
+    L.val = o;  o += (((size_t)nent * 8) + 15) & ~(size_t)15;
+    L.total = o;
+    return L;
+}
+
+struct TiledArgs {
+    const unsigned char *blob;
+    const BoxDesc *desc;
+    unsigned int *counter;
+    int num_tiles;
+    int blob_cap;        // shared-memory bytes reserved for one blob
+    int max_tile_rows;
+    int max_ext;
+    double *x;
+    const double *rhs;
+    const int *stop;
+    int *err;
+    unsigned int *flags;        // per-box completion epochs (acyclic box graphs), else NULL
+    unsigned int epoch;
+    unsigned long long *prof;   // optional phase timers (LSSPG_TRI_PROF=1): ticket, blob, gather, compute, poll, boxes
+};
+
+__device__ __forceinline__ double ldx_relaxed(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void stx_relaxed(double *p, double v)
+{
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+// One warp (= one CTA) per box.
+__global__ void __launch_bounds__(32) tri_box_kernel(const TiledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (a.stop && *a.stop) return;
+    const int lane = threadIdx.x;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
+    unsigned char *sblob = smem + 16;
+    double *srhs = reinterpret_cast<double *>(sblob + a.blob_cap);
+    double *sxs = srhs + a.max_tile_rows;
+    double *sxe = sxs + a.max_tile_rows;   // operands owned by other boxes, fetched once per box
+    const unsigned int bar_s = smem_u32(bar), blob_s = smem_u32(sblob);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned int phase = 0;
+    const unsigned int total = (unsigned int)a.num_tiles + gridDim.x;
+    for (;;) {
+        unsigned int tk = 0;
+        long long t0 = a.prof ? clock64() : 0, t_poll = 0;
+        if (lane == 0) tk = atomicInc(a.counter, total - 1);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= (unsigned int)a.num_tiles) break;
+        const BoxDesc d = a.desc[tk];
+        long long t1 = a.prof ? clock64() : 0;
+        if (lane == 0) {
+            // the previous box's generic-proxy reads of the buffer precede this async-proxy write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"((unsigned int)d.bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(blob_s), "l"(a.blob + d.off), "r"((unsigned int)d.bytes), "r"(bar_s) : "memory");
+        }
+        {   // wait for the bytes to land
+            unsigned int ok = 0;
+            while (!ok) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(bar_s), "r"(phase) : "memory");
+            }
+            phase ^= 1;
+        }
+        long long t2 = a.prof ? clock64() : 0;
+        const BoxLayout lay = box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred);
+        const int *slev = reinterpret_cast<const int *>(sblob + lay.lev);
+        const int *sptr = reinterpret_cast<const int *>(sblob + lay.ptr);
+        const int *sperm = reinterpret_cast<const int *>(sblob + lay.perm);
+        const int *sext = reinterpret_cast<const int *>(sblob + lay.ext);
+        const double *sdiag = reinterpret_cast<const double *>(sblob + lay.diag);
+        const int *scol = reinterpret_cast<const int *>(sblob + lay.col);
+        const double *sval = reinterpret_cast<const double *>(sblob + lay.val);
+        // gather the right-hand side, eight independent loads in flight per lane
+        for (int s0 = 0; s0 < d.nrows; s0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * 32 + lane;
+                v[u] = (s < d.nrows) ? __ldg(a.rhs + sperm[s]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * 32 + lane;
+                if (s < d.nrows) srhs[s] = v[u];
+            }
+        }
+        if (a.flags) {
+            // acyclic box graph: wait until every box this one reads from has finished (one flag per box)
+            const int *spred = reinterpret_cast<const int *>(sblob + lay.pred);
+            for (int q = lane; q < d.npred; q += 32) {
+                const unsigned int *f = a.flags + spred[q];
+                int spins = 0;
+                unsigned int got;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(f) : "memory");
+                    if (got != a.epoch && ++spins > 4) __nanosleep(spins > 64 ? 400 : 64);
+                    if (spins > (1 << 21)) { *a.err = 1; break; }
+                } while (got != a.epoch);
+            }
+            __syncwarp();
+        }
+        // one pass over the operands owned by other boxes (all present when flags are used; otherwise
+        // most are, and a sentinel is resolved later, where it is used)
+        for (int q0 = 0; q0 < d.next; q0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int q = q0 + u * 32 + lane;
+                v[u] = (q < d.next) ? ldx_relaxed(a.x + sext[q]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int q = q0 + u * 32 + lane;
+                if (q < d.next) sxe[q] = v[u];
+            }
+        }
+        __syncwarp();
+        long long t3 = a.prof ? clock64() : 0;
+        for (int L = 0; L < d.nlev; L++) {
+            const int sa = slev[L], sb = slev[L + 1];
+            for (int slot = sa + lane; slot < sb; slot += 32) {
+                int e = sptr[slot];
+                const int e1 = sptr[slot + 1];
+                double r = srhs[slot];
+                const double dg = sdiag[slot];
+                const int row = sperm[slot];
+                while (e < e1) {
+                    // four entries at a time: all shared-memory loads first, then the sequential subtractions
+                    int c[4];
+                    double v[4], xv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const bool on = (e + j < e1);
+                        c[j] = on ? scol[e + j] : 0x7fffffff;
+                        v[j] = on ? sval[e + j] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        xv[j] = (c[j] == 0x7fffffff) ? 0.0 : (c[j] < 0 ? sxs[-c[j] - 1] : sxe[c[j]]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (c[j] >= 0 && c[j] != 0x7fffffff &&
+                            (unsigned long long)__double_as_longlong(xv[j]) == kSentinelBitsT) {
+                            // operand of another box that had not been produced when this box started
+                            const double *src = a.x + sext[c[j]];
+                            int spins = 0;
+                            const long long tp = a.prof ? clock64() : 0;
+                            do {
+                                xv[j] = ldx_relaxed(src);
+                                if (++spins > 8) __nanosleep(spins > 128 ? 200 : 32);
+                                if (spins > (1 << 21)) { *a.err = 1; break; }
+                            } while ((unsigned long long)__double_as_longlong(xv[j]) == kSentinelBitsT);
+                            if (a.prof) t_poll += clock64() - tp;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (c[j] != 0x7fffffff) r = r - v[j] * xv[j];   // reference src/solver-tri.cxx:18 / :40
+                    e += 4;
+                }
+                const double out = (dg == 1.0) ? r : r / dg;   // :22 / :44 (x / 1.0 == x exactly)
+                sxs[slot] = out;
+                // boxes that other boxes poll (cyclic box graphs) publish every row at once; with
+                // completion flags the rows leave together when the box is done, which keeps global
+                // stores (and the barrier's wait for them) out of the group loop
+                if (!a.flags) stx_relaxed(a.x + row, out);
+            }
+            __syncwarp();   // the group's x values are visible to the whole warp before the next group
+        }
+        if (a.flags) {   // publish: every lane's x stores first, then the box's completion flag
+            for (int s = lane; s < d.nrows; s += 32) a.x[sperm[s]] = sxs[s];
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flags + tk), "r"(a.epoch) : "memory");
+        }
+        if (a.prof) {
+            const long long t4 = clock64();
+            // per-box maximum over lanes of the time spent polling
+            for (int o = 16; o > 0; o >>= 1) t_poll = max(t_poll, __shfl_xor_sync(0xffffffffu, t_poll, o));
+            if (lane == 0) {
+                atomicAdd(a.prof + 0, (unsigned long long)(t1 - t0));
+                atomicAdd(a.prof + 1, (unsigned long long)(t2 - t1));
+                atomicAdd(a.prof + 2, (unsigned long long)(t3 - t2));
+                atomicAdd(a.prof + 3, (unsigned long long)(t4 - t3));
+                atomicAdd(a.prof + 4, (unsigned long long)t_poll);
+                atomicAdd(a.prof + 5, 1ull);
+            }
+        }
+    }
+}
+
+
+// ---- acyclic box graphs: lean kernel -----------------------------------------------------
+// When no two boxes depend on each other (ILU(0)-type factors) a box simply waits for the
+// completion flags of the boxes it reads from; after that every operand it needs exists, so
+// the group loop carries no polling and no sentinel tests.  The box is stored as ELL (fixed
+// width w, column-major) whose padding entries multiply a private +0.0 operand by +0.0 --
+// r - (+0) == r bit for bit -- which removes every predicate from the inner loop.  One warp
+// executes ~50 instructions per group instead of ~350.
+//   blob: [lev: nlev+1 int][perm: nrows int][ext: next int][pred: npred int][diag: nrows f64]
+//         [ecol: w*nrows int][eval: w*nrows f64]
+//   sx  : [0,nrows) rhs -> x of the box, [nrows, nrows+next) operands of other boxes, then +0.0
+struct EllLayout {
+    size_t lev, perm, ext, pred, diag, ecol, eval, total;
+};
+
+__host__ __device__ inline EllLayout ell_layout(int nrows, int w, int nlev, int next, int npred)
+{
+    EllLayout L;
+    size_t o = 0;
+    L.lev = o;  o += (((size_t)(nlev + 1) * 4) + 15) & ~(size_t)15;
+    L.perm = o; o += (((size_t)nrows * 4) + 15) & ~(size_t)15;
+    L.ext = o;  o += (((size_t)next * 4) + 15) & ~(size_t)15;
+    L.pred = o; o += (((size_t)npred * 4) + 15) & ~(size_t)15;
+    L.diag = o; o += (((size_t)nrows * 8) + 15) & ~(size_t)15;
+    L.ecol = o; o += (((size_t)w * nrows * 4) + 15) & ~(size_t)15;
+    L.eval = o; o += (((size_t)w * nrows * 8) + 15) & ~(size_t)15;
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(32) tri_box_ell_kernel(const TiledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (a.stop && *a.stop) return;
+    const int lane = threadIdx.x;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
+    unsigned char *sblob = smem + 16;
+    double *sx = reinterpret_cast<double *>(sblob + a.blob_cap);
+    const unsigned int bar_s = smem_u32(bar), blob_s = smem_u32(sblob);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned int phase = 0;
+    const unsigned int total = (unsigned int)a.num_tiles + gridDim.x;
+    for (;;) {
+        unsigned int tk = 0;
+        if (lane == 0) tk = atomicInc(a.counter, total - 1);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= (unsigned int)a.num_tiles) break;
+        const BoxDesc d = a.desc[tk];   // d.nent holds the ELL width here
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"((unsigned int)d.bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(blob_s), "l"(a.blob + d.off), "r"((unsigned int)d.bytes), "r"(bar_s) : "memory");
+        }
+        {
+            unsigned int ok = 0;
+            while (!ok) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(bar_s), "r"(phase) : "memory");
+            }
+            phase ^= 1;
+        }
+        const int nrows = d.nrows, w = d.nent;
+        const EllLayout lay = ell_layout(nrows, w, d.nlev, d.next, d.npred);
+        const int *slev = reinterpret_cast<const int *>(sblob + lay.lev);
+        const int *sperm = reinterpret_cast<const int *>(sblob + lay.perm);
+        const int *sext = reinterpret_cast<const int *>(sblob + lay.ext);
+        const int *spred = reinterpret_cast<const int *>(sblob + lay.pred);
+        const double *sdiag = reinterpret_cast<const double *>(sblob + lay.diag);
+        const int *ecol = reinterpret_cast<const int *>(sblob + lay.ecol);
+        const double *eval = reinterpret_cast<const double *>(sblob + lay.eval);
+        // right-hand side of the box, eight independent loads in flight per lane
+        for (int s0 = 0; s0 < nrows; s0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * 32 + lane;
+                v[u] = (s < nrows) ? __ldg(a.rhs + sperm[s]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * 32 + lane;
+                if (s < nrows) sx[s] = v[u];
+            }
+        }
+        if (lane == 0) sx[nrows + d.next] = 0.0;
+        // wait for the boxes this one reads from
+        for (int q = lane; q < d.npred; q += 32) {
+            const unsigned int *f = a.flags + spred[q];
+            int spins = 0;
+            unsigned int got;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(f) : "memory");
+                if (got != a.epoch && ++spins > 16) __nanosleep(40);   // few pollers (<= 3 lanes per box): keep it tight
+                if (spins > (1 << 21)) { *a.err = 1; break; }
+            } while (got != a.epoch);
+        }
+        __syncwarp();
+        __threadfence();   // acquire side: the operands below were published before the flags
+        for (int q0 = 0; q0 < d.next; q0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int q = q0 + u * 32 + lane;
+                v[u] = (q < d.next) ? ldx_relaxed(a.x + sext[q]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int q = q0 + u * 32 + lane;
+                if (q < d.next) sx[nrows + q] = v[u];
+            }
+        }
+        __syncwarp();
+        for (int L = 0; L < d.nlev; L++) {
+            const int sa = slev[L], sb = slev[L + 1];
+            for (int slot = sa + lane; slot < sb; slot += 32) {
+                double r = sx[slot];
+                for (int k = 0; k < w; k++) {
+                    const int c = ecol[k * nrows + slot];
+                    r = r - eval[k * nrows + slot] * sx[c];   // reference src/solver-tri.cxx:18 / :40
+                }
+                const double dg = sdiag[slot];
+                if (dg != 1.0) r = r / dg;                    // :22 / :44 (x / 1.0 == x exactly)
+                sx[slot] = r;
+            }
+            __syncwarp();
+        }
+        for (int s = lane; s < nrows; s += 32) a.x[sperm[s]] = sx[s];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.flags + tk), "r"(a.epoch) : "memory");
+    }
+}
+
+int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded)
+{
+    double sentinel;
+    const unsigned long long bits = kSentinelBitsT;
+    memcpy(&sentinel, &bits, sizeof(double));
+    LSSPG_TRY(vec_set(ctx, T->n, dx, sentinel, guarded));
+    TiledArgs a;
+    a.blob = T->t_blob; a.desc = (const BoxDesc *)T->t_desc;
+    a.counter = T->d_counter; a.num_tiles = T->num_tiles; a.blob_cap = T->blob_cap; a.max_tile_rows = T->max_tile_rows;
+    a.max_ext = T->max_ext;
+    a.flags = T->box_flags ? T->t_flags : nullptr;
+    a.epoch = ++const_cast<lsspg_tri *>(T)->epoch;
+    a.x = dx; a.rhs = drhs;
+    a.stop = guarded ? ctx->d_flags + FLAG_STOP : nullptr;
+    a.err = ctx->d_flags + FLAG_TRI_TIMEOUT;
+    const size_t smem = T->box_flags ? 16 + (size_t)T->blob_cap + 8 * ((size_t)T->max_tile_rows + T->max_ext + 2)
+                                     : 16 + (size_t)T->blob_cap + 16 * (size_t)T->max_tile_rows + 8 * (size_t)T->max_ext;
+    static int env_cap = -1;
+    if (env_cap < 0) {
+        const char *e = getenv("LSSPG_TRI_TILED_CTAS_PER_SM");
+        env_cap = e ? atoi(e) : 32;
+        if (env_cap < 1) env_cap = 1;
+    }
+    int per_sm = (int)std::min<size_t>((size_t)env_cap, (size_t)(224 * 1024) / (smem + 1024));
+    per_sm = std::max(1, std::min(per_sm, 32));
+    int grid = std::min(T->num_tiles, ctx->num_sms * per_sm);
+    if (grid < 1) grid = 1;
+    static int prof_on = -1;
+    static unsigned long long *d_prof = nullptr;
+    if (prof_on < 0) {
+        prof_on = getenv("LSSPG_TRI_PROF") ? 1 : 0;
+        if (prof_on) { cudaMalloc(&d_prof, 64); cudaMemset(d_prof, 0, 64); }
+    }
+    a.prof = prof_on ? d_prof : nullptr;
+    if (T->box_flags) LSSPG_LAUNCH(ctx, tri_box_ell_kernel, grid, 32, smem, a);
+    else LSSPG_LAUNCH(ctx, tri_box_kernel, grid, 32, smem, a);
+    if (prof_on) {
+        unsigned long long h[8];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, d_prof, 64, cudaMemcpyDeviceToHost);
+        cudaMemset(d_prof, 0, 64);
+        if (h[5])
+            fprintf(stderr, "[tri_box] boxes=%llu grid=%d cycles/box: ticket %.0f blob %.0f gather %.0f compute %.0f (of which polling %.0f)\n",
+                    h[5], grid, (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5]);
+    }
+    return 0;
+}
+
+static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const std::vector<unsigned char> &blob,
+                         const std::vector<BoxDesc> &desc, size_t cap, int max_ext, bool flags)
+{
+    T->tiled = true;
+    T->num_tiles = H.num_tiles; T->max_tile_rows = H.max_tile_rows; T->num_tile_levels = H.num_tile_levels;
+    T->blob_cap = (int)cap;
+    T->max_ext = max_ext;
+    T->box_flags = flags;
+    LSSPG_CUDA(cudaMalloc(&T->t_flags, sizeof(unsigned int) * std::max(H.num_tiles, 1)));
+    LSSPG_CUDA(cudaMemsetAsync(T->t_flags, 0, sizeof(unsigned int) * std::max(H.num_tiles, 1), ctx->stream));
+    for (int k = 0; k < 3; k++) { T->tile_dims[k] = H.tile_dims[k]; T->grid_dims[k] = H.grid_dims[k]; }
+    LSSPG_CUDA(cudaMalloc(&T->t_blob, blob.size()));
+    LSSPG_CUDA(cudaMalloc(&T->t_desc, sizeof(BoxDesc) * std::max<size_t>(desc.size(), 1)));
+    LSSPG_CUDA(cudaMemcpyAsync(T->t_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!desc.empty())
+        LSSPG_CUDA(cudaMemcpyAsync(T->t_desc, desc.data(), sizeof(BoxDesc) * desc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(tri_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(tri_box_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// acyclic box graph: ELL blobs for tri_box_ell_kernel
+static int upload_ell(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
+{
+    std::vector<BoxDesc> desc(H.num_tiles);
+    size_t total = 0, cap = 0;
+    int max_ext = 0;
+    for (int k = 0; k < H.num_tiles; k++) {
+        const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
+        BoxDesc &d = desc[k];
+        d.nrows = s1 - s0;
+        d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
+        d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
+        d.next = 0;
+        int w = 0;
+        for (int s = s0; s < s1; s++) w = std::max(w, H.ptr[s + 1] - H.ptr[s]);
+        for (int e = H.ptr[s0]; e < H.ptr[s1]; e++) d.next += (H.col[e] >= 0);
+        d.nent = w;   // ELL width
+        max_ext = std::max(max_ext, d.next);
+        const EllLayout lay = ell_layout(d.nrows, w, d.nlev, d.next, d.npred);
+        d.off = (long long)total;
+        d.bytes = (int)lay.total;
+        total += lay.total;
+        cap = std::max(cap, lay.total);
+    }
+    if (16 + cap + 8 * ((size_t)H.max_tile_rows + max_ext + 2) > (size_t)200 * 1024) return 2;
+    std::vector<unsigned char> blob(std::max<size_t>(total, 16), 0);
+    for (int k = 0; k < H.num_tiles; k++) {
+        const int s0 = H.tile_ptr[k];
+        const BoxDesc &d = desc[k];
+        const int w = d.nent, nr = d.nrows;
+        const EllLayout lay = ell_layout(nr, w, d.nlev, d.next, d.npred);
+        unsigned char *b = blob.data() + d.off;
+        int *lev = (int *)(b + lay.lev), *perm = (int *)(b + lay.perm), *ext = (int *)(b + lay.ext), *pred = (int *)(b + lay.pred);
+        int *ecol = (int *)(b + lay.ecol);
+        double *diag = (double *)(b + lay.diag), *eval = (double *)(b + lay.eval);
+        for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
+        for (int q = 0; q < d.npred; q++) pred[q] = H.pred[H.pred_ptr[k] + q];
+        int q = 0;
+        for (int s = 0; s < nr; s++) {
+            perm[s] = H.perm[s0 + s];
+            diag[s] = H.diag[s0 + s];
+            const int e0 = H.ptr[s0 + s], len = H.ptr[s0 + s + 1] - e0;
+            for (int j = 0; j < w; j++) {
+                if (j < len) {
+                    const int c = H.col[e0 + j];
+                    if (c >= 0) { ext[q] = c; ecol[j * nr + s] = nr + q; q++; }
+                    else ecol[j * nr + s] = -c - 1;
+                    eval[j * nr + s] = H.val[e0 + j];
+                }
+                else {
+                    ecol[j * nr + s] = nr + d.next;   // the box's private +0.0 operand
+                    eval[j * nr + s] = 0.0;
+                }
+            }
+        }
+    }
+    return upload_common(ctx, H, T, blob, desc, cap, max_ext, true);
+}
+
+int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
+{
+    {
+        const char *e = getenv("LSSPG_TRI_BOX_FLAGS");
+        if (H.acyclic && !(e && atoi(e) == 0)) {
+            const int rc = upload_ell(ctx, H, T);
+            if (rc != 2) return rc;
+        }
+    }
+    // pack the boxes
+    std::vector<BoxDesc> desc(H.num_tiles);
+    size_t total = 0, cap = 0;
+    int max_ext = 0;
+    for (int k = 0; k < H.num_tiles; k++) {
+        const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
+        BoxDesc &d = desc[k];
+        d.nrows = s1 - s0;
+        d.nent = H.ptr[s1] - H.ptr[s0];
+        d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
+        d.next = 0;
+        d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
+        for (int e = H.ptr[s0]; e < H.ptr[s1]; e++) d.next += (H.col[e] >= 0);
+        max_ext = std::max(max_ext, d.next);
+        const BoxLayout lay = box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred);
+        d.off = (long long)total;
+        d.bytes = (int)lay.total;
+        total += lay.total;
+        cap = std::max(cap, lay.total);
+    }
+    if (16 + cap + 16 * (size_t)H.max_tile_rows + 8 * (size_t)max_ext > (size_t)200 * 1024) {
+        set_error("tri_tiled: a box needs more shared memory than one SM has");
+        return 1;
+    }
+    std::vector<unsigned char> blob(std::max<size_t>(total, 16), 0);
+    for (int k = 0; k < H.num_tiles; k++) {
+        const int s0 = H.tile_ptr[k];
+        const BoxDesc &d = desc[k];
+        const BoxLayout lay = box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred);
+        unsigned char *b = blob.data() + d.off;
+        int *lev = (int *)(b + lay.lev), *ptr = (int *)(b + lay.ptr), *perm = (int *)(b + lay.perm), *col = (int *)(b + lay.col);
+        int *ext = (int *)(b + lay.ext), *pred = (int *)(b + lay.pred);
+        for (int q = 0; q < d.npred; q++) pred[q] = H.pred[H.pred_ptr[k] + q];
+        double *diag = (double *)(b + lay.diag), *val = (double *)(b + lay.val);
+        for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
+        const int e0 = H.ptr[s0];
+        for (int s = 0; s <= d.nrows; s++) ptr[s] = H.ptr[s0 + s] - e0;
+        for (int s = 0; s < d.nrows; s++) { perm[s] = H.perm[s0 + s]; diag[s] = H.diag[s0 + s]; }
+        for (int e = 0, q = 0; e < d.nent; e++) {
+            const int c = H.col[e0 + e];
+            if (c >= 0) { ext[q] = c; col[e] = q++; }
+            else col[e] = c;
+            val[e] = H.val[e0 + e];
+        }
+    }
+    return upload_common(ctx, H, T, blob, desc, cap, max_ext, false);
+}
+
+void tri_tiled_free(lsspg_tri *T)
+{
+    cudaFree(T->t_blob);
+    cudaFree(T->t_desc);
+    cudaFree(T->t_flags);
+}
+
+}  // namespace lsspg
+
+using namespace lsspg;
+
+extern "C" {
+
+// Layout self-check for the CPU test-suite (never called by any product path): builds the
+// tile schedule on the host and walks it box by box in ticket order, local level by local
+// level, reading in-box operands from a private copy exactly as the kernel does.
+// Returns 0 and *applicable = 1 when the factor has a tile schedule.
+int lsspg_debug_tri_walk_tiled_host(int which, int n, const int *hTp, const int *hTj, const double *hTx, double *hx,
+                                    const double *hrhs, int *applicable, int *info /* [8] */)
+{
+    TiledHost H;
+    const int rc = tri_tiled_build_host(which, n, hTp, hTj, hTx, H);
+    if (applicable) *applicable = (rc == 0);
+    if (rc == 1) return 1;
+    if (rc == 2) return 0;
+    const double poison = strtod("nan", nullptr);
+    for (int i = 0; i < n; i++) hx[i] = poison;   // an operand read before it is produced poisons the result
+    // Boxes of one strongly connected component run concurrently on the device; emulate that by
+    // sweeping over all unfinished boxes repeatedly: a box advances level by level, and inside
+    // its current level every row whose operands have been produced is computed.
+    std::vector<std::vector<double>> xs(H.num_tiles);
+    std::vector<int> curL(H.num_tiles);
+    std::vector<char> done(n, 0);
+    int remaining = 0;
+    for (int tk = 0; tk < H.num_tiles; tk++) {
+        curL[tk] = H.lev_off[tk];
+        xs[tk].assign(H.tile_ptr[tk + 1] - H.tile_ptr[tk], poison);
+        if (curL[tk] < H.lev_off[tk + 1] - 1) remaining++;
+    }
+    while (remaining > 0) {
+        bool progress = false;
+        for (int tk = 0; tk < H.num_tiles; tk++) {
+            const int s0 = H.tile_ptr[tk];
+            while (curL[tk] < H.lev_off[tk + 1] - 1) {
+                const int L = curL[tk];
+                bool level_done = true;
+                for (int slot = H.lev_ptr[L]; slot < H.lev_ptr[L + 1]; slot++) {
+                    if (done[slot]) continue;
+                    bool ready = true;
+                    for (int e = H.ptr[slot]; e < H.ptr[slot + 1] && ready; e++) {
+                        const int c = H.col[e];
+                        const double v = c < 0 ? xs[tk][-c - 1] : hx[c];
+                        if (v != v) ready = false;
+                    }
+                    if (!ready) { level_done = false; continue; }
+                    double r = hrhs[H.perm[slot]];
+                    for (int e = H.ptr[slot]; e < H.ptr[slot + 1]; e++) {
+                        const int c = H.col[e];
+                        r = r - H.val[e] * (c < 0 ? xs[tk][-c - 1] : hx[c]);
+                    }
+                    const double out = (H.diag[slot] == 1.0) ? r : r / H.diag[slot];
+                    xs[tk][slot - s0] = out;
+                    hx[H.perm[slot]] = out;
+                    done[slot] = 1;
+                    progress = true;
+                }
+                if (!level_done) break;
+                curL[tk]++;
+                if (curL[tk] == H.lev_off[tk + 1] - 1) remaining--;
+            }
+        }
+        if (!progress) {
+            lsspg::set_error("tiled walk: no progress (schedule would deadlock)");
+            return 1;
+        }
+    }
+    if (info) {
+        info[0] = H.num_tiles; info[1] = H.num_tile_levels; info[2] = H.max_tile_rows; info[3] = H.num_levels;
+        info[4] = H.grid_dims[0]; info[5] = H.grid_dims[1]; info[6] = H.grid_dims[2]; info[7] = H.tile_dims[0];
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,7 +1,9 @@
 #!/bin/bash
-# parameter sweep of the triangular-solve kernel (N=128 unless given)
+# parameter sweep of the triangular-solve kernels.  usage: tri_sweep.sh N
 N=${1:-128}
-for cfg in "4 1 64 64" "4 0 64 64" "2 1 64 64" "1 1 64 64" "1 0 64 64" "8 1 64 64" "4 1 4 32" "4 1 1000000 0" "2 0 1000000 0" "1 0 1000000 0" "4 1 16 200"; do
-  set -- $cfg
-  echo "ctas=$1 hint=$2 spin=$3 sleep=$4: $(LSSPG_TRI_CTAS_PER_SM=$1 LSSPG_TRI_HINT=$2 LSSPG_TRI_SPIN=$3 LSSPG_TRI_SLEEP=$4 timeout 300 python scripts/kbench.py $N 2>&1 | python -c 'import sys,json; r=json.loads(sys.stdin.readline()); print(r["ilu0_apply_ms"], r["us_per_level"], r["cg_ilu0_ms_per_it"])')"
-done
+run() { echo "$1: $(env $1 timeout 300 python scripts/kbench.py $N 2>&1 | python -c 'import sys,json; r=json.loads(sys.stdin.readline()); print("apply_ms", r["ilu0_apply_ms"], "us/level", r["us_per_level"], "cg_it_ms", r["cg_ilu0_ms_per_it"], "bicg_it_ms", r["bicgstab_ilu0_ms_per_it"])')"; }
+timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "tri or ilu or pc" 2>&1 | tail -3
+run "LSSPG_TRI_TILED=0"
+run "LSSPG_TRI_BOX_FLAGS=0"
+run "LSSPG_TRI_BOX_FLAGS=1"
+for t in "4,4,4" "8,8,4" "8,4,4" "16,4,4" "16,8,8" "16,16,4"; do run "LSSPG_TRI_TILE=$t"; done

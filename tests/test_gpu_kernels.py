@@ -188,6 +188,42 @@ def test_trisolve_and_ilu_apply_bit_exact(ctx, golden, checker, name, tag, kw):
     assert np.array_equal(pc.apply_host(rhs), x)
 
 
+def test_both_tri_schedules_are_exercised(ctx, checker):
+    """Stencil factors take the box schedule, everything else the slice schedule; with the box
+    schedule disabled (LSSPG_TRI_TILED=0 at analysis time) the same factor must give the same bits."""
+    import os
+    A = matrix("lap3d_32")
+    n = len(A[0]) - 1
+    for level in (0, 1):
+        L, U = api.ilu_factor(A, "iluk", level=level)
+        rhs = tvec(n, 4)
+        want = checker.tri_lower(L, rhs)
+        # ILU(0): acyclic box graph -> box schedule by default.  ILU(1): boxes depend on each other
+        # both ways -> slice schedule by default, polling box schedule only on request.
+        os.environ["LSSPG_TRI_TILED_CYCLIC"] = "1"
+        try:
+            T = api.Tri(ctx, 0, L)
+        finally:
+            del os.environ["LSSPG_TRI_TILED_CYCLIC"]
+        assert T.schedule()["tiled"] and T.schedule()["boxes"] == 64
+        Td = api.Tri(ctx, 0, L)
+        assert Td.schedule()["tiled"] == (level == 0)
+        os.environ["LSSPG_TRI_TILED"] = "0"
+        try:
+            T0 = api.Tri(ctx, 0, L)
+        finally:
+            del os.environ["LSSPG_TRI_TILED"]
+        assert not T0.schedule()["tiled"]
+        drhs, dx = ctx.upload(rhs), ctx.empty(n)
+        for t in (T, Td, T0):
+            t.solve(dx, drhs)
+            assert np.array_equal(dx.get(), want)
+            t.solve(dx, drhs)      # a second sweep reuses flags / counters (epoch bump, ticket wrap)
+            assert np.array_equal(dx.get(), want)
+    Tp = api.Tri(ctx, 0, api.ilu_factor(matrix("powerlaw_4000"), "iluk", level=0)[0])
+    assert not Tp.schedule()["tiled"]
+
+
 def test_trisolve_single_chain_and_diagonal(ctx, checker):
     # worst case for level scheduling: a bidiagonal chain (n levels) and a pure diagonal (1 level)
     n = 4000

@@ -111,6 +111,40 @@ def test_level_ordered_layout_reproduces_reference_sweeps(golden, name, tag, kw)
     assert pad >= int(L[0][-1]) - n and ns >= (n + 31) // 32
 
 
+@pytest.mark.parametrize("name", ["lap3d_32", "cd3d_32", "lap2d_100"])
+@pytest.mark.parametrize("tag,kw", [FACTOR_CASES[0], FACTOR_CASES[1], FACTOR_CASES[2]])
+def test_box_schedule_reproduces_reference_sweeps(golden, monkeypatch, name, tag, kw):
+    """Structured-grid factors get the box (tile) schedule: one warp per 8x8x8 (16x16) box,
+    in-box operands from shared memory.  Emulating it on the host -- boxes of one strongly
+    connected component advancing concurrently, level barriers inside each box -- must give
+    the reference's sweeps bit for bit and must never stall (ILU(1)/(2) fill makes the box
+    graph cyclic)."""
+    A = matrix(name)
+    n = len(A[0]) - 1
+    L, U = api.ilu_factor(A, **kw)
+    e = golden["factors"][name + "/" + tag]
+    if tag != "iluk0":
+        # cyclic box graphs are opt-in (they need per-operand polling, measured slower than slices)
+        assert api.tri_walk_tiled_host(0, L, tvec(n))[1] is None
+        monkeypatch.setenv("LSSPG_TRI_TILED_CYCLIC", "1")
+    y, info = api.tri_walk_tiled_host(0, L, tvec(n))
+    assert info is not None, "expected a box schedule for a stencil factor"
+    assert info["nx"] * info["ny"] * info["nz"] == n and info["max_box_rows"] <= 512
+    assert sha(y) == e["lower_sha"]
+    x, info_u = api.tri_walk_tiled_host(1, U, y)
+    assert sha(x) == e["apply_sha"]
+    if tag == "iluk0":
+        N = info["nx"]
+        assert info["row_levels"] == (3 * N - 2 if info["nz"] > 1 else 2 * N - 1)
+        assert info["box_levels"] < info["row_levels"] / 5    # most hops of the critical path stay in a box
+
+
+def test_box_schedule_not_used_for_irregular_factors():
+    A = matrix("powerlaw_4000")
+    L, U = api.ilu_factor(A, "iluk", level=0)
+    assert api.tri_walk_tiled_host(0, L, tvec(len(A[0]) - 1))[0] is None
+
+
 def test_tri_analysis_rejects_malformed_factors():
     Lp = np.array([0, 1, 3], np.int32)
     Lj = np.array([0, 1, 0], np.int32)     # row 1 stores its diagonal first, not last
