@@ -179,6 +179,29 @@ double lsspg_pc_bytes(const lsspg_pc *pc);
 int lsspg_pc_apply(lsspg_ctx *ctx, lsspg_pc *pc, double *dx, const double *drhs);
 int lsspg_pc_apply_host(lsspg_ctx *ctx, lsspg_pc *pc, double *hx, const double *hrhs);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch -------------------------
+ * The reference is serial; the path shards by contiguous row blocks of ceil(n/P) rows, the
+ * block boundaries of lssp_mat_get_block_diag (src/matrix-utils.cxx:615,626-628), so that the
+ * per-GPU ILU equals the reference's blocked ILU (src/pc-iluk.cxx:411-552) = block-Jacobi.
+ * A rank holds its rows with columns renumbered [owned ; ghost]; every vector handed to
+ * lsspg_mv / the drivers as SpMV input has num_cols = owned + ghost entries. */
+typedef struct lsspg_halo lsspg_halo;
+int lsspg_comm_unique_id(void *out128);                       /* rank 0: 128-byte NCCL id to broadcast */
+int lsspg_comm_init(lsspg_ctx *ctx, int rank, int nranks, const void *id128);
+int lsspg_comm_destroy(lsspg_ctx *ctx);
+int lsspg_comm_size(lsspg_ctx *ctx, int *rank, int *nranks);
+int lsspg_allreduce_sum(lsspg_ctx *ctx, double *d_buf, int count);   /* in place */
+/* peers[p] receives x[send_idx[send_off[p] .. send_off[p+1])] (owned row indices) and sends the
+ * recv_counts[p] entries that fill this rank's ghost segment, peers in the given order */
+int lsspg_halo_create(lsspg_ctx *ctx, int n_owned, int npeers, const int *peers, const int *send_counts,
+                      const int *h_send_idx, const int *recv_counts, lsspg_halo **out);
+int lsspg_halo_destroy(lsspg_ctx *ctx, lsspg_halo *H);
+int lsspg_halo_sizes(const lsspg_halo *H, int *n_owned, int *n_ghost, int *n_send);
+int lsspg_halo_exchange(lsspg_ctx *ctx, const lsspg_halo *H, double *dx);
+/* attach to a matrix uploaded with num_rows = owned, num_cols = owned + ghost: every SpMV
+ * on it refreshes the ghost tail of x first */
+int lsspg_csr_set_halo(lsspg_csr *A, lsspg_halo *H);
+
 /* ---- Krylov drivers (replace int lssp_solver_<m>(LSSP_SOLVER&, LSSP_PC&),
  *      src/solver-*.cxx; numbering = LSSP_SOLVER_TYPE with every USE_* = 0,
  *      include/type-defs.h:156-174) ------------------------------------------ */

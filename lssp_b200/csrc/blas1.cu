@@ -6,6 +6,7 @@
 // are run-to-run reproducible.  Element-wise arithmetic keeps the reference's
 // operand order and is compiled without FMA, hence bit-identical to the CPU.
 #include "blas1.cuh"
+#include "comm.cuh"
 
 namespace lsspg {
 
@@ -43,6 +44,7 @@ struct RedArgs {
     const int *stop;
     double *seq;          // sequential-order verification mode: per-element terms, [K][seq_n]
     long long seq_n;
+    int defer_fin;        // multi-GPU: sums are combined across ranks before `fin` runs (comm.cu)
     FinProg fin;
 };
 
@@ -54,6 +56,7 @@ static RedArgs red_args(lsspg_ctx *ctx, const RedOut &o)
     r.stop = o.guarded ? ctx->d_flags + FLAG_STOP : nullptr;
     r.seq = ctx->opt_reduce_sequential ? ctx->d_seq : nullptr;
     r.seq_n = (long long)ctx->seq_len;
+    r.defer_fin = distributed(ctx) ? 1 : 0;
     return r;
 }
 
@@ -77,7 +80,7 @@ __global__ void k_seq_sum(long long n, int K, RedArgs ra)
         ra.scal[ra.out_slot + threadIdx.x] = s;
     }
     __syncthreads();
-    if (threadIdx.x == 0) fin_run(ra.fin, ra.scal, ra.flags);
+    if (threadIdx.x == 0 && !ra.defer_fin) fin_run(ra.fin, ra.scal, ra.flags);
 }
 
 int seq_prepare(lsspg_ctx *ctx, long long n)
@@ -86,10 +89,12 @@ int seq_prepare(lsspg_ctx *ctx, long long n)
     return ensure_seq(ctx, (size_t)(n > 0 ? n : 1));
 }
 
+// called after every reducing kernel: sequential-order adder (verification mode) and, on
+// several GPUs, the cross-rank combination of the sums followed by the deferred FinProg
 int seq_finish(lsspg_ctx *ctx, long long n, int K, const RedOut &o)
 {
-    if (!ctx->opt_reduce_sequential) return 0;
-    LSSPG_LAUNCH(ctx, k_seq_sum, 1, 32, 0, n, K, red_args(ctx, o));
+    if (ctx->opt_reduce_sequential) LSSPG_LAUNCH(ctx, k_seq_sum, 1, 32, 0, n, K, red_args(ctx, o));
+    if (distributed(ctx)) return red_post(ctx, o.out_slot, K, o.fin, o.guarded);
     return 0;
 }
 
@@ -101,10 +106,11 @@ __device__ __forceinline__ void finish(double (&acc)[K], const RedArgs &ra)
     int *flags = ra.flags;
     const int slot = ra.out_slot;
     const FinProg &fin = ra.fin;
+    const int defer = ra.defer_fin;
     grid_sum<K>(acc, ra.partials, ra.ticket, [&](double(&s)[K]) {
 #pragma unroll
         for (int k = 0; k < K; k++) scal[slot + k] = s[k];
-        fin_run(fin, scal, flags);
+        if (!defer) fin_run(fin, scal, flags);
     });
 }
 

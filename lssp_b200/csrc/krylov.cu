@@ -24,7 +24,7 @@ int krylov_cg(KrylovArgs &k)
     lsspg_ctx *ctx = k.ctx;
     const int n = k.n;
     const bool non = (k.pc->kind == LSSPG_PC_NON);
-    Workspace W(ctx, n);
+    Workspace W(ctx, k.nvec);
     double *r = W.vec(), *p = W.vec(), *q = W.vec();
     double *z = non ? r : W.vec();   // pc NON: z is a bitwise copy of r (src/pc.cxx:67-70) -> alias
     LSSPG_CHECK(r && p && q && z, "cg: out of device memory");
@@ -106,7 +106,7 @@ int krylov_bicgstab(KrylovArgs &k)
     lsspg_ctx *ctx = k.ctx;
     const int n = k.n;
     const bool non = (k.pc->kind == LSSPG_PC_NON);
-    Workspace W(ctx, n);
+    Workspace W(ctx, k.nvec);
     double *r = W.vec(), *rh = W.vec(), *p = W.vec(), *s = W.vec(), *t = W.vec(), *v = W.vec();
     double *ph = non ? p : W.vec();   // pc NON: ph is a bitwise copy of p -> alias
     double *sh = non ? s : W.vec();
@@ -224,9 +224,10 @@ static int resolve(KrylovArgs &k, lsspg_ctx *ctx, const lsspg_csr *A, lsspg_pc *
                    const lsspg_solver_opts *o, lsspg_solve_info *info)
 {
     LSSPG_CHECK(ctx && A && pc && db && dx && o && info, "krylov: NULL argument");
-    LSSPG_CHECK(A->num_rows == A->num_cols, "krylov: matrix is not square");   // assert in every driver
+    LSSPG_CHECK(A->num_rows == A->num_cols || A->halo, "krylov: matrix is not square");   // assert in every driver
     LSSPG_CHECK(pc->n == A->num_rows, "krylov: preconditioner size %d != matrix size %d", pc->n, A->num_rows);
     k.ctx = ctx; k.A = A; k.pc = pc; k.b = db; k.x = dx; k.n = A->num_rows;
+    k.nvec = A->num_cols > A->num_rows ? A->num_cols : A->num_rows;
     // option resolution as at the top of every reference driver (e.g. src/solver-cg.cxx:36-38)
     k.maxit = o->maxit <= 0 ? kDefMaxit : o->maxit;
     k.tol_abs = o->tol_abs < 0 ? kDefAtol : o->tol_abs;
@@ -288,7 +289,7 @@ int lsspg_krylov_solve_host(lsspg_ctx *ctx, int solver, const lsspg_csr *A, lssp
 {
     LSSPG_CHECK(ctx && A && hb && hx, "lsspg_krylov_solve_host: NULL argument");
     const size_t n = A->num_rows;
-    LSSPG_TRY(ensure_stage(ctx, n));
+    LSSPG_TRY(ensure_stage(ctx, (size_t)(A->num_cols > A->num_rows ? A->num_cols : A->num_rows)));
     LSSPG_CUDA(cudaMemcpyAsync(ctx->stage[0], hx, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     LSSPG_CUDA(cudaMemcpyAsync(ctx->stage[1], hb, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     LSSPG_TRY(lsspg_krylov_solve(ctx, solver, A, pc, ctx->stage[1], ctx->stage[0], opts, info));

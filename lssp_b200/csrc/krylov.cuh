@@ -56,7 +56,8 @@ struct KrylovArgs {
     lsspg_pc *pc;
     const double *b;
     double *x;
-    int n;
+    int n;      // owned rows (length of every reduction / update)
+    int nvec;   // allocated vector length: owned rows + ghost columns of a distributed matrix
     // resolved options
     double tol_abs, tol_rel, tol_rb;
     int maxit, restart, aug_k, bgsl, idrs, verb;

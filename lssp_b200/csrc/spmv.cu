@@ -16,6 +16,7 @@
 // x is gathered through L1/L2 (read-only path); val/col/Ap/y/z cross HBM once.
 #include <algorithm>
 #include "blas1.cuh"
+#include "comm.cuh"
 #include "spmv.cuh"
 
 namespace lsspg {
@@ -67,6 +68,7 @@ struct SpmvArgs {
     const int *stop;
     double *seq;          // sequential-order verification mode (see blas1.cu)
     long long seq_n;
+    int defer_fin;        // multi-GPU: `fin` runs after the cross-rank all-reduce (comm.cu)
     FinProg fin;
 };
 
@@ -171,10 +173,11 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
         int *flags = a.flags;
         const int slot = a.out_slot;
         const FinProg &fin = a.fin;
+        const int defer = a.defer_fin;
         grid_sum<(NDOT > 0 ? NDOT : 1)>(acc, a.partials, a.ticket, [&](double(&s)[NDOT > 0 ? NDOT : 1]) {
 #pragma unroll
             for (int k = 0; k < NDOT; k++) scal[slot + k] = s[k];
-            fin_run(fin, scal, flags);
+            if (!defer) fin_run(fin, scal, flags);
         });
     }
 }
@@ -215,6 +218,8 @@ int spmv_launch(lsspg_ctx *ctx, int kind, const lsspg_csr *A, Coef alpha, const 
     LSSPG_CHECK(dx != dz, "spmv: x and z must not alias");
     const int n = A->num_rows;
     if (n == 0) return 0;
+    // row shard of a distributed matrix: refresh the ghost tail of x (NCCL send/recv over NVLink)
+    if (A->halo) LSSPG_TRY(halo_exchange(ctx, A->halo, const_cast<double *>(dx)));
     if (A->zero) {
         LSSPG_CHECK(!dots || dots->ndot == 0, "spmv: fused dots are not supported on the zero matrix");
         const int grid = stream_grid(ctx, n, kBlock);
@@ -240,6 +245,7 @@ int spmv_launch(lsspg_ctx *ctx, int kind, const lsspg_csr *A, Coef alpha, const 
     args.out_slot = dots ? dots->out_slot : 0;
     args.stop = guarded ? ctx->d_flags : nullptr;  // FLAG_STOP == 0
     args.seq = nullptr; args.seq_n = 0;
+    args.defer_fin = distributed(ctx) ? 1 : 0;
     if (dots) args.fin = dots->fin;
     const int ndot = dots ? dots->ndot : 0;
     LSSPG_CHECK(ndot >= 0 && ndot <= 2, "spmv: ndot %d out of range", ndot);
@@ -260,7 +266,7 @@ int spmv_launch(lsspg_ctx *ctx, int kind, const lsspg_csr *A, Coef alpha, const 
         case 2: rc = launch_kind<2>(ctx, A, args, ndot, grid, smem); break;
         default: rc = launch_kind<3>(ctx, A, args, ndot, grid, smem); break;
     }
-    if (rc || ndot == 0 || !ctx->opt_reduce_sequential) return rc;
+    if (rc || ndot == 0 || !(ctx->opt_reduce_sequential || distributed(ctx))) return rc;
     RedOut o;
     o.out_slot = dots->out_slot; o.fin = dots->fin; o.guarded = guarded;
     return seq_finish(ctx, n, ndot, o);

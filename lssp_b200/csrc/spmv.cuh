@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "scalars.cuh"
 
+struct lsspg_halo;
+
 struct lsspg_csr {
     int num_rows = 0, num_cols = 0, num_nnzs = 0;
     bool zero = false;          // reference "Ap == NULL" zero-matrix branch
@@ -16,6 +18,7 @@ struct lsspg_csr {
     int max_tile_nnz = 0;       // smem sizing of the stream kernel
     int *d_tile_row = nullptr;  // [num_tiles + 1] first row of every tile
     unsigned char *d_tile_kind = nullptr;  // [num_tiles]
+    lsspg_halo *halo = nullptr;            // row shard of a distributed matrix: ghost columns follow the owned ones
 };
 
 namespace lsspg {

@@ -54,6 +54,32 @@ def stencil_7pt(N, conv=(0.0, 0.0, 0.0), chunk_planes=16):
     return Ap.astype(np.int32), np.concatenate(Aj_parts), np.concatenate(Ax_parts)
 
 
+def stencil_7pt_rows(dims, r0, r1, conv=(0.0, 0.0, 0.0), chunk=1 << 20):
+    """Rows [r0, r1) of the 7-point operator on an nx x ny x nz grid, with GLOBAL column
+    indices (int64) -- what one rank of a row-sharded run generates for itself.
+    Returns (Ap int32 relative to r0, Aj int64 global, Ax)."""
+    nx, ny, nz = dims
+    cx, cy, cz = conv
+    stencil = np.array([-1.0 - cz, -1.0 - cy, -1.0 - cx, 6.0, -1.0 + cx, -1.0 + cy, -1.0 + cz])
+    offs = np.array([-nx * ny, -nx, -1, 0, 1, nx, nx * ny], dtype=np.int64)
+    Ap = np.zeros(r1 - r0 + 1, dtype=np.int64)
+    Aj_parts, Ax_parts = [], []
+    for a in range(r0, r1, chunk):
+        idx = np.arange(a, min(r1, a + chunk), dtype=np.int64)
+        x, y, z = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+        mask = np.stack([z > 0, y > 0, x > 0, np.ones(len(idx), bool), x < nx - 1, y < ny - 1,
+                         z < nz - 1], axis=1)
+        cols = idx[:, None] + offs[None, :]
+        Ap[idx - r0 + 1] = mask.sum(axis=1)
+        Aj_parts.append(cols[mask])
+        Ax_parts.append(np.broadcast_to(stencil, mask.shape)[mask])
+    np.cumsum(Ap, out=Ap)
+    assert Ap[-1] < 2 ** 31
+    Aj = np.concatenate(Aj_parts) if Aj_parts else np.zeros(0, np.int64)
+    Ax = np.concatenate(Ax_parts) if Ax_parts else np.zeros(0)
+    return Ap.astype(np.int32), Aj, Ax
+
+
 def lap3d(N):
     return stencil_7pt(N)
 
