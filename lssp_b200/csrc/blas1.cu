@@ -162,6 +162,12 @@ __global__ void __launch_bounds__(kBlock) k_scale(long long n, Coef ca, const do
     ew_loop(n, [&](long long i, int u) { a[u] = x[i]; }, [&](long long i, int u) { x[i] = a[u] * al; });
 }
 
+__global__ void __launch_bounds__(kBlock) k_div(long long n, double d, double *x)
+{
+    double a[kU];
+    ew_loop(n, [&](long long i, int u) { a[u] = x[i]; }, [&](long long i, int u) { x[i] = a[u] / d; });
+}
+
 struct DotPtrs {
     const double *x[kMaxRedK];
     const double *y[kMaxRedK];
@@ -331,6 +337,13 @@ int vec_scale(lsspg_ctx *ctx, int n, double *x, Coef a)
 {
     if (n <= 0) return 0;
     LSSPG_LAUNCH(ctx, k_scale, ew_grid(ctx, n), kBlock, 0, (long long)n, a, ctx->d_scal, x);
+    return 0;
+}
+
+int vec_scale_div(lsspg_ctx *ctx, int n, double *x, double d)
+{
+    if (n <= 0) return 0;
+    LSSPG_LAUNCH(ctx, k_div, ew_grid(ctx, n), kBlock, 0, (long long)n, d, x);
     return 0;
 }
 

@@ -23,6 +23,7 @@ int vec_axy(lsspg_ctx *ctx, int n, Coef a, const double *x, double *y);         
 int vec_axpby(lsspg_ctx *ctx, int n, Coef a, const double *x, Coef b, double *y);                // y = y*b + x*a
 int vec_axpbyz(lsspg_ctx *ctx, int n, Coef a, const double *x, Coef b, const double *y, double *z);  // z = y*b + x*a
 int vec_scale(lsspg_ctx *ctx, int n, double *x, Coef a);                                         // x *= a
+int vec_scale_div(lsspg_ctx *ctx, int n, double *x, double d);                                   // x /= d (IEEE division, as `v.d[k] /= beta`)
 // k dot products xs[i].ys[i] in one pass (k <= kMaxRedK)
 int vec_multidot(lsspg_ctx *ctx, int n, int k, const double *const *xs, const double *const *ys, const RedOut &out);
 

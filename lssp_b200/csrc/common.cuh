@@ -48,7 +48,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 constexpr int kMaxRedBlocks = 4096;  // upper bound on gridDim.x of any reducing kernel
 constexpr int kMaxRedK = 8;          // sums reduced together by one kernel
-constexpr int kNumScalars = 128;     // device scalar slab (doubles)
+constexpr int kNumScalars = 512;     // device scalar slab (doubles)
 constexpr int kBlock = 256;          // default CTA size of streaming kernels
 
 }  // namespace lsspg

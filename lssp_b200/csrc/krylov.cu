@@ -256,7 +256,10 @@ int lsspg_solver_opts_default(lsspg_solver_opts *o)
     return 0;
 }
 
-int lsspg_solver_supported(int solver) { return solver == LSSPG_CG || solver == LSSPG_BICGSTAB; }
+int lsspg_solver_supported(int solver)
+{
+    return solver == LSSPG_CG || solver == LSSPG_BICGSTAB || solver == LSSPG_GMRES || solver == LSSPG_IDRS;
+}
 
 int lsspg_krylov_solve(lsspg_ctx *ctx, int solver, const lsspg_csr *A, lsspg_pc *pc, const double *db, double *dx,
                        const lsspg_solver_opts *opts, lsspg_solve_info *info)
@@ -270,6 +273,8 @@ int lsspg_krylov_solve(lsspg_ctx *ctx, int solver, const lsspg_csr *A, lsspg_pc 
     switch (solver) {
         case LSSPG_CG: rc = krylov_cg(k); break;
         case LSSPG_BICGSTAB: rc = krylov_bicgstab(k); break;
+        case LSSPG_GMRES: rc = krylov_gmres(k); break;
+        case LSSPG_IDRS: rc = krylov_idrs(k, opts); break;
         default:
             set_error("lsspg_krylov_solve: solver %d is not implemented", solver);
             return 1;

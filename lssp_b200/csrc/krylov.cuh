@@ -17,9 +17,9 @@ constexpr double kDefAtol = 1e-7, kDefRtol = 1e-7, kDefRb = 1e-7, kBreakdown = 1
 // compared against the zero-initialising oracle build).
 struct Workspace {
     lsspg_ctx *ctx;
-    int n;
+    long long n;
     std::vector<double *> ptrs;
-    Workspace(lsspg_ctx *c, int n_) : ctx(c), n(n_) {}
+    Workspace(lsspg_ctx *c, long long n_) : ctx(c), n(n_) {}
     std::vector<size_t> sizes;
     ~Workspace()
     {
@@ -86,5 +86,7 @@ inline void record(const KrylovArgs &k, int it, double res)
 
 int krylov_cg(KrylovArgs &k);
 int krylov_bicgstab(KrylovArgs &k);
+int krylov_gmres(KrylovArgs &k);
+int krylov_idrs(KrylovArgs &k, const lsspg_solver_opts *raw);
 
 }  // namespace lsspg

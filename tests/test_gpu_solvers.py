@@ -178,6 +178,57 @@ def test_sequential_reduction_mode_is_bit_identical(golden, m, s, pc, kw):
     c.close()
 
 
+GMRES_IDRS = [("cd3d_32", "gmres", "ilut", dict(restart=30)), ("cd3d_32", "gmres", "non", dict(restart=30)),
+              ("cd3d_32", "idrs", "non", {}), ("cd3d_32", "idrs", "iluk", dict(iluk_level=0)),
+              ("powerlaw_4000", "idrs", "non", {})]
+
+
+def run2(ctx, m, s, pc, kw, **opts):
+    A = matrix(m)
+    n = len(A[0]) - 1
+    dA = api.Csr(ctx, A)
+    P = make_pc(ctx, A, pc, kw)
+    x = np.zeros(n)
+    o = dict(maxit=3000)
+    if "restart" in kw:
+        o["restart"] = kw["restart"]
+    o.update(opts)
+    return api.lssp_solver_solve(ctx, s, dA, P, rhs_for(m, n), x, **o)
+
+
+@pytest.mark.parametrize("m,s,pc,kw", GMRES_IDRS)
+def test_gmres_idrs_match_reference(ctx, golden, m, s, pc, kw):
+    """GMRES(30) (modified Gram-Schmidt kept, updates fused with the next dot) and IDR(4)
+    (shadow vectors from the host's glibc rand() stream, as in the reference)."""
+    e = golden["solves"][key_of(m, s, pc, kw)]
+    r = run2(ctx, m, s, pc, kw)
+    tol = 1 if s == "gmres" else max(1, int(np.ceil(0.15 * e["nits"])))
+    assert abs(r["nits"] - e["nits"]) <= tol, (r["nits"], e["nits"])
+    assert r["residual"] <= 1.0001e-7 * np.linalg.norm(rhs_for(m, len(r["x"]))) * 1.5 or e["nits"] >= 3000
+    assert abs(np.linalg.norm(r["x"]) - e["xnorm"]) <= 1e-5 * e["xnorm"]
+
+
+@pytest.mark.parametrize("m,s,pc,kw", GMRES_IDRS)
+def test_gmres_idrs_sequential_mode_exact(golden, m, s, pc, kw):
+    c = api.Context(0)
+    c.set_option(api.OPT_REDUCE_SEQUENTIAL, 1)
+    c.set_option(api.OPT_SPMV_EXACT, 1)
+    e = golden["solves"][key_of(m, s, pc, kw)]
+    r = run2(c, m, s, pc, kw)
+    assert r["nits"] == e["nits"] and r["residual"] == e["residual"]
+    c.close()
+
+
+@pytest.mark.parametrize("pc,kw", [("non", {}), ("iluk0", dict(iluk_level=0)), ("iluk1", dict(iluk_level=1)), ("ilut", {})])
+@pytest.mark.parametrize("s", ["gmres", "idrs"])
+def test_appendix_a1_table_gmres_idrs(ctx, golden, s, pc, kw):
+    e = golden["solves"]["lap2d_100/%s/%s" % (s, pc)]
+    kw = dict(kw, restart=30)
+    r = run2(ctx, "lap2d_100", s, "non" if pc == "non" else pc[:4], kw)
+    tol = max(1, int(np.ceil((0.03 if s == "gmres" else 0.15) * e["nits"])))
+    assert abs(r["nits"] - e["nits"]) <= tol, (r["nits"], e["nits"])
+
+
 def test_check_every_batches_do_not_change_results(golden):
     """Residual read-back every 8 iterations (device-side stop flag) must give
     exactly the iteration count and history of the per-iteration read-back."""
