@@ -163,6 +163,7 @@ int lsspg_factors_destroy(lsspg_factors *F);
 #define LSSPG_PC_ILU   1   /* x = U^-1 L^-1 rhs                src/solver-tri.cxx:48-60    */
 #define LSSPG_PC_BILU  2   /* x = U^-1 D L^-1 rhs              src/pc-biluk.cxx:22-60      */
 #define LSSPG_PC_AMG   3   /* one SX-AMG-style V-cycle from x  src/pc-sxamg.cxx:42-73      */
+#define LSSPG_PC_USER  4   /* host callback (LSSP_PC_USER)     src/pc.cxx:219-227          */
 int lsspg_pc_create_non(lsspg_ctx *ctx, int n, lsspg_pc **out);
 /* takes host L/U in the reference layout (as produced by lsspg_ilu_factor) */
 int lsspg_pc_create_ilu(lsspg_ctx *ctx, int n, const int *Lp, const int *Lj, const double *Lx,
@@ -170,6 +171,10 @@ int lsspg_pc_create_ilu(lsspg_ctx *ctx, int n, const int *Lp, const int *Lj, con
 int lsspg_pc_create_bilu(lsspg_ctx *ctx, int n, const int *Lp, const int *Lj, const double *Lx,
                          const int *Dp, const int *Dj, const double *Dx, const int *Up,
                          const int *Uj, const double *Ux, lsspg_pc **out);
+/* user-supplied host preconditioner: fn(user, x, rhs, n) with HOST vectors; x holds the incoming
+ * contents on entry.  Costs a device<->host round trip per application. */
+int lsspg_pc_create_user(lsspg_ctx *ctx, int n, void (*fn)(void *user, double *hx, const double *hrhs, int n),
+                         void *user, lsspg_pc **out);
 int lsspg_pc_destroy(lsspg_ctx *ctx, lsspg_pc *pc);
 int lsspg_pc_kind(const lsspg_pc *pc);
 int lsspg_pc_info(const lsspg_pc *pc, int *levels_L, int *levels_U, long long *padded_L,

@@ -1,0 +1,628 @@
+// lssp_facade.cpp -- the LSSP C++ API (lssp.h / mvops.h / vector.h / pc*.h / solver-*.h) on top of
+// the C ABI of liblsspg.so.  Written fresh for the B200 build; signatures, defaults, ownership and
+// error behaviour follow the reference (cited per function), so that example/exam.cxx-style
+// programs recompile and relink unchanged.  No arithmetic happens here: vectors and matrices are
+// host objects as in the reference, every operation is forwarded to the sm_100a kernels.
+#include <strings.h>
+#include <sys/resource.h>
+#include <sys/time.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "lssp.h"
+#include "lsspg.h"
+
+// ---- globals: defaults of the reference (src/lssp.cxx:5-14, src/pc.cxx:3-7, src/utils.cxx:19-22) ----
+int LSSP_RESTART = 50;
+int LSSP_AUG_K = 3;
+int LSSP_BGSL = 4;
+int LSSP_IDRS = 4;
+int LSSP_MAXIT = 1000;
+double LSSP_ATOL = 1e-7;
+double LSSP_RTOL = 1e-7;
+double LSSP_RB = 1e-7;
+double LSSP_BREAKDOWN = 1e-40;
+int lssp_pc_iluk_level_default = 1;
+double lssp_pc_ilut_tol = 1e-3;
+double lssp_pc_ilut_p = -1;
+int lssp_verbosity = 2;
+static FILE *lssp_log_handle = NULL;
+
+// ---- utils (reference src/utils.cxx) -----------------------------------------------------------
+void lssp_set_log(FILE *io) { lssp_log_handle = io; }
+int lssp_comp_int_asc(const void *p, const void *n) { return *(const int *)p - *(const int *)n; }
+int lssp_comp_int_des(const void *p, const void *n) { return *(const int *)n - *(const int *)p; }
+
+double lssp_get_time()
+{
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    return tv.tv_sec + tv.tv_usec * 1e-6;
+}
+
+double lssp_get_mem_usage(double *peak)
+{
+    struct rusage ru;
+    getrusage(RUSAGE_SELF, &ru);
+    const double mb = ru.ru_maxrss / 1024.;
+    if (peak) *peak = mb;
+    return mb;
+}
+
+static int vprint(const char *prefix, const char *fmt, va_list ap)
+{
+    char buf[4096];
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    int r = fprintf(stdout, "%s%s", prefix, buf);
+    fflush(stdout);
+    if (lssp_log_handle) {
+        fprintf(lssp_log_handle, "%s%s", prefix, buf);
+        fflush(lssp_log_handle);
+    }
+    return r;
+}
+
+int lssp_printf(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    int r = vprint("", fmt, ap);
+    va_end(ap);
+    return r;
+}
+
+void lssp_error(int code, const char *fmt, ...)   // reference src/utils.cxx:114-135: print, then exit(code)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vprint("error: ", fmt, ap);
+    va_end(ap);
+    if (code != 0) exit(code);
+}
+
+void lssp_warning(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vprint("warning: ", fmt, ap);
+    va_end(ap);
+}
+
+// ---- device context ------------------------------------------------------------------------------
+static lsspg_ctx *g_ctx = NULL;
+
+static lsspg_ctx *ctx()
+{
+    if (!g_ctx) {
+        const char *e = getenv("LSSP_GPU");
+        if (lsspg_ctx_create(e ? atoi(e) : 0, &g_ctx)) lssp_error(1, "lssp: %s\n", lsspg_last_error());
+    }
+    return g_ctx;
+}
+
+#define GPU(call)                                                   \
+    do {                                                            \
+        if (call) lssp_error(1, "lssp: %s\n", lsspg_last_error());  \
+    } while (0)
+
+// ---- matrix utils (reference src/matrix-utils.cxx:3-60, :249-279, :387-481) -----------------------
+void lssp_mat_init(lssp_mat_csr &A) { bzero(&A, sizeof(A)); }
+void lssp_mat_init(lssp_mat_coo &A) { bzero(&A, sizeof(A)); }
+void lssp_mat_init(lssp_mat_bcsr &A) { bzero(&A, sizeof(A)); }
+void lssp_mat_destroy(lssp_mat_csr &A) { lssp_free(A.Ap); lssp_free(A.Aj); lssp_free(A.Ax); lssp_mat_init(A); }
+void lssp_mat_destroy(lssp_mat_coo &A) { lssp_free(A.Ai); lssp_free(A.Aj); lssp_free(A.Ax); lssp_mat_init(A); }
+void lssp_mat_destroy(lssp_mat_bcsr &A) { lssp_free(A.Aj); lssp_free(A.Ap); lssp_free(A.Ax); lssp_mat_init(A); }
+
+lssp_mat_csr lssp_mat_create(int nrows, int ncols, int *Ap, int *Aj, double *Ax)
+{
+    lssp_mat_csr A;
+    assert(nrows > 0 && ncols > 0 && Ap != NULL);
+    lssp_mat_init(A);
+    A.num_rows = nrows;
+    A.num_cols = ncols;
+    A.num_nnzs = Ap[nrows];
+    A.Ap = lssp_copy_on<int>(Ap, nrows + 1);
+    A.Aj = lssp_copy_on<int>(Aj, Ap[nrows]);
+    A.Ax = lssp_copy_on<double>(Ax, Ap[nrows]);
+    return A;
+}
+
+bool lssp_mat_csr_is_sorted(const lssp_mat_csr A)
+{
+    for (int i = 0; i < A.num_rows; i++)
+        for (int k = A.Ap[i] + 1; k < A.Ap[i + 1]; k++)
+            if (A.Aj[k - 1] > A.Aj[k]) return false;
+    return true;
+}
+
+void lssp_mat_sort_column(lssp_mat_csr &A)
+{
+    std::vector<int> idx, tj;
+    std::vector<double> tx;
+    for (int i = 0; i < A.num_rows; i++) {
+        const int b = A.Ap[i], n = A.Ap[i + 1] - b;
+        idx.resize(n);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int p, int q) { return A.Aj[b + p] < A.Aj[b + q]; });
+        tj.assign(A.Aj + b, A.Aj + b + n);
+        tx.assign(A.Ax + b, A.Ax + b + n);
+        for (int k = 0; k < n; k++) { A.Aj[b + k] = tj[idx[k]]; A.Ax[b + k] = tx[idx[k]]; }
+    }
+}
+
+// ---- vector (reference src/vector.cxx) ------------------------------------------------------------
+lssp_vec lssp_vec_create(int n)
+{
+    lssp_vec v;
+    assert(n > 0);
+    v.n = n;
+    v.d = lssp_malloc<double>(n);
+    return v;
+}
+
+void lssp_vec_destroy(lssp_vec &v) { lssp_free(v.d); v.n = 0; }
+void lssp_vec_set_value(lssp_vec x, double val) { for (int i = 0; i < x.n; i++) x.d[i] = val; }        // plain stores, as :31-38
+void lssp_vec_set_value_by_array(lssp_vec x, double *val) { memcpy(x.d, val, sizeof(double) * x.n); }
+void lssp_vec_set_value_by_index(lssp_vec x, int i, double val) { assert(i >= 0 && i < x.n); x.d[i] = val; }
+void lssp_vec_get_value(double *val, lssp_vec x) { memcpy(val, x.d, sizeof(double) * x.n); }
+double lssp_vec_get_value_by_index(lssp_vec x, int i) { assert(i >= 0 && i < x.n); return x.d[i]; }
+void lssp_vec_copy(lssp_vec des, const lssp_vec src) { assert(des.n == src.n); memcpy(des.d, src.d, sizeof(double) * src.n); }
+
+// arithmetic on host vectors: staged through device memory, computed by the BLAS-1 kernels
+struct DevVec {
+    double *d = NULL;
+    int n;
+    DevVec(const lssp_vec &h, bool upload = true) : n(h.n)
+    {
+        GPU(lsspg_malloc(ctx(), sizeof(double) * (size_t)n, (void **)&d));
+        if (upload) GPU(lsspg_h2d(ctx(), d, h.d, sizeof(double) * (size_t)n));
+    }
+    void download(lssp_vec h) { GPU(lsspg_d2h(ctx(), h.d, d, sizeof(double) * (size_t)n)); }
+    ~DevVec() { lsspg_free(ctx(), d); }
+};
+
+void lssp_vec_axy(double alpha, const lssp_vec x, lssp_vec y)
+{
+    assert(x.n == y.n);
+    DevVec dx(x), dy(y, false);
+    GPU(lsspg_vec_axy(ctx(), x.n, alpha, dx.d, dy.d));
+    dy.download(y);
+}
+
+void lssp_vec_axpby(double alpha, const lssp_vec x, double beta, lssp_vec y)
+{
+    assert(x.n == y.n);
+    DevVec dx(x), dy(y);
+    GPU(lsspg_vec_axpby(ctx(), x.n, alpha, dx.d, beta, dy.d));
+    dy.download(y);
+}
+
+void lssp_vec_axpbyz(double alpha, const lssp_vec x, double beta, lssp_vec y, lssp_vec z)
+{
+    assert(x.n == y.n && z.n == y.n);
+    DevVec dx(x), dy(y), dz(z, false);
+    GPU(lsspg_vec_axpbyz(ctx(), x.n, alpha, dx.d, beta, dy.d, dz.d));
+    dz.download(z);
+}
+
+double lssp_vec_dot(const lssp_vec x, const lssp_vec y)
+{
+    assert(x.n == y.n);
+    DevVec dx(x), dy(y);
+    double r = 0;
+    GPU(lsspg_vec_dot(ctx(), x.n, dx.d, dy.d, &r));
+    return r;
+}
+
+double lssp_vec_norm(const lssp_vec x) { return sqrt(lssp_vec_dot(x, x)); }   // :135-138
+
+void lssp_vec_scale(lssp_vec x, double a)
+{
+    DevVec dx(x);
+    GPU(lsspg_vec_scale(ctx(), x.n, dx.d, a));
+    dx.download(x);
+}
+
+// ---- mvops (reference src/mvops.cxx) ---------------------------------------------------------------
+// Standalone calls upload the matrix for the call; inside the solvers the matrix is resident.
+static void mv_host(int kind, const lssp_mat_csr &A, double alpha, const lssp_vec &x, double beta, const double *y, lssp_vec &z)
+{
+    assert(x.n == A.num_cols);
+    lsspg_csr *dA = NULL;
+    GPU(lsspg_csr_upload(ctx(), A.num_rows, A.num_cols, A.Ap, A.Aj, A.Ax, &dA));
+    GPU(lsspg_mv_host(ctx(), kind, dA, alpha, x.d, beta, y, z.d));
+    lsspg_csr_destroy(ctx(), dA);
+}
+
+void lssp_mv_amxpby(double alpha, const lssp_mat_csr A, const lssp_vec x, double beta, lssp_vec y)
+{
+    assert(x.n && y.n);
+    mv_host(LSSPG_MV_AMXPBY, A, alpha, x, beta, y.d, y);
+}
+
+void lssp_mv_amxpbyz(double alpha, const lssp_mat_csr A, const lssp_vec x, double beta, const lssp_vec y, lssp_vec z)
+{
+    assert(x.n == y.n && y.n == z.n);
+    mv_host(LSSPG_MV_AMXPBYZ, A, alpha, x, beta, y.d, z);
+}
+
+void lssp_mv_amxy(double a, const lssp_mat_csr A, const lssp_vec x, lssp_vec y)
+{
+    assert(x.n == y.n);
+    mv_host(LSSPG_MV_AMXY, A, a, x, 0., NULL, y);
+}
+
+void lssp_mv_mxy(const lssp_mat_csr A, const lssp_vec x, lssp_vec y)
+{
+    assert(x.n == y.n);
+    mv_host(LSSPG_MV_MXY, A, 1., x, 0., NULL, y);
+}
+
+// ---- triangular sweeps (reference src/solver-tri.cxx) ------------------------------------------------
+static void tri_host(int which, const lssp_mat_csr &T, double *x, const double *rhs)
+{
+    assert(x != NULL && rhs != NULL);
+    lsspg_tri *dT = NULL;
+    const size_t nb = sizeof(double) * (size_t)T.num_rows;
+    double *dx = NULL, *dr = NULL;
+    GPU(lsspg_tri_analyse(ctx(), which, T.num_rows, T.Ap, T.Aj, T.Ax, &dT));
+    GPU(lsspg_malloc(ctx(), nb, (void **)&dx));
+    GPU(lsspg_malloc(ctx(), nb, (void **)&dr));
+    GPU(lsspg_h2d(ctx(), dr, rhs, nb));
+    GPU(lsspg_tri_solve(ctx(), dT, dx, dr));
+    GPU(lsspg_d2h(ctx(), x, dx, nb));
+    lsspg_free(ctx(), dx);
+    lsspg_free(ctx(), dr);
+    lsspg_tri_destroy(ctx(), dT);
+}
+
+void lssp_pc_ilu_solve_lower_matrix(lssp_mat_csr L, double *x, double *rhs) { tri_host(LSSPG_TRI_LOWER, L, x, rhs); }
+void lssp_pc_ilu_solve_upper_matrix(lssp_mat_csr U, double *x, double *rhs) { tri_host(LSSPG_TRI_UPPER, U, x, rhs); }
+
+void lssp_pc_ilu_solve_lu_matrix(lssp_mat_csr L, lssp_mat_csr U, double *x, double *rhs, double *cache)
+{
+    assert(x != NULL && rhs != NULL && cache != NULL);
+    lssp_pc_ilu_solve_lower_matrix(L, cache, rhs);
+    lssp_pc_ilu_solve_upper_matrix(U, x, cache);
+}
+
+// pc.solve of ILUK / ILUT (reference src/solver-tri.cxx:57-60): the factors are resident on the device
+void lssp_pc_ilu_solve(LSSP_PC *pc, lssp_vec x, lssp_vec rhs)
+{
+    assert(pc->gpu != NULL);
+    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc->gpu, x.d, rhs.d));
+}
+
+// ---- preconditioners (reference src/pc.cxx, src/pc-iluk.cxx:554-592, src/pc-ilut.cxx:423-466) ----------
+void lssp_pc_create(LSSP_PC &pc, LSSP_PC_TYPE type)
+{
+    pc.type = type;
+    pc.iluk_level = lssp_pc_iluk_level_default;
+    pc.ilut_tol = lssp_pc_ilut_tol;
+    pc.ilut_p = (int)lssp_pc_ilut_p;
+    pc.cache = NULL;
+    pc.solve = NULL;
+    pc.destroy = NULL;
+    pc.data = NULL;
+    pc.gpu = NULL;
+    lssp_mat_init(pc.L);
+    lssp_mat_init(pc.U);
+    lssp_mat_init(pc.D);
+    pc.verb = lssp_verbosity - 1;
+    pc.log = NULL;
+    pc.assembled = false;
+}
+
+static void release_device_pc(LSSP_PC *pc)
+{
+    if (pc->gpu) lsspg_pc_destroy(ctx(), (lsspg_pc *)pc->gpu);
+    pc->gpu = NULL;
+}
+
+void lssp_pc_destroy(LSSP_PC &pc)
+{
+    assert(pc.assembled);
+    if (pc.destroy != NULL) (*pc.destroy)(&pc);
+    release_device_pc(&pc);
+    pc.assembled = false;
+}
+
+static void non_solve(LSSP_PC *pc, lssp_vec x, lssp_vec rhs) { lssp_memcpy_on(x.d, rhs.d, pc->A.num_rows); }   // src/pc.cxx:67-70
+
+static void adopt_factors(LSSP_PC &pc, lsspg_factors *F)
+{
+    int n, nl, nu;
+    lsspg_factors_sizes(F, &n, &nl, &nu);
+    pc.L.num_rows = pc.L.num_cols = pc.U.num_rows = pc.U.num_cols = n;
+    pc.L.num_nnzs = nl;
+    pc.U.num_nnzs = nu;
+    pc.L.Ap = lssp_malloc<int>(n + 1); pc.L.Aj = lssp_malloc<int>(nl); pc.L.Ax = lssp_malloc<double>(nl);
+    pc.U.Ap = lssp_malloc<int>(n + 1); pc.U.Aj = lssp_malloc<int>(nu); pc.U.Ax = lssp_malloc<double>(nu);
+    lsspg_factors_get(F, pc.L.Ap, pc.L.Aj, pc.L.Ax, pc.U.Ap, pc.U.Aj, pc.U.Ax);
+    lsspg_factors_destroy(F);
+    lsspg_pc *d = NULL;
+    GPU(lsspg_pc_create_ilu(ctx(), n, pc.L.Ap, pc.L.Aj, pc.L.Ax, pc.U.Ap, pc.U.Aj, pc.U.Ax, &d));
+    pc.gpu = d;
+    pc.cache = lssp_malloc<double>(n);
+    pc.solve = lssp_pc_ilu_solve;
+}
+
+void lssp_pc_iluk_destroy(LSSP_PC *pc)
+{
+    assert(pc->assembled);
+    lssp_mat_destroy(pc->L);
+    lssp_mat_destroy(pc->U);
+    lssp_free<double>(pc->cache);
+    release_device_pc(pc);
+    pc->assembled = false;
+}
+
+void lssp_pc_iluk_assemble(LSSP_PC &pc, LSSP_SOLVER s)
+{
+    assert(s.A.num_rows == s.A.num_cols && s.A.num_rows > 0 && s.A.num_nnzs > 0);
+    lsspg_factors *F = NULL;
+    GPU(lsspg_ilu_factor(LSSPG_ILUK, s.A.num_rows, s.A.Ap, s.A.Aj, s.A.Ax, pc.iluk_level, 0, 0., 0, &F));
+    adopt_factors(pc, F);
+    pc.destroy = lssp_pc_iluk_destroy;
+}
+
+void lssp_pc_iluk_set_level(LSSP_PC &pc, int level)
+{
+    if (level < 0) {
+        lssp_warning("pc: level is too small, set it to %d!\n", lssp_pc_iluk_level_default);
+        pc.iluk_level = lssp_pc_iluk_level_default;
+    }
+    else pc.iluk_level = level;
+}
+
+void lssp_pc_ilut_destroy(LSSP_PC *pc) { lssp_pc_iluk_destroy(pc); }
+
+void lssp_pc_ilut_assemble(LSSP_PC &pc, LSSP_SOLVER s)
+{
+    assert(s.A.num_rows == s.A.num_cols && s.A.num_rows > 0 && s.A.num_nnzs > 0);
+    if (pc.ilut_p <= 0) pc.ilut_p = (s.A.num_nnzs + s.A.num_rows - 1) / s.A.num_rows;   // written back, as :436-438
+    if (pc.ilut_tol < 0) pc.ilut_tol = lssp_pc_ilut_tol;
+    if (pc.verb > 1) lssp_printf("pc: ilut, tol: %f, p: %d\n", pc.ilut_tol, pc.ilut_p);
+    lsspg_factors *F = NULL;
+    GPU(lsspg_ilu_factor(LSSPG_ILUT, s.A.num_rows, s.A.Ap, s.A.Aj, s.A.Ax, 0, pc.ilut_p, pc.ilut_tol, 0, &F));
+    adopt_factors(pc, F);
+    pc.destroy = lssp_pc_ilut_destroy;
+}
+
+void lssp_pc_ilut_set_drop_tol(LSSP_PC &pc, double tol) { pc.ilut_tol = fabs(tol); }
+void lssp_pc_ilut_set_p(LSSP_PC &pc, int p) { pc.ilut_p = p; }
+
+// user-defined preconditioner: its pc.solve works on host vectors
+static void user_pc_trampoline(void *user, double *hx, const double *hrhs, int n)
+{
+    LSSP_PC *pc = (LSSP_PC *)user;
+    lssp_vec x, rhs;
+    x.n = rhs.n = n;
+    x.d = hx;
+    rhs.d = const_cast<double *>(hrhs);
+    pc->solve(pc, x, rhs);
+}
+
+void lssp_pc_assemble(LSSP_PC &pc, LSSP_SOLVER s)
+{
+    double tm = 0;
+    if (!s.assembled) lssp_error(1, "pc: solver hasn't been assembled, call lssp_assemble first!\n");
+    if (s.verb > 0) tm = lssp_get_time();
+    pc.verb = s.verb - 1;
+    pc.log = s.log;
+    lssp_mat_init(pc.L);
+    lssp_mat_init(pc.U);
+    lssp_mat_init(pc.D);
+    pc.A = s.A;
+    pc.gpu = NULL;
+    switch (pc.type) {
+        case LSSP_PC_NON: {
+            pc.cache = NULL;
+            pc.solve = non_solve;
+            pc.destroy = NULL;
+            lsspg_pc *d = NULL;
+            GPU(lsspg_pc_create_non(ctx(), s.A.num_rows, &d));
+            pc.gpu = d;
+            break;
+        }
+        case LSSP_PC_ILUK:
+            if (pc.verb >= 0) lssp_printf("pc: type: ILUK\n");
+            lssp_pc_iluk_assemble(pc, s);
+            break;
+        case LSSP_PC_ILUT:
+            if (pc.verb >= 0) lssp_printf("pc: type: ILUT\n");
+            lssp_pc_ilut_assemble(pc, s);
+            break;
+        case LSSP_PC_USER: {
+            if (pc.verb >= 0) lssp_printf("pc: type: user defined\n");
+            assert(pc.assemble != NULL);
+            pc.assemble(pc, s);
+            assert(pc.solve != NULL);
+            lsspg_pc *d = NULL;
+            GPU(lsspg_pc_create_user(ctx(), s.A.num_rows, user_pc_trampoline, &pc, &d));
+            pc.gpu = d;
+            break;
+        }
+        default:
+            lssp_error(1, "pc: incorrect preconditioner type !\n");
+            break;
+    }
+    if (pc.verb > 0) lssp_printf("pc: time for pc assemble: %f s\n", lssp_get_time() - tm);
+    pc.assembled = true;
+}
+
+// ---- solver life cycle (reference src/lssp.cxx:16-249, :416-535) ----------------------------------------
+void lssp_solver_create(LSSP_SOLVER &s, LSSP_SOLVER_TYPE s_type, LSSP_PC &pc, LSSP_PC_TYPE p_type)
+{
+    bzero(&s, sizeof(LSSP_SOLVER));
+    s.type = s_type;
+    s.residual = 0;
+    s.tol_rel = LSSP_RTOL;
+    s.tol_abs = LSSP_ATOL;
+    s.tol_rb = LSSP_RB;
+    s.restart = LSSP_RESTART;
+    s.aug_k = LSSP_AUG_K;
+    s.maxit = LSSP_MAXIT;
+    s.nits = 0;
+    s.bgsl = LSSP_BGSL;
+    s.idrs = LSSP_IDRS;
+    lssp_mat_init(s.A);
+    s.num_blks = -1;
+    s.blk_size = NULL;
+    s.log = NULL;
+    s.verb = lssp_verbosity;
+    lssp_pc_create(pc, p_type);
+    s.assembled = false;
+}
+
+void lssp_solver_assemble(LSSP_SOLVER &s, lssp_mat_csr &Ax, lssp_vec x, lssp_vec b, LSSP_PC &pc)
+{
+    double t = 0.;
+    if (Ax.num_rows <= 0) lssp_error(1, "solver: wrong input matrix, number of rows should be greater than 0\n");
+    else if (Ax.num_rows != Ax.num_cols) lssp_error(1, "solver: wrong input matrix, number of rows != number of columns\n");
+    if (Ax.num_nnzs < Ax.num_rows) lssp_error(1, "solver: wrong input matrix, singular\n");
+    if (s.verb > 1) t = lssp_get_time();
+    lssp_mat_csr A;
+    A.num_rows = Ax.num_rows;
+    A.num_cols = Ax.num_cols;
+    A.num_nnzs = Ax.num_nnzs;
+    A.Ap = lssp_copy_on<int>(Ax.Ap, Ax.num_rows + 1);            // deep copy, :169-171
+    A.Aj = lssp_copy_on<int>(Ax.Aj, Ax.num_nnzs);
+    A.Ax = lssp_copy_on<double>(Ax.Ax, Ax.num_nnzs);
+    if (!lssp_mat_csr_is_sorted(A)) lssp_mat_sort_column(A);    // :173
+    s.rhs = b;                                                  // aliases, :175-176
+    s.x = x;
+    s.A = A;
+    lsspg_csr *dA = NULL;
+    GPU(lsspg_csr_upload(ctx(), A.num_rows, A.num_cols, A.Ap, A.Aj, A.Ax, &dA));
+    s.gpu = dA;
+    if (s.verb > 1) lssp_printf("solver: assemble time: %g\n", lssp_get_time() - t);
+    s.assembled = true;
+    lssp_pc_assemble(pc, s);
+}
+
+void lssp_solver_destroy(LSSP_SOLVER &s, LSSP_PC &pc)
+{
+    assert(s.assembled);
+    lssp_mat_destroy(s.A);
+    if (s.gpu) lsspg_csr_destroy(ctx(), (lsspg_csr *)s.gpu);
+    s.gpu = NULL;
+    lssp_pc_destroy(pc);
+    s.assembled = false;
+}
+
+void lssp_solver_reset_rhs(LSSP_SOLVER &s, lssp_vec rhs) { assert(s.assembled); s.rhs = rhs; }
+void lssp_solver_reset_unknown(LSSP_SOLVER &s, lssp_vec x) { assert(s.assembled); s.x = x; }
+void lssp_solver_reset_type(LSSP_SOLVER &s, LSSP_SOLVER_TYPE type) { s.type = type; }
+
+#define SETTER(name, field, type, cond, msg)            \
+    void name(LSSP_SOLVER &s, type v)                   \
+    {                                                   \
+        if (cond) lssp_warning(msg);                    \
+        else s.field = v;                               \
+    }
+SETTER(lssp_solver_set_rtol, tol_rel, double, v < 0, "solver: tol is less than zero!\n")
+SETTER(lssp_solver_set_atol, tol_abs, double, v < 0, "solver: tol is less than zero!\n")
+SETTER(lssp_solver_set_rbtol, tol_rb, double, v < 0, "solver: tol is less than zero!\n")
+SETTER(lssp_solver_set_maxit, maxit, int, v <= 0, "solver: maxit is less or equal to zero!\n")
+SETTER(lssp_solver_set_restart, restart, int, v <= 0, "solver: restart is too small!\n")
+SETTER(lssp_solver_set_augk, aug_k, int, v <= 0, "solver: aug_k is less or equal to zero!\n")
+SETTER(lssp_solver_set_bgsl, bgsl, int, v <= 0, "solver: bgsl is less or equal to zero!\n")
+SETTER(lssp_solver_set_idrs, idrs, int, v <= 0, "solver: idrs is less or equal to zero!\n")
+#undef SETTER
+
+void lssp_solver_reset_verbosity(LSSP_SOLVER &s, int v) { s.verb = v; }
+double lssp_solver_get_residual(LSSP_SOLVER s) { return s.residual; }
+int lssp_solver_get_nits(LSSP_SOLVER s) { return s.nits; }
+
+void lssp_solver_set_log(LSSP_SOLVER &s, FILE *io)
+{
+    assert(io != NULL);
+    s.log = io;
+    lssp_set_log(io);
+}
+
+// ---- Krylov drivers: int lssp_solver_<m>(LSSP_SOLVER&, LSSP_PC&) (reference src/solver-*.cxx) -----------
+static int drive(LSSP_SOLVER &solver, LSSP_PC &pc, int kind, const char *name)
+{
+    assert(solver.assembled);
+    assert(pc.assembled);
+    if (!lsspg_solver_supported(kind))
+        lssp_error(1, "%s: this driver has no GPU implementation yet in this build\n", name);
+    const double t0 = lssp_get_time();
+    lsspg_solver_opts o;
+    lsspg_solver_opts_default(&o);
+    o.tol_rel = solver.tol_rel; o.tol_abs = solver.tol_abs; o.tol_rb = solver.tol_rb;
+    o.maxit = solver.maxit; o.restart = solver.restart; o.aug_k = solver.aug_k; o.bgsl = solver.bgsl; o.idrs = solver.idrs;
+    o.verb = solver.verb;
+    if (solver.verb >= 2) {
+        lssp_printf("%s: maximal iteration: %d\n", name, solver.maxit <= 0 ? LSSP_MAXIT : solver.maxit);
+        lssp_printf("%s: tolerance abs: %g\n", name, solver.tol_abs < 0 ? LSSP_ATOL : solver.tol_abs);
+        lssp_printf("%s: tolerance rel: %g\n", name, solver.tol_rel < 0 ? LSSP_RTOL : solver.tol_rel);
+        lssp_printf("%s: tolerance rbn: %g\n", name, solver.tol_rb);
+    }
+    lsspg_solve_info info;
+    GPU(lsspg_krylov_solve_host(ctx(), kind, (lsspg_csr *)solver.gpu, (lsspg_pc *)pc.gpu, solver.rhs.d, solver.x.d, &o, &info));
+    solver.residual = info.residual;
+    solver.nits = info.nits;
+    if (solver.verb >= 2) {
+        lssp_printf("%s: total iteration: %d\n", name, info.nits);
+        lssp_printf("%s: total time: %g\n", name, lssp_get_time() - t0);
+    }
+    return info.nits;
+}
+
+#define DRIVER(fn, kind, name) \
+    int fn(LSSP_SOLVER &solver, LSSP_PC &pc) { return drive(solver, pc, kind, name); }
+DRIVER(lssp_solver_gmres, LSSPG_GMRES, "gmres")
+DRIVER(lssp_solver_gmres_r, LSSPG_RGMRES, "rgmres")
+DRIVER(lssp_solver_lgmres, LSSPG_LGMRES, "lgmres")
+DRIVER(lssp_solver_lgmres_r, LSSPG_RLGMRES, "rlgmres")
+DRIVER(lssp_solver_bicgstab, LSSPG_BICGSTAB, "bicgstab")
+DRIVER(lssp_solver_bicgstabl, LSSPG_BICGSTABL, "bicgstabl")
+DRIVER(lssp_solver_bicgsafe, LSSPG_BICGSAFE, "bicgsafe")
+DRIVER(lssp_solver_cg, LSSPG_CG, "cg")
+DRIVER(lssp_solver_cgs, LSSPG_CGS, "cgs")
+DRIVER(lssp_solver_gpbicg, LSSPG_GPBICG, "gpbicg")
+DRIVER(lssp_solver_cr, LSSPG_CR, "cr")
+DRIVER(lssp_solver_crs, LSSPG_CRS, "crs")
+DRIVER(lssp_solver_bicrstab, LSSPG_BICRSTAB, "bicrstab")
+DRIVER(lssp_solver_bicrsafe, LSSPG_BICRSAFE, "bicrsafe")
+DRIVER(lssp_solver_gpbicr, LSSPG_GPBICR, "gpbicr")
+DRIVER(lssp_solver_qmrcgstab, LSSPG_QMRCGSTAB, "qmrcgstab")
+DRIVER(lssp_solver_tfqmr, LSSPG_TFQMR, "tfqmr")
+DRIVER(lssp_solver_orthomin, LSSPG_ORTHOMIN, "orthomin")
+DRIVER(lssp_solver_idrs, LSSPG_IDRS, "idrs")
+#undef DRIVER
+
+int lssp_solver_solve(LSSP_SOLVER &solver, LSSP_PC &pc)   // dispatch switch, reference src/lssp.cxx:250-414
+{
+    assert(solver.assembled);
+    assert(pc.assembled);
+    switch (solver.type) {
+        case LSSP_SOLVER_GMRES: return lssp_solver_gmres(solver, pc);
+        case LSSP_SOLVER_LGMRES: return lssp_solver_lgmres(solver, pc);
+        case LSSP_SOLVER_RGMRES: return lssp_solver_gmres_r(solver, pc);
+        case LSSP_SOLVER_RLGMRES: return lssp_solver_lgmres_r(solver, pc);
+        case LSSP_SOLVER_BICGSTAB: return lssp_solver_bicgstab(solver, pc);
+        case LSSP_SOLVER_BICGSTABL: return lssp_solver_bicgstabl(solver, pc);
+        case LSSP_SOLVER_BICGSAFE: return lssp_solver_bicgsafe(solver, pc);
+        case LSSP_SOLVER_CG: return lssp_solver_cg(solver, pc);
+        case LSSP_SOLVER_CGS: return lssp_solver_cgs(solver, pc);
+        case LSSP_SOLVER_GPBICG: return lssp_solver_gpbicg(solver, pc);
+        case LSSP_SOLVER_CR: return lssp_solver_cr(solver, pc);
+        case LSSP_SOLVER_CRS: return lssp_solver_crs(solver, pc);
+        case LSSP_SOLVER_BICRSTAB: return lssp_solver_bicrstab(solver, pc);
+        case LSSP_SOLVER_BICRSAFE: return lssp_solver_bicrsafe(solver, pc);
+        case LSSP_SOLVER_GPBICR: return lssp_solver_gpbicr(solver, pc);
+        case LSSP_SOLVER_QMRCGSTAB: return lssp_solver_qmrcgstab(solver, pc);
+        case LSSP_SOLVER_TFQMR: return lssp_solver_tfqmr(solver, pc);
+        case LSSP_SOLVER_ORTHOMIN: return lssp_solver_orthomin(solver, pc);
+        case LSSP_SOLVER_IDRS: return lssp_solver_idrs(solver, pc);
+        default:
+            lssp_error(0, "solver: unsupported solver type!\n");
+            return -1;
+    }
+}

@@ -24,6 +24,16 @@ int pc_apply(lsspg_ctx *ctx, lsspg_pc *pc, double *dx, const double *drhs, bool 
             LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_MXY, pc->D, coef_imm(1.0), y, coef_imm(0.0), nullptr, z, nullptr, guarded));
             return tri_solve(ctx, pc->U, dx, z, guarded);
         }
+        case LSSPG_PC_USER: {
+            // a user-supplied pc.solve works on host vectors: round trip per application (documented slow path)
+            const size_t nb = sizeof(double) * (size_t)pc->n;
+            LSSPG_CUDA(cudaMemcpyAsync(pc->h_x, dx, nb, cudaMemcpyDeviceToHost, ctx->stream));
+            LSSPG_CUDA(cudaMemcpyAsync(pc->h_rhs, drhs, nb, cudaMemcpyDeviceToHost, ctx->stream));
+            LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+            pc->user_fn(pc->user, pc->h_x, pc->h_rhs, pc->n);
+            LSSPG_CUDA(cudaMemcpyAsync(dx, pc->h_x, nb, cudaMemcpyHostToDevice, ctx->stream));
+            return 0;
+        }
         default:
             set_error("pc_apply: preconditioner kind %d is not implemented", pc->kind);
             return 1;
@@ -94,10 +104,28 @@ int lsspg_pc_create_bilu(lsspg_ctx *ctx, int n, const int *Lp, const int *Lj, co
     return 0;
 }
 
+int lsspg_pc_create_user(lsspg_ctx *ctx, int n, void (*fn)(void *, double *, const double *, int), void *user,
+                         lsspg_pc **out)
+{
+    LSSPG_CHECK(ctx && out && fn && n >= 0, "lsspg_pc_create_user: bad argument");
+    lsspg_pc *pc = new lsspg_pc();
+    pc->kind = LSSPG_PC_USER;
+    pc->n = n;
+    pc->user_fn = fn;
+    pc->user = user;
+    LSSPG_CUDA(cudaMallocHost(&pc->h_x, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+    LSSPG_CUDA(cudaMallocHost(&pc->h_rhs, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+    pc->bytes = 32.0 * n;
+    *out = pc;
+    return 0;
+}
+
 int lsspg_pc_destroy(lsspg_ctx *ctx, lsspg_pc *pc)
 {
     if (!pc) return 0;
     if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (pc->h_x) cudaFreeHost(pc->h_x);
+    if (pc->h_rhs) cudaFreeHost(pc->h_rhs);
     lsspg_tri_destroy(ctx, pc->L);
     lsspg_tri_destroy(ctx, pc->U);
     lsspg_csr_destroy(ctx, pc->D);

@@ -13,6 +13,10 @@ struct lsspg_pc {
     lsspg_csr *D = nullptr;     // block-ILU: block-diagonal of inverted pivot blocks
     double *cache = nullptr;    // n doubles (ILU) / 2n doubles (block-ILU), as pc.cache in the reference
     double bytes = 0.0;         // algorithmic bytes of one application
+    // LSSPG_PC_USER: host callback (the reference's LSSP_PC_USER hook, src/pc.cxx:219-227)
+    void (*user_fn)(void *user, double *hx, const double *hrhs, int n) = nullptr;
+    void *user = nullptr;
+    double *h_x = nullptr, *h_rhs = nullptr;   // pinned staging for the callback
 };
 
 namespace lsspg {

@@ -1,0 +1,92 @@
+"""The LSSP C++ API facade (include/lssp/*.h + liblssp.so): the drop-in boundary of SURVEY.md 8b.
+
+CPU part: liblssp.so exports the same C++ symbols (mangled) as the reference library for every
+function of the hot path.  GPU part: an exam.cxx-style program compiled against include/lssp
+runs and reproduces the reference's own example output."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "lssp_b200", "liblssp.so")
+REF = os.path.join(ROOT, "oracle", "_ref", "liblssp_ref.so")
+EXAM = os.path.join(ROOT, "examples", "exam")
+
+DRIVERS = ["gmres", "gmres_r", "lgmres", "lgmres_r", "bicgstab", "bicgstabl", "bicgsafe", "cg", "cgs", "gpbicg",
+           "cr", "crs", "bicrstab", "bicrsafe", "gpbicr", "qmrcgstab", "tfqmr", "orthomin", "idrs"]
+REQUIRED = (["lssp_solver_%s(LSSP_SOLVER_&, LSSP_PC_&)" % d for d in DRIVERS] +
+            ["lssp_mv_mxy(lssp_mat_csr_, lssp_vec_, lssp_vec_)", "lssp_mv_amxy(double, lssp_mat_csr_, lssp_vec_, lssp_vec_)",
+             "lssp_mv_amxpby(double, lssp_mat_csr_, lssp_vec_, double, lssp_vec_)",
+             "lssp_mv_amxpbyz(double, lssp_mat_csr_, lssp_vec_, double, lssp_vec_, lssp_vec_)",
+             "lssp_vec_create(int)", "lssp_vec_destroy(lssp_vec_&)", "lssp_vec_set_value(lssp_vec_, double)",
+             "lssp_vec_set_value_by_array(lssp_vec_, double*)", "lssp_vec_set_value_by_index(lssp_vec_, int, double)",
+             "lssp_vec_get_value(double*, lssp_vec_)", "lssp_vec_get_value_by_index(lssp_vec_, int)",
+             "lssp_vec_copy(lssp_vec_, lssp_vec_)", "lssp_vec_axy(double, lssp_vec_, lssp_vec_)",
+             "lssp_vec_axpby(double, lssp_vec_, double, lssp_vec_)",
+             "lssp_vec_axpbyz(double, lssp_vec_, double, lssp_vec_, lssp_vec_)", "lssp_vec_dot(lssp_vec_, lssp_vec_)",
+             "lssp_vec_norm(lssp_vec_)", "lssp_vec_scale(lssp_vec_, double)",
+             "lssp_pc_ilu_solve(LSSP_PC_*, lssp_vec_, lssp_vec_)",
+             "lssp_pc_ilu_solve_lower_matrix(lssp_mat_csr_, double*, double*)",
+             "lssp_pc_ilu_solve_upper_matrix(lssp_mat_csr_, double*, double*)",
+             "lssp_pc_ilu_solve_lu_matrix(lssp_mat_csr_, lssp_mat_csr_, double*, double*, double*)",
+             "lssp_solver_create(LSSP_SOLVER_&, LSSP_SOLVER_TYPE_, LSSP_PC_&, LSSP_PC_TYPE_)",
+             "lssp_solver_assemble(LSSP_SOLVER_&, lssp_mat_csr_&, lssp_vec_, lssp_vec_, LSSP_PC_&)",
+             "lssp_solver_solve(LSSP_SOLVER_&, LSSP_PC_&)", "lssp_solver_destroy(LSSP_SOLVER_&, LSSP_PC_&)",
+             "lssp_solver_set_rtol(LSSP_SOLVER_&, double)", "lssp_solver_set_maxit(LSSP_SOLVER_&, int)",
+             "lssp_solver_set_restart(LSSP_SOLVER_&, int)", "lssp_solver_reset_rhs(LSSP_SOLVER_&, lssp_vec_)",
+             "lssp_pc_create(LSSP_PC_&, LSSP_PC_TYPE_)", "lssp_pc_assemble(LSSP_PC_&, LSSP_SOLVER_)",
+             "lssp_pc_destroy(LSSP_PC_&)", "lssp_pc_iluk_set_level(LSSP_PC_&, int)",
+             "lssp_pc_ilut_set_drop_tol(LSSP_PC_&, double)", "lssp_pc_ilut_set_p(LSSP_PC_&, int)",
+             "lssp_mat_create(int, int, int*, int*, double*)", "lssp_mat_destroy(lssp_mat_csr_&)",
+             "lssp_printf(char const*, ...)", "lssp_error(int, char const*, ...)", "lssp_get_time()"])
+
+
+def exported(path):
+    out = subprocess.run(["nm", "-DC", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return {re.sub(r"^\S+\s+\S\s+", "", ln).strip() for ln in out.splitlines() if " T " in ln}
+
+
+def mangled(path):
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+
+
+def test_facade_exports_the_reference_cxx_symbols():
+    have = exported(LIB)
+    missing = [s for s in REQUIRED if s not in have]
+    assert not missing, missing
+
+
+def test_facade_symbols_are_link_compatible_with_the_reference():
+    """Same MANGLED names as the reference build for every hot-path function, so an object file
+    compiled against the reference headers would also resolve against liblssp.so."""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref not built")
+    ours, ref_dem, ref_m = mangled(LIB), exported(REF), mangled(REF)
+    for s in REQUIRED:
+        assert s in ref_dem, "not a reference symbol: " + s
+    hot = {m for m in ref_m if re.match(r"_Z\d+lssp_(solver_(?!sxamg|amg|fasp|petsc|mumps|lis|laspack|umfpack|klu|superlu|pardiso|mi20|qrmumps)|mv_|vec_|pc_(create|destroy|assemble|ilu_solve|iluk_(assemble|destroy|set)|ilut_(assemble|destroy|set)))", m)}
+    assert len(hot) > 60
+    assert not (hot - ours), sorted(hot - ours)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,nits,residual,xnorm", [
+    ([], 49, 8.18058783e-06, 4.25082937e+04),                      # the reference's own example run
+    (["100", "cg", "iluk"], 51, 8.65389630e-06, 4.25082937e+04),   # App. A.1: CG + ILUK(1)
+    (["100", "bicgstab", "ilut"], 28, 5.27499238e-06, 4.25082937e+04),
+    (["100", "idrs", "non"], 192, 8.64842582e-06, 4.25082937e+04)])
+def test_exam_program_reproduces_reference_output(args, nits, residual, xnorm):
+    out = subprocess.run([EXAM] + args, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"iterations: (\d+), solver residual: (\S+)", out.stdout)
+    n = re.search(r"solution L2 norm: (\S+) residual: (\S+)", out.stdout)
+    got_its, got_res = int(m.group(1)), float(m.group(2))
+    slack = 1 if args[:2] != ["100", "idrs"] and "bicgstab" not in args else max(2, nits // 7)
+    assert abs(got_its - nits) <= slack, out.stdout
+    if got_its == nits and slack == 1:
+        assert abs(got_res - residual) <= 1e-5 * residual, out.stdout
+    assert abs(float(n.group(1)) - xnorm) <= 1e-6 * xnorm
+    assert abs(float(n.group(2)) - got_res) <= 1e-3 * got_res + 1e-9   # verification residual == solver residual
