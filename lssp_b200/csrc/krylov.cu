@@ -10,6 +10,7 @@
 // iteration counts stay exactly those of the reference.
 #include <algorithm>
 #include "krylov.cuh"
+#include "krylov_ops.cuh"
 
 namespace lsspg {
 
@@ -256,10 +257,7 @@ int lsspg_solver_opts_default(lsspg_solver_opts *o)
     return 0;
 }
 
-int lsspg_solver_supported(int solver)
-{
-    return solver == LSSPG_CG || solver == LSSPG_BICGSTAB || solver == LSSPG_GMRES || solver == LSSPG_IDRS;
-}
+int lsspg_solver_supported(int solver) { return solver >= LSSPG_GMRES && solver <= LSSPG_IDRS; }
 
 int lsspg_krylov_solve(lsspg_ctx *ctx, int solver, const lsspg_csr *A, lsspg_pc *pc, const double *db, double *dx,
                        const lsspg_solver_opts *opts, lsspg_solve_info *info)
@@ -275,6 +273,21 @@ int lsspg_krylov_solve(lsspg_ctx *ctx, int solver, const lsspg_csr *A, lsspg_pc 
         case LSSPG_BICGSTAB: rc = krylov_bicgstab(k); break;
         case LSSPG_GMRES: rc = krylov_gmres(k); break;
         case LSSPG_IDRS: rc = krylov_idrs(k, opts); break;
+        case LSSPG_CGS: rc = krylov_cgs(k, opts); break;
+        case LSSPG_CR: rc = krylov_cr(k, opts); break;
+        case LSSPG_CRS: rc = krylov_crs(k, opts); break;
+        case LSSPG_BICRSTAB: rc = krylov_bicrstab(k, opts); break;
+        case LSSPG_TFQMR: rc = krylov_tfqmr(k, opts); break;
+        case LSSPG_QMRCGSTAB: rc = krylov_qmrcgstab(k); break;
+        case LSSPG_ORTHOMIN: rc = krylov_orthomin(k); break;
+        case LSSPG_BICGSAFE: rc = krylov_bicgsafe(k, opts); break;
+        case LSSPG_BICRSAFE: rc = krylov_bicrsafe(k, opts); break;
+        case LSSPG_GPBICG: rc = krylov_gpbicg(k, opts); break;
+        case LSSPG_GPBICR: rc = krylov_gpbicr(k, opts); break;
+        case LSSPG_BICGSTABL: rc = krylov_bicgstabl(k, opts); break;
+        case LSSPG_RGMRES: rc = krylov_rgmres(k); break;
+        case LSSPG_LGMRES: rc = krylov_lgmres(k); break;
+        case LSSPG_RLGMRES: rc = krylov_rlgmres(k); break;
         default:
             set_error("lsspg_krylov_solve: solver %d is not implemented", solver);
             return 1;

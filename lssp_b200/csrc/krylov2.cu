@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include "comm.cuh"
 #include "krylov.cuh"
+#include "krylov_ops.cuh"
 
 namespace lsspg {
 
@@ -58,12 +59,33 @@ __global__ void __launch_bounds__(kBlock) k_axpby_dot(long long n, Coef ca, Coef
 
 // mode 0 (GMRES x-update, src/solver-gmres.cxx:196-204):  t = 0; t += V_i[j]*c_i (i ascending); out[j] += t
 // mode 1 (IDR(s) combos,  src/solver-idrs.cxx:198-214):   h = s0*base[j]; h -= V_i[j]*c_i (i ascending); out[j] = h
+// mode 2 (LGMRES update,   src/solver-lgmres.cxx:229-257): t = 0; t += V_i[j]*c_i; t += Z_i[j]*c2_i; out[j] += t; out2[j] = t
+struct Lincomb2 {
+    const double *Z;
+    const double *coef2;
+    int count2;
+    double *out2;
+};
+
+__global__ void __launch_bounds__(kBlock) k_div_into(long long n, double d, const double *__restrict__ in, double *__restrict__ out)
+{
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
+        out[j] = in[j] / d;   // src/solver-lgmres.cxx:190-192
+}
+
 __global__ void __launch_bounds__(kBlock) k_lincomb(long long n, int mode, int count, const double *__restrict__ V,
                                                     long long stride, const double *__restrict__ coef, double s0,
-                                                    const double *base, double *out)
+                                                    const double *base, double *out, Lincomb2 ex)
 {
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
-        if (mode == 0) {
+        if (mode == 2) {
+            double t = 0;
+            for (int i = 0; i < count; i++) t += V[i * stride + j] * coef[i];
+            for (int i = 0; i < ex.count2; i++) t += ex.Z[i * stride + j] * ex.coef2[i];
+            out[j] += t;
+            ex.out2[j] = t;
+        }
+        else if (mode == 0) {
             double t = 0;
             for (int i = 0; i < count; i++) t += V[i * stride + j] * coef[i];
             out[j] += t;
@@ -75,31 +97,6 @@ __global__ void __launch_bounds__(kBlock) k_lincomb(long long n, int mode, int c
         }
     }
 }
-
-// ---- host-scalar toolkit ------------------------------------------------------------------
-// The reference's drivers interleave BLAS-1 calls with host arithmetic on the returned scalars;
-// these helpers keep that shape (each dot is one reduction kernel + one 8-byte read-back).
-struct Ops {
-    lsspg_ctx *ctx;
-    int n;
-    static constexpr int S_TMP = 96;   // scratch slots of the scalar slab
-    int dots(int k, const double *const *xs, const double *const *ys, double *out)
-    {
-        RedOut o; o.out_slot = S_TMP;
-        LSSPG_TRY(vec_multidot(ctx, n, k, xs, ys, o));
-        LSSPG_TRY(read_scalars(ctx, S_TMP, k, false));
-        for (int i = 0; i < k; i++) out[i] = ctx->h_scal[S_TMP + i];
-        return 0;
-    }
-    int dot(const double *x, const double *y, double *out) { const double *xs[1] = {x}, *ys[1] = {y}; return dots(1, xs, ys, out); }
-    int norm(const double *x, double *out) { double d; LSSPG_TRY(dot(x, x, &d)); *out = sqrt(d); return 0; }
-    int axpby(double a, const double *x, double b, double *y) { return vec_axpby(ctx, n, coef_imm(a), x, coef_imm(b), y); }
-    int axpbyz(double a, const double *x, double b, const double *y, double *z) { return vec_axpbyz(ctx, n, coef_imm(a), x, coef_imm(b), y, z); }
-    int axy(double a, const double *x, double *y) { return vec_axy(ctx, n, coef_imm(a), x, y); }
-    int scale(double *x, double a) { return vec_scale(ctx, n, x, coef_imm(a)); }
-    int copy(double *d, const double *s) { return vec_copy(ctx, n, d, s); }
-    int set(double *x, double v) { return vec_set(ctx, n, x, v); }
-};
 
 static int axpby_dot(lsspg_ctx *ctx, int n, Coef a, const double *x, Coef b, double *y, const double *z, int out_slot)
 {
@@ -226,7 +223,7 @@ int krylov_gmres(KrylovArgs &k)
         if (kk > 0) {
             LSSPG_TRY(upload_coefs(ctx, ym.data(), kk, S_H));
             LSSPG_LAUNCH(ctx, k_lincomb, stream_grid(ctx, n, kBlock), kBlock, 0, (long long)n, 0, kk, V, ld,
-                         ctx->d_scal + S_H, 0.0, (const double *)nullptr, k.x);               // :196-204
+                         ctx->d_scal + S_H, 0.0, (const double *)nullptr, k.x, Lincomb2{nullptr, nullptr, 0, nullptr});   // :196-204
         }
         LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_AMXPBYZ, k.A, coef_imm(-1.0), k.x, coef_imm(1.0), k.b, rg, nullptr));   // :206
         LSSPG_TRY(op.norm(rg, &beta));
@@ -379,12 +376,12 @@ int krylov_idrs(KrylovArgs &k, const lsspg_solver_opts *raw)
                 LSSPG_TRY(op.dots(2, xs, ys, d2));
                 h = d2[0];
                 om = d2[1] / h;
-                LSSPG_LAUNCH(ctx, k_lincomb, grid, kBlock, 0, (long long)n, 1, s, dX, ld, ctx->d_scal + S_C, om, av, dxo);    // :198-205
-                LSSPG_LAUNCH(ctx, k_lincomb, grid, kBlock, 0, (long long)n, 1, s, dR, ld, ctx->d_scal + S_C, -om, t, dro);    // :207-214
+                LSSPG_LAUNCH(ctx, k_lincomb, grid, kBlock, 0, (long long)n, 1, s, dX, ld, ctx->d_scal + S_C, om, av, dxo, Lincomb2{nullptr, nullptr, 0, nullptr});    // :198-205
+                LSSPG_LAUNCH(ctx, k_lincomb, grid, kBlock, 0, (long long)n, 1, s, dR, ld, ctx->d_scal + S_C, -om, t, dro, Lincomb2{nullptr, nullptr, 0, nullptr});    // :207-214
             }
             else {
                 LSSPG_TRY(apply_pc(k, av, v));
-                LSSPG_LAUNCH(ctx, k_lincomb, grid, kBlock, 0, (long long)n, 1, s, dX, ld, ctx->d_scal + S_C, om, av, dxo);    // :219-226
+                LSSPG_LAUNCH(ctx, k_lincomb, grid, kBlock, 0, (long long)n, 1, s, dX, ld, ctx->d_scal + S_C, om, av, dxo, Lincomb2{nullptr, nullptr, 0, nullptr});    // :219-226
                 LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_MXY, k.A, coef_imm(1.0), dxo, coef_imm(0.0), nullptr, dro, nullptr));
                 LSSPG_TRY(op.scale(dro, -1.));
             }
@@ -409,6 +406,315 @@ int krylov_idrs(KrylovArgs &k, const lsspg_solver_opts *raw)
     }
     k.info->nits = iter;
     k.info->residual = nrm2;
+    return 0;
+}
+
+// ---- shared Arnoldi pieces of the GMRES family ------------------------------------------------------
+// modified Gram-Schmidt of wj against v_0..v_i with the h_j kept on the device (see krylov_gmres);
+// returns the Hessenberg column in col[0..i] and ||wj|| in *hnorm
+static int mgs_column(lsspg_ctx *ctx, int n, double *wj, const double *V, long long ld, int i, int S_H, double *col,
+                      double *hnorm)
+{
+    {
+        const double *xs[1] = {wj}, *ys[1] = {V};
+        RedOut o; o.out_slot = S_H;
+        LSSPG_TRY(vec_multidot(ctx, n, 1, xs, ys, o));
+    }
+    for (int j = 0; j <= i; j++) {
+        const double *vj = V + (long long)j * ld;
+        const double *next = (j < i) ? V + (long long)(j + 1) * ld : nullptr;
+        LSSPG_TRY(axpby_dot(ctx, n, coef_slot(S_H + j, true), vj, coef_imm(1.0), wj, next, S_H + j + 1));
+    }
+    LSSPG_TRY(read_scalars(ctx, S_H, i + 2, false));
+    for (int j = 0; j <= i; j++) col[j] = ctx->h_scal[S_H + j];
+    *hnorm = sqrt(ctx->h_scal[S_H + i + 1]);
+    return 0;
+}
+
+struct Hess {
+    int m;
+    std::vector<double> Hg, gg, ym, c, s;
+    explicit Hess(int m_) : m(m_), Hg((size_t)(m_ + 1) * m_, 0.0), gg(m_ + 1, 0.0), ym(m_, 0.0), c(m_, 0.0), s(m_, 0.0) {}
+    double &H(int r, int col) { return Hg[(size_t)r * m + col]; }
+    void clear(int mm)   // as the reference: only the (mm+1) x mm leading part of the current cycle
+    {
+        for (int kk = 0; kk <= mm; kk++)
+            for (int i = 0; i < mm; i++) H(kk, i) = 0;
+    }
+    // Givens update of column i (src/solver-gmres.cxx:160-177); returns |gg[i+1]|
+    double rotate(int i)
+    {
+        for (int j = 0; j < i; j++) {
+            const double h1 = c[j] * H(j, i) + s[j] * H(j + 1, i);
+            const double h2 = -s[j] * H(j, i) + c[j] * H(j + 1, i);
+            H(j, i) = h1;
+            H(j + 1, i) = h2;
+        }
+        double gma = sqrt(H(i, i) * H(i, i) + H(i + 1, i) * H(i + 1, i));
+        if (fabs(gma) == 0.) gma = 1e-20;
+        c[i] = H(i, i) / gma;
+        s[i] = H(i + 1, i) / gma;
+        gg[i + 1] = -s[i] * gg[i];
+        gg[i] = c[i] * gg[i];
+        H(i, i) = c[i] * H(i, i) + s[i] * H(i + 1, i);
+        return fabs(gg[i + 1]);
+    }
+    void back_substitute(int kk)
+    {
+        for (int i = kk - 1; i >= 0; i--) {
+            ym[i] = gg[i] / H(i, i);
+            for (int j = 0; j < i; j++) gg[j] = gg[j] - ym[i] * H(j, i);
+        }
+    }
+};
+
+// ---- RGMRES(m), right preconditioning: src/solver-gmres.cxx:257-479 -----------------------------------
+int krylov_rgmres(KrylovArgs &k)
+{
+    lsspg_ctx *ctx = k.ctx;
+    const int n = k.n;
+    int m = k.restart;
+    if (m < 0) m = kDefRestart;
+    double tol_rb = k.tol_rb;
+    if (tol_rb < 0) tol_rb = kDefRb;
+    constexpr int S_H = 128;
+    LSSPG_CHECK(m >= 1 && S_H + m + 2 <= kNumScalars, "rgmres: restart %d not supported", m);
+    Ops op{ctx, n};
+    Workspace W(ctx, k.nvec);
+    double *wj = W.vec(), *rg = W.vec();
+    Workspace WV(ctx, (long long)k.nvec * m);
+    double *V = WV.vec();
+    LSSPG_CHECK(wj && rg && V, "rgmres: out of device memory");
+    const long long ld = k.nvec;
+    Hess h(m);
+    double b_norm, beta;
+    LSSPG_TRY(op.norm(k.b, &b_norm));
+    tol_rb *= b_norm;
+    LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_AMXPBYZ, k.A, coef_imm(-1.0), k.x, coef_imm(1.0), k.b, rg, nullptr));
+    LSSPG_TRY(op.norm(rg, &beta));
+    if (beta <= k.tol_abs) { k.info->nits = 0; k.info->residual = beta; return 0; }
+    const double err_rel = beta;
+    double tol = k.tol_rel * err_rel;
+    if (tol < k.tol_abs) tol = k.tol_abs;
+    if (tol < tol_rb) tol = tol_rb;
+    int itr_inner = 0;
+    std::vector<double> col(m + 1);
+    while (itr_inner < k.maxit) {
+        int i, kk;
+        for (kk = 1; kk <= m; kk++) h.gg[kk] = 0;
+        h.clear(m);
+        LSSPG_TRY(op.norm(rg, &beta));
+        h.gg[0] = beta;
+        LSSPG_TRY(op.axy(1 / beta, rg, V));
+        for (i = 0; i < m && itr_inner < k.maxit; i++) {
+            double hij;
+            itr_inner++;
+            LSSPG_TRY(op.set(rg, 0.));
+            LSSPG_TRY(apply_pc(k, rg, V + (long long)i * ld));
+            LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_MXY, k.A, coef_imm(1.0), rg, coef_imm(0.0), nullptr, wj, nullptr));
+            LSSPG_TRY(mgs_column(ctx, n, wj, V, ld, i, S_H, col.data(), &hij));
+            for (int j = 0; j <= i; j++) h.H(j, i) = col[j];
+            h.H(i + 1, i) = hij;
+            if (fabs(hij) <= kBreakdown) { i -= 1; break; }
+            else if (i + 1 < m) LSSPG_TRY(op.axy(1 / hij, wj, V + (long long)(i + 1) * ld));
+            beta = h.rotate(i);
+            record(k, itr_inner - 1, beta);
+            if (k.verb >= 1)
+                printf("rgmres: itr: %4d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_inner, beta,
+                       (err_rel == 0 ? 0 : beta / err_rel), (b_norm == 0 ? 0 : beta / b_norm));
+            if (beta <= tol) break;
+        }
+        kk = (i == m) ? m : i + 1;
+        h.back_substitute(kk);
+        if (kk > 0) {                                            // :424-438
+            LSSPG_TRY(op.axy(h.ym[kk - 1], V + (long long)(kk - 1) * ld, rg));
+            for (i = kk - 2; i >= 0; i--) LSSPG_TRY(op.axpby(h.ym[i], V + (long long)i * ld, 1, rg));
+            LSSPG_TRY(apply_pc(k, wj, rg));
+            LSSPG_TRY(op.axpby(1, wj, 1, k.x));
+        }
+        if (beta <= tol) break;
+        LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_AMXPBYZ, k.A, coef_imm(-1.0), k.x, coef_imm(1.0), k.b, rg, nullptr));
+    }
+    k.info->nits = itr_inner;
+    k.info->residual = beta;
+    return 0;
+}
+
+// ---- LGMRES(m, k), left preconditioning: src/solver-lgmres.cxx:12-311 ---------------------------------
+int krylov_lgmres(KrylovArgs &k)
+{
+    lsspg_ctx *ctx = k.ctx;
+    const int n = k.n;
+    int mk = k.restart, auk = k.aug_k;
+    if (mk < 0) mk = kDefRestart;
+    if (auk < 0) auk = kDefAugK;
+    double tol_rb = k.tol_rb;
+    if (tol_rb < 0) tol_rb = kDefRb;
+    int m = mk + auk;
+    constexpr int S_H = 128;
+    LSSPG_CHECK(mk >= 1 && auk >= 1 && S_H + m + 2 <= kNumScalars, "lgmres: restart %d + aug %d not supported", mk, auk);
+    Ops op{ctx, n};
+    Workspace W(ctx, k.nvec);
+    double *wj = W.vec(), *rg = W.vec();
+    Workspace WV(ctx, (long long)k.nvec * m), WZ(ctx, (long long)k.nvec * auk);
+    double *V = WV.vec(), *Z = WZ.vec();
+    LSSPG_CHECK(wj && rg && V && Z, "lgmres: out of device memory");
+    const long long ld = k.nvec;
+    Hess h(m);
+    double b_norm, beta;
+    LSSPG_TRY(op.norm(k.b, &b_norm));
+    tol_rb *= b_norm;
+    LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_AMXPBYZ, k.A, coef_imm(-1.0), k.x, coef_imm(1.0), k.b, rg, nullptr));
+    LSSPG_TRY(op.norm(rg, &beta));
+    if (beta <= k.tol_abs) { k.info->nits = 0; k.info->residual = beta; return 0; }
+    const double err_rel = beta;
+    double tol = k.tol_rel * err_rel;
+    if (tol < k.tol_abs) tol = k.tol_abs;
+    if (tol < tol_rb) tol = tol_rb;
+    const double rtol = tol / beta;
+    double gstol = 0.;
+    int itr_outer = 0, itr_inner = 0;
+    std::vector<double> col(m + 1);
+    const int grid = stream_grid(ctx, n, kBlock);
+    while (itr_inner < k.maxit) {
+        int kk, i;
+        double gs_norm = 0.;
+        LSSPG_TRY(op.set(V, 0.));
+        LSSPG_TRY(apply_pc(k, V, rg));
+        LSSPG_TRY(op.norm(V, &beta));
+        m = (itr_outer < auk) ? mk + itr_outer : mk + auk;                  // "tune m", :113-118
+        h.gg[0] = beta;
+        for (kk = 1; kk <= m; kk++) h.gg[kk] = 0;
+        if (itr_outer == 0) gstol = rtol * beta * 0.5;
+        {   // the reference clears Hg[0..m][0..m) of an array whose rows have mk+auk columns
+            for (kk = 0; kk <= m; kk++)
+                for (i = 0; i < m; i++) h.H(kk, i) = 0;
+        }
+        LSSPG_TRY(vec_scale_div(ctx, n, V, beta));
+        for (i = 0; i < m; i++) {
+            double hij;
+            itr_inner++;
+            const double *src = (i < mk) ? V + (long long)i * ld : Z + (long long)(i - mk) * ld;
+            LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_MXY, k.A, coef_imm(1.0), src, coef_imm(0.0), nullptr, rg, nullptr));
+            LSSPG_TRY(op.set(wj, 0.));
+            LSSPG_TRY(apply_pc(k, wj, rg));
+            LSSPG_TRY(mgs_column(ctx, n, wj, V, ld, i, S_H, col.data(), &hij));
+            for (int j = 0; j <= i; j++) h.H(j, i) = col[j];
+            h.H(i + 1, i) = hij;
+            if (fabs(hij) <= kBreakdown) { i--; break; }
+            else if (i + 1 < m)
+                LSSPG_LAUNCH(ctx, k_div_into, grid, kBlock, 0, (long long)n, hij, wj, V + (long long)(i + 1) * ld);
+            gs_norm = h.rotate(i);
+            if (gs_norm <= gstol) break;
+        }
+        kk = i;                                                              // the reference's quirk, :214
+        h.back_substitute(kk);
+        const int zn = itr_outer % auk;
+        {
+            int cv, cz;
+            if (kk <= mk) { cv = kk; cz = 0; }
+            else { cv = mk; cz = (itr_outer <= auk) ? itr_outer : auk; }
+            if (cz > auk) cz = auk;
+            if (kk > 0 || true) {
+                LSSPG_TRY(upload_coefs(ctx, h.ym.data(), std::max(1, std::min(m, mk + auk)), S_H));
+                Lincomb2 ex{Z, ctx->d_scal + S_H + mk, cz, Z + (long long)zn * ld};
+                LSSPG_LAUNCH(ctx, k_lincomb, grid, kBlock, 0, (long long)n, 2, cv > 0 ? cv : 0, V, ld, ctx->d_scal + S_H, 0.0,
+                             (const double *)nullptr, k.x, ex);              // :229-257
+            }
+        }
+        LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_AMXPBYZ, k.A, coef_imm(-1.0), k.x, coef_imm(1.0), k.b, rg, nullptr));
+        LSSPG_TRY(op.norm(rg, &beta));
+        record(k, itr_outer, beta);
+        if (k.verb >= 1)
+            printf("lgmres: itr: %4d / %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_outer, itr_inner, beta,
+                   (err_rel == 0 ? 0 : beta / err_rel), (b_norm == 0 ? 0 : beta / b_norm));
+        if (beta <= tol) break;
+        gstol = rtol * gs_norm / (beta / err_rel) * 0.5;
+        itr_outer++;
+    }
+    k.info->nits = itr_inner;
+    k.info->residual = beta;
+    return 0;
+}
+
+// ---- RLGMRES(m, k), right preconditioning: src/solver-lgmres.cxx:313-604 ------------------------------
+int krylov_rlgmres(KrylovArgs &k)
+{
+    lsspg_ctx *ctx = k.ctx;
+    const int n = k.n;
+    int mk = k.restart, auk = k.aug_k;
+    if (mk < 0) mk = kDefRestart;
+    if (auk < 0) auk = kDefAugK;
+    double tol_rb = k.tol_rb;
+    if (tol_rb < 0) tol_rb = kDefRb;
+    int m = mk + auk;
+    constexpr int S_H = 128;
+    LSSPG_CHECK(mk >= 1 && auk >= 1 && S_H + m + 2 <= kNumScalars, "rlgmres: restart %d + aug %d not supported", mk, auk);
+    Ops op{ctx, n};
+    Workspace W(ctx, k.nvec);
+    double *wj = W.vec(), *rg = W.vec();
+    Workspace WV(ctx, (long long)k.nvec * m), WZ(ctx, (long long)k.nvec * auk);
+    double *V = WV.vec(), *Z = WZ.vec();
+    LSSPG_CHECK(wj && rg && V && Z, "rlgmres: out of device memory");
+    const long long ld = k.nvec;
+    Hess h(m);
+    double b_norm, beta;
+    LSSPG_TRY(op.norm(k.b, &b_norm));
+    tol_rb *= b_norm;
+    LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_AMXPBYZ, k.A, coef_imm(-1.0), k.x, coef_imm(1.0), k.b, rg, nullptr));
+    LSSPG_TRY(op.norm(rg, &beta));
+    if (beta <= k.tol_abs) { k.info->nits = 0; k.info->residual = beta; return 0; }
+    const double err_rel = beta;
+    double tol = k.tol_rel * err_rel;
+    if (tol < k.tol_abs) tol = k.tol_abs;
+    if (tol < tol_rb) tol = tol_rb;
+    int itr_outer = 0, itr_inner = 0;
+    std::vector<double> col(m + 1);
+    while (itr_inner < k.maxit) {
+        int kk, i;
+        m = (itr_outer < auk) ? mk + itr_outer : mk + auk;
+        for (kk = 1; kk <= m; kk++) h.gg[kk] = 0;
+        for (kk = 0; kk <= m; kk++)
+            for (i = 0; i < m; i++) h.H(kk, i) = 0;
+        LSSPG_TRY(op.norm(rg, &beta));
+        h.gg[0] = beta;
+        LSSPG_TRY(op.axy(1 / beta, rg, V));
+        for (i = 0; i < m && itr_inner < k.maxit; i++) {
+            double hij;
+            itr_inner++;
+            LSSPG_TRY(op.set(rg, 0.));
+            LSSPG_TRY(apply_pc(k, rg, (i < mk) ? V + (long long)i * ld : Z + (long long)(i - mk) * ld));
+            LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_MXY, k.A, coef_imm(1.0), rg, coef_imm(0.0), nullptr, wj, nullptr));
+            LSSPG_TRY(mgs_column(ctx, n, wj, V, ld, i, S_H, col.data(), &hij));
+            for (int j = 0; j <= i; j++) h.H(j, i) = col[j];
+            h.H(i + 1, i) = hij;
+            if (fabs(hij) <= kBreakdown) { i--; break; }
+            else if (i + 1 < m) LSSPG_TRY(op.axy(1 / hij, wj, V + (long long)(i + 1) * ld));
+            beta = h.rotate(i);
+            record(k, itr_inner - 1, beta);
+            if (k.verb >= 1)
+                printf("rlgmres: itr: %4d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_inner, beta,
+                       (err_rel == 0 ? 0 : beta / err_rel), (b_norm == 0 ? 0 : beta / b_norm));
+            if (beta <= tol) break;
+        }
+        kk = i;                                                              // :506
+        h.back_substitute(kk);
+        if (kk > 0) {
+            // after the back substitution the reference's loop index is -1, so its `if (i <= mk)` always
+            // takes the first branch: only the v_i enter the correction (:519-524), also for kk > mk
+            LSSPG_TRY(op.axy(h.ym[0], V, rg));
+            for (i = 1; i < kk; i++) LSSPG_TRY(op.axpby(h.ym[i], V + (long long)i * ld, 1, rg));
+            LSSPG_TRY(apply_pc(k, wj, rg));
+            LSSPG_TRY(op.axpby(1, wj, 1, k.x));
+            LSSPG_TRY(op.copy(Z + (long long)(itr_outer % auk) * ld, rg));
+        }
+        if (beta <= tol) break;
+        LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_AMXPBYZ, k.A, coef_imm(-1.0), k.x, coef_imm(1.0), k.b, rg, nullptr));
+        LSSPG_TRY(op.norm(rg, &beta));
+        itr_outer++;
+    }
+    k.info->nits = itr_inner;
+    k.info->residual = beta;
     return 0;
 }
 
