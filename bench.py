@@ -91,6 +91,10 @@ def build_problem(args):
         A = g.cd3d(N)
         name = "cd3d_%d BiCGStab+ILU(0)" % N
         solver, pc = "bicgstab", "iluk"
+    elif args.workload == "cg_amg":
+        A = g.lap3d(N)
+        name = "lap3d_%d CG+SXAMG-style V-cycle, zero initial guess (BASELINE.json configs[3] operator)" % N
+        solver, pc = "cg", "amg"
     elif args.workload == "cg_non":
         A = g.lap3d(N)
         name = "lap3d_%d CG unpreconditioned" % N
@@ -107,11 +111,36 @@ def reference_arm(args, rank):
     if rank != 0:
         return 0
     import oracle
-    if not oracle.Ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference at build time)"}))
-        return 0
     A, name, solver, pc = build_problem(args)
     n = len(A[0]) - 1
+    if pc == "amg" or not oracle.Ref.available():
+        # no compiled reference for this path (libsxamg is not in the tree / _ref not built): the C port
+        from lssp_b200 import api   # host set-up only (factors / hierarchy); no GPU work
+        P = oracle.Port()
+        kw = {}
+        if pc == "amg":
+            H = api.AmgHierarchy(A)
+            kw["amg"] = P.amg(H.levels, coarse_inv=H.coarse_inv, zero_guess=1)
+        elif pc == "iluk":
+            kw["LU"] = api.ilu_factor(A, "iluk", level=0)
+        its, secs = 0, 0.0
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            r = P.solve(solver, A, np.ones(n), maxit=args.ref_iters, **kw)
+            if step >= args.warmup:
+                its += r["nits"]
+                secs += time.perf_counter() - t0
+        val = its / secs
+        print(json.dumps({"impl": "reference", "metric": "%s_iterations_per_second" % args.workload, "value": val,
+                          "unit": "iter/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": name, "n": n, "nnz": int(A[0][-1]), "iterations_per_step": args.ref_iters},
+                          "cpu_baseline": {"value": val, "unit": "iter/s", "cores": 1, "kind": "port",
+                                           "sample": "%d steps x %d iterations of the same solve, oracle/*.c"
+                                                     % (args.steps, args.ref_iters)},
+                          "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
     R = oracle.Ref()
     L = R.lib
     L.ref_session_create.restype = C.c_void_p
@@ -145,9 +174,19 @@ def reference_arm(args, rank):
     return 0
 
 
-def cpu_baseline(args, A, solver, pc):
+def cpu_baseline(args, A, solver, pc, pcobj=None):
     import oracle
     n = len(A[0]) - 1
+    if pc == "amg":
+        # libsxamg is not in the reference tree: the CPU side is the restated cycle (parity unpinned)
+        H = pcobj.hierarchy
+        m = oracle.Port().amg(H.levels, coarse_inv=H.coarse_inv, zero_guess=1)
+        t0 = time.perf_counter()
+        r = oracle.Port().solve(solver, A, np.ones(n), amg=m, maxit=args.ref_iters)
+        t = time.perf_counter() - t0
+        return {"value": r["nits"] / t, "unit": "iter/s", "cores": 1, "kind": "port",
+                "sample": "%d iterations of the same solve, oracle/oracle.c + amg_oracle.c on the same hierarchy"
+                          % r["nits"], "host_cores_total": os.cpu_count()}
     if oracle.Ref.available():
         R = oracle.Ref()
         L = R.lib
@@ -215,7 +254,12 @@ def main():
     ctx.set_option(api.OPT_CHECK_EVERY, args.check_every)
     dA = api.Csr(ctx, A)
     t0 = time.perf_counter()
-    pc = api.Preconditioner.iluk(ctx, A, level=0) if pckind == "iluk" else api.Preconditioner.non(ctx, n)
+    if pckind == "iluk":
+        pc = api.Preconditioner.iluk(ctx, A, level=0)
+    elif pckind == "amg":
+        pc = api.Preconditioner.sxamg(ctx, A, share=dA, zero_guess=1)
+    else:
+        pc = api.Preconditioner.non(ctx, n)
     t_pc = time.perf_counter() - t0
     L = lib()
     b, x = ctx.upload(np.ones(n)), ctx.zeros(n)
@@ -291,6 +335,15 @@ def main():
                 "bytes": pc.bytes, "share_of_iteration": ms_pcap / ms_per_it, "peak_kind": peak_kind,
                 "note": "latency-bound by %d dependency levels per sweep, not by HBM" % pc.info()["levels_L"]}
         info = pc.info()
+    elif pckind == "amg":
+        ms_pcap = timed(lambda: pc.apply(y, b), 10)
+        pc_gbs = pc.bytes / ms_pcap / 1e6
+        lv = pc.hierarchy.levels
+        roof = {"bound": "hbm", "achieved": pc_gbs, "peak": peak, "unit": "GB/s", "frac": pc_gbs / peak, "traffic": None,
+                "kernel": "one V-cycle (gs_sweep_kernel x4 + residual/restriction/prolongation SpMVs per level)",
+                "ms": ms_pcap, "bytes": pc.bytes, "share_of_iteration": ms_pcap / ms_per_it, "peak_kind": peak_kind,
+                "levels": [[L["n"], int(L["A"][0][-1])] for L in lv]}
+        info = {}
     else:
         roof = dict(roof_spmv, kernel="spmv_tiles_kernel", share_of_iteration=ms_spmv / ms_per_it)
         info = {}
@@ -304,9 +357,9 @@ def main():
                              % (dA.spmv_bytes / 1e9)},
             "ms_per_iteration": ms_per_it, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
             "roofline": roof, "roofline_spmv": roof_spmv,
-            "setup_s": {"generate": t_gen, "ilu0_host_factor_and_upload": t_pc}}
+            "setup_s": {"generate": t_gen, "pc_host_setup_and_upload": t_pc}}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, A, solver, pckind)
+        line["cpu_baseline"] = cpu_baseline(args, A, solver, pckind, pc)
     print(json.dumps(line))
     check(L.lsspg_host_free(hb))
     check(L.lsspg_host_free(hx))

@@ -184,6 +184,58 @@ double lsspg_pc_bytes(const lsspg_pc *pc);
 int lsspg_pc_apply(lsspg_ctx *ctx, lsspg_pc *pc, double *dx, const double *drhs);
 int lsspg_pc_apply_host(lsspg_ctx *ctx, lsspg_pc *pc, double *hx, const double *hrhs);
 
+/* ---- SX-AMG-style classical AMG (replaces the libsxamg calls of src/pc-sxamg.cxx and
+ *      src/solver-sxamg.cxx; libsxamg itself is not in the reference tree -- the algorithm is
+ *      specified in DESIGN.md "AMG", parity with libsxamg is UNPINNED) ---------------------- */
+typedef struct lsspg_amg_pars {          /* the role of SX_AMG_PARS (sx_amg_pars_init) */
+    int    max_levels;        /* 30  */
+    int    coarse_dof;        /* 100: stop coarsening at or below this many unknowns */
+    double strong_threshold;  /* 0.3 */
+    double max_row_sum;       /* 0.9 */
+    double trunc_threshold;   /* 0.2: interpolation truncation */
+    int    pre_iter;          /* 2 Gauss-Seidel sweeps before restriction */
+    int    post_iter;         /* 2 after prolongation */
+    int    cf_order;          /* 1: sweeps visit C points then F points (pre) / F then C (post); 0: natural */
+    int    zero_guess;        /* 0: the cycle starts from the incoming x, as the reference's adapter does
+                                 (src/pc-sxamg.cxx:58-64); 1: from x = 0 (a fixed linear operator) */
+    int    coarse_dense_max;  /* 4096: coarsest level solved with its dense inverse up to this size */
+    int    coarse_sweeps;     /* 40 natural-order sweeps on a coarsest level larger than that */
+    double tol;               /* 1e-8  stand-alone solver: stop when ||b - A x|| / ||b|| <= tol */
+    int    maxit;             /* 100   stand-alone solver: most cycles */
+    int    verb;
+} lsspg_amg_pars;
+int lsspg_amg_pars_default(lsspg_amg_pars *p);
+typedef struct lsspg_amg_host lsspg_amg_host;   /* host image of the hierarchy */
+/* Setup (host; GPU setup is SURVEY.md 8f row 2).  Columns of A must be sorted. */
+int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hAx,
+                         const lsspg_amg_pars *pars, lsspg_amg_host **out);
+int lsspg_amg_host_levels(const lsspg_amg_host *H, int *num_levels, int *coarse_dense);
+/* level l: unknowns, C points, nnz of A_l, of P_l (n_l x n_{l+1}) and of R_l = P_l^T; the last
+ * level has nc = nnzP = nnzR = 0 */
+int lsspg_amg_host_level_sizes(const lsspg_amg_host *H, int l, int *n, int *nc, int *nnzA,
+                               int *nnzP, int *nnzR);
+/* any pointer may be NULL; cf[i] = 1 for C points, 0 for F points */
+int lsspg_amg_host_level_get(const lsspg_amg_host *H, int l, int *Ap, int *Aj, double *Ax,
+                             int *Pp, int *Pj, double *Px, int *Rp, int *Rj, double *Rx, int *cf);
+/* row-major n x n inverse of the coarsest operator (only when coarse_dense != 0) */
+int lsspg_amg_host_coarse_inverse(const lsspg_amg_host *H, double *inv);
+int lsspg_amg_host_pars(const lsspg_amg_host *H, lsspg_amg_pars *pars);
+int lsspg_amg_host_destroy(lsspg_amg_host *H);
+/* CPU self-check of the smoother layout (as lsspg_debug_tri_walk_layout_host): walks the
+ * level-ordered image of level l in ticket order, one sweep x_new <- GS(x_old).  post: bit 0 =
+ * post-smoothing order; bits 1..2 = 0: the schedule the device would use, 1: slices, 2: rows. */
+int lsspg_debug_amg_walk_gs_host(const lsspg_amg_host *H, int l, int post, const double *hb,
+                                 const double *hx_old, double *hx_new, int *info /* [4]: slices,
+                                 C-block levels, F-block levels, padded entries / 32 */);
+/* device hierarchy; A0 (optional) is an already uploaded copy of the level-0 operator to share */
+int lsspg_pc_create_amg(lsspg_ctx *ctx, const lsspg_amg_host *H, const lsspg_csr *A0, lsspg_pc **out);
+/* stand-alone AMG iteration (lssp_solver_sxamg, src/solver-sxamg.cxx:25-99): cycles from x until
+ * ||b - A x|| / ||b|| <= tol or maxit cycles; returns cycles in *nits, ||b - A x|| in *ares */
+int lsspg_amg_solve(lsspg_ctx *ctx, lsspg_pc *amg, const double *db, double *dx, double tol, int maxit,
+                    int *nits, double *ares);
+int lsspg_amg_solve_host(lsspg_ctx *ctx, lsspg_pc *amg, const double *hb, double *hx, double tol,
+                         int maxit, int *nits, double *ares);
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch -------------------------
  * The reference is serial; the path shards by contiguous row blocks of ceil(n/P) rows, the
  * block boundaries of lssp_mat_get_block_diag (src/matrix-utils.cxx:615,626-628), so that the

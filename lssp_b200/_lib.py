@@ -30,6 +30,13 @@ class SolveInfo(C.Structure):
                 ("solve_ms", C.c_double), ("launches", C.c_longlong), ("breakdown", C.c_int)]
 
 
+class AmgPars(C.Structure):
+    _fields_ = [("max_levels", C.c_int), ("coarse_dof", C.c_int), ("strong_threshold", C.c_double),
+                ("max_row_sum", C.c_double), ("trunc_threshold", C.c_double), ("pre_iter", C.c_int),
+                ("post_iter", C.c_int), ("cf_order", C.c_int), ("zero_guess", C.c_int), ("coarse_dense_max", C.c_int),
+                ("coarse_sweeps", C.c_int), ("tol", C.c_double), ("maxit", C.c_int), ("verb", C.c_int)]
+
+
 def lib():
     """Load liblsspg.so (once).  Fails loudly when it has not been built."""
     global _lib

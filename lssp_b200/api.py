@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import SolveInfo, SolverOpts, check, lib
+from ._lib import AmgPars, SolveInfo, SolverOpts, check, lib
 
 SOLVERS = {"gmres": 0, "lgmres": 1, "rgmres": 2, "rlgmres": 3, "bicgstab": 4, "bicgstabl": 5,
            "bicgsafe": 6, "cg": 7, "cgs": 8, "gpbicg": 9, "cr": 10, "crs": 11, "bicrstab": 12,
@@ -352,6 +352,30 @@ class Preconditioner:
         L, U = ilu_factor(A, "ilut", p=p, tol=tol, blk_size=blk_size)
         return cls(ctx, "ilu", len(L[0]) - 1, L, U)
 
+    @classmethod
+    def sxamg(cls, ctx, A, hierarchy=None, share=None, **pars):
+        """lssp_pc_sxamg_assemble (reference src/pc-sxamg.cxx:75-126): classical AMG hierarchy of A,
+        one V-cycle per application.  `hierarchy`: an AmgHierarchy to reuse; `share`: a device Csr
+        holding the same A (saves a second copy of the level-0 operator)."""
+        H = hierarchy if hierarchy is not None else AmgHierarchy(A, **pars)
+        self = cls.__new__(cls)
+        self.ctx, self.kind, self.n = ctx, "amg", H.levels[0]["n"]
+        self.h = C.c_void_p()
+        self.hierarchy = H
+        self._share = share   # keep the shared operator alive
+        check(lib().lsspg_pc_create_amg(ctx.h, H.h, share.h if share is not None else None, C.byref(self.h)))
+        return self
+
+    def amg_solve(self, b, x, tol=1e-8, maxit=100):
+        """lssp_solver_sxamg (reference src/solver-sxamg.cxx:25-99) with HOST b / x: cycles from x
+        until ||b - A x|| / ||b|| <= tol; returns dict(nits, residual, x)."""
+        b = _f64(b)
+        assert isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous
+        nits, ares = C.c_int(), C.c_double()
+        check(lib().lsspg_amg_solve_host(self.ctx.h, self.h, _p(b), _p(x), C.c_double(tol), int(maxit),
+                                         C.byref(nits), C.byref(ares)))
+        return dict(nits=nits.value, residual=ares.value, x=x)
+
     @property
     def bytes(self):
         return lib().lsspg_pc_bytes(self.h)
@@ -375,6 +399,68 @@ class Preconditioner:
     def free(self):
         if self.h and self.ctx.h:
             lib().lsspg_pc_destroy(self.ctx.h, self.h)
+        self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class AmgHierarchy:
+    """Host image of the SX-AMG-style hierarchy (lsspg_amg_setup_host; the role of sx_amg_setup,
+    reference src/pc-sxamg.cxx:107-110).  `levels[l]` holds n, nc, A, P, R (CSR triples) and cf."""
+
+    def __init__(self, A, **pars):
+        Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
+        p = AmgPars()
+        check(lib().lsspg_amg_pars_default(C.byref(p)))
+        for k, v in pars.items():
+            if not hasattr(p, k):
+                raise TypeError("unknown AMG parameter %r" % k)
+            setattr(p, k, v)
+        self.pars = p
+        self.h = C.c_void_p()
+        check(lib().lsspg_amg_setup_host(len(Ap) - 1, _p(Ap), _p(Aj), _p(Ax), C.byref(p), C.byref(self.h)))
+        nl, dense = C.c_int(), C.c_int()
+        check(lib().lsspg_amg_host_levels(self.h, C.byref(nl), C.byref(dense)))
+        self.coarse_dense = bool(dense.value)
+        self.levels = []
+        for l in range(nl.value):
+            n, nc, za, zp, zr = (C.c_int() for _ in range(5))
+            check(lib().lsspg_amg_host_level_sizes(self.h, l, C.byref(n), C.byref(nc), C.byref(za), C.byref(zp),
+                                                   C.byref(zr)))
+            n, nc, za, zp, zr = n.value, nc.value, za.value, zp.value, zr.value
+            last = l == nl.value - 1
+            a = (np.zeros(n + 1, np.int32), np.zeros(za, np.int32), np.zeros(za))
+            P = (np.zeros(n + 1, np.int32), np.zeros(zp, np.int32), np.zeros(zp))
+            R = (np.zeros(nc + 1, np.int32), np.zeros(zr, np.int32), np.zeros(zr))
+            cf = np.zeros(n, np.int32)
+            check(lib().lsspg_amg_host_level_get(self.h, l, _p(a[0]), _p(a[1]), _p(a[2]),
+                                                 None if last else _p(P[0]), None if last else _p(P[1]),
+                                                 None if last else _p(P[2]), None if last else _p(R[0]),
+                                                 None if last else _p(R[1]), None if last else _p(R[2]), _p(cf)))
+            self.levels.append(dict(n=n, nc=nc, A=a, P=None if last else P, R=None if last else R, cf=cf))
+        self.coarse_inv = None
+        if self.coarse_dense:
+            nlast = self.levels[-1]["n"]
+            self.coarse_inv = np.zeros((nlast, nlast))
+            check(lib().lsspg_amg_host_coarse_inverse(self.h, _p(self.coarse_inv)))
+
+    def walk_gs_host(self, l, post, b, x_old, mode=0):
+        """CPU self-check of the smoother schedule of level l (not a compute path): one sweep.
+        mode 0: the schedule the device would pick, 1: 32-row slices, 2: one ticket per row."""
+        post = int(post) | (int(mode) << 1)
+        b, x_old = _f64(b), _f64(x_old)
+        x_new = np.full(len(b), np.nan)
+        info = np.zeros(4, np.int32)
+        check(lib().lsspg_debug_amg_walk_gs_host(self.h, int(l), int(post), _p(b), _p(x_old), _p(x_new), _p(info)))
+        return x_new, dict(slices=int(info[0]), levels_c=int(info[1]), levels_f=int(info[2]), width=int(info[3]))
+
+    def free(self):
+        if self.h:
+            lib().lsspg_amg_host_destroy(self.h)
         self.h = C.c_void_p()
 
     def __del__(self):

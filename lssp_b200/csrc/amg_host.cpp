@@ -1,0 +1,673 @@
+// amg_host.cpp -- set-up of the SX-AMG-style hierarchy (host; the GPU runs the cycle, amg.cu).
+//
+// The reference reaches its AMG through libsxamg (sx_amg_setup, src/pc-sxamg.cxx:107-110), which
+// is not part of the reference tree; what is built here is the classical Ruge-Stueben method that
+// library implements, from its published description.  DESIGN.md "AMG" is the
+// specification; parity with libsxamg itself is UNPINNED.
+//   strength     j strongly influences i  <=>  -s a_ij >= theta * max_k(-s a_ik), s = sign(a_ii);
+//                rows with |sum_j a_ij| > max_row_sum |a_ii| have no strong couplings
+//   C/F split    first Ruge-Stueben pass with bucket lists (measure = #points influenced), then
+//                every F point left without a strong C neighbour is promoted to C
+//   P            direct interpolation, w_ij = -alpha_i a_ij / a~_ii over the strong C neighbours,
+//                truncated at trunc_threshold * max|w| with rescaling; C rows are unit rows
+//   coarse grid  R = P^T, A_c = R A P (two row-wise sparse products, columns sorted)
+//   last level   dense inverse by Gauss-Jordan with partial pivoting (<= coarse_dense_max rows)
+// Also builds the dependency schedule of a Gauss-Seidel sweep (gs_build_host) and walks it on
+// the CPU for the test-suite (lsspg_debug_amg_walk_gs_host) -- a layout check, not a fallback.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "amg_host.h"
+
+namespace lsspg {
+void set_error(const char *fmt, ...);
+}
+using namespace lsspg;
+
+#define AMG_CHECK(cond, ...)               \
+    do {                                   \
+        if (!(cond)) {                     \
+            lsspg::set_error(__VA_ARGS__); \
+            return 1;                      \
+        }                                  \
+    } while (0)
+
+namespace {
+
+struct Graph {
+    std::vector<int> p, j;
+};
+
+// strong couplings of every row, in the row's column order
+void strong_couplings(const AmgLevelHost &L, const lsspg_amg_pars &pr, Graph &S)
+{
+    const int n = L.n;
+    S.p.assign(n + 1, 0);
+    S.j.clear();
+    S.j.reserve(L.Aj.size());
+    for (int i = 0; i < n; i++) {
+        double diag = 0.0, row_sum = 0.0;
+        for (int k = L.Ap[i]; k < L.Ap[i + 1]; k++) {
+            if (L.Aj[k] == i) diag = L.Ax[k];
+            row_sum += L.Ax[k];
+        }
+        const double s = diag < 0.0 ? -1.0 : 1.0;
+        double most = 0.0;   // largest -s a_ij over the off-diagonals
+        for (int k = L.Ap[i]; k < L.Ap[i + 1]; k++)
+            if (L.Aj[k] != i) most = std::max(most, -s * L.Ax[k]);
+        const bool dominated = pr.max_row_sum < 1.0 && fabs(row_sum) > pr.max_row_sum * fabs(diag);
+        if (most > 0.0 && !dominated) {
+            const double cut = pr.strong_threshold * most;
+            for (int k = L.Ap[i]; k < L.Ap[i + 1]; k++)
+                if (L.Aj[k] != i && -s * L.Ax[k] >= cut) S.j.push_back(L.Aj[k]);
+        }
+        S.p[i + 1] = (int)S.j.size();
+    }
+}
+
+void transpose_graph(int n, const Graph &S, Graph &T)
+{
+    T.p.assign(n + 1, 0);
+    T.j.resize(S.j.size());
+    for (int v : S.j) T.p[v + 1]++;
+    for (int i = 0; i < n; i++) T.p[i + 1] += T.p[i];
+    std::vector<int> pos(T.p.begin(), T.p.end() - 1);
+    for (int i = 0; i < n; i++)
+        for (int k = S.p[i]; k < S.p[i + 1]; k++) T.j[pos[S.j[k]]++] = i;
+}
+
+// bucket lists keyed by the measure; the most recently touched point of a bucket is its head
+struct Buckets {
+    std::vector<int> head, next, prev, key;
+    int top = 0;
+    explicit Buckets(int n) : next(n, -1), prev(n, -1), key(n, -1) {}
+    void insert(int i, int k)
+    {
+        if (k >= (int)head.size()) head.resize(k + 16, -1);
+        key[i] = k;
+        prev[i] = -1;
+        next[i] = head[k];
+        if (head[k] >= 0) prev[head[k]] = i;
+        head[k] = i;
+        top = std::max(top, k);
+    }
+    void remove(int i)
+    {
+        const int k = key[i];
+        if (prev[i] >= 0) next[prev[i]] = next[i];
+        else head[k] = next[i];
+        if (next[i] >= 0) prev[next[i]] = prev[i];
+        key[i] = -1;
+    }
+    void move(int i, int k)
+    {
+        remove(i);
+        insert(i, k);
+    }
+    int pop_max()
+    {
+        while (top > 0 && (top >= (int)head.size() || head[top] < 0)) top--;
+        return (top >= (int)head.size()) ? -1 : head[top];
+    }
+};
+
+constexpr int UNDECIDED = -1, FPT = 0, CPT = 1;
+
+int cf_split(int n, const Graph &S, const Graph &T, std::vector<int> &cf)
+{
+    cf.assign(n, UNDECIDED);
+    std::vector<int> lambda(n);
+    for (int i = 0; i < n; i++) lambda[i] = T.p[i + 1] - T.p[i];
+    // points nobody depends on become F at once; their influencers gain weight
+    for (int i = 0; i < n; i++) {
+        if (S.p[i + 1] == S.p[i]) cf[i] = FPT;   // no strong coupling at all: smoothing alone treats it
+        else if (T.p[i + 1] == T.p[i]) {
+            cf[i] = FPT;
+            for (int k = S.p[i]; k < S.p[i + 1]; k++) lambda[S.j[k]]++;
+        }
+    }
+    Buckets B(n);
+    for (int i = 0; i < n; i++)
+        if (cf[i] == UNDECIDED) B.insert(i, lambda[i]);
+    for (;;) {
+        const int i = B.pop_max();
+        if (i < 0 || B.top == 0) break;
+        cf[i] = CPT;
+        B.remove(i);
+        for (int k = T.p[i]; k < T.p[i + 1]; k++) {
+            const int j = T.j[k];   // j depends on i
+            if (cf[j] != UNDECIDED) continue;
+            cf[j] = FPT;
+            B.remove(j);
+            for (int q = S.p[j]; q < S.p[j + 1]; q++) {
+                const int m = S.j[q];
+                if (cf[m] == UNDECIDED) B.move(m, ++lambda[m]);
+            }
+        }
+        for (int k = S.p[i]; k < S.p[i + 1]; k++) {
+            const int j = S.j[k];   // i depends on j
+            if (cf[j] != UNDECIDED) continue;
+            if (lambda[j] > 0) lambda[j]--;
+            B.move(j, lambda[j]);
+        }
+    }
+    for (int i = 0; i < n; i++)
+        if (cf[i] == UNDECIDED) cf[i] = FPT;
+    // an F point with strong couplings but no strong C neighbour cannot be interpolated: promote it
+    int nc = 0;
+    for (int i = 0; i < n; i++) {
+        if (cf[i] == FPT && S.p[i + 1] > S.p[i]) {
+            bool has_c = false;
+            for (int k = S.p[i]; k < S.p[i + 1] && !has_c; k++) has_c = (cf[S.j[k]] == CPT);
+            if (!has_c) cf[i] = CPT;
+        }
+        nc += (cf[i] == CPT);
+    }
+    return nc;
+}
+
+void direct_interpolation(AmgLevelHost &L, const Graph &S, const lsspg_amg_pars &pr)
+{
+    const int n = L.n;
+    std::vector<int> cidx(n, -1);
+    int nc = 0;
+    for (int i = 0; i < n; i++)
+        if (L.cf[i] == CPT) cidx[i] = nc++;
+    L.nc = nc;
+    L.Pp.assign(n + 1, 0);
+    L.Pj.clear();
+    L.Px.clear();
+    std::vector<int> mark(n, -1);
+    std::vector<double> w;
+    std::vector<int> wc;
+    for (int i = 0; i < n; i++) {
+        if (L.cf[i] == CPT) {
+            L.Pj.push_back(cidx[i]);
+            L.Px.push_back(1.0);
+        }
+        else if (S.p[i + 1] > S.p[i]) {
+            for (int k = S.p[i]; k < S.p[i + 1]; k++)
+                if (L.cf[S.j[k]] == CPT) mark[S.j[k]] = i;
+            double diag = 0.0;
+            for (int k = L.Ap[i]; k < L.Ap[i + 1]; k++)
+                if (L.Aj[k] == i) diag = L.Ax[k];
+            const double s = diag < 0.0 ? -1.0 : 1.0;
+            double all_neg = 0.0, all_pos = 0.0, c_neg = 0.0;
+            for (int k = L.Ap[i]; k < L.Ap[i + 1]; k++) {
+                const int j = L.Aj[k];
+                if (j == i) continue;
+                const double a = s * L.Ax[k];
+                if (a < 0.0) {
+                    all_neg += a;
+                    if (mark[j] == i) c_neg += a;
+                }
+                else all_pos += a;
+            }
+            // strong couplings are all of the "negative" kind: the others are lumped into the diagonal
+            const double dd = s * diag + all_pos;
+            w.clear();
+            wc.clear();
+            if (c_neg != 0.0 && dd != 0.0) {
+                const double alpha = all_neg / c_neg;
+                double wmax = 0.0, total = 0.0;
+                for (int k = L.Ap[i]; k < L.Ap[i + 1]; k++) {
+                    const int j = L.Aj[k];
+                    if (j == i || mark[j] != i) continue;
+                    const double v = -alpha * (s * L.Ax[k]) / dd;
+                    w.push_back(v);
+                    wc.push_back(cidx[j]);
+                    wmax = std::max(wmax, fabs(v));
+                    total += v;
+                }
+                // truncation: drop the small weights, keep the row sum
+                double kept = 0.0;
+                for (double v : w)
+                    if (fabs(v) >= pr.trunc_threshold * wmax) kept += v;
+                const double scale = (kept != 0.0) ? total / kept : 1.0;
+                for (size_t q = 0; q < w.size(); q++) {
+                    if (fabs(w[q]) >= pr.trunc_threshold * wmax) {
+                        L.Pj.push_back(wc[q]);
+                        L.Px.push_back(w[q] * scale);
+                    }
+                }
+            }
+        }
+        L.Pp[i + 1] = (int)L.Pj.size();
+    }
+}
+
+void transpose_csr(int nrows, int ncols, const std::vector<int> &p, const std::vector<int> &j,
+                   const std::vector<double> &x, std::vector<int> &tp, std::vector<int> &tj, std::vector<double> &tx)
+{
+    tp.assign(ncols + 1, 0);
+    tj.resize(j.size());
+    tx.resize(x.size());
+    for (int v : j) tp[v + 1]++;
+    for (int i = 0; i < ncols; i++) tp[i + 1] += tp[i];
+    std::vector<int> pos(tp.begin(), tp.end() - 1);
+    for (int i = 0; i < nrows; i++)
+        for (int k = p[i]; k < p[i + 1]; k++) {
+            const int q = pos[j[k]]++;
+            tj[q] = i;
+            tx[q] = x[k];
+        }
+}
+
+// C = A * B, row by row with a dense accumulator; columns of every row sorted ascending
+int spgemm(int nrows, int ncolsB, const std::vector<int> &Ap, const std::vector<int> &Aj, const std::vector<double> &Ax,
+           const std::vector<int> &Bp, const std::vector<int> &Bj, const std::vector<double> &Bx,
+           std::vector<int> &Cp, std::vector<int> &Cj, std::vector<double> &Cx)
+{
+    Cp.assign(nrows + 1, 0);
+    Cj.clear();
+    Cx.clear();
+    std::vector<int> where(ncolsB, -1), cols;
+    std::vector<double> acc(ncolsB, 0.0);
+    for (int i = 0; i < nrows; i++) {
+        cols.clear();
+        for (int k = Ap[i]; k < Ap[i + 1]; k++) {
+            const int m = Aj[k];
+            const double a = Ax[k];
+            for (int q = Bp[m]; q < Bp[m + 1]; q++) {
+                const int c = Bj[q];
+                if (where[c] != i) {
+                    where[c] = i;
+                    acc[c] = 0.0;
+                    cols.push_back(c);
+                }
+                acc[c] += a * Bx[q];
+            }
+        }
+        std::sort(cols.begin(), cols.end());
+        for (int c : cols) {
+            Cj.push_back(c);
+            Cx.push_back(acc[c]);
+        }
+        AMG_CHECK(Cj.size() < (size_t)0x7fffffff, "amg: coarse operator exceeds int32 indexing");
+        Cp[i + 1] = (int)Cj.size();
+    }
+    return 0;
+}
+
+template <class T>
+void copy_out(T *dst, const std::vector<T> &src)
+{
+    if (dst && !src.empty()) memcpy(dst, src.data(), sizeof(T) * src.size());
+}
+
+// row-major inverse by Gauss-Jordan with partial pivoting
+int dense_inverse(const AmgLevelHost &L, std::vector<double> &inv)
+{
+    const int n = L.n;
+    std::vector<double> a((size_t)n * n, 0.0);
+    inv.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) {
+        for (int k = L.Ap[i]; k < L.Ap[i + 1]; k++) a[(size_t)i * n + L.Aj[k]] = L.Ax[k];
+        inv[(size_t)i * n + i] = 1.0;
+    }
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int r = c + 1; r < n; r++)
+            if (fabs(a[(size_t)r * n + c]) > fabs(a[(size_t)piv * n + c])) piv = r;
+        AMG_CHECK(a[(size_t)piv * n + c] != 0.0, "amg: coarsest operator is singular (column %d)", c);
+        if (piv != c) {
+            for (int q = 0; q < n; q++) {
+                std::swap(a[(size_t)piv * n + q], a[(size_t)c * n + q]);
+                std::swap(inv[(size_t)piv * n + q], inv[(size_t)c * n + q]);
+            }
+        }
+        const double d = a[(size_t)c * n + c];
+        for (int q = 0; q < n; q++) {
+            a[(size_t)c * n + q] /= d;
+            inv[(size_t)c * n + q] /= d;
+        }
+        for (int r = 0; r < n; r++) {
+            if (r == c) continue;
+            const double f = a[(size_t)r * n + c];
+            if (f == 0.0) continue;
+            for (int q = 0; q < n; q++) {
+                a[(size_t)r * n + q] -= f * a[(size_t)c * n + q];
+                inv[(size_t)r * n + q] -= f * inv[(size_t)c * n + q];
+            }
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+namespace lsspg {
+
+int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const int *cf, GsHost &G, int mode)
+{
+    G.n = n;
+    std::vector<int> lev(n, 0);
+    int nlev[2] = {0, 0};   // [0] F block, [1] C block
+    for (int i = 0; i < n; i++) {
+        const int mine = cf ? cf[i] : 1;
+        int l = 0;
+        bool has_diag = false;
+        for (int k = Ap[i]; k < Ap[i + 1]; k++) {
+            const int c = Aj[k];
+            AMG_CHECK(c >= 0 && c < n, "amg: row %d references column %d", i, c);
+            if (c == i) {
+                has_diag = Ax[k] != 0.0;
+                continue;
+            }
+            if (c < i && (cf ? cf[c] : 1) == mine) l = std::max(l, lev[c] + 1);
+        }
+        AMG_CHECK(has_diag, "amg: row %d has no (or a zero) diagonal entry", i);
+        lev[i] = l;
+        nlev[mine] = std::max(nlev[mine], l + 1);
+    }
+    G.levels_c = nlev[1];
+    G.levels_f = nlev[0];
+    // order: C block by level, then F block by level; ascending row index inside a level
+    const int total_lev = nlev[1] + nlev[0];
+    std::vector<int> start(total_lev + 1, 0);
+    auto bucket = [&](int i) { return (cf ? cf[i] : 1) ? lev[i] : nlev[1] + lev[i]; };
+    for (int i = 0; i < n; i++) start[bucket(i) + 1]++;
+    for (int l = 0; l < total_lev; l++) start[l + 1] += start[l];
+    std::vector<int> order(n);
+    {
+        std::vector<int> pos(start.begin(), start.end() - 1);
+        for (int i = 0; i < n; i++) order[pos[bucket(i)]++] = i;
+    }
+    // deep schedules of wide rows: one ticket per ROW (a warp works on it), entries contiguous
+    if (mode < 0) mode = (total_lev > kGsShallowDepth && n > 0 && (double)(Ap[n] - n) / n > 28.0) ? 1 : 0;
+    G.mode = mode;
+    if (mode == 1) {
+        G.num_slices = n;
+        G.slices_c = nlev[1] > 0 ? start[nlev[1]] : 0;
+        G.perm = order;
+        G.diag.assign(n, 1.0);
+        G.slice_ptr.assign((size_t)n + 1, 0);
+        G.offdiag_nnz = (long long)Ap[n] - n;
+        G.padded_nnz = G.offdiag_nnz;
+        G.col.resize((size_t)G.offdiag_nnz);
+        G.val.resize((size_t)G.offdiag_nnz);
+        int k = 0;
+        for (int p = 0; p < n; p++) {
+            const int i = order[p];
+            G.slice_ptr[p] = k;
+            for (int q = Ap[i]; q < Ap[i + 1]; q++) {
+                const int c = Aj[q];
+                if (c == i) {
+                    G.diag[p] = Ax[q];
+                    continue;
+                }
+                G.col[k] = (c << 1) | ((cf ? cf[c] : 1) & 1);
+                G.val[k] = Ax[q];
+                k++;
+            }
+        }
+        G.slice_ptr[n] = k;
+        return 0;
+    }
+    long long nslices = 0, cslices = 0;
+    for (int l = 0; l < total_lev; l++) {
+        nslices += (start[l + 1] - start[l] + 31) / 32;
+        if (l == nlev[1] - 1) cslices = nslices;
+    }
+    AMG_CHECK(nslices * 32 < (1ll << 31), "amg: too many slices");
+    G.num_slices = (int)nslices;
+    G.slices_c = (int)cslices;
+    G.perm.assign((size_t)nslices * 32, -1);
+    G.diag.assign((size_t)nslices * 32, 1.0);
+    G.slice_ptr.assign((size_t)nslices + 1, 0);
+    long long s = 0, wsum = 0;
+    G.offdiag_nnz = 0;
+    for (int l = 0; l < total_lev; l++) {
+        for (int r0 = start[l]; r0 < start[l + 1]; r0 += 32, s++) {
+            const int cnt = std::min(32, start[l + 1] - r0);
+            int w = 0;
+            for (int q = 0; q < cnt; q++) {
+                const int i = order[r0 + q];
+                G.perm[s * 32 + q] = i;
+                w = std::max(w, Ap[i + 1] - Ap[i] - 1);
+                G.offdiag_nnz += Ap[i + 1] - Ap[i] - 1;
+            }
+            G.slice_ptr[s] = (int)wsum;
+            wsum += w;
+            AMG_CHECK(wsum < (1ll << 31) / 32, "amg: padded smoother layout too large for int32 offsets");
+        }
+    }
+    G.slice_ptr[nslices] = (int)wsum;
+    G.padded_nnz = wsum * 32;
+    G.col.assign((size_t)G.padded_nnz, -1);
+    G.val.assign((size_t)G.padded_nnz, 0.0);
+    for (long long sl = 0; sl < nslices; sl++) {
+        const long long base = (long long)G.slice_ptr[sl] * 32;
+        for (int q = 0; q < 32; q++) {
+            const int i = G.perm[sl * 32 + q];
+            if (i < 0) continue;
+            int k = 0;
+            for (int p = Ap[i]; p < Ap[i + 1]; p++) {
+                const int c = Aj[p];
+                if (c == i) {
+                    G.diag[sl * 32 + q] = Ax[p];
+                    continue;
+                }
+                G.col[base + (long long)k * 32 + q] = (c << 1) | ((cf ? cf[c] : 1) & 1);
+                G.val[base + (long long)k * 32 + q] = Ax[p];
+                k++;
+            }
+        }
+    }
+    return 0;
+}
+
+}  // namespace lsspg
+
+extern "C" {
+
+int lsspg_amg_pars_default(lsspg_amg_pars *p)
+{
+    AMG_CHECK(p, "lsspg_amg_pars_default: NULL");
+    p->max_levels = 30;
+    p->coarse_dof = 100;
+    p->strong_threshold = 0.3;
+    p->max_row_sum = 0.9;
+    p->trunc_threshold = 0.2;
+    p->pre_iter = 2;
+    p->post_iter = 2;
+    p->cf_order = 1;
+    p->zero_guess = 0;
+    p->coarse_dense_max = 4096;
+    p->coarse_sweeps = 40;
+    p->tol = 1e-8;
+    p->maxit = 100;
+    p->verb = 0;
+    return 0;
+}
+
+int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hAx, const lsspg_amg_pars *pars,
+                         lsspg_amg_host **out)
+{
+    AMG_CHECK(out && n > 0 && hAp && hAj && hAx, "lsspg_amg_setup_host: bad argument");
+    lsspg_amg_pars pr;
+    if (pars) pr = *pars;
+    else lsspg_amg_pars_default(&pr);
+    AMG_CHECK(pr.max_levels >= 1 && pr.coarse_dof >= 1 && pr.pre_iter >= 0 && pr.post_iter >= 0,
+              "lsspg_amg_setup_host: bad parameters");
+    for (int i = 0; i < n; i++)
+        for (int k = hAp[i] + 1; k < hAp[i + 1]; k++)
+            AMG_CHECK(hAj[k - 1] < hAj[k], "lsspg_amg_setup_host: columns of row %d are not sorted", i);
+    lsspg_amg_host *H = new lsspg_amg_host();
+    H->pars = pr;
+    H->levels.emplace_back();
+    {
+        AmgLevelHost &L = H->levels[0];
+        L.n = n;
+        L.Ap.assign(hAp, hAp + n + 1);
+        L.Aj.assign(hAj, hAj + hAp[n]);
+        L.Ax.assign(hAx, hAx + hAp[n]);
+    }
+    int rc = 0;
+    while ((int)H->levels.size() < pr.max_levels && H->levels.back().n > pr.coarse_dof) {
+        AmgLevelHost &L = H->levels.back();
+        Graph S, T;
+        strong_couplings(L, pr, S);
+        transpose_graph(L.n, S, T);
+        const int nc = cf_split(L.n, S, T, L.cf);
+        if (nc == 0 || nc >= L.n) {   // coarsening stalled: this level is the last one
+            L.cf.clear();
+            break;
+        }
+        direct_interpolation(L, S, pr);
+        transpose_csr(L.n, L.nc, L.Pp, L.Pj, L.Px, L.Rp, L.Rj, L.Rx);
+        std::vector<int> Tp, Tj;
+        std::vector<double> Tx;
+        AmgLevelHost C;
+        C.n = L.nc;
+        rc = spgemm(L.n, L.nc, L.Ap, L.Aj, L.Ax, L.Pp, L.Pj, L.Px, Tp, Tj, Tx);
+        if (!rc) rc = spgemm(L.nc, L.nc, L.Rp, L.Rj, L.Rx, Tp, Tj, Tx, C.Ap, C.Aj, C.Ax);
+        if (rc) break;
+        if (pr.verb > 0)
+            printf("amg: level %d: n = %d, nnz = %d, C points = %d\n", (int)H->levels.size() - 1, L.n, L.Ap[L.n], L.nc);
+        H->levels.push_back(std::move(C));
+    }
+    if (!rc) {
+        AmgLevelHost &L = H->levels.back();
+        L.nc = 0;
+        L.cf.assign(L.n, 1);
+        L.Pp.clear();
+        L.Rp.clear();
+        if (L.n <= pr.coarse_dense_max) {
+            rc = dense_inverse(L, H->coarse_inv);
+            H->coarse_dense = (rc == 0);
+        }
+        if (pr.verb > 0)
+            printf("amg: level %d (last): n = %d, nnz = %d, %s\n", (int)H->levels.size() - 1, L.n, L.Ap[L.n],
+                   H->coarse_dense ? "dense inverse" : "Gauss-Seidel sweeps");
+    }
+    if (rc) {
+        delete H;
+        return rc;
+    }
+    *out = H;
+    return 0;
+}
+
+int lsspg_amg_host_levels(const lsspg_amg_host *H, int *num_levels, int *coarse_dense)
+{
+    AMG_CHECK(H, "lsspg_amg_host_levels: NULL");
+    if (num_levels) *num_levels = (int)H->levels.size();
+    if (coarse_dense) *coarse_dense = H->coarse_dense ? 1 : 0;
+    return 0;
+}
+
+int lsspg_amg_host_level_sizes(const lsspg_amg_host *H, int l, int *n, int *nc, int *nnzA, int *nnzP, int *nnzR)
+{
+    AMG_CHECK(H && l >= 0 && l < (int)H->levels.size(), "lsspg_amg_host_level_sizes: bad level");
+    const AmgLevelHost &L = H->levels[l];
+    if (n) *n = L.n;
+    if (nc) *nc = L.nc;
+    if (nnzA) *nnzA = L.Ap[L.n];
+    if (nnzP) *nnzP = L.Pp.empty() ? 0 : L.Pp[L.n];
+    if (nnzR) *nnzR = L.Rp.empty() ? 0 : L.Rp[L.nc];
+    return 0;
+}
+
+int lsspg_amg_host_level_get(const lsspg_amg_host *H, int l, int *Ap, int *Aj, double *Ax, int *Pp, int *Pj,
+                             double *Px, int *Rp, int *Rj, double *Rx, int *cf)
+{
+    AMG_CHECK(H && l >= 0 && l < (int)H->levels.size(), "lsspg_amg_host_level_get: bad level");
+    const AmgLevelHost &L = H->levels[l];
+    copy_out(Ap, L.Ap); copy_out(Aj, L.Aj); copy_out(Ax, L.Ax);
+    copy_out(Pp, L.Pp); copy_out(Pj, L.Pj); copy_out(Px, L.Px);
+    copy_out(Rp, L.Rp); copy_out(Rj, L.Rj); copy_out(Rx, L.Rx);
+    copy_out(cf, L.cf);
+    return 0;
+}
+
+int lsspg_amg_host_coarse_inverse(const lsspg_amg_host *H, double *inv)
+{
+    AMG_CHECK(H && inv && H->coarse_dense, "lsspg_amg_host_coarse_inverse: no dense inverse");
+    copy_out(inv, H->coarse_inv);
+    return 0;
+}
+
+int lsspg_amg_host_pars(const lsspg_amg_host *H, lsspg_amg_pars *pars)
+{
+    AMG_CHECK(H && pars, "lsspg_amg_host_pars: NULL");
+    *pars = H->pars;
+    return 0;
+}
+
+int lsspg_amg_host_destroy(lsspg_amg_host *H)
+{
+    delete H;
+    return 0;
+}
+
+int lsspg_debug_amg_walk_gs_host(const lsspg_amg_host *H, int l, int post, const double *hb, const double *hx_old,
+                                 double *hx_new, int *info)
+{
+    AMG_CHECK(H && l >= 0 && l < (int)H->levels.size() && hb && hx_old && hx_new, "lsspg_debug_amg_walk_gs_host: bad argument");
+    const AmgLevelHost &L = H->levels[l];
+    GsHost G;
+    const bool cf_on = H->pars.cf_order && l + 1 < (int)H->levels.size();
+    const int mode = (post >> 1) - 1;   // post bits 1..2: 0 = schedule chosen as on the device, 1 = slices, 2 = rows
+    post &= 1;
+    if (gs_build_host(L.n, L.Ap.data(), L.Aj.data(), L.Ax.data(), cf_on ? L.cf.data() : nullptr, G, mode)) return 1;
+    std::vector<char> written(L.n, 0);
+    const int nf = G.num_slices - G.slices_c;
+    if (info) {
+        info[0] = G.num_slices;
+        info[1] = G.levels_c;
+        info[2] = G.levels_f;
+        info[3] = G.mode == 1 ? -1 : (int)(G.padded_nnz / 32);
+    }
+    if (G.mode == 1) {   // one ticket per row
+        for (int t = 0; t < G.num_slices; t++) {
+            const int p = post ? (t < nf ? G.slices_c + t : t - nf) : t;
+            const bool row_c = p < G.slices_c;
+            const int row = G.perm[p];
+            double r = hb[row];
+            for (int k = G.slice_ptr[p]; k < G.slice_ptr[p + 1]; k++) {
+                const int enc = G.col[k], c = enc >> 1;
+                const bool col_c = enc & 1;
+                const bool is_new = (col_c == row_c) ? (c < row) : (col_c == !post);
+                if (is_new) AMG_CHECK(written[c], "amg walk: row %d (ticket %d) needs x[%d] before it is written", row, t, c);
+                r = r - G.val[k] * (is_new ? hx_new[c] : hx_old[c]);
+            }
+            hx_new[row] = r / G.diag[p];
+            written[row] = 1;
+        }
+        return 0;
+    }
+    for (int t = 0; t < G.num_slices; t++) {
+        const int s = post ? (t < nf ? G.slices_c + t : t - nf) : t;
+        const bool row_c = s < G.slices_c;
+        const long long base = (long long)G.slice_ptr[s] * 32;
+        const int w = G.slice_ptr[s + 1] - G.slice_ptr[s];
+        double res[32];
+        for (int q = 0; q < 32; q++) {
+            const int row = G.perm[(long long)s * 32 + q];
+            if (row < 0) continue;
+            double r = hb[row];
+            for (int k = 0; k < w; k++) {
+                const int enc = G.col[base + (long long)k * 32 + q];
+                if (enc < 0) continue;
+                const int c = enc >> 1;
+                const bool col_c = enc & 1;
+                const bool is_new = (col_c == row_c) ? (c < row) : (col_c == !post);
+                if (is_new) AMG_CHECK(written[c], "amg walk: row %d (ticket %d) needs x[%d] before it is written", row, t, c);
+                r = r - G.val[base + (long long)k * 32 + q] * (is_new ? hx_new[c] : hx_old[c]);
+            }
+            res[q] = r / G.diag[(long long)s * 32 + q];
+        }
+        for (int q = 0; q < 32; q++) {   // a slice publishes its rows together
+            const int row = G.perm[(long long)s * 32 + q];
+            if (row < 0) continue;
+            hx_new[row] = res[q];
+            written[row] = 1;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

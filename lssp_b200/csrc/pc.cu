@@ -24,6 +24,8 @@ int pc_apply(lsspg_ctx *ctx, lsspg_pc *pc, double *dx, const double *drhs, bool 
             LSSPG_TRY(spmv_launch(ctx, LSSPG_MV_MXY, pc->D, coef_imm(1.0), y, coef_imm(0.0), nullptr, z, nullptr, guarded));
             return tri_solve(ctx, pc->U, dx, z, guarded);
         }
+        case LSSPG_PC_AMG:
+            return amg_cycle(ctx, pc->amg, dx, drhs, guarded);
         case LSSPG_PC_USER: {
             // a user-supplied pc.solve works on host vectors: round trip per application (documented slow path)
             const size_t nb = sizeof(double) * (size_t)pc->n;
@@ -129,6 +131,7 @@ int lsspg_pc_destroy(lsspg_ctx *ctx, lsspg_pc *pc)
     lsspg_tri_destroy(ctx, pc->L);
     lsspg_tri_destroy(ctx, pc->U);
     lsspg_csr_destroy(ctx, pc->D);
+    amg_free(ctx, pc->amg);
     if (pc->cache) cudaFree(pc->cache);
     delete pc;
     return 0;

@@ -160,12 +160,53 @@ class Ref:
 
 class OrcPC(C.Structure):
     _fields_ = [("kind", C.c_int), ("Lp", C.c_void_p), ("Lj", C.c_void_p), ("Lx", C.c_void_p),
-                ("Up", C.c_void_p), ("Uj", C.c_void_p), ("Ux", C.c_void_p), ("cache", C.c_void_p)]
+                ("Up", C.c_void_p), ("Uj", C.c_void_p), ("Ux", C.c_void_p), ("cache", C.c_void_p),
+                ("amg", C.c_void_p)]
 
 
 class OrcOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("rbtol", C.c_double),
                 ("maxit", C.c_int)]
+
+
+class OrcAmg:
+    """amg_oracle.c over a hierarchy given as plain arrays (parity with libsxamg UNPINNED)."""
+
+    def __init__(self, lib, levels, pre, post, cf_order, coarse_inv, coarse_sweeps, zero_guess=0):
+        self.lib, self.levels = lib, levels
+        self.n = levels[0]["n"]
+        self.inv = None if coarse_inv is None else np.ascontiguousarray(coarse_inv, dtype=np.float64)
+        lib.orc_amg_create.restype = C.c_void_p
+        lib.orc_amg_solve.restype = C.c_int
+        self.h = C.c_void_p(lib.orc_amg_create(len(levels), int(pre), int(post), int(cf_order),
+                                               int(self.inv is not None), int(coarse_sweeps), int(zero_guess),
+                                               _ptr(self.inv)))
+        self.keep = []
+        for l, L in enumerate(levels):
+            arrs = [np.ascontiguousarray(a) for a in L["A"]]
+            for key in ("P", "R"):
+                arrs += [None] * 3 if L[key] is None else [np.ascontiguousarray(a) for a in L[key]]
+            arrs.append(np.ascontiguousarray(L["cf"], dtype=np.int32))
+            self.keep.append(arrs)
+            lib.orc_amg_set_level(self.h, l, int(L["n"]), int(L["nc"]), *[_ptr(a) for a in arrs])
+
+    def cycle(self, rhs, x0=None):
+        x = np.zeros(self.n) if x0 is None else np.array(x0, dtype=np.float64)
+        self.lib.orc_amg_cycle(self.h, _ptr(x), _ptr(np.ascontiguousarray(rhs, dtype=np.float64)))
+        return x
+
+    def solve(self, b, x0=None, tol=1e-8, maxit=100):
+        x = np.zeros(self.n) if x0 is None else np.array(x0, dtype=np.float64)
+        ares = C.c_double()
+        nits = self.lib.orc_amg_solve(self.h, _ptr(np.ascontiguousarray(b, dtype=np.float64)), _ptr(x),
+                                      C.c_double(tol), int(maxit), C.byref(ares))
+        return dict(nits=nits, residual=ares.value, x=x)
+
+    def __del__(self):
+        try:
+            self.lib.orc_amg_destroy(self.h)
+        except Exception:
+            pass
 
 
 class Port:
@@ -229,13 +270,25 @@ class Port:
                                 _ptr(rhs), _ptr(cache))
         return x
 
+    def gs_sweep(self, A, cf, post, b, x):
+        """one in-place Gauss-Seidel sweep (amg_oracle.c); cf=None: natural order"""
+        x = np.array(x, dtype=np.float64)
+        self.lib.orc_gs_sweep(len(b), _ptr(A[0]), _ptr(A[1]), _ptr(A[2]), _ptr(cf), int(post), _ptr(b), _ptr(x))
+        return x
+
+    def amg(self, levels, pre=2, post=2, cf_order=1, coarse_inv=None, coarse_sweeps=40, zero_guess=0):
+        """restated cycle over a given hierarchy: levels = [dict(n, nc, A, P, R, cf)], see OrcAmg"""
+        return OrcAmg(self.lib, levels, pre, post, cf_order, coarse_inv, coarse_sweeps, zero_guess)
+
     def solve(self, solver, A, b, x0=None, LU=None, rtol=1e-7, atol=1e-7, rbtol=1e-7, maxit=1000,
-              nhist=0):
+              nhist=0, amg=None):
         Ap, Aj, Ax = A
         n = len(Ap) - 1
         x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64)
         pc = OrcPC(kind=0)
         keep = []
+        if amg is not None:
+            pc = OrcPC(kind=2, amg=amg.h.value)
         if LU is not None:
             (Lp, Lj, Lx), (Up, Uj, Ux) = LU
             cache = np.zeros(n)

@@ -104,17 +104,22 @@ void orc_bilu_apply(int n, const int *Lp, const int *Lj, const double *Lx, const
 
 /* ------------------------------------------------------ Krylov drivers --- */
 /* Preconditioner handed to the drivers: kind 0 = none (memcpy, src/pc.cxx:67-70),
- * kind 1 = ILU apply with the given L/U (src/solver-tri.cxx:57-60). */
+ * kind 1 = ILU apply with the given L/U (src/solver-tri.cxx:57-60), kind 2 = one AMG cycle
+ * from the incoming x (src/pc-sxamg.cxx:42-73; amg_oracle.c, parity unpinned). */
 typedef struct orc_pc_ {
     int kind;
     const int *Lp, *Lj; const double *Lx;
     const int *Up, *Uj; const double *Ux;
     double *cache;
+    void *amg;
 } orc_pc;
+struct orc_amg_;
+void orc_amg_cycle(struct orc_amg_ *m, double *x, const double *rhs);
 
 static void pc_apply(const orc_pc *pc, int n, double *x, const double *rhs)
 {
     if (pc == NULL || pc->kind == 0) memcpy(x, rhs, sizeof(double) * n);
+    else if (pc->kind == 2) orc_amg_cycle((struct orc_amg_ *)pc->amg, x, rhs);
     else orc_ilu_apply(n, pc->Lp, pc->Lj, pc->Lx, pc->Up, pc->Uj, pc->Ux, x, rhs, pc->cache);
 }
 

@@ -1,0 +1,132 @@
+"""GPU suite, part 4: the SX-AMG-style cycle (lssp_b200/csrc/amg.cu) against its CPU restatement
+(oracle/amg_oracle.c).  Parity with libsxamg itself is UNPINNED; the bar
+here is the north star's "preconditioner application within 1e-12 relative" -- and, because every
+operator of the cycle keeps the serial order of its sums, the results are in fact bit-identical."""
+import numpy as np
+import pytest
+
+from lssp_b200 import api
+from util import matrix, relerr, tvec
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["lap2d_100", "lap3d_32", "cd3d_12", "random_600"]
+_cache = {}
+
+
+def setup(ctx, name, **pars):
+    key = (name, tuple(sorted(pars.items())))
+    if key not in _cache:
+        A = matrix(name)
+        H = api.AmgHierarchy(A, **pars)
+        dA = api.Csr(ctx, A)
+        _cache[key] = (A, H, dA, api.Preconditioner.sxamg(ctx, A, hierarchy=H, share=dA))
+    return _cache[key]
+
+
+def oracle_amg(port, H):
+    p = H.pars
+    return port.amg(H.levels, pre=p.pre_iter, post=p.post_iter, cf_order=p.cf_order, coarse_inv=H.coarse_inv,
+                    coarse_sweeps=p.coarse_sweeps, zero_guess=p.zero_guess)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("pars", [dict(), dict(cf_order=0), dict(zero_guess=1, pre_iter=1, post_iter=3),
+                                  dict(coarse_dense_max=0, coarse_sweeps=7, coarse_dof=300)])
+def test_cycle_equals_restatement(ctx, port, name, pars):
+    A, H, dA, pc = setup(ctx, name, **pars)
+    n = H.levels[0]["n"]
+    m = oracle_amg(port, H)
+    for k in range(2):
+        rhs, x0 = tvec(n, k), tvec(n, k + 7)
+        got = pc.apply_host(rhs, x0=x0)
+        want = m.cycle(rhs, x0)
+        assert relerr(got, want) <= 1e-12
+        if max(np.diff(L["A"][0]).max() for L in H.levels) <= 64:   # no shuffle-reduced long rows anywhere
+            assert np.array_equal(got, want)
+
+
+def test_cycle_is_bit_identical_with_exact_spmv(port):
+    """Coarse operators have rows longer than 64 entries, which the fast SpMV sums with a warp
+    shuffle; with LSSPG_OPT_SPMV_EXACT the whole cycle is bit-identical to the serial one."""
+    c = api.Context(0)
+    c.set_option(api.OPT_SPMV_EXACT, 1)
+    A = matrix("lap3d_32")
+    H = api.AmgHierarchy(A)
+    assert max(np.diff(L["A"][0]).max() for L in H.levels) > 64
+    pc = api.Preconditioner.sxamg(c, A, hierarchy=H)
+    m = oracle_amg(port, H)
+    n = H.levels[0]["n"]
+    assert np.array_equal(pc.apply_host(tvec(n), x0=tvec(n, 2)), m.cycle(tvec(n), tvec(n, 2)))
+    pc.free()
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["lap2d_100", "lap3d_32", "cd3d_12"])
+def test_standalone_amg_iteration(ctx, port, name):
+    """lssp_solver_sxamg: cycles until ||b - A x|| / ||b|| <= tol; same count, same residual"""
+    A, H, dA, pc = setup(ctx, name)
+    n = H.levels[0]["n"]
+    want = oracle_amg(port, H).solve(np.ones(n), tol=1e-8, maxit=50)
+    x = np.zeros(n)
+    got = pc.amg_solve(np.ones(n), x, tol=1e-8, maxit=50)
+    assert got["nits"] == want["nits"] and 0 < got["nits"] < 15
+    # the residual has dropped 8 orders: rounding differences of the long coarse rows (shuffle-summed
+    # in fast mode) are measured against where it started
+    assert abs(got["residual"] - want["residual"]) <= 1e-13 * np.sqrt(n)
+    assert relerr(x, want["x"]) <= 1e-12
+    # maxit is honoured
+    x = np.zeros(n)
+    assert pc.amg_solve(np.ones(n), x, tol=1e-30, maxit=3)["nits"] == 3
+
+
+@pytest.mark.parametrize("name", ["lap2d_100", "lap3d_32"])
+def test_pcg_with_amg_matches_restatement(ctx, port, name):
+    A, H, dA, pc = setup(ctx, name, zero_guess=1)
+    n = H.levels[0]["n"]
+    want = port.solve("cg", A, np.ones(n), amg=oracle_amg(port, H), maxit=100, nhist=30)
+    x = np.zeros(n)
+    got = api.lssp_solver_solve(ctx, "cg", dA, pc, np.ones(n), x, maxit=100, nhist=30)
+    assert got["nits"] == want["nits"] and got["nits"] <= 10
+    k = want["nits"]
+    assert np.allclose(got["hist"][:k], want["hist"][:k], rtol=1e-9, atol=1e-12 * want["hist"][0])
+    assert relerr(x, want["x"]) <= 1e-9
+
+
+def test_literal_initial_guess_semantics_reproduced(ctx, port):
+    """default: the cycle starts from the vector the driver hands in (src/pc-sxamg.cxx:58-64) --
+    PCG then follows the restatement step for step (and stagnates, as it does there)"""
+    A, H, dA, pc = setup(ctx, "lap3d_32")
+    n = H.levels[0]["n"]
+    want = port.solve("cg", A, np.ones(n), amg=oracle_amg(port, H), maxit=12, nhist=12)
+    x = np.zeros(n)
+    got = api.lssp_solver_solve(ctx, "cg", dA, pc, np.ones(n), x, maxit=12, nhist=12)
+    assert got["nits"] == want["nits"] == 12
+    assert np.allclose(got["hist"][:12], want["hist"][:12], rtol=1e-8)
+
+
+@pytest.mark.parametrize("solver", ["gmres", "bicgstab", "idrs"])
+def test_other_drivers_accept_the_amg_preconditioner(ctx, solver):
+    A, H, dA, pc = setup(ctx, "cd3d_12", zero_guess=1)
+    n = H.levels[0]["n"]
+    x = np.zeros(n)
+    got = api.lssp_solver_solve(ctx, solver, dA, pc, np.ones(n), x, maxit=200, restart=30)
+    assert got["nits"] <= 15
+    import scipy.sparse as sp
+    M = sp.csr_matrix((A[2], A[1], A[0]), shape=(n, n))
+    assert np.linalg.norm(np.ones(n) - M @ x) <= 2e-7 * np.sqrt(n)
+
+
+def test_amg_on_a_larger_grid_has_grid_independent_convergence(ctx):
+    from lssp_b200 import generators as g
+    A = g.lap3d(64)
+    n = 64 ** 3
+    dA = api.Csr(ctx, A)
+    pc = api.Preconditioner.sxamg(ctx, A, share=dA, zero_guess=1)
+    x = np.zeros(n)
+    got = api.lssp_solver_solve(ctx, "cg", dA, pc, np.ones(n), x, maxit=100)
+    assert got["nits"] <= 8
+    x = np.zeros(n)
+    assert pc.amg_solve(np.ones(n), x)["nits"] <= 12
+    pc.free()
+    dA.free()
