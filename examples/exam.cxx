@@ -41,9 +41,11 @@ int main(int argc, char **argv)
     if (sname == "cg") st = LSSP_SOLVER_CG;
     if (sname == "bicgstab") st = LSSP_SOLVER_BICGSTAB;
     if (sname == "idrs") st = LSSP_SOLVER_IDRS;
+    if (sname == "sxamg") st = LSSP_SOLVER_SXAMG;      // stand-alone AMG iteration
     LSSP_PC_TYPE pt = LSSP_PC_ILUK;
     if (pname == "non") pt = LSSP_PC_NON;
     if (pname == "ilut") pt = LSSP_PC_ILUT;
+    if (pname == "sxamg") pt = LSSP_PC_SXAMG;          // one V-cycle per application
 
     lssp_mat_csr A = poisson2d(N);
     const int n = A.num_rows;
@@ -57,6 +59,13 @@ int main(int argc, char **argv)
     lssp_solver_set_restart(solver, 60);
     lssp_solver_set_maxit(solver, 3000);
     lssp_solver_reset_verbosity(solver, 0);
+    if (pt == LSSP_PC_SXAMG && argc > 4) {             // 5th argument: zero_guess (see include/lssp/sxamg.h)
+        SX_AMG_PARS pars;
+        sx_amg_pars_init(&pars);
+        pars.maxit = 1;
+        pars.zero_guess = atoi(argv[4]);
+        lssp_pc_sxamg_set_pars(pc, &pars);
+    }
     lssp_solver_assemble(solver, A, x, b, pc);
     const int nits = lssp_solver_solve(solver, pc);
 

@@ -19,5 +19,5 @@
 #define USE_PARDISO 0
 #define USE_FASP    0
 #define USE_HSL_MI20 0
-#define USE_SXAMG   0
+#define USE_SXAMG   1   /* the B200 build ships its own SX-AMG-style AMG (sxamg.h stand-in) */
 #endif

@@ -21,6 +21,7 @@
 #include "solver-lgmres.h"
 #include "solver-orthomin.h"
 #include "solver-qmrcgstab.h"
+#include "solver-sxamg.h"
 #include "solver-tfqmr.h"
 
 void lssp_solver_create(LSSP_SOLVER &s, LSSP_SOLVER_TYPE s_type, LSSP_PC &pc, LSSP_PC_TYPE p_type);

@@ -4,6 +4,7 @@
 
 #include "pc-iluk.h"
 #include "pc-ilut.h"
+#include "pc-sxamg.h"
 
 void lssp_pc_create(LSSP_PC &pc, LSSP_PC_TYPE type);
 void lssp_pc_destroy(LSSP_PC &pc);

@@ -48,6 +48,9 @@ typedef enum LSSP_PC_TYPE_ {
     LSSP_PC_NON,
     LSSP_PC_ILUK,
     LSSP_PC_ILUT,
+#if USE_SXAMG
+    LSSP_PC_SXAMG,              /* AMG, SX-AMG style (reference include/type-defs.h:92-94) */
+#endif
     LSSP_PC_USER,
 } LSSP_PC_TYPE;
 
@@ -64,6 +67,10 @@ typedef struct LSSP_PC_ {
     double ilut_tol;
 
     lssp_mat_csr A, L, D, U;     /* host copies of the factors (L: diagonal last, U: diagonal first) */
+
+#if USE_SXAMG
+    struct SX_DATA_ *sxamg;      /* reference include/type-defs.h:135-137 */
+#endif
 
     void *data;
     double *cache;
@@ -100,6 +107,9 @@ typedef enum LSSP_SOLVER_TYPE_ {
     LSSP_SOLVER_TFQMR,
     LSSP_SOLVER_ORTHOMIN,
     LSSP_SOLVER_IDRS,
+#if USE_SXAMG
+    LSSP_SOLVER_SXAMG,           /* stand-alone AMG (reference include/type-defs.h:219-221) */
+#endif
 } LSSP_SOLVER_TYPE;
 
 typedef struct LSSP_SOLVER_ {
@@ -116,6 +126,10 @@ typedef struct LSSP_SOLVER_ {
 
     double residual;
     int nits;
+
+#if USE_SXAMG
+    struct SXAMG_DATA_ *sxamg;   /* reference include/type-defs.h:280-282 */
+#endif
 
     int verb;
     FILE *log;

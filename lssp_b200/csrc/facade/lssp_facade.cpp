@@ -313,7 +313,148 @@ void lssp_pc_create(LSSP_PC &pc, LSSP_PC_TYPE type)
     pc.verb = lssp_verbosity - 1;
     pc.log = NULL;
     pc.assembled = false;
+#if USE_SXAMG
+    pc.sxamg = NULL;
+    if (type == LSSP_PC_SXAMG) lssp_pc_sxamg_create(pc);   // src/pc.cxx:36-40
+#endif
 }
+
+#if USE_SXAMG
+// ---- SX-AMG adapters (reference src/pc-sxamg.cxx, src/solver-sxamg.cxx).  libsxamg itself is not in the
+// reference tree: the hierarchy and the cycle are this build's own (lsspg_amg_*, DESIGN.md "AMG").
+struct SX_DATA_ {
+    SX_AMG_PARS pars;
+};
+struct SXAMG_DATA_ {
+    SX_AMG_PARS pars;
+};
+
+void sx_amg_pars_init(SX_AMG_PARS *p)
+{
+    lsspg_amg_pars d;
+    lsspg_amg_pars_default(&d);
+    bzero(p, sizeof(*p));
+    p->verb = 0;
+    p->cycle_itr = 1;
+    p->tol = d.tol;
+    p->ctol = 1e-7;
+    p->maxit = d.maxit;
+    p->cs_type = 1;
+    p->interp_type = 1;
+    p->max_levels = d.max_levels;
+    p->max_coarsest_dof = d.coarse_dof;
+    p->strong_threshold = d.strong_threshold;
+    p->max_row_sum = d.max_row_sum;
+    p->trunc_threshold = d.trunc_threshold;
+    p->smoother = 1;
+    p->relaxation = 1.0;
+    p->cf_order = d.cf_order;
+    p->pre_iter = d.pre_iter;
+    p->post_iter = d.post_iter;
+    const char *e = getenv("LSSP_SXAMG_ZERO_GUESS");
+    p->zero_guess = e ? atoi(e) : d.zero_guess;
+}
+
+static lsspg_amg_pars to_native(const SX_AMG_PARS &p)
+{
+    lsspg_amg_pars d;
+    lsspg_amg_pars_default(&d);
+    d.max_levels = p.max_levels;
+    d.coarse_dof = p.max_coarsest_dof;
+    d.strong_threshold = p.strong_threshold;
+    d.max_row_sum = p.max_row_sum;
+    d.trunc_threshold = p.trunc_threshold;
+    d.pre_iter = p.pre_iter;
+    d.post_iter = p.post_iter;
+    d.cf_order = p.cf_order;
+    d.zero_guess = p.zero_guess;
+    d.tol = p.tol;
+    d.maxit = p.maxit;
+    d.verb = p.verb > 0 ? p.verb : 0;
+    return d;
+}
+
+static lsspg_pc *build_device_amg(const lssp_mat_csr &A, const lsspg_csr *dA, const SX_AMG_PARS &pars)
+{
+    const lsspg_amg_pars np = to_native(pars);
+    lsspg_amg_host *H = NULL;
+    GPU(lsspg_amg_setup_host(A.num_rows, A.Ap, A.Aj, A.Ax, &np, &H));
+    lsspg_pc *d = NULL;
+    GPU(lsspg_pc_create_amg(ctx(), H, dA, &d));
+    lsspg_amg_host_destroy(H);
+    return d;
+}
+
+void lssp_pc_sxamg_create(LSSP_PC &pc)   // src/pc-sxamg.cxx:12-25
+{
+    pc.sxamg = lssp_malloc<SX_DATA_>(1);
+    sx_amg_pars_init(&pc.sxamg->pars);
+    pc.sxamg->pars.maxit = 1;
+    pc.sxamg->pars.verb = pc.verb;
+}
+
+static void lssp_pc_sxamg_destroy(LSSP_PC *pc)   // src/pc-sxamg.cxx:27-40
+{
+    if (pc == NULL || pc->sxamg == NULL) return;
+    lssp_free(pc->sxamg);
+    pc->sxamg = NULL;
+}
+
+// pc.solve: one cycle from the incoming x (src/pc-sxamg.cxx:42-73)
+static void amg_solve(LSSP_PC *pc, lssp_vec x, lssp_vec rhs)
+{
+    assert(pc != NULL && pc->gpu != NULL);
+    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc->gpu, x.d, rhs.d));
+}
+
+void lssp_pc_sxamg_assemble(LSSP_PC &pc, LSSP_SOLVER s)   // src/pc-sxamg.cxx:75-126
+{
+    assert(pc.sxamg != NULL);
+    pc.gpu = build_device_amg(s.A, (const lsspg_csr *)s.gpu, pc.sxamg->pars);
+    pc.solve = amg_solve;
+    pc.destroy = lssp_pc_sxamg_destroy;
+}
+
+void lssp_pc_sxamg_set_pars(LSSP_PC &pc, SX_AMG_PARS *pars)   // src/pc-sxamg.cxx:128-131
+{
+    if (pars != NULL && pc.sxamg != NULL) pc.sxamg->pars = *pars;
+}
+
+void lssp_solver_sxamg_create(LSSP_SOLVER &s)   // src/solver-sxamg.cxx:11-15
+{
+    s.sxamg = lssp_malloc<SXAMG_DATA_>(1);
+    sx_amg_pars_init(&s.sxamg->pars);
+}
+
+void lssp_solver_sxamg_destroy(LSSP_SOLVER &s)   // src/solver-sxamg.cxx:17-23
+{
+    if (s.sxamg != NULL) {
+        lssp_free(s.sxamg);
+        s.sxamg = NULL;
+    }
+}
+
+// stand-alone AMG iteration (src/solver-sxamg.cxx:25-99): set-up and cycles in one call, as sx_solver_amg
+int lssp_solver_sxamg(LSSP_SOLVER *solver)
+{
+    solver->sxamg->pars.maxit = solver->maxit;
+    solver->sxamg->pars.verb = solver->verb;
+    solver->sxamg->pars.tol = solver->tol_rel;
+    lsspg_pc *d = build_device_amg(solver->A, (const lsspg_csr *)solver->gpu, solver->sxamg->pars);
+    int nits = 0;
+    double ares = 0.;
+    GPU(lsspg_amg_solve_host(ctx(), d, solver->rhs.d, solver->x.d, solver->tol_rel, solver->maxit, &nits, &ares));
+    lsspg_pc_destroy(ctx(), d);
+    solver->residual = ares;   // :96
+    solver->nits = nits;
+    return nits;
+}
+
+void lssp_solver_sxamg_set_pars(LSSP_SOLVER *solver, SX_AMG_PARS *pars)   // src/solver-sxamg.cxx:102-105
+{
+    if (pars != NULL && solver->sxamg != NULL) solver->sxamg->pars = *pars;
+}
+#endif
 
 static void release_device_pc(LSSP_PC *pc)
 {
@@ -435,6 +576,12 @@ void lssp_pc_assemble(LSSP_PC &pc, LSSP_SOLVER s)
             if (pc.verb >= 0) lssp_printf("pc: type: ILUT\n");
             lssp_pc_ilut_assemble(pc, s);
             break;
+#if USE_SXAMG
+        case LSSP_PC_SXAMG:   // src/pc.cxx:208-217
+            if (pc.verb >= 0) lssp_printf("pc: type: SX-AMG\n");
+            lssp_pc_sxamg_assemble(pc, s);
+            break;
+#endif
         case LSSP_PC_USER: {
             if (pc.verb >= 0) lssp_printf("pc: type: user defined\n");
             assert(pc.assemble != NULL);
@@ -473,6 +620,12 @@ void lssp_solver_create(LSSP_SOLVER &s, LSSP_SOLVER_TYPE s_type, LSSP_PC &pc, LS
     s.blk_size = NULL;
     s.log = NULL;
     s.verb = lssp_verbosity;
+#if USE_SXAMG
+    if (s_type == LSSP_SOLVER_SXAMG) {   // src/lssp.cxx:131-136
+        p_type = LSSP_PC_NON;
+        lssp_solver_sxamg_create(s);
+    }
+#endif
     lssp_pc_create(pc, p_type);
     s.assembled = false;
 }
@@ -507,9 +660,12 @@ void lssp_solver_destroy(LSSP_SOLVER &s, LSSP_PC &pc)
 {
     assert(s.assembled);
     lssp_mat_destroy(s.A);
+#if USE_SXAMG
+    if (s.type == LSSP_SOLVER_SXAMG) lssp_solver_sxamg_destroy(s);   // src/lssp.cxx:240-244
+#endif
+    lssp_pc_destroy(pc);   // before the matrix: an AMG preconditioner shares the device copy of A
     if (s.gpu) lsspg_csr_destroy(ctx(), (lsspg_csr *)s.gpu);
     s.gpu = NULL;
-    lssp_pc_destroy(pc);
     s.assembled = false;
 }
 
@@ -621,6 +777,9 @@ int lssp_solver_solve(LSSP_SOLVER &solver, LSSP_PC &pc)   // dispatch switch, re
         case LSSP_SOLVER_TFQMR: return lssp_solver_tfqmr(solver, pc);
         case LSSP_SOLVER_ORTHOMIN: return lssp_solver_orthomin(solver, pc);
         case LSSP_SOLVER_IDRS: return lssp_solver_idrs(solver, pc);
+#if USE_SXAMG
+        case LSSP_SOLVER_SXAMG: return lssp_solver_sxamg(&solver);   // src/lssp.cxx:404-408
+#endif
         default:
             lssp_error(0, "solver: unsupported solver type!\n");
             return -1;

@@ -73,6 +73,28 @@ def test_facade_symbols_are_link_compatible_with_the_reference():
 
 
 @pytest.mark.gpu
+def test_exam_program_with_the_amg_preconditioner_and_the_amg_solver(port):
+    """LSSP_PC_SXAMG / LSSP_SOLVER_SXAMG through the C++ API; expected counts from the restated
+    cycle (oracle/amg_oracle.c) on the same hierarchy"""
+    import numpy as np
+    from lssp_b200 import api, generators as g
+    A = g.laplacian_5pt(100)
+    H = api.AmgHierarchy(A)
+    n = 10000
+    want_cg = port.solve("cg", A, np.ones(n), amg=port.amg(H.levels, coarse_inv=H.coarse_inv, zero_guess=1), maxit=3000)
+    want_amg = port.amg(H.levels, coarse_inv=H.coarse_inv).solve(np.ones(n), tol=1e-7, maxit=3000)
+    for args, want in ((["100", "cg", "sxamg", "1"], want_cg), (["100", "sxamg", "non"], want_amg)):
+        out = subprocess.run([EXAM] + args, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        m = re.search(r"iterations: (\d+), solver residual: (\S+)", out.stdout)
+        k = re.search(r"solution L2 norm: (\S+) residual: (\S+)", out.stdout)
+        assert int(m.group(1)) == want["nits"] and 0 < want["nits"] < 15, out.stdout
+        assert abs(float(m.group(2)) - want["residual"]) <= 1e-6 * want["residual"], out.stdout
+        assert abs(float(k.group(1)) - 4.25082937e+04) <= 1e-6 * 4.25082937e+04
+        assert abs(float(k.group(2)) - float(m.group(2))) <= 1e-3 * float(m.group(2)) + 1e-9
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("args,nits,residual,xnorm", [
     ([], 49, 8.18058783e-06, 4.25082937e+04),                      # the reference's own example run (SURVEY.md 4)
     (["100", "cg", "iluk"], 51, 8.65389630e-06, 4.25082937e+04),   # App. A.1: CG + ILUK(1)
