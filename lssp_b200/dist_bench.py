@@ -17,6 +17,8 @@ import numpy as np
 
 
 def main(args, rank, world, local_rank):
+    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as td
 
