@@ -8,10 +8,17 @@
 //                 shared memory with coalesced 128-bit loads, then one thread
 //                 per row adds its products SEQUENTIALLY in storage order:
 //                 bit-identical to the reference loop (src/mvops.cxx:130-132).
-//   WARP tile   : <= 8 consecutive long rows, one warp per row, lanes stride the
-//                 row and a shuffle tree adds the lane sums (<= 1e-14 relative).
-//   SERIAL tile : long rows in LSSPG_OPT_SPMV_EXACT mode, one thread per row
-//                 straight from global memory (bit-exact, slow; opt-in).
+//   MIXED tile  : the same, but the tile also holds rows of 65 .. 2048 entries
+//                 (irregular matrices: the row-length histogram decides per row).
+//                 Those rows are taken by the warps of the CTA after the short
+//                 ones: lanes stride the row IN SHARED MEMORY, 4 gathers of x in
+//                 flight per lane, shuffle tree over the lane sums (<= 1e-14).
+//                 Tiles are never cut at a long row, so they stay ~2048 nnz.
+//   BLOCK tile  : rows longer than a tile (> 2048 nnz): the whole CTA strides the
+//                 row from global memory, fixed-order block reduction.
+//   SERIAL tile : rows longer than a tile in LSSPG_OPT_SPMV_EXACT mode, one thread
+//                 per row straight from global memory (bit-exact, slow; opt-in);
+//                 in that mode every other row is summed sequentially (STREAM).
 // Algorithmic bytes per launch: 12 nnz + 4 (n+1) + 16 n (+ 8 n when y is read).
 // x is gathered through L1/L2 (read-only path); val/col/Ap/y/z cross HBM once.
 #include <algorithm>
@@ -108,7 +115,8 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
         const int r0 = a.tile_row[tile];
         const int nr = a.tile_row[tile + 1] - r0;
         const int kind = a.tile_kind[tile];
-        if (kind == TILE_STREAM) {
+        if (kind == TILE_STREAM || kind == TILE_MIXED) {
+            const bool mixed = (kind == TILE_MIXED);
             for (int i = tid; i <= nr; i += kBlock) sap[i] = a.Ap[r0 + i];
             __syncthreads();
             const int e0 = sap[0], e1 = sap[nr];
@@ -126,6 +134,7 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
             for (int r = tid; r < nr; r += kBlock) {
                 int k = sap[r] - a0;
                 const int k1 = sap[r + 1] - a0;
+                if (mixed && k1 - k > kLongRow) continue;   // left to the warps below
                 double sum = 0.0;
                 for (; k + 4 <= k1; k += 4) {
                     const double x0 = __ldg(x + scol[k]), x1 = __ldg(x + scol[k + 1]);
@@ -139,22 +148,55 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
                 a.z[r0 + r] = out;
                 dots_add<NDOT>(a, acc, r0 + r, out);
             }
-            __syncthreads();
-        }
-        else if (kind == TILE_WARP) {
-            const int w = tid >> 5, lane = tid & 31;
-            if (w < nr) {
-                const int r = r0 + w;
-                const int e0 = a.Ap[r], e1 = a.Ap[r + 1];
-                double s = 0.0;
-                for (int k = e0 + lane; k < e1; k += 32) s += __ldg(x + a.Aj[k]) * a.Ax[k];
-                s = warp_sum(s);
-                if (lane == 0) {
-                    const double out = epilogue<KIND>(s, alpha, beta, a.y, r);
-                    a.z[r] = out;
-                    dots_add<NDOT>(a, acc, r, out);
+            if (mixed) {
+                const int w = tid >> 5, lane = tid & 31;
+                for (int r = w; r < nr; r += kBlock / 32) {
+                    int k = sap[r] - a0 + lane;
+                    const int k1 = sap[r + 1] - a0;
+                    if (k1 - (k - lane) <= kLongRow) continue;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    for (; k + 96 < k1; k += 128) {
+                        const double x0 = __ldg(x + scol[k]), x1 = __ldg(x + scol[k + 32]);
+                        const double x2 = __ldg(x + scol[k + 64]), x3 = __ldg(x + scol[k + 96]);
+                        s0 += x0 * sval[k]; s1 += x1 * sval[k + 32]; s2 += x2 * sval[k + 64]; s3 += x3 * sval[k + 96];
+                    }
+                    for (; k < k1; k += 32) s0 += __ldg(x + scol[k]) * sval[k];
+                    const double s = warp_sum((s0 + s1) + (s2 + s3));
+                    if (lane == 0) {
+                        const double out = epilogue<KIND>(s, alpha, beta, a.y, r0 + r);
+                        a.z[r0 + r] = out;
+                        dots_add<NDOT>(a, acc, r0 + r, out);
+                    }
                 }
             }
+            __syncthreads();
+        }
+        else if (kind == TILE_BLOCK) {
+            for (int rr = 0; rr < nr; rr++) {
+                const int r = r0 + rr;
+                const int e1 = a.Ap[r + 1];
+                int k = a.Ap[r] + tid;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                for (; k + 3 * kBlock < e1; k += 4 * kBlock) {
+                    const int c0 = a.Aj[k], c1 = a.Aj[k + kBlock], c2 = a.Aj[k + 2 * kBlock], c3 = a.Aj[k + 3 * kBlock];
+                    s0 += __ldg(x + c0) * a.Ax[k]; s1 += __ldg(x + c1) * a.Ax[k + kBlock];
+                    s2 += __ldg(x + c2) * a.Ax[k + 2 * kBlock]; s3 += __ldg(x + c3) * a.Ax[k + 3 * kBlock];
+                }
+                for (; k < e1; k += kBlock) s0 += __ldg(x + a.Aj[k]) * a.Ax[k];
+                double s = warp_sum((s0 + s1) + (s2 + s3));
+                __syncthreads();   // sval is free here: no stream tile is in flight in this CTA
+                if ((tid & 31) == 0) sval[tid >> 5] = s;
+                __syncthreads();
+                if (tid < 32) {
+                    s = warp_sum(tid < kBlock / 32 ? sval[tid] : 0.0);
+                    if (tid == 0) {
+                        const double out = epilogue<KIND>(s, alpha, beta, a.y, r);
+                        a.z[r] = out;
+                        dots_add<NDOT>(a, acc, r, out);
+                    }
+                }
+            }
+            __syncthreads();
         }
         else {  // TILE_SERIAL
             for (int rr = tid; rr < nr; rr += kBlock) {
@@ -281,26 +323,30 @@ static void build_tiles(int n, const int *Ap, bool exact, std::vector<int> &rows
     max_nnz = 0;
     nstream = 0;
     auto len = [&](int i) { return Ap[i + 1] - Ap[i]; };
-    auto is_long = [&](int i) { return exact ? len(i) > kTileNnzCap : len(i) > kLongRow; };
+    auto is_huge = [&](int i) { return len(i) > kTileNnzCap - 4; };   // does not fit a tile (4 = alignment slack)
     int i = 0;
     while (i < n) {
         int j = i;
-        if (is_long(i)) {
+        if (is_huge(i)) {
             const int lim = exact ? kTileRows : kWarpRowsPerTile;
-            while (j < n && j - i < lim && is_long(j)) j++;
-            kinds.push_back(exact ? TILE_SERIAL : TILE_WARP);
+            while (j < n && j - i < lim && is_huge(j)) j++;
+            kinds.push_back(exact ? TILE_SERIAL : TILE_BLOCK);
         }
         else {
             int cnt = 0;
-            while (j < n && j - i < kTileRows && !is_long(j) && cnt + len(j) <= kTileNnzCap) {
+            bool has_long = false;
+            while (j < n && j - i < kTileRows && !is_huge(j) && cnt + len(j) <= kTileNnzCap - 4) {
                 cnt += len(j);
+                has_long |= len(j) > kLongRow;
                 j++;
             }
             // the tile is loaded from the previous multiple of 4 elements
             const int span = (Ap[j] - (Ap[i] & ~3) + 3) & ~3;
             max_nnz = std::max(max_nnz, span);
-            kinds.push_back(TILE_STREAM);
-            nstream++;
+            // exact mode: every row of a tile is summed sequentially by one thread, however long
+            const bool mixed = has_long && !exact;
+            kinds.push_back(mixed ? TILE_MIXED : TILE_STREAM);
+            if (!mixed) nstream++;
         }
         rows.push_back(i);
         i = j;
