@@ -8,12 +8,15 @@
 //                 shared memory with coalesced 128-bit loads, then one thread
 //                 per row adds its products SEQUENTIALLY in storage order:
 //                 bit-identical to the reference loop (src/mvops.cxx:130-132).
-//   MIXED tile  : the same, but the tile also holds rows of 65 .. 2048 entries
-//                 (irregular matrices: the row-length histogram decides per row).
-//                 Those rows are taken by the warps of the CTA after the short
-//                 ones: lanes stride the row IN SHARED MEMORY, 4 gathers of x in
-//                 flight per lane, shuffle tree over the lane sums (<= 1e-14).
-//                 Tiles are never cut at a long row, so they stay ~2048 nnz.
+//   BALANCED    : irregular tiles (longest row > 2 x average + 4, from the tile's
+//   tile          row-length histogram): the products x[col]*val of the whole tile
+//                 are formed first, spread evenly over the threads (8 independent
+//                 gathers in flight each), and written back over val; then one
+//                 thread per row adds its products in storage order from shared
+//                 memory.  Same roundings in the same order: still bit-identical.
+//   MIXED tile  : BALANCED, but rows of 65 .. 2048 entries are added by a warp
+//                 (lanes stride the products, shuffle tree; <= 1e-14).  Tiles are
+//                 never cut at a long row, so they stay ~2048 nnz.
 //   BLOCK tile  : rows longer than a tile (> 2048 nnz): the whole CTA strides the
 //                 row from global memory, fixed-order block reduction.
 //   SERIAL tile : rows longer than a tile in LSSPG_OPT_SPMV_EXACT mode, one thread
@@ -94,7 +97,9 @@ __device__ __forceinline__ void dots_add(const SpmvArgs &a, double (&acc)[NDOT >
     }
 }
 
-template <int KIND, int NDOT>
+// IRR = false: the matrix has STREAM (and SERIAL) tiles only -- the lean instantiation, 32 registers,
+// 8 resident CTAs per SM; IRR = true adds the BALANCED / MIXED / BLOCK paths of irregular matrices.
+template <int KIND, int NDOT, bool IRR>
 __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
         const int r0 = a.tile_row[tile];
         const int nr = a.tile_row[tile + 1] - r0;
         const int kind = a.tile_kind[tile];
-        if (kind == TILE_STREAM || kind == TILE_MIXED) {
+        if (kind == TILE_STREAM || (IRR && (kind == TILE_MIXED || kind == TILE_BALANCED))) {
             const bool mixed = (kind == TILE_MIXED);
             for (int i = tid; i <= nr; i += kBlock) sap[i] = a.Ap[r0 + i];
             __syncthreads();
@@ -131,47 +136,79 @@ __global__ void __launch_bounds__(kBlock) spmv_tiles_kernel(const SpmvArgs a)
 #pragma unroll 2
             for (int i = tid; i < nvec; i += kBlock) sc[i] = ld_stream_i4(gc + i);
             __syncthreads();
-            for (int r = tid; r < nr; r += kBlock) {
-                int k = sap[r] - a0;
-                const int k1 = sap[r + 1] - a0;
-                if (mixed && k1 - k > kLongRow) continue;   // left to the warps below
-                double sum = 0.0;
-                for (; k + 4 <= k1; k += 4) {
-                    const double x0 = __ldg(x + scol[k]), x1 = __ldg(x + scol[k + 1]);
-                    const double x2 = __ldg(x + scol[k + 2]), x3 = __ldg(x + scol[k + 3]);
-                    const double p0 = x0 * sval[k], p1 = x1 * sval[k + 1];
-                    const double p2 = x2 * sval[k + 2], p3 = x3 * sval[k + 3];
-                    sum += p0; sum += p1; sum += p2; sum += p3;
-                }
-                for (; k < k1; k++) sum += __ldg(x + scol[k]) * sval[k];
-                const double out = epilogue<KIND>(sum, alpha, beta, a.y, r0 + r);
-                a.z[r0 + r] = out;
-                dots_add<NDOT>(a, acc, r0 + r, out);
-            }
-            if (mixed) {
-                const int w = tid >> 5, lane = tid & 31;
-                for (int r = w; r < nr; r += kBlock / 32) {
-                    int k = sap[r] - a0 + lane;
+            if (!IRR || kind == TILE_STREAM) {
+                // regular rows: one thread per row gathers and adds in storage order
+                for (int r = tid; r < nr; r += kBlock) {
+                    int k = sap[r] - a0;
                     const int k1 = sap[r + 1] - a0;
-                    if (k1 - (k - lane) <= kLongRow) continue;
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                    for (; k + 96 < k1; k += 128) {
-                        const double x0 = __ldg(x + scol[k]), x1 = __ldg(x + scol[k + 32]);
-                        const double x2 = __ldg(x + scol[k + 64]), x3 = __ldg(x + scol[k + 96]);
-                        s0 += x0 * sval[k]; s1 += x1 * sval[k + 32]; s2 += x2 * sval[k + 64]; s3 += x3 * sval[k + 96];
+                    double sum = 0.0;
+                    for (; k + 4 <= k1; k += 4) {
+                        const double x0 = __ldg(x + scol[k]), x1 = __ldg(x + scol[k + 1]);
+                        const double x2 = __ldg(x + scol[k + 2]), x3 = __ldg(x + scol[k + 3]);
+                        const double p0 = x0 * sval[k], p1 = x1 * sval[k + 1];
+                        const double p2 = x2 * sval[k + 2], p3 = x3 * sval[k + 3];
+                        sum += p0; sum += p1; sum += p2; sum += p3;
                     }
-                    for (; k < k1; k += 32) s0 += __ldg(x + scol[k]) * sval[k];
-                    const double s = warp_sum((s0 + s1) + (s2 + s3));
-                    if (lane == 0) {
-                        const double out = epilogue<KIND>(s, alpha, beta, a.y, r0 + r);
-                        a.z[r0 + r] = out;
-                        dots_add<NDOT>(a, acc, r0 + r, out);
+                    for (; k < k1; k++) sum += __ldg(x + scol[k]) * sval[k];
+                    const double out = epilogue<KIND>(sum, alpha, beta, a.y, r0 + r);
+                    a.z[r0 + r] = out;
+                    dots_add<NDOT>(a, acc, r0 + r, out);
+                }
+            }
+            else {
+                // irregular rows: first every product x[col]*val of the tile, spread evenly over the
+                // threads whatever the row lengths (8 independent gathers in flight per thread), written
+                // back over val; then one thread per row adds ITS products in storage order from shared
+                // memory -- the same two roundings per entry, in the same order, as src/mvops.cxx:130-132
+                const int kb = e0 - a0, ke = e1 - a0;
+                int k = kb + tid;
+                for (; k + 7 * kBlock < ke; k += 8 * kBlock) {
+                    double xv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) xv[j] = __ldg(x + scol[k + j * kBlock]);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sval[k + j * kBlock] = xv[j] * sval[k + j * kBlock];
+                }
+                for (; k < ke; k += kBlock) sval[k] = __ldg(x + scol[k]) * sval[k];
+                __syncthreads();
+                for (int r = tid; r < nr; r += kBlock) {
+                    int q = sap[r] - a0;
+                    const int q1 = sap[r + 1] - a0;
+                    if (mixed && q1 - q > kLongRow) continue;   // left to the warps below
+                    double sum = 0.0;
+                    for (; q + 4 <= q1; q += 4) {
+                        const double p0 = sval[q], p1 = sval[q + 1], p2 = sval[q + 2], p3 = sval[q + 3];
+                        sum += p0; sum += p1; sum += p2; sum += p3;
+                    }
+                    for (; q < q1; q++) sum += sval[q];
+                    const double out = epilogue<KIND>(sum, alpha, beta, a.y, r0 + r);
+                    a.z[r0 + r] = out;
+                    dots_add<NDOT>(a, acc, r0 + r, out);
+                }
+                if (mixed) {   // rows of 65 .. 2048 entries: a warp per row, lanes stride, shuffle tree (<= 1e-14)
+                    const int w = tid >> 5, lane = tid & 31;
+                    for (int r = w; r < nr; r += kBlock / 32) {
+                        int q = sap[r] - a0 + lane;
+                        const int q1 = sap[r + 1] - a0;
+                        if (q1 - (q - lane) <= kLongRow) continue;
+                        double s0 = 0.0, s1 = 0.0;
+                        for (; q + 32 < q1; q += 64) {
+                            s0 += sval[q];
+                            s1 += sval[q + 32];
+                        }
+                        if (q < q1) s0 += sval[q];
+                        const double s = warp_sum(s0 + s1);
+                        if (lane == 0) {
+                            const double out = epilogue<KIND>(s, alpha, beta, a.y, r0 + r);
+                            a.z[r0 + r] = out;
+                            dots_add<NDOT>(a, acc, r0 + r, out);
+                        }
                     }
                 }
             }
             __syncthreads();
         }
-        else if (kind == TILE_BLOCK) {
+        else if (IRR && kind == TILE_BLOCK) {
             for (int rr = 0; rr < nr; rr++) {
                 const int r = r0 + rr;
                 const int e1 = a.Ap[r + 1];
@@ -239,16 +276,39 @@ __global__ void __launch_bounds__(kBlock) spmv_zero_kernel(int n, Coef ca, Coef 
     (void)alpha;
 }
 
-template <int KIND>
-static int launch_kind(lsspg_ctx *ctx, const lsspg_csr *A, const SpmvArgs &args, int ndot, int grid, size_t smem)
+// Persistent grid: exactly the CTAs that are resident at once (a grid sized for more than the
+// register / shared-memory limit allows leaves a tail wave at a fraction of the occupancy).
+template <int KIND, int NDOT, bool IRR>
+static int launch_one(lsspg_ctx *ctx, const lsspg_csr *A, const SpmvArgs &args, size_t smem)
 {
-    switch (ndot) {
-        case 0: LSSPG_LAUNCH(ctx, (spmv_tiles_kernel<KIND, 0>), grid, kBlock, smem, args); break;
-        case 1: LSSPG_LAUNCH(ctx, (spmv_tiles_kernel<KIND, 1>), grid, kBlock, smem, args); break;
-        default: LSSPG_LAUNCH(ctx, (spmv_tiles_kernel<KIND, 2>), grid, kBlock, smem, args); break;
+    int &per_sm = A->occupancy[KIND][NDOT];   // per matrix: the limit depends on its tile size (smem)
+    if (per_sm == 0) {
+        cudaFuncSetAttribute(spmv_tiles_kernel<KIND, NDOT, IRR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        int nb = 0;
+        LSSPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmv_tiles_kernel<KIND, NDOT, IRR>, kBlock, smem));
+        per_sm = nb > 0 ? nb : 1;
     }
-    (void)A;
+    int grid = std::min(A->num_tiles, ctx->num_sms * per_sm);
+    if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+    LSSPG_LAUNCH(ctx, (spmv_tiles_kernel<KIND, NDOT, IRR>), grid, kBlock, smem, args);
     return 0;
+}
+
+template <int KIND>
+static int launch_kind(lsspg_ctx *ctx, const lsspg_csr *A, const SpmvArgs &args, int ndot, size_t smem)
+{
+    if (A->irregular) {
+        switch (ndot) {
+            case 0: return launch_one<KIND, 0, true>(ctx, A, args, smem);
+            case 1: return launch_one<KIND, 1, true>(ctx, A, args, smem);
+            default: return launch_one<KIND, 2, true>(ctx, A, args, smem);
+        }
+    }
+    switch (ndot) {
+        case 0: return launch_one<KIND, 0, false>(ctx, A, args, smem);
+        case 1: return launch_one<KIND, 1, false>(ctx, A, args, smem);
+        default: return launch_one<KIND, 2, false>(ctx, A, args, smem);
+    }
 }
 
 int spmv_launch(lsspg_ctx *ctx, int kind, const lsspg_csr *A, Coef alpha, const double *dx, Coef beta,
@@ -296,17 +356,12 @@ int spmv_launch(lsspg_ctx *ctx, int kind, const lsspg_csr *A, Coef alpha, const 
         args.seq = ctx->d_seq; args.seq_n = (long long)ctx->seq_len;
     }
     const size_t smem = (size_t)(args.cap + 8) * (sizeof(double) + sizeof(int)) + (kTileRows + 1) * sizeof(int);
-    // resident CTAs per SM: limited by threads (2048/256 = 8) and shared memory
-    int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    int grid = std::min(A->num_tiles, ctx->num_sms * per_sm);
-    if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
     int rc;
     switch (kind) {
-        case 0: rc = launch_kind<0>(ctx, A, args, ndot, grid, smem); break;
-        case 1: rc = launch_kind<1>(ctx, A, args, ndot, grid, smem); break;
-        case 2: rc = launch_kind<2>(ctx, A, args, ndot, grid, smem); break;
-        default: rc = launch_kind<3>(ctx, A, args, ndot, grid, smem); break;
+        case 0: rc = launch_kind<0>(ctx, A, args, ndot, smem); break;
+        case 1: rc = launch_kind<1>(ctx, A, args, ndot, smem); break;
+        case 2: rc = launch_kind<2>(ctx, A, args, ndot, smem); break;
+        default: rc = launch_kind<3>(ctx, A, args, ndot, smem); break;
     }
     if (rc || ndot == 0 || !(ctx->opt_reduce_sequential || distributed(ctx))) return rc;
     RedOut o;
@@ -333,19 +388,23 @@ static void build_tiles(int n, const int *Ap, bool exact, std::vector<int> &rows
             kinds.push_back(exact ? TILE_SERIAL : TILE_BLOCK);
         }
         else {
-            int cnt = 0;
+            int cnt = 0, longest = 0;
             bool has_long = false;
             while (j < n && j - i < kTileRows && !is_huge(j) && cnt + len(j) <= kTileNnzCap - 4) {
                 cnt += len(j);
+                longest = std::max(longest, len(j));
                 has_long |= len(j) > kLongRow;
                 j++;
             }
+            // row-length histogram of the tile: rows much longer than the average would leave most
+            // threads of a thread-per-row pass idle -> products first, balanced over the threads
+            const bool irregular = longest > 2 * (cnt / std::max(j - i, 1)) + 4;
             // the tile is loaded from the previous multiple of 4 elements
             const int span = (Ap[j] - (Ap[i] & ~3) + 3) & ~3;
             max_nnz = std::max(max_nnz, span);
             // exact mode: every row of a tile is summed sequentially by one thread, however long
             const bool mixed = has_long && !exact;
-            kinds.push_back(mixed ? TILE_MIXED : TILE_STREAM);
+            kinds.push_back(mixed ? TILE_MIXED : (irregular || has_long) ? TILE_BALANCED : TILE_STREAM);
             if (!mixed) nstream++;
         }
         rows.push_back(i);
@@ -398,16 +457,7 @@ int lsspg_csr_upload(lsspg_ctx *ctx, int num_rows, int num_cols, const int *hAp,
     if (!kinds.empty())
         LSSPG_CUDA(cudaMemcpyAsync(A->d_tile_kind, kinds.data(), kinds.size(), cudaMemcpyHostToDevice, ctx->stream));
     LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    // opt in to the shared-memory footprint of the stream kernel once per process
-    static bool attr_done = false;
-    if (!attr_done) {
-        const int maxsmem = 200 * 1024;
-#define SET_ATTR(K, D) cudaFuncSetAttribute(spmv_tiles_kernel<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem)
-        SET_ATTR(0, 0); SET_ATTR(0, 1); SET_ATTR(0, 2); SET_ATTR(1, 0); SET_ATTR(1, 1); SET_ATTR(1, 2);
-        SET_ATTR(2, 0); SET_ATTR(2, 1); SET_ATTR(2, 2); SET_ATTR(3, 0); SET_ATTR(3, 1); SET_ATTR(3, 2);
-#undef SET_ATTR
-        attr_done = true;
-    }
+    for (unsigned char k : kinds) A->irregular |= (k == TILE_MIXED || k == TILE_BALANCED || k == TILE_BLOCK);
     *out = A;
     return 0;
 }

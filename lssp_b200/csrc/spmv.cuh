@@ -16,6 +16,8 @@ struct lsspg_csr {
     int num_tiles = 0;
     int num_stream_tiles = 0;   // tiles whose rows are all summed sequentially (bit-exact)
     int max_tile_nnz = 0;       // smem sizing of the stream kernel
+    bool irregular = false;     // has BALANCED / MIXED / BLOCK tiles: needs the full kernel instantiation
+    mutable int occupancy[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // resident CTAs / SM per (kind, ndot)
     int *d_tile_row = nullptr;  // [num_tiles + 1] first row of every tile
     unsigned char *d_tile_kind = nullptr;  // [num_tiles]
     lsspg_halo *halo = nullptr;            // row shard of a distributed matrix: ghost columns follow the owned ones
@@ -28,7 +30,7 @@ constexpr int kTileNnzCap = 2048;  // nnz per stream tile
 constexpr int kLongRow = 64;       // rows longer than this take the warp-per-row path
 constexpr int kWarpRowsPerTile = 8;
 
-enum TileKind : unsigned char { TILE_STREAM = 0, TILE_MIXED = 1, TILE_SERIAL = 2, TILE_BLOCK = 3 };
+enum TileKind : unsigned char { TILE_STREAM = 0, TILE_MIXED = 1, TILE_SERIAL = 2, TILE_BLOCK = 3, TILE_BALANCED = 4 };
 
 // Fused SpMV: z = epilogue(A x) and up to two dot products of the result in the
 // same pass:  sums[k] = sum_r z_r * (w_k ? w_k[r] : z_r).  The sums land in
