@@ -506,7 +506,95 @@ __host__ __device__ inline EllLayout ell_layout(int nrows, int w, int nlev, int 
     return L;
 }
 
-__global__ void __launch_bounds__(32) tri_box_ell_kernel(const TiledArgs a)
+// The dependency levels of one box, ELL width W known at compile time.  Only the loads of sx[col]
+// depend on earlier levels; the row's columns, values, divisor and right-hand side do not, so they
+// are fetched one pass AHEAD.  A pass = up to 32*R rows of ONE level, R rows per lane side by side
+// (rows of a level are independent: their fp64 chains overlap), so a level of <= 64 rows costs one
+// chain  LDS sx[col] -> W products -> W dependent subtractions (-> divide) -> STS -> __syncwarp.
+template <int W, int R>
+__device__ __forceinline__ void box_levels(const int *__restrict__ slev, int nlev, int nrows, int dummy,
+                                           const int *__restrict__ ecol, const double *__restrict__ eval,
+                                           const double *__restrict__ sdiag, double *sx, int lane)
+{
+    // Lanes without a row in the pass work on row 0's data and store into the spare slot `dummy`:
+    // no predicates anywhere in the pass.
+    int L = 0, base = slev[0];
+    int st[R], c[R][W];
+    double v[R][W], dg[R], r[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int slot = base + j * 32 + lane;
+        const bool act = slot < slev[1];
+        const int ls = act ? slot : 0;
+        st[j] = act ? slot : dummy;
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            c[j][k] = ecol[k * nrows + ls];
+            v[j][k] = eval[k * nrows + ls];
+        }
+        dg[j] = sdiag[ls];
+        r[j] = sx[ls];
+    }
+    for (;;) {
+        int nL = L, nbase = base + 32 * R;
+        bool newlevel = false;
+        if (nbase >= slev[L + 1]) {
+            nL = L + 1;
+            newlevel = true;
+            nbase = (nL < nlev) ? slev[nL] : 0;
+        }
+        const bool more = nL < nlev;
+        const int nend = more ? slev[nL + 1] : 0;
+        int nst[R], nc[R][W];
+        double nv[R][W], ndg[R], nr[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int nslot = nbase + j * 32 + lane;
+            const bool nact = nslot < nend;
+            const int ls = nact ? nslot : 0;
+            nst[j] = nact ? nslot : dummy;
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                nc[j][k] = ecol[k * nrows + ls];
+                nv[j][k] = eval[k * nrows + ls];
+            }
+            ndg[j] = sdiag[ls];
+            nr[j] = sx[ls];   // rows of later passes still hold their right-hand side (row 0: any value, unused)
+        }
+        double xv[R][W];
+#pragma unroll
+        for (int j = 0; j < R; j++)
+#pragma unroll
+            for (int k = 0; k < W; k++) xv[j][k] = sx[c[j][k]];
+#pragma unroll
+        for (int k = 0; k < W; k++)
+#pragma unroll
+            for (int j = 0; j < R; j++) r[j] = r[j] - v[j][k] * xv[j][k];   // reference src/solver-tri.cxx:18 / :40
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (dg[j] != 1.0) r[j] = r[j] / dg[j];                         // :22 / :44 (x / 1.0 == x exactly)
+            sx[st[j]] = r[j];
+        }
+        if (!more) break;
+        if (newlevel) __syncwarp();
+        L = nL;
+        base = nbase;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            st[j] = nst[j];
+            dg[j] = ndg[j];
+            r[j] = nr[j];
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                c[j][k] = nc[j][k];
+                v[j][k] = nv[j][k];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32, 8) tri_box_ell_kernel(const TiledArgs a)   // smem allows <= 7 boxes per SM anyway
 {
     extern __shared__ __align__(128) unsigned char smem[];
     if (a.stop && *a.stop) return;
@@ -527,6 +615,8 @@ __global__ void __launch_bounds__(32) tri_box_ell_kernel(const TiledArgs a)
         if (lane == 0) tk = atomicInc(a.counter, total - 1);
         tk = __shfl_sync(0xffffffffu, tk, 0);
         if (tk >= (unsigned int)a.num_tiles) break;
+        long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        if (a.prof) t0 = clock64();
         const BoxDesc d = a.desc[tk];   // d.nent holds the ELL width here
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -566,19 +656,22 @@ __global__ void __launch_bounds__(32) tri_box_ell_kernel(const TiledArgs a)
             }
         }
         if (lane == 0) sx[nrows + d.next] = 0.0;
-        // wait for the boxes this one reads from
+        if (a.prof) t1 = clock64();
+        // Hand-off between boxes without flags or fences: x is pre-filled with the sentinel NaN, so
+        // every 8-byte operand announces itself.  (1) light gate: one lane per predecessor box polls
+        // ONE operand of that box (the one it stores last) -- a handful of pollers per box, no storm;
+        // (2) then all operands are fetched in one round and any that is still the sentinel (stores
+        // of a box may land out of order) is re-polled on its own.
         for (int q = lane; q < d.npred; q += 32) {
-            const unsigned int *f = a.flags + spred[q];
+            const double *f = a.x + spred[q];
             int spins = 0;
-            unsigned int got;
-            do {
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(f) : "memory");
-                if (got != a.epoch && ++spins > 16) __nanosleep(40);   // few pollers (<= 3 lanes per box): keep it tight
+            while ((unsigned long long)__double_as_longlong(ldx_relaxed(f)) == kSentinelBitsT) {
+                if (++spins > 16) __nanosleep(40);
                 if (spins > (1 << 21)) { *a.err = 1; break; }
-            } while (got != a.epoch);
+            }
         }
         __syncwarp();
-        __threadfence();   // acquire side: the operands below were published before the flags
+        if (a.prof) t2 = clock64();
         for (int q0 = 0; q0 < d.next; q0 += 256) {
             double v[8];
 #pragma unroll
@@ -589,28 +682,52 @@ __global__ void __launch_bounds__(32) tri_box_ell_kernel(const TiledArgs a)
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int q = q0 + u * 32 + lane;
-                if (q < d.next) sx[nrows + q] = v[u];
-            }
-        }
-        __syncwarp();
-        for (int L = 0; L < d.nlev; L++) {
-            const int sa = slev[L], sb = slev[L + 1];
-            for (int slot = sa + lane; slot < sb; slot += 32) {
-                double r = sx[slot];
-                for (int k = 0; k < w; k++) {
-                    const int c = ecol[k * nrows + slot];
-                    r = r - eval[k * nrows + slot] * sx[c];   // reference src/solver-tri.cxx:18 / :40
+                if (q < d.next) {
+                    int spins = 0;
+                    while ((unsigned long long)__double_as_longlong(v[u]) == kSentinelBitsT) {
+                        v[u] = ldx_relaxed(a.x + sext[q]);
+                        if (++spins > (1 << 21)) { *a.err = 1; break; }
+                    }
+                    sx[nrows + q] = v[u];
                 }
-                const double dg = sdiag[slot];
-                if (dg != 1.0) r = r / dg;                    // :22 / :44 (x / 1.0 == x exactly)
-                sx[slot] = r;
             }
-            __syncwarp();
         }
-        for (int s = lane; s < nrows; s += 32) a.x[sperm[s]] = sx[s];
-        __threadfence();
         __syncwarp();
-        if (lane == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.flags + tk), "r"(a.epoch) : "memory");
+        if (a.prof) t3 = clock64();
+        switch (w) {   // fixed widths: fully unrolled and software-pipelined (7-point ILU(0): 3, 5-point: 2)
+            case 1: box_levels<1, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+            case 2: box_levels<2, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+            case 3: box_levels<3, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+            case 4: box_levels<4, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+            default:
+                for (int L = 0; L < d.nlev; L++) {
+                    const int sa = slev[L], sb = slev[L + 1];
+                    for (int slot = sa + lane; slot < sb; slot += 32) {
+                        double r = sx[slot];
+                        for (int k = 0; k < w; k++) {
+                            const int c = ecol[k * nrows + slot];
+                            r = r - eval[k * nrows + slot] * sx[c];   // reference src/solver-tri.cxx:18 / :40
+                        }
+                        const double dg = sdiag[slot];
+                        if (dg != 1.0) r = r / dg;                    // :22 / :44 (x / 1.0 == x exactly)
+                        sx[slot] = r;
+                    }
+                    __syncwarp();
+                }
+        }
+        if (a.prof) t4 = clock64();
+        // publish: the values are their own ready flags (see the hand-off above): no fence, no flag store
+        for (int s = lane; s < nrows; s += 32)
+            asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(a.x + sperm[s]), "d"(sx[s]) : "memory");
+        if (a.prof && lane == 0) {   // LSSPG_TRI_PROF=1: cycles per box by phase
+            const long long t5 = clock64();
+            atomicAdd(a.prof + 0, (unsigned long long)(t1 - t0));   // descriptor, blob, rhs gather
+            atomicAdd(a.prof + 1, (unsigned long long)(t2 - t1));   // waiting for predecessor boxes
+            atomicAdd(a.prof + 2, (unsigned long long)(t3 - t2));   // operands of other boxes
+            atomicAdd(a.prof + 3, (unsigned long long)(t4 - t3));   // in-box levels
+            atomicAdd(a.prof + 4, (unsigned long long)(t5 - t4));   // publish
+            atomicAdd(a.prof + 5, 1ull);
+        }
     }
 }
 
@@ -656,7 +773,8 @@ int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double
         cudaMemcpy(h, d_prof, 64, cudaMemcpyDeviceToHost);
         cudaMemset(d_prof, 0, 64);
         if (h[5])
-            fprintf(stderr, "[tri_box] boxes=%llu grid=%d cycles/box: ticket %.0f blob %.0f gather %.0f compute %.0f (of which polling %.0f)\n",
+            fprintf(stderr, T->box_flags ? "[tri_box_ell] boxes=%llu grid=%d cycles/box: fetch %.0f wait %.0f operands %.0f levels %.0f publish %.0f\n"
+                                         : "[tri_box] boxes=%llu grid=%d cycles/box: ticket %.0f blob %.0f gather %.0f compute %.0f (of which polling %.0f)\n",
                     h[5], grid, (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5]);
     }
     return 0;
@@ -714,6 +832,8 @@ static int upload_ell(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
     }
     if (16 + cap + 8 * ((size_t)H.max_tile_rows + max_ext + 2) > (size_t)200 * 1024) return 2;
     std::vector<unsigned char> blob(std::max<size_t>(total, 16), 0);
+    std::vector<int> pos_of_row(H.n, 0);   // row -> position in box-major order
+    for (int s = 0; s < H.n; s++) pos_of_row[H.perm[s]] = s;
     for (int k = 0; k < H.num_tiles; k++) {
         const int s0 = H.tile_ptr[k];
         const BoxDesc &d = desc[k];
@@ -724,7 +844,19 @@ static int upload_ell(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
         int *ecol = (int *)(b + lay.ecol);
         double *diag = (double *)(b + lay.diag), *eval = (double *)(b + lay.eval);
         for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
-        for (int q = 0; q < d.npred; q++) pred[q] = H.pred[H.pred_ptr[k] + q];
+        // gate operand per predecessor box: of the rows this box reads from it, the one that box stores last
+        for (int q = 0; q < d.npred; q++) {
+            const int p = H.pred[H.pred_ptr[k] + q];
+            int best = -1;
+            for (int e = H.ptr[s0]; e < H.ptr[s0 + nr]; e++) {
+                const int c = H.col[e];
+                if (c < 0) continue;
+                const int pos = pos_of_row[c];
+                if (pos >= H.tile_ptr[p] && pos < H.tile_ptr[p + 1] && (best < 0 || pos > pos_of_row[best])) best = c;
+            }
+            if (best < 0) return 1;   // a predecessor without operands: the schedule is inconsistent
+            pred[q] = best;
+        }
         int q = 0;
         for (int s = 0; s < nr; s++) {
             perm[s] = H.perm[s0 + s];
