@@ -103,7 +103,8 @@ def build_problem(args):
         solver, pc = "bicgstab", "iluk"
     elif args.workload == "cg_amg":
         A = g.lap3d(N)
-        name = "lap3d_%d CG+SXAMG-style V-cycle, zero initial guess (BASELINE.json configs[3] operator)" % N
+        name = "lap3d_%d CG+SXAMG-style V-cycle, zero initial guess, %s Gauss-Seidel (BASELINE.json configs[3] operator)" % (
+            N, {0: "natural-order", 1: "C/F-ordered", 2: "C/F-ordered multicolour"}[args.amg_order])
         solver, pc = "cg", "amg"
     elif args.workload == "cg_non":
         A = g.lap3d(N)
@@ -129,8 +130,8 @@ def reference_arm(args, rank):
         P = oracle.Port()
         kw = {}
         if pc == "amg":
-            H = api.AmgHierarchy(A)
-            kw["amg"] = P.amg(H.levels, coarse_inv=H.coarse_inv, zero_guess=1)
+            H = api.AmgHierarchy(A, cf_order=args.amg_order)
+            kw["amg"] = P.amg(H.levels, coarse_inv=H.coarse_inv, zero_guess=1, cf_order=args.amg_order)
         elif pc == "iluk":
             kw["LU"] = api.ilu_factor(A, "iluk", level=0)
         its, secs = 0, 0.0
@@ -190,7 +191,7 @@ def cpu_baseline(args, A, solver, pc, pcobj=None):
     if pc == "amg":
         # libsxamg is not in the reference tree: the CPU side is the restated cycle (parity unpinned)
         H = pcobj.hierarchy
-        m = oracle.Port().amg(H.levels, coarse_inv=H.coarse_inv, zero_guess=1)
+        m = oracle.Port().amg(H.levels, coarse_inv=H.coarse_inv, zero_guess=1, cf_order=H.pars.cf_order)
         t0 = time.perf_counter()
         r = oracle.Port().solve(solver, A, np.ones(n), amg=m, maxit=args.ref_iters)
         t = time.perf_counter() - t0
@@ -240,6 +241,7 @@ def main():
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--workload", default="cg_ilu0")
     ap.add_argument("--check-every", type=int, default=1)
+    ap.add_argument("--amg-order", type=int, default=1, help="cf_order of the AMG smoother (cg_amg): 1 C/F by index, 2 multicolour")
     ap.add_argument("--ref-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -267,7 +269,7 @@ def main():
     if pckind == "iluk":
         pc = api.Preconditioner.iluk(ctx, A, level=0)
     elif pckind == "amg":
-        pc = api.Preconditioner.sxamg(ctx, A, share=dA, zero_guess=1)
+        pc = api.Preconditioner.sxamg(ctx, A, share=dA, zero_guess=1, cf_order=args.amg_order)
     else:
         pc = api.Preconditioner.non(ctx, n)
     t_pc = time.perf_counter() - t0

@@ -195,7 +195,9 @@ typedef struct lsspg_amg_pars {          /* the role of SX_AMG_PARS (sx_amg_pars
     double trunc_threshold;   /* 0.2: interpolation truncation */
     int    pre_iter;          /* 2 Gauss-Seidel sweeps before restriction */
     int    post_iter;         /* 2 after prolongation */
-    int    cf_order;          /* 1: sweeps visit C points then F points (pre) / F then C (post); 0: natural */
+    int    cf_order;          /* 1: sweeps visit C points then F points (pre) / F then C (post), ascending index
+                                 inside a block; 0: natural; 2: as 1, but colour by colour inside a block
+                                 (multicolour Gauss-Seidel: short dependency chains, made for the GPU) */
     int    zero_guess;        /* 0: the cycle starts from the incoming x, as the reference's adapter does
                                  (src/pc-sxamg.cxx:58-64); 1: from x = 0 (a fixed linear operator) */
     int    coarse_dense_max;  /* 4096: coarsest level solved with its dense inverse up to this size */
@@ -217,6 +219,9 @@ int lsspg_amg_host_level_sizes(const lsspg_amg_host *H, int l, int *n, int *nc, 
 /* any pointer may be NULL; cf[i] = 1 for C points, 0 for F points */
 int lsspg_amg_host_level_get(const lsspg_amg_host *H, int l, int *Ap, int *Aj, double *Ax,
                              int *Pp, int *Pj, double *Px, int *Rp, int *Rj, double *Rx, int *cf);
+/* visiting rank of every point of level l inside its C / F block (cf_order 0/1: the index;
+ * cf_order 2: multicolour order, see amg_host.cpp) */
+int lsspg_amg_host_level_rank(const lsspg_amg_host *H, int l, int *rank);
 /* row-major n x n inverse of the coarsest operator (only when coarse_dense != 0) */
 int lsspg_amg_host_coarse_inverse(const lsspg_amg_host *H, double *inv);
 int lsspg_amg_host_pars(const lsspg_amg_host *H, lsspg_amg_pars *pars);

@@ -441,7 +441,9 @@ class AmgHierarchy:
                                                  None if last else _p(P[0]), None if last else _p(P[1]),
                                                  None if last else _p(P[2]), None if last else _p(R[0]),
                                                  None if last else _p(R[1]), None if last else _p(R[2]), _p(cf)))
-            self.levels.append(dict(n=n, nc=nc, A=a, P=None if last else P, R=None if last else R, cf=cf))
+            rank = np.zeros(n, np.int32)
+            check(lib().lsspg_amg_host_level_rank(self.h, l, _p(rank)))
+            self.levels.append(dict(n=n, nc=nc, A=a, P=None if last else P, R=None if last else R, cf=cf, rank=rank))
         self.coarse_inv = None
         if self.coarse_dense:
             nlast = self.levels[-1]["n"]

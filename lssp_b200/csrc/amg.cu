@@ -70,7 +70,7 @@ struct GsArgs {
     const int *col;
     const double *val;
     unsigned int *counter;
-    int num_slices, slices_c, post;
+    int num_slices, slices_c, post, exact;
     const double *xold;
     double *xnew;
     const double *rhs;
@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(kBlock, MINB) gs_sweep_kernel(const GsArgs a)
                     enc = __ldg(a.col + base + (long long)(k0 + j) * 32);
                     v[j] = __ldg(a.val + base + (long long)(k0 + j) * 32);
                 }
-                c[j] = enc >> 1;   // -1 stays -1
+                c[j] = enc >> 2;   // -1 stays -1
                 const bool col_c = enc & 1;
-                fresh[j] = (enc >= 0) && ((col_c == row_c) ? (c[j] < row) : (col_c == first_c));
+                fresh[j] = (enc >= 0) && ((col_c == row_c) ? ((enc & 2) != 0) : (col_c == first_c));
             }
 #pragma unroll
             for (int j = 0; j < kGsChunk; j++)
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(kBlock, MINB) gs_sweep_kernel(const GsArgs a)
 // memory -- the same sequence of IEEE operations as the serial sweep.
 constexpr int kRowGroup = 128;
 
-__global__ void __launch_bounds__(kBlock, 1) gs_rows_kernel(const GsArgs a)
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) gs_rows_kernel(const GsArgs a)
 {
     __shared__ double sprod[kBlock / 32][kRowGroup];
     if (a.stop && *a.stop) return;
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(kBlock, 1) gs_rows_kernel(const GsArgs a)
         const int row = __ldg(a.perm + p);
         const double dg = __ldg(a.diag + p);
         const int beg = __ldg(a.slice_ptr + p), end = __ldg(a.slice_ptr + p + 1);
+        const bool tree = !a.exact && end - beg > 64;
         double r = __ldg(a.rhs + row);
         for (int base = beg; base < end; base += kRowGroup) {
             int c[4];
@@ -201,9 +203,9 @@ __global__ void __launch_bounds__(kBlock, 1) gs_rows_kernel(const GsArgs a)
                     enc = __ldg(a.col + k);
                     v[q] = __ldg(a.val + k);
                 }
-                c[q] = enc >> 1;
+                c[q] = enc >> 2;
                 const bool col_c = enc & 1;
-                fresh[q] = (enc >= 0) && ((col_c == row_c) ? (c[q] < row) : (col_c == first_c));
+                fresh[q] = (enc >= 0) && ((col_c == row_c) ? ((enc & 2) != 0) : (col_c == first_c));
             }
 #pragma unroll
             for (int q = 0; q < 4; q++)
@@ -227,6 +229,16 @@ __global__ void __launch_bounds__(kBlock, 1) gs_rows_kernel(const GsArgs a)
                     }
                 }
             } while (pending);
+            if (tree) {
+                // rows longer than 64 entries (as the SpMV does with them, spmv.cu): the lanes add their own
+                // products, a shuffle tree adds the lanes -- <= 1e-14 relative instead of bit-identical, and
+                // the row no longer costs one fp64 add latency per entry.  LSSPG_OPT_SPMV_EXACT turns it off.
+                double s = (v[0] * xv[0] + v[1] * xv[1]) + (v[2] * xv[2] + v[3] * xv[3]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                r = r - s;
+                continue;
+            }
 #pragma unroll
             for (int q = 0; q < 4; q++) prod[q * 32 + lane] = v[q] * xv[q];
             __syncwarp();
@@ -315,12 +327,19 @@ static int gs_sweep(lsspg_ctx *ctx, const GsDev &D, int post, const double *xold
         env_deep = std::min(std::max(env_deep, 1), 8);
     }
     // few dependency levels: a streaming kernel, fill the SMs; many: polling, keep residency low (tri.cu)
+    a.exact = ctx->opt_spmv_exact;
     const bool shallow = D.depth <= kGsShallowDepth;
-    const int per_sm = shallow ? env_shallow : env_deep;
-    int grid = std::min((D.num_slices + 7) / 8, ctx->num_sms * per_sm);
-    if (grid < 1) grid = 1;
-    if (D.mode == 1) LSSPG_LAUNCH(ctx, gs_rows_kernel, grid, kBlock, 0, a);
-    else if (shallow) LSSPG_LAUNCH(ctx, (gs_sweep_kernel<3, 8>), grid, kBlock, 0, a);
+    const bool streaming = D.depth <= kGsStreamDepth;
+    if (D.mode == 1) {   // a warp per row: 4 CTAs per SM unless the schedule is deep (polling)
+        const int per_sm = shallow ? 4 : env_deep;
+        const int grid = std::max(1, std::min((D.num_slices + 7) / 8, ctx->num_sms * per_sm));
+        if (shallow) LSSPG_LAUNCH(ctx, gs_rows_kernel<4>, grid, kBlock, 0, a);
+        else LSSPG_LAUNCH(ctx, gs_rows_kernel<1>, grid, kBlock, 0, a);
+        return 0;
+    }
+    const int per_sm = streaming ? env_shallow : env_deep;
+    const int grid = std::max(1, std::min((D.num_slices + 7) / 8, ctx->num_sms * per_sm));
+    if (streaming) LSSPG_LAUNCH(ctx, (gs_sweep_kernel<3, 8>), grid, kBlock, 0, a);
     else LSSPG_LAUNCH(ctx, (gs_sweep_kernel<1, 32>), grid, kBlock, 0, a);
     return 0;
 }
@@ -435,7 +454,8 @@ int lsspg_pc_create_amg(lsspg_ctx *ctx, const lsspg_amg_host *H, const lsspg_csr
         if (!rc && (!last || !H->coarse_dense)) {
             GsHost G;
             const bool cf_on = H->pars.cf_order && !last;
-            rc = gs_build_host(Lh.n, Lh.Ap.data(), Lh.Aj.data(), Lh.Ax.data(), cf_on ? Lh.cf.data() : nullptr, G);
+            rc = gs_build_host(Lh.n, Lh.Ap.data(), Lh.Aj.data(), Lh.Ax.data(), cf_on ? Lh.cf.data() : nullptr,
+                               cf_on ? Lh.rank.data() : nullptr, G);
             if (!rc) rc = gs_upload(ctx, G, L.gs);
         }
         const size_t vb = sizeof(double) * (size_t)std::max(Lh.n, 1);

@@ -238,6 +238,41 @@ void direct_interpolation(AmgLevelHost &L, const Graph &S, const lsspg_amg_pars 
     }
 }
 
+// Visiting order of the points inside their C / F block.  cf_order 0 / 1: ascending index (the serial
+// sweep of the library).  cf_order 2: MULTICOLOUR -- greedy colouring of each block's own coupling graph
+// (a point takes the smallest colour none of its already coloured same-block neighbours has), points
+// visited colour by colour, ascending index inside a colour.  Still a Gauss-Seidel sweep with exact
+// sequential semantics, but its dependency chains are as long as the number of colours (tens) instead
+// of the grid diameter (hundreds to thousands on the coarse levels), which is what a GPU needs.
+void visiting_ranks(AmgLevelHost &L, int cf_order)
+{
+    const int n = L.n;
+    L.rank.resize(n);
+    if (cf_order != 2) {
+        for (int i = 0; i < n; i++) L.rank[i] = i;
+        return;
+    }
+    std::vector<int> colour(n, -1), used;
+    int ncol = 0;
+    for (int i = 0; i < n; i++) {
+        used.assign(ncol + 1, 0);
+        for (int k = L.Ap[i]; k < L.Ap[i + 1]; k++) {
+            const int c = L.Aj[k];
+            if (c != i && L.cf[c] == L.cf[i] && colour[c] >= 0) used[colour[c]] = 1;
+        }
+        int col = 0;
+        while (col < ncol && used[col]) col++;
+        colour[i] = col;
+        ncol = std::max(ncol, col + 1);
+    }
+    // a coupling a_ij without a_ji would let two neighbours share a colour seen from j's side only:
+    // the schedule below never relies on colours being proper, only on ranks being a total order
+    std::vector<int> start(ncol + 1, 0);
+    for (int i = 0; i < n; i++) start[colour[i] + 1]++;
+    for (int c = 0; c < ncol; c++) start[c + 1] += start[c];
+    for (int i = 0; i < n; i++) L.rank[i] = start[colour[i]]++;
+}
+
 void transpose_csr(int nrows, int ncols, const std::vector<int> &p, const std::vector<int> &j,
                    const std::vector<double> &x, std::vector<int> &tp, std::vector<int> &tj, std::vector<double> &tx)
 {
@@ -340,13 +375,22 @@ int dense_inverse(const AmgLevelHost &L, std::vector<double> &inv)
 
 namespace lsspg {
 
-int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const int *cf, GsHost &G, int mode)
+int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const int *cf, const int *rank, GsHost &G,
+                  int mode)
 {
     G.n = n;
+    AMG_CHECK(n < (1 << 29), "amg: level too large for the smoother's column encoding");
+    auto blk = [&](int i) { return cf ? cf[i] : 1; };
+    auto rk = [&](int i) { return rank ? rank[i] : i; };
+    // rows in visiting order of their block (ranks are distinct inside a block)
+    std::vector<int> by_rank(n);
+    for (int i = 0; i < n; i++) by_rank[i] = i;
+    if (rank) std::sort(by_rank.begin(), by_rank.end(), [&](int a, int b) { return rank[a] < rank[b] || (rank[a] == rank[b] && a < b); });
     std::vector<int> lev(n, 0);
     int nlev[2] = {0, 0};   // [0] F block, [1] C block
-    for (int i = 0; i < n; i++) {
-        const int mine = cf ? cf[i] : 1;
+    for (int t = 0; t < n; t++) {
+        const int i = by_rank[t];
+        const int mine = blk(i);
         int l = 0;
         bool has_diag = false;
         for (int k = Ap[i]; k < Ap[i + 1]; k++) {
@@ -356,7 +400,7 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
                 has_diag = Ax[k] != 0.0;
                 continue;
             }
-            if (c < i && (cf ? cf[c] : 1) == mine) l = std::max(l, lev[c] + 1);
+            if (blk(c) == mine && rk(c) < rk(i)) l = std::max(l, lev[c] + 1);
         }
         AMG_CHECK(has_diag, "amg: row %d has no (or a zero) diagonal entry", i);
         lev[i] = l;
@@ -364,19 +408,21 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
     }
     G.levels_c = nlev[1];
     G.levels_f = nlev[0];
-    // order: C block by level, then F block by level; ascending row index inside a level
+    // order: C block by level, then F block by level; ascending rank inside a level
     const int total_lev = nlev[1] + nlev[0];
     std::vector<int> start(total_lev + 1, 0);
-    auto bucket = [&](int i) { return (cf ? cf[i] : 1) ? lev[i] : nlev[1] + lev[i]; };
+    auto bucket = [&](int i) { return blk(i) ? lev[i] : nlev[1] + lev[i]; };
     for (int i = 0; i < n; i++) start[bucket(i) + 1]++;
     for (int l = 0; l < total_lev; l++) start[l + 1] += start[l];
     std::vector<int> order(n);
     {
         std::vector<int> pos(start.begin(), start.end() - 1);
-        for (int i = 0; i < n; i++) order[pos[bucket(i)]++] = i;
+        for (int t = 0; t < n; t++) order[pos[bucket(by_rank[t])]++] = by_rank[t];
     }
+    auto encode = [&](int i, int c) { return (c << 2) | ((blk(c) == blk(i) && rk(c) < rk(i)) ? 2 : 0) | (blk(c) & 1); };
     // deep schedules of wide rows: one ticket per ROW (a warp works on it), entries contiguous
-    if (mode < 0) mode = (total_lev > kGsShallowDepth && n > 0 && (double)(Ap[n] - n) / n > 28.0) ? 1 : 0;
+    // (wide rows in 32-row slices would walk the row in chunks, two memory latencies per chunk and level)
+    if (mode < 0) mode = (n > 0 && (double)(Ap[n] - n) / n > 28.0) ? 1 : 0;
     G.mode = mode;
     if (mode == 1) {
         G.num_slices = n;
@@ -398,7 +444,7 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
                     G.diag[p] = Ax[q];
                     continue;
                 }
-                G.col[k] = (c << 1) | ((cf ? cf[c] : 1) & 1);
+                G.col[k] = encode(i, c);
                 G.val[k] = Ax[q];
                 k++;
             }
@@ -450,7 +496,7 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
                     G.diag[sl * 32 + q] = Ax[p];
                     continue;
                 }
-                G.col[base + (long long)k * 32 + q] = (c << 1) | ((cf ? cf[c] : 1) & 1);
+                G.col[base + (long long)k * 32 + q] = encode(i, c);
                 G.val[base + (long long)k * 32 + q] = Ax[p];
                 k++;
             }
@@ -517,6 +563,7 @@ int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hA
             break;
         }
         direct_interpolation(L, S, pr);
+        visiting_ranks(L, pr.cf_order);
         transpose_csr(L.n, L.nc, L.Pp, L.Pj, L.Px, L.Rp, L.Rj, L.Rx);
         std::vector<int> Tp, Tj;
         std::vector<double> Tx;
@@ -533,6 +580,7 @@ int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hA
         AmgLevelHost &L = H->levels.back();
         L.nc = 0;
         L.cf.assign(L.n, 1);
+        visiting_ranks(L, 0);   // the last level is swept in natural order (when it is swept at all)
         L.Pp.clear();
         L.Rp.clear();
         if (L.n <= pr.coarse_dense_max) {
@@ -583,6 +631,13 @@ int lsspg_amg_host_level_get(const lsspg_amg_host *H, int l, int *Ap, int *Aj, d
     return 0;
 }
 
+int lsspg_amg_host_level_rank(const lsspg_amg_host *H, int l, int *rank)
+{
+    AMG_CHECK(H && l >= 0 && l < (int)H->levels.size() && rank, "lsspg_amg_host_level_rank: bad argument");
+    copy_out(rank, H->levels[l].rank);
+    return 0;
+}
+
 int lsspg_amg_host_coarse_inverse(const lsspg_amg_host *H, double *inv)
 {
     AMG_CHECK(H && inv && H->coarse_dense, "lsspg_amg_host_coarse_inverse: no dense inverse");
@@ -612,7 +667,8 @@ int lsspg_debug_amg_walk_gs_host(const lsspg_amg_host *H, int l, int post, const
     const bool cf_on = H->pars.cf_order && l + 1 < (int)H->levels.size();
     const int mode = (post >> 1) - 1;   // post bits 1..2: 0 = schedule chosen as on the device, 1 = slices, 2 = rows
     post &= 1;
-    if (gs_build_host(L.n, L.Ap.data(), L.Aj.data(), L.Ax.data(), cf_on ? L.cf.data() : nullptr, G, mode)) return 1;
+    if (gs_build_host(L.n, L.Ap.data(), L.Aj.data(), L.Ax.data(), cf_on ? L.cf.data() : nullptr,
+                      cf_on ? L.rank.data() : nullptr, G, mode)) return 1;
     std::vector<char> written(L.n, 0);
     const int nf = G.num_slices - G.slices_c;
     if (info) {
@@ -628,9 +684,9 @@ int lsspg_debug_amg_walk_gs_host(const lsspg_amg_host *H, int l, int post, const
             const int row = G.perm[p];
             double r = hb[row];
             for (int k = G.slice_ptr[p]; k < G.slice_ptr[p + 1]; k++) {
-                const int enc = G.col[k], c = enc >> 1;
+                const int enc = G.col[k], c = enc >> 2;
                 const bool col_c = enc & 1;
-                const bool is_new = (col_c == row_c) ? (c < row) : (col_c == !post);
+                const bool is_new = (col_c == row_c) ? ((enc & 2) != 0) : (col_c == !post);
                 if (is_new) AMG_CHECK(written[c], "amg walk: row %d (ticket %d) needs x[%d] before it is written", row, t, c);
                 r = r - G.val[k] * (is_new ? hx_new[c] : hx_old[c]);
             }
@@ -652,9 +708,9 @@ int lsspg_debug_amg_walk_gs_host(const lsspg_amg_host *H, int l, int post, const
             for (int k = 0; k < w; k++) {
                 const int enc = G.col[base + (long long)k * 32 + q];
                 if (enc < 0) continue;
-                const int c = enc >> 1;
+                const int c = enc >> 2;
                 const bool col_c = enc & 1;
-                const bool is_new = (col_c == row_c) ? (c < row) : (col_c == !post);
+                const bool is_new = (col_c == row_c) ? ((enc & 2) != 0) : (col_c == !post);
                 if (is_new) AMG_CHECK(written[c], "amg walk: row %d (ticket %d) needs x[%d] before it is written", row, t, c);
                 r = r - G.val[base + (long long)k * 32 + q] * (is_new ? hx_new[c] : hx_old[c]);
             }

@@ -50,8 +50,8 @@ def main(args, rank, world, local_rank):
         pc = api.Preconditioner.non(ctx, shard.n_owned)
         pcname = "no preconditioner"
     elif args.workload == "cg_amg":
-        pc = api.Preconditioner.sxamg(ctx, shard.diag_block(), zero_guess=1)
-        pcname = "block-Jacobi SX-AMG-style V-cycle (zero initial guess)"
+        pc = api.Preconditioner.sxamg(ctx, shard.diag_block(), zero_guess=1, cf_order=args.amg_order)
+        pcname = "block-Jacobi SX-AMG-style V-cycle (zero initial guess, cf_order %d)" % args.amg_order
     else:
         Lf, Uf = api.ilu_factor(shard.diag_block(), "iluk", level=0)
         pc = api.Preconditioner(ctx, "ilu", shard.n_owned, Lf, Uf)

@@ -187,6 +187,7 @@ class OrcAmg:
             for key in ("P", "R"):
                 arrs += [None] * 3 if L[key] is None else [np.ascontiguousarray(a) for a in L[key]]
             arrs.append(np.ascontiguousarray(L["cf"], dtype=np.int32))
+            arrs.append(None if L.get("rank") is None else np.ascontiguousarray(L["rank"], dtype=np.int32))
             self.keep.append(arrs)
             lib.orc_amg_set_level(self.h, l, int(L["n"]), int(L["nc"]), *[_ptr(a) for a in arrs])
 
@@ -270,10 +271,13 @@ class Port:
                                 _ptr(rhs), _ptr(cache))
         return x
 
-    def gs_sweep(self, A, cf, post, b, x):
-        """one in-place Gauss-Seidel sweep (amg_oracle.c); cf=None: natural order"""
+    def gs_sweep(self, A, cf, post, b, x, rank=None):
+        """one in-place Gauss-Seidel sweep (amg_oracle.c); cf=None: natural order; rank: visiting
+        order inside a block (None: by index)"""
         x = np.array(x, dtype=np.float64)
-        self.lib.orc_gs_sweep(len(b), _ptr(A[0]), _ptr(A[1]), _ptr(A[2]), _ptr(cf), int(post), _ptr(b), _ptr(x))
+        rank = None if rank is None else np.ascontiguousarray(rank, dtype=np.int32)
+        self.lib.orc_gs_sweep_ranked(len(b), _ptr(A[0]), _ptr(A[1]), _ptr(A[2]), _ptr(cf), _ptr(rank), int(post),
+                                     _ptr(b), _ptr(x))
         return x
 
     def amg(self, levels, pre=2, post=2, cf_order=1, coarse_inv=None, coarse_sweeps=40, zero_guess=0):

@@ -28,7 +28,7 @@ typedef struct orc_amg_level_ {
     const int *Ap, *Aj; const double *Ax;
     const int *Pp, *Pj; const double *Px;
     const int *Rp, *Rj; const double *Rx;
-    const int *cf;
+    const int *cf, *rank;
     double *x, *b, *r;
 } orc_amg_level;
 
@@ -41,14 +41,22 @@ typedef struct orc_amg_ {
 /* One Gauss-Seidel sweep in place, sequential: pre-smoothing visits the C points in ascending
  * order and then the F points, post-smoothing the F points and then the C points; cf == NULL is
  * the natural order.  Row update: t = b_i; t -= a_ij x_j for j != i in column order; x_i = t / a_ii. */
-void orc_gs_sweep(int n, const int *Ap, const int *Aj, const double *Ax, const int *cf, int post,
-                  const double *b, double *x)
+void orc_gs_sweep_ranked(int n, const int *Ap, const int *Aj, const double *Ax, const int *cf, const int *rank,
+                         int post, const double *b, double *x)
 {
-    int pass, i, k;
+    /* rank (a permutation of 0..n-1, NULL = identity) is the visiting order inside a block: the
+     * multicolour variant (cf_order 2) visits a block colour by colour instead of by index */
+    int pass, q, k;
+    int *seq = NULL;
+    if (rank != NULL) {
+        seq = malloc(sizeof(int) * (n > 0 ? n : 1));
+        for (q = 0; q < n; q++) seq[rank[q]] = q;
+    }
     for (pass = 0; pass < 2; pass++) {
         const int want = post ? pass : 1 - pass;
         if (cf == NULL && pass == 1) break;
-        for (i = 0; i < n; i++) {
+        for (q = 0; q < n; q++) {
+            const int i = seq ? seq[q] : q;
             double t, d = 0.;
             if (cf != NULL && cf[i] != want) continue;
             t = b[i];
@@ -59,6 +67,13 @@ void orc_gs_sweep(int n, const int *Ap, const int *Aj, const double *Ax, const i
             x[i] = t / d;
         }
     }
+    free(seq);
+}
+
+void orc_gs_sweep(int n, const int *Ap, const int *Aj, const double *Ax, const int *cf, int post,
+                  const double *b, double *x)
+{
+    orc_gs_sweep_ranked(n, Ap, Aj, Ax, cf, NULL, post, b, x);
 }
 
 orc_amg *orc_amg_create(int nl, int pre, int post, int cf_order, int coarse_dense, int coarse_sweeps,
@@ -73,12 +88,13 @@ orc_amg *orc_amg_create(int nl, int pre, int post, int cf_order, int coarse_dens
 
 void orc_amg_set_level(orc_amg *m, int l, int n, int nc, const int *Ap, const int *Aj, const double *Ax,
                        const int *Pp, const int *Pj, const double *Px, const int *Rp, const int *Rj,
-                       const double *Rx, const int *cf)
+                       const double *Rx, const int *cf, const int *rank)
 {
     orc_amg_level *L = &m->lv[l];
     L->n = n; L->nc = nc;
     L->Ap = Ap; L->Aj = Aj; L->Ax = Ax; L->Pp = Pp; L->Pj = Pj; L->Px = Px; L->Rp = Rp; L->Rj = Rj; L->Rx = Rx;
     L->cf = cf;
+    L->rank = rank;
     L->x = calloc(n > 0 ? n : 1, sizeof(double));
     L->b = calloc(n > 0 ? n : 1, sizeof(double));
     L->r = calloc(n > 0 ? n : 1, sizeof(double));
@@ -104,7 +120,7 @@ void orc_amg_cycle(orc_amg *m, double *x, const double *rhs)
         double *xl = l ? L->x : x;
         const double *bl = l ? L->b : rhs;
         const int *cf = m->cf_order ? L->cf : NULL;
-        for (s = 0; s < m->pre; s++) orc_gs_sweep(L->n, L->Ap, L->Aj, L->Ax, cf, 0, bl, xl);
+        for (s = 0; s < m->pre; s++) orc_gs_sweep_ranked(L->n, L->Ap, L->Aj, L->Ax, cf, cf ? L->rank : NULL, 0, bl, xl);
         orc_mv(3, L->n, L->Ap, L->Aj, L->Ax, -1., xl, 1., bl, L->r);       /* r = b - A x */
         orc_mv(0, L->nc, L->Rp, L->Rj, L->Rx, 1., L->r, 0., NULL, C->b);   /* b_c = R r */
         for (i = 0; i < C->n; i++) C->x[i] = 0.;
@@ -130,7 +146,7 @@ void orc_amg_cycle(orc_amg *m, double *x, const double *rhs)
         const double *bl = l ? L->b : rhs;
         const int *cf = m->cf_order ? L->cf : NULL;
         orc_mv(2, L->n, L->Pp, L->Pj, L->Px, 1., C->x, 1., xl, xl);        /* x += P x_c */
-        for (s = 0; s < m->post; s++) orc_gs_sweep(L->n, L->Ap, L->Aj, L->Ax, cf, 1, bl, xl);
+        for (s = 0; s < m->post; s++) orc_gs_sweep_ranked(L->n, L->Ap, L->Aj, L->Ax, cf, cf ? L->rank : NULL, 1, bl, xl);
     }
 }
 

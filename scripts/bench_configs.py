@@ -66,8 +66,8 @@ def run_case(ctx, tag, desc, A, solver, pckind, maxit=3000, **kw):
         pc = api.Preconditioner.iluk(ctx, A, level=1)
     elif pckind == "ilut":
         pc = api.Preconditioner.ilut(ctx, A)
-    elif pckind == "amg":
-        pc = api.Preconditioner.sxamg(ctx, A, share=dA, zero_guess=1)
+    elif pckind in ("amg", "amg_mc"):
+        pc = api.Preconditioner.sxamg(ctx, A, share=dA, zero_guess=1, cf_order=2 if pckind == "amg_mc" else 1)
     t_setup = time.perf_counter() - t0
     # b = 1 as exam.cxx; the power-law operator has unit row sums (x = 1 would solve it at once): oscillating b
     rhs = np.ones(n) if not tag.startswith("C5") else np.sin(np.arange(n) * 0.37) + 1.5
@@ -113,6 +113,7 @@ def main():
         ("C3a", "cd3d_%d BiCGStab+ILUK(1)" % N3, lambda: g.cd3d(N3), "bicgstab", "iluk1", {}),
         ("C3b", "cd3d_%d GMRES(30)+ILUT" % N3, lambda: g.cd3d(N3), "gmres", "ilut", dict(restart=30)),
         ("C4", "lap3d_%d CG+SX-AMG-style V-cycle (zero initial guess)" % N3, lambda: g.lap3d(N3), "cg", "amg", {}),
+        ("C4b", "lap3d_%d CG+SX-AMG-style V-cycle, multicolour smoother (zero initial guess)" % N3, lambda: g.lap3d(N3), "cg", "amg_mc", {}),
         ("C5", "powerlaw n=%d IDRS(4) unpreconditioned" % NP, lambda: g.powerlaw(NP), "idrs", "non", dict(idrs=4)),
     ]
     for tag, desc, gen, solver, pckind, kw in cases:

@@ -110,7 +110,7 @@ def test_interpolation_reproduces_constants_on_zero_row_sum_rows(hier):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("cf_order", [1, 0])
+@pytest.mark.parametrize("cf_order", [1, 0, 2])
 def test_smoother_schedule_walk_equals_the_sequential_sweep(hier, port, name, cf_order):
     """Slices walked in ticket order, operands taken from x_new / x_old by the schedule's rule,
     every x_new operand already written when it is read: same bits as the serial in-place sweep."""
@@ -118,14 +118,39 @@ def test_smoother_schedule_walk_equals_the_sequential_sweep(hier, port, name, cf
     for l, L in enumerate(H.levels):
         last = l == len(H.levels) - 1
         b, x0 = tvec(L["n"], l), tvec(L["n"], l + 5)
+        assert sorted(L["rank"]) == list(range(L["n"]))          # a total visiting order
+        if cf_order != 2 or last:
+            assert np.array_equal(L["rank"], np.arange(L["n"]))
         for post in (0, 1):
-            xo = port.gs_sweep(L["A"], L["cf"] if (cf_order and not last) else None, post, b, x0)
+            xo = port.gs_sweep(L["A"], L["cf"] if (cf_order and not last) else None, post, b, x0,
+                               rank=L["rank"] if (cf_order and not last) else None)
             for mode in (0, 1, 2):    # device's choice, 32-row slices, one ticket per row
                 xn, info = H.walk_gs_host(l, post, b, x0, mode=mode)
                 assert np.array_equal(xn, xo)
         if l == 0 and cf_order and name in ("lap2d_100", "lap3d_32", "cd3d_12"):
             # red-black: C points are mutually independent and so are the F points
             assert info["levels_c"] == 1 and info["levels_f"] == 1
+
+
+def test_multicolour_order_has_short_dependency_chains(hier, port):
+    """cf_order=2: each block is visited colour by colour -- still a sequential Gauss-Seidel sweep
+    (the walk above equals the serial loop in that order), but the chains are tens of rows long
+    where the index order gives hundreds: every level becomes a streaming sweep on the GPU."""
+    deep = hier("lap3d_32")
+    flat = hier("lap3d_32", cf_order=2)
+    n = flat.levels[0]["n"]
+    for l in range(len(flat.levels) - 1):
+        L = flat.levels[l]
+        b, x0 = np.ones(L["n"]), np.zeros(L["n"])
+        d_new = flat.walk_gs_host(l, 0, b, x0)[1]
+        d_old = deep.walk_gs_host(l, 0, b, x0)[1]
+        assert d_new["levels_c"] + d_new["levels_f"] <= 64
+        assert d_new["levels_c"] + d_new["levels_f"] <= d_old["levels_c"] + d_old["levels_f"]
+    assert deep.walk_gs_host(1, 0, np.ones(deep.levels[1]["n"]), np.zeros(deep.levels[1]["n"]))[1]["levels_f"] > 64
+    # and it smooths as well: same cycle counts to 1e-8
+    a = port.amg(deep.levels, coarse_inv=deep.coarse_inv).solve(np.ones(n), tol=1e-8, maxit=50)
+    b = port.amg(flat.levels, coarse_inv=flat.coarse_inv, cf_order=2).solve(np.ones(n), tol=1e-8, maxit=50)
+    assert abs(a["nits"] - b["nits"]) <= 2 and b["nits"] <= 10
 
 
 def test_setup_rejects_unsorted_columns_and_missing_diagonals():

@@ -31,7 +31,7 @@ def oracle_amg(port, H):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("pars", [dict(), dict(cf_order=0), dict(zero_guess=1, pre_iter=1, post_iter=3),
+@pytest.mark.parametrize("pars", [dict(), dict(cf_order=0), dict(cf_order=2), dict(zero_guess=1, pre_iter=1, post_iter=3),
                                   dict(coarse_dense_max=0, coarse_sweeps=7, coarse_dof=300)])
 def test_cycle_equals_restatement(ctx, port, name, pars):
     A, H, dA, pc = setup(ctx, name, **pars)
@@ -115,6 +115,17 @@ def test_other_drivers_accept_the_amg_preconditioner(ctx, solver):
     import scipy.sparse as sp
     M = sp.csr_matrix((A[2], A[1], A[0]), shape=(n, n))
     assert np.linalg.norm(np.ones(n) - M @ x) <= 2e-7 * np.sqrt(n)
+
+
+def test_pcg_with_multicolour_amg_matches_restatement(ctx, port):
+    A, H, dA, pc = setup(ctx, "lap3d_32", zero_guess=1, cf_order=2)
+    n = H.levels[0]["n"]
+    want = port.solve("cg", A, np.ones(n), amg=oracle_amg(port, H), maxit=100, nhist=30)
+    x = np.zeros(n)
+    got = api.lssp_solver_solve(ctx, "cg", dA, pc, np.ones(n), x, maxit=100, nhist=30)
+    assert got["nits"] == want["nits"] and got["nits"] <= 10
+    k = want["nits"]
+    assert np.allclose(got["hist"][:k], want["hist"][:k], rtol=1e-9, atol=1e-12 * want["hist"][0])
 
 
 def test_amg_on_a_larger_grid_has_grid_independent_convergence(ctx):
