@@ -17,8 +17,12 @@ import numpy as np
 
 
 def main(args, rank, world, local_rank):
-    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...") on fd 1 from C,
+    # so fd 1 is pointed at stderr for the run and the JSON line goes to the saved descriptor
+    import sys
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as td
 
@@ -143,7 +147,8 @@ def main(args, rank, world, local_rank):
                         "d2h_bytes_per_step": 8 * no * world},
                 "roofline": roof,
                 "setup_s": {"generate_and_shard": t_gen, "pc_host_setup_and_upload": t_pc}}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     D.close()
     td.barrier()
     td.destroy_process_group()
