@@ -34,7 +34,8 @@ namespace lsspg {
 constexpr unsigned long long kGsSentinelBits = 0xFFF8DEADBEEF0002ull;
 
 struct GsDev {
-    int n = 0, num_slices = 0, slices_c = 0, depth = 0, mode = 0;
+    int n = 0, num_slices = 0, slices_c = 0, depth = 0, mode = 0, levels_c = 0;
+    std::vector<int> level_ptr;   // host copy: slices of every dependency level (per-level launches)
     int *perm = nullptr;
     double *diag = nullptr;
     int *slice_ptr = nullptr;
@@ -162,6 +163,51 @@ __global__ void __launch_bounds__(kBlock, MINB) gs_sweep_kernel(const GsArgs a)
     }
 }
 
+// Shallow schedules (a handful of dependency levels: the fine level of a stencil operator under C/F
+// ordering has two, multicolour levels have about ten): ONE LAUNCH PER DEPENDENCY LEVEL.  Stream order
+// then guarantees that every x_new operand of the level exists -- no sentinel fill, no polling, a lean
+// streaming kernel at full occupancy; a warp takes a 32-row slice, a lane its row, products subtracted
+// in column order as everywhere else.
+__global__ void __launch_bounds__(kBlock) gs_level_kernel(const GsArgs a, int s_begin, int s_end, int row_c, int first_c)
+{
+    if (a.stop && *a.stop) return;
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int s = s_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < s_end; s += warps) {
+        const long long slot = (long long)s * 32 + lane;
+        const int row = __ldg(a.perm + slot);
+        const double dg = __ldg(a.diag + slot);
+        const int p0 = __ldg(a.slice_ptr + s);
+        const int w = __ldg(a.slice_ptr + s + 1) - p0;
+        double r = (row >= 0) ? __ldg(a.rhs + row) : 0.0;
+        const long long base = (long long)p0 * 32 + lane;
+        for (int k0 = 0; k0 < w; k0 += 4) {
+            int enc[4];
+            double v[4], xv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                enc[j] = -1;
+                v[j] = 0.0;
+                if (k0 + j < w) {
+                    enc[j] = __ldg(a.col + base + (long long)(k0 + j) * 32);
+                    v[j] = __ldg(a.val + base + (long long)(k0 + j) * 32);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = enc[j] >> 2;
+                const bool col_c = enc[j] & 1;
+                const bool fresh = (col_c == (bool)row_c) ? ((enc[j] & 2) != 0) : (col_c == (bool)first_c);
+                xv[j] = (enc[j] < 0) ? 0.0 : (fresh ? __ldcg(a.xnew + c) : __ldg(a.xold + c));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (enc[j] >= 0) r = r - v[j] * xv[j];
+        }
+        if (row >= 0) a.xnew[row] = r / dg;
+    }
+}
+
 // Row schedule (deep schedules of wide rows, GsHost mode 1): one ticket = one row, worked on by a
 // warp.  The lanes fetch the row's entries and operands side by side (one memory latency for up to
 // 128 entries), form the products, and every lane then subtracts them in column order from shared
@@ -277,6 +323,8 @@ static int gs_upload(lsspg_ctx *ctx, const GsHost &G, GsDev &D)
     D.slices_c = G.slices_c;
     D.depth = G.levels_c + G.levels_f;
     D.mode = G.mode;
+    D.levels_c = G.levels_c;
+    D.level_ptr = G.level_ptr;
     const size_t slots = G.perm.size();
     LSSPG_CUDA(cudaMalloc(&D.perm, sizeof(int) * std::max<size_t>(slots, 1)));
     LSSPG_CUDA(cudaMalloc(&D.diag, sizeof(double) * std::max<size_t>(slots, 1)));
@@ -308,16 +356,32 @@ static void gs_free(GsDev &D)
 static int gs_sweep(lsspg_ctx *ctx, const GsDev &D, int post, const double *xold, double *xnew, const double *rhs, bool guarded)
 {
     if (D.n == 0) return 0;
-    double sentinel;
-    const unsigned long long bits = kGsSentinelBits;
-    memcpy(&sentinel, &bits, sizeof(double));
-    LSSPG_TRY(vec_set(ctx, D.n, xnew, sentinel, guarded));
     GsArgs a;
     a.perm = D.perm; a.diag = D.diag; a.slice_ptr = D.slice_ptr; a.col = D.col; a.val = D.val;
     a.counter = D.counter; a.num_slices = D.num_slices; a.slices_c = D.slices_c; a.post = post;
     a.xold = xold; a.xnew = xnew; a.rhs = rhs;
     a.stop = guarded ? ctx->d_flags + FLAG_STOP : nullptr;
     a.err = ctx->d_flags + FLAG_TRI_TIMEOUT;
+    a.exact = ctx->opt_spmv_exact;
+    static int per_level = -1;
+    if (per_level < 0) per_level = getenv("LSSPG_GS_PER_LEVEL") ? atoi(getenv("LSSPG_GS_PER_LEVEL")) : 1;
+    if (D.mode == 0 && D.depth <= kGsStreamDepth && per_level) {
+        // one launch per dependency level, block order as the sweep visits them
+        const int nlev = (int)D.level_ptr.size() - 1;
+        for (int t = 0; t < nlev; t++) {
+            const int nf = nlev - D.levels_c;
+            const int l = post ? (t < nf ? D.levels_c + t : t - nf) : t;
+            const int s0 = D.level_ptr[l], s1 = D.level_ptr[l + 1];
+            if (s1 <= s0) continue;
+            const int grid = std::max(1, std::min((s1 - s0 + 7) / 8, ctx->num_sms * 6));   // 40 registers: 6 CTAs / SM
+            LSSPG_LAUNCH(ctx, gs_level_kernel, grid, kBlock, 0, a, s0, s1, l < D.levels_c ? 1 : 0, post ? 0 : 1);
+        }
+        return 0;
+    }
+    double sentinel;
+    const unsigned long long bits = kGsSentinelBits;
+    memcpy(&sentinel, &bits, sizeof(double));
+    LSSPG_TRY(vec_set(ctx, D.n, xnew, sentinel, guarded));
     static int env_shallow = -1, env_deep = -1;
     if (env_shallow < 0) {
         const char *e;

@@ -453,10 +453,13 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
         return 0;
     }
     long long nslices = 0, cslices = 0;
+    G.level_ptr.assign((size_t)total_lev + 1, 0);
     for (int l = 0; l < total_lev; l++) {
+        G.level_ptr[l] = (int)nslices;
         nslices += (start[l + 1] - start[l] + 31) / 32;
         if (l == nlev[1] - 1) cslices = nslices;
     }
+    G.level_ptr[total_lev] = (int)nslices;
     AMG_CHECK(nslices * 32 < (1ll << 31), "amg: too many slices");
     G.num_slices = (int)nslices;
     G.slices_c = (int)cslices;

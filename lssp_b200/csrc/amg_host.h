@@ -34,6 +34,7 @@ struct GsHost {
     std::vector<int> perm;        // [num_slices*32] row of the slot, -1 = empty
     std::vector<double> diag;     // [num_slices*32]
     std::vector<int> slice_ptr;   // [num_slices+1]
+    std::vector<int> level_ptr;   // mode 0: first slice of every dependency level, C levels then F levels (+ end)
     std::vector<int> col;
     std::vector<double> val;
 };
