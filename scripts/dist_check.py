@@ -78,6 +78,35 @@ def main():
             print("%-28s P=%d spmv_bit_exact=%s nits=%d (reference blocked ILU: %s) true_residual=%.3e ok=%s"
                   % (key, world, spmv_ok, r["nits"], want["nits"] if want else "-", res, its_ok and res_ok and spmv_ok))
         ok = ok and spmv_ok and its_ok and res_ok
+    # every driver, sharded: same block-Jacobi ILU(0) as a 1-GPU run of the blocked preconditioner on the whole
+    # matrix (a second, non-distributed context on this rank) -- only the order of the reduction sums differs
+    A = matrix("lap3d_32")
+    n = len(A[0]) - 1
+    blk, r0, r1 = dist.block_rows(n, world, rank)
+    S = dist.make_shard(dist.slice_rows(A, r0, r1), n, world, rank)
+    D = dist.DeviceShard(ctx, S, None)
+    others.append(D)
+    Lb, Ub = api.ilu_factor(S.diag_block(), "iluk", level=0)
+    pc = api.Preconditioner(ctx, "ilu", S.n_owned, Lb, Ub)
+    solo = api.Context(local)
+    sA = api.Csr(solo, A)
+    spc = api.Preconditioner.iluk(solo, A, level=0, blk_size=blk)
+    for s in ("gmres", "lgmres", "rgmres", "rlgmres", "bicgstab", "bicgstabl", "bicgsafe", "cg", "cgs", "gpbicg", "cr",
+              "crs", "bicrstab", "bicrsafe", "gpbicr", "qmrcgstab", "tfqmr", "orthomin"):
+        x1 = np.zeros(n)
+        want = api.lssp_solver_solve(solo, s, sA, spc, np.ones(n), x1, maxit=3000, restart=30)
+        hx = np.zeros(S.n_owned)
+        got = api.lssp_solver_solve(ctx, s, D.A, pc, np.ones(S.n_owned), hx, maxit=3000, restart=30)
+        xs = [None] * world
+        td.all_gather_object(xs, hx)
+        xfull = np.concatenate(xs)
+        res = np.linalg.norm(np.ones(n) - port.mv(0, A, xfull))
+        good = abs(got["nits"] - want["nits"]) <= max(2, int(0.15 * want["nits"])) and res <= 3e-7 * np.sqrt(n)
+        if rank == 0:
+            print("lap3d_32/%-10s sharded P=%d nits=%d (1 GPU, same blocked ILU(0): %d) true_residual=%.3e ok=%s"
+                  % (s, world, got["nits"], want["nits"], res, good))
+        ok = ok and good
+    solo.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     td.all_reduce(flag, op=td.ReduceOp.MIN)
     for D in others:
