@@ -337,8 +337,11 @@ def main():
     ms_spmv = timed(lambda: dA.mv(api.MV_MXY, b, y), 20)
     spmv_gbs = dA.spmv_bytes / ms_spmv / 1e6
     roof_spmv = {"bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
-                 "traffic": ncu_traffic("spmv_tiles_kernel@lap3d_%d" % args.grid) if args.workload != "bicgstab_ilu0" else None,
-                 "ms": ms_spmv, "bytes": dA.spmv_bytes, "peak_kind": peak_kind}
+                 "traffic": ncu_traffic("spmv_pipe_kernel@lap3d_%d" % args.grid) if args.workload != "bicgstab_ilu0" else None,
+                 "ms": ms_spmv, "bytes": dA.spmv_bytes, "peak_kind": peak_kind, "frac_of_8TBs": spmv_gbs / 8000.0,
+                 "kernel": "spmv_pipe_kernel (cp.async.bulk double-buffered tiles)",
+                 "note": "peak is MEASURED_PEAKS.json's torch copy_ figure (half reads, half writes); this kernel's "
+                         "traffic is 94 % reads and can exceed it -- see frac_of_8TBs for the nominal HBM3e roofline"}
     ms_per_it = total_ms / its
     if pckind == "iluk":
         ms_pcap = timed(lambda: pc.apply(y, b), 10)

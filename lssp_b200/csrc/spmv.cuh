@@ -20,6 +20,8 @@ struct lsspg_csr {
     mutable int occupancy[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // resident CTAs / SM per (kind, ndot)
     int *d_tile_row = nullptr;  // [num_tiles + 1] first row of every tile
     unsigned char *d_tile_kind = nullptr;  // [num_tiles]
+    int *d_tile_e0 = nullptr;              // [num_tiles + 1] first nnz of every tile (bulk-copy pipeline kernel)
+    mutable int occupancy_pipe[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     lsspg_halo *halo = nullptr;            // row shard of a distributed matrix: ghost columns follow the owned ones
 };
 

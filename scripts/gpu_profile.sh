@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-2000} -c 40
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit: $?"
 $CMD > gpurun_out/prof_plain2.json 2>> gpurun_out/prof_plain.err &&
-ncu --set full --clock-control none --import-source on -k regex:spmv_tiles_kernel -s 20 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:spmv_ -s 20 -c 1 \
     -o gpurun_out/prof_spmv -f $CMD > gpurun_out/ncu_spmv.log 2>&1
 echo "spmv capture exit: $?"
 $CMD > gpurun_out/prof_plain3.json 2>> gpurun_out/prof_plain.err &&

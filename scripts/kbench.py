@@ -36,6 +36,10 @@ def main():
     sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [128, 256]
     opts = [a for a in sys.argv[1:] if not a.isdigit()]
     ctx = api.Context(0)
+    if "pipe" in opts:      # SpMV through the bulk-copy pipeline kernel
+        ctx.set_option(api.OPT_SPMV_KERNEL, 2)
+    if "ldg" in opts:       # SpMV through the register-staged kernel
+        ctx.set_option(api.OPT_SPMV_KERNEL, 1)
     out = []
     for N in sizes:
         t0 = time.time()
