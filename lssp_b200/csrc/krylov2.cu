@@ -278,7 +278,6 @@ int krylov_idrs(KrylovArgs &k, const lsspg_solver_opts *raw)
 {
     lsspg_ctx *ctx = k.ctx;
     const int n = k.n;
-    LSSPG_CHECK(!distributed(ctx), "idrs: the shadow vectors come from one global rand() stream; single GPU only");
     int s = k.idrs;
     if (s <= 0) s = 4;                                                // :101
     // this driver reads the raw settings, without the usual defaults (:97-100, :121-130)
@@ -310,11 +309,36 @@ int krylov_idrs(KrylovArgs &k, const lsspg_solver_opts *raw)
     h *= tol_rbs;
     if (tol < tol_abs) tol = tol_abs;
     if (tol < h) tol = h;
-    {   // shadow space: glibc stream, k outer / i inner (:139-144), generated on the host
+    {   // shadow space: glibc stream, k outer / i inner (:139-144), generated on the host.  Row-sharded: every
+        // rank walks the SAME global stream and keeps the entries of its own rows, so the shadow vectors --
+        // and with them the iteration -- are those of the serial run whatever the number of GPUs
+        long long row0 = 0, n_global = n;
+        if (distributed(ctx)) {
+            int rank = 0, nranks = 1;
+            LSSPG_TRY(lsspg_comm_size(ctx, &rank, &nranks));
+            std::vector<double> cnt((size_t)nranks, 0.0);
+            cnt[rank] = (double)n;
+            double *d_cnt = nullptr;
+            LSSPG_CUDA(cudaMalloc(&d_cnt, sizeof(double) * (size_t)nranks));
+            LSSPG_CUDA(cudaMemcpyAsync(d_cnt, cnt.data(), sizeof(double) * (size_t)nranks, cudaMemcpyHostToDevice, ctx->stream));
+            int rc = comm_allreduce(ctx, d_cnt, nranks);
+            if (!rc && cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(double) * (size_t)nranks, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = 1;
+            if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = 1;
+            cudaFree(d_cnt);
+            LSSPG_CHECK(rc == 0, "idrs: could not gather the row counts of the ranks");
+            n_global = 0;
+            for (int q = 0; q < nranks; q++) {
+                if (q < rank) row0 += (long long)cnt[q];
+                n_global += (long long)cnt[q];
+            }
+        }
         std::vector<double> hp((size_t)n);
         srand(0);
         for (int kq = 0; kq < s; kq++) {
-            for (int i = 0; i < n; i++) hp[i] = (rand() * 1.) / (1. * RAND_MAX);
+            for (long long i = 0; i < n_global; i++) {
+                const double val = (rand() * 1.) / (1. * RAND_MAX);
+                if (i >= row0 && i < row0 + n) hp[(size_t)(i - row0)] = val;
+            }
             LSSPG_CUDA(cudaMemcpyAsync(P + kq * ld, hp.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
             LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
         }

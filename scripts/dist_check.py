@@ -92,7 +92,7 @@ def main():
     sA = api.Csr(solo, A)
     spc = api.Preconditioner.iluk(solo, A, level=0, blk_size=blk)
     for s in ("gmres", "lgmres", "rgmres", "rlgmres", "bicgstab", "bicgstabl", "bicgsafe", "cg", "cgs", "gpbicg", "cr",
-              "crs", "bicrstab", "bicrsafe", "gpbicr", "qmrcgstab", "tfqmr", "orthomin"):
+              "crs", "bicrstab", "bicrsafe", "gpbicr", "qmrcgstab", "tfqmr", "orthomin", "idrs"):
         x1 = np.zeros(n)
         want = api.lssp_solver_solve(solo, s, sA, spc, np.ones(n), x1, maxit=3000, restart=30)
         hx = np.zeros(S.n_owned)
