@@ -34,13 +34,15 @@ def main(args, rank, world, local_rank):
     td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = lib()
     N = args.grid
+    powerlaw = args.workload == "idrs_powerlaw"
     dims = (N, N, N * world)
-    n = dims[0] * dims[1] * dims[2]
+    n = args.pl_rows * world if powerlaw else dims[0] * dims[1] * dims[2]
     blk, r0, r1 = dist.block_rows(n, world, rank)
     conv = (0.3, 0.2, 0.1) if args.workload == "bicgstab_ilu0" else (0.0, 0.0, 0.0)
-    solver = "bicgstab" if args.workload == "bicgstab_ilu0" else "cg"
+    solver = "idrs" if powerlaw else "bicgstab" if args.workload == "bicgstab_ilu0" else "cg"
     t0 = time.perf_counter()
-    rows = g.stencil_7pt_rows(dims, r0, r1, conv=conv)
+    # BASELINE.json configs[4] (power-law CSR, IDRS(4)): --pl-rows rows per GPU, every rank generates its own block
+    rows = g.powerlaw_rows(n, r0, r1) if powerlaw else g.stencil_7pt_rows(dims, r0, r1, conv=conv)
     shard = dist.make_shard(rows, n, world, rank)          # metadata exchange: all_gather_object
     t_gen = time.perf_counter() - t0
     ids = [dist.DeviceShard.unique_id() if rank == 0 else None]
@@ -50,7 +52,7 @@ def main(args, rank, world, local_rank):
     D = dist.DeviceShard(ctx, shard, ids[0])
     t0 = time.perf_counter()
     pcname = "block-Jacobi ILU(0)"
-    if args.workload == "cg_non":
+    if args.workload == "cg_non" or powerlaw:
         pc = api.Preconditioner.non(ctx, shard.n_owned)
         pcname = "no preconditioner"
     elif args.workload == "cg_amg":
@@ -61,12 +63,17 @@ def main(args, rank, world, local_rank):
         pc = api.Preconditioner(ctx, "ilu", shard.n_owned, Lf, Uf)
     t_pc = time.perf_counter() - t0
     no, nc = shard.n_owned, shard.n_owned + shard.n_ghost
-    b = ctx.upload(np.ones(nc))
+    # b = 1 as exam.cxx; the power-law operator has unit row sums (x = 1 would solve it at once): oscillating b
+    hb_full = np.ones(nc)
+    if powerlaw:
+        hb_full[:no] = np.sin(np.arange(r0, r1) * 0.37) + 1.5
+    b = ctx.upload(hb_full)
     x = ctx.zeros(nc)
+    kw = dict(idrs=4) if powerlaw else {}
 
     def solve():
         check(L.lsspg_memset_zero(ctx.h, x.ptr, C.c_size_t(8 * nc)))
-        return api.solve_device(ctx, solver, D.A, pc, b, x, maxit=3000)
+        return api.solve_device(ctx, solver, D.A, pc, b, x, maxit=3000, **kw)
 
     for _ in range(args.warmup):
         r = solve()
@@ -93,14 +100,14 @@ def main(args, rank, world, local_rank):
     total_ms = float(t[0])
     launches = ctx.launches - launches0
     # e2e: host b / x shards through the reference-facing call, copies inside the timed region
-    hb, hx = np.ones(no), np.zeros(no)
+    hb, hx = np.ascontiguousarray(hb_full[:no]), np.zeros(no)
     e2e_its, e2e_s = 0, 0.0
     for step in range(1 + args.steps):
         hx[:] = 0.0
         ctx.sync()
         td.barrier()
         t0 = time.perf_counter()
-        re = api.lssp_solver_solve(ctx, solver, D.A, pc, hb, hx, maxit=3000)
+        re = api.lssp_solver_solve(ctx, solver, D.A, pc, hb, hx, maxit=3000, **kw)
         _ = float(hx[no // 2])
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         td.all_reduce(dt, op=td.ReduceOp.MAX)
@@ -132,7 +139,9 @@ def main(args, rank, world, local_rank):
         line = {"metric": "%s_iterations_per_second" % args.workload, "value": value, "unit": "iter/s x n_gpus",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "lap3d %dx%dx%d %s + %s, row-sharded over %d GPUs "
+                "config": {"workload": ("power-law CSR n=%d (nnz %d on rank 0) IDRS(4), %s, row-sharded over %d GPUs "
+                                        "(%d rows per GPU)" % (n, int(rows[0][-1]), pcname, world, args.pl_rows)) if powerlaw else
+                                       "lap3d %dx%dx%d %s + %s, row-sharded over %d GPUs "
                                        "(%d^3 rows per GPU)" % (dims[0], dims[1], dims[2], solver.upper(), pcname, world, N),
                            "n": n, "rows_per_gpu": no, "ghost_per_gpu": shard.n_ghost, "tol_rel": 1e-7,
                            "iterations_per_solve": r["nits"], "residual": r["residual"],

@@ -109,18 +109,26 @@ def powerlaw(n, seed=20261018, lmin=5, gamma=2.3, lmax=4096, window=65536, local
     (-1,0), duplicates merged (summed), diagonal = 1 + sum |off| (strictly
     diagonally dominant, nonsymmetric).  Counter-based splitmix64 hashing of
     (seed, row, k) makes the matrix reproducible anywhere."""
+    return powerlaw_rows(n, 0, n, seed, lmin, gamma, lmax, window, local)
+
+
+def powerlaw_rows(n, r0, r1, seed=20261018, lmin=5, gamma=2.3, lmax=4096, window=65536, local=0.9):
+    """Rows [r0, r1) of powerlaw(n) with GLOBAL column indices (a rank's row block): every row is a
+    function of (seed, row) only, so the blocks of all ranks tile the same matrix."""
+    m = r1 - r0
     with np.errstate(over="ignore"):
-        rows = np.arange(n, dtype=np.uint64)
+        rows = np.arange(r0, r1, dtype=np.uint64)
         base = _splitmix64(np.uint64(seed) ^ (rows * np.uint64(0xD1342543DE82EF95)))
         u = _u01(_splitmix64(base))
         ell = np.floor(lmin * u ** (-1.0 / (gamma - 1.0)))
         ell = np.clip(ell, 1, min(lmax, max(1, n - 1))).astype(np.int64)
         tot = int(ell.sum())
-        r = np.repeat(np.arange(n, dtype=np.int64), ell)
-        starts = np.zeros(n + 1, dtype=np.int64)
+        rl = np.repeat(np.arange(m, dtype=np.int64), ell)      # local row of every draw
+        r = rl + r0                                            # its global row
+        starts = np.zeros(m + 1, dtype=np.int64)
         np.cumsum(ell, out=starts[1:])
-        k = np.arange(tot, dtype=np.int64) - starts[r]
-        h = _splitmix64(base[r] + (k.astype(np.uint64) + np.uint64(1)) * np.uint64(0x2545F4914F6CDD1D))
+        k = np.arange(tot, dtype=np.int64) - starts[rl]
+        h = _splitmix64(base[rl] + (k.astype(np.uint64) + np.uint64(1)) * np.uint64(0x2545F4914F6CDD1D))
         h2 = _splitmix64(h)
         h3 = _splitmix64(h2)
         is_local = _u01(h) < local
@@ -133,7 +141,7 @@ def powerlaw(n, seed=20261018, lmin=5, gamma=2.3, lmax=4096, window=65536, local
         c = np.where(c == r, (c + 1) % n, c)
         v = -_u01(h3)
     # merge duplicates, sort columns, add the diagonal
-    key = r * n + c
+    key = rl * n + c
     order = np.argsort(key, kind="stable")
     key, v = key[order], v[order]
     first = np.ones(len(key), bool)
@@ -143,14 +151,14 @@ def powerlaw(n, seed=20261018, lmin=5, gamma=2.3, lmax=4096, window=65536, local
     np.add.at(vs, grp, v)
     ku = key[first]
     ru, cu = ku // n, ku % n
-    dsum = np.zeros(n)
+    dsum = np.zeros(m)
     np.add.at(dsum, ru, np.abs(vs))
-    rr = np.concatenate([ru, np.arange(n, dtype=np.int64)])
-    cc = np.concatenate([cu, np.arange(n, dtype=np.int64)])
+    rr = np.concatenate([ru, np.arange(m, dtype=np.int64)])
+    cc = np.concatenate([cu, np.arange(r0, r1, dtype=np.int64)])
     vv = np.concatenate([vs, 1.0 + dsum])
     order = np.argsort(rr * n + cc, kind="stable")
     rr, cc, vv = rr[order], cc[order], vv[order]
-    Ap = np.zeros(n + 1, dtype=np.int64)
+    Ap = np.zeros(m + 1, dtype=np.int64)
     np.add.at(Ap, rr + 1, 1)
     np.cumsum(Ap, out=Ap)
     return Ap.astype(np.int32), cc.astype(np.int32), vv.astype(np.float64)

@@ -60,6 +60,28 @@ def test_stencil_halo_is_one_plane_per_side():
         assert all(abs(p - S.rank) == 1 for p in S.peers)
 
 
+def test_powerlaw_row_blocks_tile_the_global_matrix(port):
+    """every rank generates its own rows of the irregular matrix (counter-based hashing): the blocks
+    must be exactly the rows of the matrix a single process generates, and shard like any other"""
+    from lssp_b200 import generators as g
+    n, P = 4000, 3
+    A = g.powerlaw(n, window=300)
+    x = tvec(n)
+    want = port.mv(0, A, x)
+    blocks, needs = [], []
+    for rank in range(P):
+        blk, r0, r1 = dist.block_rows(n, P, rank)
+        rows = g.powerlaw_rows(n, r0, r1, window=300)
+        ref = dist.slice_rows(A, r0, r1)
+        assert all(np.array_equal(u, v) for u, v in zip(rows, ref))
+        blocks.append(rows)
+        needs.append(dist.needed_ghosts(rows[1], r0, r1, blk))
+    for rank in range(P):
+        S = dist.make_shard(blocks[rank], n, P, rank, all_needs=needs)
+        xl = np.concatenate([x[S.r0:S.r1], x[S.ghost_global]])
+        assert np.array_equal(port.mv(0, (S.Ap, S.Aj, S.Ax), xl)[:S.n_owned], want[S.r0:S.r1])
+
+
 @pytest.mark.parametrize("P", [2, 4])
 def test_block_jacobi_factor_equals_reference_blocked_ilu(golden, P):
     """The ILU(0) a rank computes from its own diagonal block is the corresponding block of the
