@@ -153,6 +153,11 @@ typedef struct lsspg_factors lsspg_factors;   /* host L and U in the reference's
  * (the reference's blocked driver, src/pc-iluk.cxx:411-552). */
 int lsspg_ilu_factor(int kind, int n, const int *hAp, const int *hAj, const double *hAx,
                      int level, int p, double tol, int blk_size, lsspg_factors **out);
+/* ILU(k) with the NUMERIC phase on the GPU (src/pc-iluk.cxx:347-409): rows are
+ * factored level by level of the dependency graph of L, one thread per row, same operations in the
+ * same order as the host loop -> bit-identical factors.  Symbolic phase and L/U split stay on the host. */
+int lsspg_ilu_factor_device(lsspg_ctx *ctx, int n, const int *hAp, const int *hAj, const double *hAx,
+                            int level, int blk_size, lsspg_factors **out);
 int lsspg_factors_sizes(const lsspg_factors *F, int *n, int *nnzL, int *nnzU);
 int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int *Up, int *Uj,
                       double *Ux);

@@ -296,14 +296,18 @@ class Tri:
             pass
 
 
-def ilu_factor(A, kind="iluk", level=0, p=-1, tol=1e-3, blk_size=0):
-    """Host-side ILU(k) / ILUT set-up (reference src/pc-iluk.cxx, src/pc-ilut.cxx).
-    Returns (L, U) CSR triples in the reference's layout."""
+def ilu_factor(A, kind="iluk", level=0, p=-1, tol=1e-3, blk_size=0, ctx=None):
+    """ILU(k) / ILUT set-up (reference src/pc-iluk.cxx, src/pc-ilut.cxx).  Returns (L, U) CSR
+    triples in the reference's layout.  ctx given (ILU(k) only): the numeric phase runs on the GPU
+    (lsspg_ilu_factor_device), with bit-identical factors."""
     Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
     n = len(Ap) - 1
     h = C.c_void_p()
-    check(lib().lsspg_ilu_factor(0 if kind == "iluk" else 1, n, _p(Ap), _p(Aj), _p(Ax), int(level), int(p),
-                                 C.c_double(tol), int(blk_size), C.byref(h)))
+    if ctx is not None and kind == "iluk":
+        check(lib().lsspg_ilu_factor_device(ctx.h, n, _p(Ap), _p(Aj), _p(Ax), int(level), int(blk_size), C.byref(h)))
+    else:
+        check(lib().lsspg_ilu_factor(0 if kind == "iluk" else 1, n, _p(Ap), _p(Aj), _p(Ax), int(level), int(p),
+                                     C.c_double(tol), int(blk_size), C.byref(h)))
     nn, nl, nu = C.c_int(), C.c_int(), C.c_int()
     lib().lsspg_factors_sizes(h, C.byref(nn), C.byref(nl), C.byref(nu))
     Lp, Lj, Lx = np.empty(n + 1, np.int32), np.empty(nl.value, np.int32), np.empty(nl.value)

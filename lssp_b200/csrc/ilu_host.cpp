@@ -389,6 +389,41 @@ struct lsspg_factors {
     Factors f;
 };
 
+namespace lsspg {
+
+// Host half of the GPU factorisation (ilu_gpu.cu): the matrix the numeric phase works on -- A with
+// its diagonal repaired, scattered into the ILU(level) pattern, restricted to the diagonal blocks.
+int ilu_prepare(int n, const int *Ap, const int *Aj, const double *Ax, int level, int bs, std::vector<int> &Mp,
+                std::vector<int> &Mj, std::vector<double> &Mx)
+{
+    Csr A;
+    A.n = n;
+    A.p.assign(Ap, Ap + n + 1);
+    A.j.assign(Aj, Aj + Ap[n]);
+    A.x.assign(Ax, Ax + Ap[n]);
+    sort_rows(A);
+    Csr Ad = with_diagonal(A, kPivotTol);
+    Csr M = (level > 0) ? block_diagonal(iluk_pattern(Ad, level), bs) : block_diagonal(Ad, bs);
+    Mp.swap(M.p);
+    Mj.swap(M.j);
+    Mx.swap(M.x);
+    return 0;
+}
+
+// ... and the split of the factored rows into L (unit diagonal last) and U (diagonal first)
+lsspg_factors *ilu_split(int n, const std::vector<int> &Mp, const std::vector<int> &Mj, const std::vector<double> &Mx)
+{
+    lsspg_factors *F = new lsspg_factors();
+    F->f.n = n;
+    F->f.L.n = F->f.U.n = n;
+    F->f.L.p.push_back(0);
+    F->f.U.p.push_back(0);
+    for (int i = 0; i < n; i++) split_row(&Mj[Mp[i]], &Mx[Mp[i]], Mp[i + 1] - Mp[i], i, F->f.L, F->f.U);
+    return F;
+}
+
+}  // namespace lsspg
+
 extern "C" {
 
 int lsspg_ilu_factor(int kind, int n, const int *hAp, const int *hAj, const double *hAx, int level, int p,

@@ -101,6 +101,30 @@ def test_spmv_bulk_copy_pipeline_kernel_is_bit_exact(checker, golden):
     c2.close()
 
 
+@pytest.mark.parametrize("name,level,blk", [("lap2d_100", 0, 0), ("lap3d_32", 0, 0), ("cd3d_32", 1, 0), ("cd3d_12", 2, 0),
+                                            ("random_600", 1, 0), ("lap3d_32", 0, 8192), ("cd3d_32", 1, 4096)])
+def test_gpu_ilu_numeric_factorisation_is_bit_identical(ctx, name, level, blk):
+    """the IKJ numeric phase level by level on the GPU gives the host's -- and so
+    the reference's -- L and U bit for bit, pivot repair and block-Jacobi variants included"""
+    A = matrix(name)
+    Lh, Uh = api.ilu_factor(A, "iluk", level=level, blk_size=blk)
+    Lg, Ug = api.ilu_factor(A, "iluk", level=level, blk_size=blk, ctx=ctx)
+    for h, d in zip(Lh + Uh, Lg + Ug):
+        assert np.array_equal(h, d)
+
+
+def test_gpu_ilu_repairs_small_pivots_like_the_host(ctx):
+    # rows without a diagonal, tiny and negative-tiny pivots (src/pc.cxx:6-7, src/matrix-utils.cxx:483-587)
+    A = g.random_csr(400, 4, seed=11, diag=False)
+    Ap, Aj, Ax = A[0], A[1], A[2].copy()
+    Ax[::7] *= 1e-13
+    A = (Ap, Aj, Ax)
+    Lh, Uh = api.ilu_factor(A, "iluk", level=1)
+    Lg, Ug = api.ilu_factor(A, "iluk", level=1, ctx=ctx)
+    for h, d in zip(Lh + Uh, Lg + Ug):
+        assert np.array_equal(h, d, equal_nan=True)
+
+
 def test_spmv_long_rows_use_warp_path_within_1e14(ctx, checker):
     rng = np.random.default_rng(5)
     n = 3000
