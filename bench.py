@@ -246,7 +246,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--workload", default="cg_ilu0")
-    ap.add_argument("--check-every", type=int, default=1)
+    ap.add_argument("--check-every", type=int, default=8)
     ap.add_argument("--pl-rows", type=int, default=4000000, help="rows per GPU of the power-law workload (idrs_powerlaw, --gpus > 1)")
     ap.add_argument("--amg-order", type=int, default=1, help="cf_order of the AMG smoother (cg_amg): 1 C/F by index, 2 multicolour")
     ap.add_argument("--ref-iters", type=int, default=10)

@@ -54,7 +54,9 @@ int lsspg_ctx_set_option(lsspg_ctx *ctx, int option, int value);
 #define LSSPG_OPT_SPMV_KERNEL   1   /* 0 auto, 1 stream (LDG staging), 2 stream (bulk-copy pipeline), 3 vector only */
 #define LSSPG_OPT_SPMV_EXACT    2   /* 1: never use the shuffle-reduced long-row path, in the SpMV and in the AMG
                                        smoother (rows of more than 64 entries): bit-exact always */
-#define LSSPG_OPT_CHECK_EVERY   3   /* Krylov drivers: residual read-back every k iterations (default 1) */
+#define LSSPG_OPT_CHECK_EVERY   3   /* CG / BiCGStab: the host reads the residuals back every k iterations (default 8;
+                                       a device-side stop flag freezes the state at convergence, so the iteration
+                                       count, history and solution do not depend on k) */
 #define LSSPG_OPT_REDUCE_SEQUENTIAL 4 /* 1: every dot/norm is summed in the reference's sequential order
                                        (src/vector.cxx:129) -> whole solves become bit-identical to the
                                        CPU reference; verification mode, one thread does the adds */

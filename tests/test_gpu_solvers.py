@@ -233,7 +233,8 @@ def test_check_every_batches_do_not_change_results(golden):
     """Residual read-back every 8 iterations (device-side stop flag) must give
     exactly the iteration count and history of the per-iteration read-back."""
     c1, c8 = api.Context(0), api.Context(0)
-    c8.set_option(api.OPT_CHECK_EVERY, 8)
+    c1.set_option(api.OPT_CHECK_EVERY, 1)
+    c8.set_option(api.OPT_CHECK_EVERY, 8)      # (the default)
     for m, s, pc, kw in (("lap3d_32", "cg", "iluk", dict(iluk_level=0)), ("cd3d_32", "bicgstab", "iluk", dict(iluk_level=1)),
                          ("cd3d_32", "bicgstab", "non", {}), ("lap3d_32", "cg", "non", {})):
         _, r1 = run(c1, m, s, pc, kw, nhist=100)
