@@ -141,3 +141,28 @@ def test_amg_on_a_larger_grid_has_grid_independent_convergence(ctx):
     assert pc.amg_solve(np.ones(n), x)["nits"] <= 12
     pc.free()
     dA.free()
+
+
+@pytest.mark.parametrize("name", ["lap2d_100", "lap3d_32", "cd3d_12"])
+@pytest.mark.parametrize("order", [1, 2])
+def test_gpu_cycle_matches_the_committed_fixture_bit_for_bit(name, order):
+    """tests/golden/amg_golden.json (restated cycle on the committed hierarchy): with exact long-row sums the
+    GPU cycle has the same SHA-256, and the stand-alone iteration the same cycle count"""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "amg_golden.json")) as f:
+        e = json.load(f)["%s/cf%d" % (name, order)]
+    c = api.Context(0)
+    c.set_option(api.OPT_SPMV_EXACT, 1)
+    A = matrix(name)
+    pc = api.Preconditioner.sxamg(c, A, cf_order=order)
+    n = pc.hierarchy.levels[0]["n"]
+    y = pc.apply_host(tvec(n), x0=tvec(n, 3))
+    assert hashlib.sha256(np.ascontiguousarray(y).tobytes()).hexdigest() == e["cycle_sha"]
+    x = np.zeros(n)
+    r = pc.amg_solve(np.ones(n), x, tol=1e-8, maxit=50)
+    assert r["nits"] == e["standalone_nits"]
+    assert abs(r["residual"] - e["standalone_residual"]) <= 1e-13 * np.sqrt(n)
+    pc.free()
+    c.close()
