@@ -18,6 +18,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <thread>
 #include <vector>
 #include "amg_host.h"
 
@@ -290,38 +291,72 @@ void transpose_csr(int nrows, int ncols, const std::vector<int> &p, const std::v
         }
 }
 
-// C = A * B, row by row with a dense accumulator; columns of every row sorted ascending
+// C = A * B, row by row with a dense accumulator; columns of every row sorted ascending.  Rows are
+// independent: contiguous row ranges are handed to host threads (each with its own accumulator) and
+// the pieces concatenated, so the result does not depend on the number of threads.
 int spgemm(int nrows, int ncolsB, const std::vector<int> &Ap, const std::vector<int> &Aj, const std::vector<double> &Ax,
            const std::vector<int> &Bp, const std::vector<int> &Bj, const std::vector<double> &Bx,
            std::vector<int> &Cp, std::vector<int> &Cj, std::vector<double> &Cx)
 {
-    Cp.assign(nrows + 1, 0);
-    Cj.clear();
-    Cx.clear();
-    std::vector<int> where(ncolsB, -1), cols;
-    std::vector<double> acc(ncolsB, 0.0);
-    for (int i = 0; i < nrows; i++) {
-        cols.clear();
-        for (int k = Ap[i]; k < Ap[i + 1]; k++) {
-            const int m = Aj[k];
-            const double a = Ax[k];
-            for (int q = Bp[m]; q < Bp[m + 1]; q++) {
-                const int c = Bj[q];
-                if (where[c] != i) {
-                    where[c] = i;
-                    acc[c] = 0.0;
-                    cols.push_back(c);
+    int nt = (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 16));
+    if (nrows < 20000) nt = 1;
+    struct Piece {
+        std::vector<int> len, j;
+        std::vector<double> x;
+    };
+    std::vector<Piece> pieces(nt);
+    auto work = [&](int t) {
+        const int r0 = (int)((long long)nrows * t / nt), r1 = (int)((long long)nrows * (t + 1) / nt);
+        Piece &P = pieces[t];
+        P.len.assign(r1 - r0, 0);
+        std::vector<int> where(ncolsB, -1), cols;
+        std::vector<double> acc(ncolsB, 0.0);
+        for (int i = r0; i < r1; i++) {
+            cols.clear();
+            for (int k = Ap[i]; k < Ap[i + 1]; k++) {
+                const int m = Aj[k];
+                const double a = Ax[k];
+                for (int q = Bp[m]; q < Bp[m + 1]; q++) {
+                    const int c = Bj[q];
+                    if (where[c] != i) {
+                        where[c] = i;
+                        acc[c] = 0.0;
+                        cols.push_back(c);
+                    }
+                    acc[c] += a * Bx[q];
                 }
-                acc[c] += a * Bx[q];
             }
+            std::sort(cols.begin(), cols.end());
+            for (int c : cols) {
+                P.j.push_back(c);
+                P.x.push_back(acc[c]);
+            }
+            P.len[i - r0] = (int)cols.size();
         }
-        std::sort(cols.begin(), cols.end());
-        for (int c : cols) {
-            Cj.push_back(c);
-            Cx.push_back(acc[c]);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto &q : th) q.join();
+    }
+    size_t total = 0;
+    for (const Piece &P : pieces) total += P.j.size();
+    AMG_CHECK(total < (size_t)0x7fffffff, "amg: coarse operator exceeds int32 indexing");
+    Cp.assign(nrows + 1, 0);
+    Cj.resize(total);
+    Cx.resize(total);
+    size_t off = 0;
+    int row = 0;
+    for (const Piece &P : pieces) {
+        std::copy(P.j.begin(), P.j.end(), Cj.begin() + off);
+        std::copy(P.x.begin(), P.x.end(), Cx.begin() + off);
+        off += P.j.size();
+        for (int l : P.len) {
+            Cp[row + 1] = Cp[row] + l;
+            row++;
         }
-        AMG_CHECK(Cj.size() < (size_t)0x7fffffff, "amg: coarse operator exceeds int32 indexing");
-        Cp[i + 1] = (int)Cj.size();
     }
     return 0;
 }
