@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU parity check (run under torchrun, one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 \
-        --master-port 29511 scripts/dist_check.py
+        --master-port 29511 tests/dist_check_gpu.py
 Row-sharded CG / BiCGStab with block-Jacobi ILU against the golden fixtures generated from the
 reference's own blocked ILU (tests/golden/golden.json "blockjacobi"), plus a bit-exact check of
 the sharded SpMV (halo exchange over NCCL) against the CPU oracle."""
