@@ -141,6 +141,12 @@ int lsspg_debug_tri_walk_tiled_host(int which, int n, const int *hTp, const int 
                                     const double *hTx, double *hx, const double *hrhs,
                                     int *applicable, int *info /* [8]: boxes, box levels, max rows
                                     per box, row levels, grid nx ny nz, box edge */);
+/* Fingerprint (64-bit hash) and size of the device image lsspg_tri_analyse would upload for this factor,
+ * built on the host without any CUDA call; kind: 0 slice schedule, 1 box blobs, 2 ELL box blobs.
+ * For the CPU test-suite (pins the set-up code's output) and set-up profiling; seconds[2] = schedule, packing. */
+int lsspg_debug_tri_pack_host(int which, int n, const int *hTp, const int *hTj, const double *hTx,
+                              int *kind, unsigned long long *fingerprint, long long *bytes,
+                              double *seconds);
 /* schedule of a device-resident factor: tiled != 0 when the box schedule is in use */
 int lsspg_tri_schedule(const lsspg_tri *T, int *tiled, int *num_tiles, int *num_tile_levels,
                        int *max_tile_rows);

@@ -261,6 +261,17 @@ def tri_walk_tiled_host(which, T, rhs):
     return x, dict(zip(keys, list(info)))
 
 
+def tri_pack_host(which, T):
+    """Fingerprint of the device image `Tri` would upload for this factor, built without a GPU (tests and set-up
+    profiling only).  Returns dict(kind, fingerprint, bytes, schedule_s, pack_s); kind 0 = slice schedule,
+    1 = box blobs, 2 = ELL box blobs."""
+    Tp, Tj, Tx = _i32(T[0]), _i32(T[1]), _f64(T[2])
+    n = len(Tp) - 1
+    kind, fp, nb, sec = C.c_int(), C.c_ulonglong(), C.c_longlong(), (C.c_double * 2)()
+    check(lib().lsspg_debug_tri_pack_host(which, n, _p(Tp), _p(Tj), _p(Tx), C.byref(kind), C.byref(fp), C.byref(nb), sec))
+    return dict(kind=kind.value, fingerprint=fp.value, bytes=nb.value, schedule_s=sec[0], pack_s=sec[1])
+
+
 class Tri:
     """Device-resident triangular factor in level order (lsspg_tri)."""
 

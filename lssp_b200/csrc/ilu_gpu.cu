@@ -12,13 +12,13 @@
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
+#include "host_par.h"
 
 struct lsspg_factors;
 
 namespace lsspg {
-int ilu_prepare(int n, const int *Ap, const int *Aj, const double *Ax, int level, int bs, std::vector<int> &Mp,
-                std::vector<int> &Mj, std::vector<double> &Mx);
-lsspg_factors *ilu_split(int n, const std::vector<int> &Mp, const std::vector<int> &Mj, const std::vector<double> &Mx);
+int ilu_prepare(int n, const int *Ap, const int *Aj, const double *Ax, int level, int bs, IVec &Mp, IVec &Mj, DVec &Mx);
+lsspg_factors *ilu_split(int n, IVec &Mp, IVec &Mj, DVec &Mx);
 
 constexpr double kPivotTolG = 1e-10;    // mat_zero_diag_tol,   reference src/pc.cxx:7
 constexpr double kPivotValueG = 1e-3;   // mat_zero_diag_value, reference src/pc.cxx:6
@@ -72,8 +72,8 @@ extern "C" int lsspg_ilu_factor_device(lsspg_ctx *ctx, int n, const int *hAp, co
     LSSPG_CUDA(cudaSetDevice(ctx->device));
     if (level < 0) level = 0;
     const int bs = (blk_size <= 0 || blk_size > n) ? n : blk_size;
-    std::vector<int> Mp, Mj;
-    std::vector<double> Mx;
+    IVec Mp, Mj;
+    DVec Mx;
     LSSPG_TRY(ilu_prepare(n, hAp, hAj, hAx, level, bs, Mp, Mj, Mx));
     const size_t nnz = Mj.size();
     // dependency level of every row (its strictly lower columns), rows grouped by level

@@ -16,11 +16,15 @@
 //     same L/U split (src/pc-ilut.cxx:375-402).
 // No FMA: built with -ffp-contract=off.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <numeric>
 #include <vector>
 #include "../../include/lsspg.h"
+#include "host_par.h"
 
 namespace lsspg {
 void set_error(const char *fmt, ...);
@@ -28,13 +32,41 @@ void set_error(const char *fmt, ...);
 
 namespace {
 
+// LSSPG_SETUP_PROF=1: phase times of the set-up on stderr
+static double prof_now()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+static bool prof_on()
+{
+    static const bool on = getenv("LSSPG_SETUP_PROF") && atoi(getenv("LSSPG_SETUP_PROF")) != 0;
+    return on;
+}
+#define PROF_T0 double prof_t = prof_now()
+#define PROF(what)                                                                   \
+    do {                                                                             \
+        if (prof_on()) {                                                             \
+            const double t_ = prof_now();                                            \
+            fprintf(stderr, "[setup] %-26s %.3f s\n", what, t_ - prof_t);            \
+            prof_t = t_;                                                             \
+        }                                                                            \
+    } while (0)
+
 constexpr double kPivotTol = 1e-10;   // mat_zero_diag_tol,   reference src/pc.cxx:7
 constexpr double kPivotValue = 1e-3;  // mat_zero_diag_value, reference src/pc.cxx:6
 
+using lsspg::DVec;
+using lsspg::IVec;
+using lsspg::parallel_copy;
+using lsspg::parallel_exclusive_scan;
+using lsspg::parallel_ranges;
+
 struct Csr {
     int n = 0;
-    std::vector<int> p, j;
-    std::vector<double> x;
+    IVec p, j;
+    DVec x;
     int nnz() const { return p.empty() ? 0 : p[n]; }
 };
 
@@ -93,31 +125,76 @@ Csr with_diagonal(const Csr &A, double tol)
 }
 
 // Entries outside the row's own block are discarded; a row left empty becomes a unit row.
-Csr block_diagonal(const Csr &A, int bs)
+Csr block_diagonal(Csr &&A, int bs)
 {
-    if (bs >= A.n) return A;
+    if (bs >= A.n) return std::move(A);
     Csr M;
-    M.n = A.n;
-    M.p.assign(A.n + 1, 0);
-    M.j.reserve(A.j.size());
-    M.x.reserve(A.x.size());
-    for (int i = 0; i < A.n; i++) {
-        const int lo = (i / bs) * bs, hi = std::min(A.n, lo + bs);
-        int kept = 0;
-        for (int k = A.p[i]; k < A.p[i + 1]; k++) {
-            if (A.j[k] >= lo && A.j[k] < hi) {
-                M.j.push_back(A.j[k]);
-                M.x.push_back(A.x[k]);
-                kept++;
+    const int n = A.n;
+    M.n = n;
+    M.p.resize((size_t)n + 1);
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) {
+            const int lo = (i / bs) * bs, hi = std::min(n, lo + bs);
+            int kept = 0;
+            for (int k = A.p[i]; k < A.p[i + 1]; k++) kept += (A.j[k] >= lo && A.j[k] < hi);
+            M.p[i] = kept ? kept : 1;
+        }
+    });
+    const long long total = parallel_exclusive_scan(M.p.data(), n);
+    M.p[n] = (int)total;
+    M.j.resize((size_t)total);
+    M.x.resize((size_t)total);
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) {
+            const int lo = (i / bs) * bs, hi = std::min(n, lo + bs);
+            int o = M.p[i];
+            for (int k = A.p[i]; k < A.p[i + 1]; k++) {
+                if (A.j[k] >= lo && A.j[k] < hi) {
+                    M.j[o] = A.j[k];
+                    M.x[o] = A.x[k];
+                    o++;
+                }
+            }
+            if (o == M.p[i]) {
+                M.j[o] = i;
+                M.x[o] = 1.0;
             }
         }
-        if (kept == 0) {
-            M.j.push_back(i);
-            M.x.push_back(1.0);
-        }
-        M.p[i + 1] = (int)M.j.size();
-    }
+    });
     return M;
+}
+
+// The caller's matrix -> the matrix the factorisations work on: rows sorted by column (what
+// lssp_solver_assemble guarantees, src/lssp.cxx:173), missing diagonals inserted (src/pc-iluk.cxx:573,
+// src/pc-ilut.cxx:448).  The usual case -- sorted rows that all store their diagonal -- is ONE copy, made
+// by the host threads; otherwise the serial repair path runs.
+Csr ingest(int n, const int *Ap, const int *Aj, const double *Ax)
+{
+    const size_t nnz = (size_t)Ap[n];
+    std::vector<char> bad(lsspg::host_threads() + 1, 0);
+    parallel_ranges(n, [&](long long r0, long long r1, int piece) {
+        char b = 0;
+        for (int i = (int)r0; i < (int)r1 && !b; i++) {
+            bool diag = false;
+            for (int k = Ap[i]; k < Ap[i + 1]; k++) {
+                if (Aj[k] == i) diag = true;
+                if (k > Ap[i] && Aj[k - 1] > Aj[k]) b = 1;
+            }
+            if (!diag) b = 1;
+        }
+        bad[piece] = b;
+    }, lsspg::host_threads());
+    Csr A;
+    A.n = n;
+    A.p.resize((size_t)n + 1);
+    A.j.resize(nnz);
+    A.x.resize(nnz);
+    parallel_copy(A.p.data(), Ap, sizeof(int) * ((size_t)n + 1));
+    parallel_copy(A.j.data(), Aj, sizeof(int) * nnz);
+    parallel_copy(A.x.data(), Ax, sizeof(double) * nnz);
+    if (std::find(bad.begin(), bad.end(), (char)1) == bad.end()) return A;
+    sort_rows(A);
+    return with_diagonal(A, kPivotTol);
 }
 
 // ---- ILU(k) symbolic ----------------------------------------------------------
@@ -244,18 +321,60 @@ void split_row(const int *cj, const double *cx, int len, int row, Csr &L, Csr &U
     U.p.push_back((int)U.j.size());
 }
 
-Factors factor_iluk(const Csr &A, int level, int bs)
+// all rows of the factored matrix at once: sizes counted and scanned first, rows written by the host threads
+void split_all(const Csr &M, Csr &L, Csr &U)
 {
-    Csr M = (level > 0) ? block_diagonal(iluk_pattern(A, level), bs) : block_diagonal(A, bs);
+    const int n = M.n;
+    L.n = U.n = n;
+    L.p.resize((size_t)n + 1);
+    U.p.resize((size_t)n + 1);
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) {
+            int nl = 0, nu = 0;
+            for (int k = M.p[i]; k < M.p[i + 1]; k++) {
+                const int c = M.j[k];
+                nl += (c <= i);
+                nu += (c >= i);
+            }
+            L.p[i] = nl;
+            U.p[i] = nu;
+        }
+    });
+    const long long tl = parallel_exclusive_scan(L.p.data(), n), tu = parallel_exclusive_scan(U.p.data(), n);
+    L.p[n] = (int)tl;
+    U.p[n] = (int)tu;
+    L.j.resize((size_t)tl); L.x.resize((size_t)tl);
+    U.j.resize((size_t)tu); U.x.resize((size_t)tu);
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) {
+            int ol = L.p[i], ou = U.p[i];
+            for (int k = M.p[i]; k < M.p[i + 1]; k++) {
+                const int c = M.j[k];
+                const double v = M.x[k];
+                if (c < i) { L.j[ol] = c; L.x[ol] = v; ol++; }
+                else if (c == i) {
+                    L.j[ol] = i; L.x[ol] = 1; ol++;
+                    U.j[ou] = i; U.x[ou] = v; ou++;
+                }
+                else { U.j[ou] = c; U.x[ou] = v; ou++; }
+            }
+        }
+    });
+}
+
+Factors factor_iluk(Csr &&A, int level, int bs)
+{
+    PROF_T0;
     const int n = A.n;
+    Csr M = (level > 0) ? block_diagonal(iluk_pattern(A, level), bs) : block_diagonal(std::move(A), bs);
+    PROF("pattern+block_diagonal");
     std::vector<double> wk(n, 0.0), inv(n, 0.0);
     for (int r0 = 0; r0 < n; r0 += bs) ilu0_block(M, r0, std::min(n, r0 + bs), wk, inv);
+    PROF("numeric");
     Factors F;
     F.n = n;
-    F.L.n = F.U.n = n;
-    F.L.p.push_back(0);
-    F.U.p.push_back(0);
-    for (int i = 0; i < n; i++) split_row(&M.j[M.p[i]], &M.x[M.p[i]], M.p[i + 1] - M.p[i], i, F.L, F.U);
+    split_all(M, F.L, F.U);
+    PROF("split");
     return F;
 }
 
@@ -371,15 +490,16 @@ void ilut_block(const Csr &B, int r0, int r1, double tau, int p, Csr &L, Csr &U)
     }
 }
 
-Factors factor_ilut(const Csr &A, double tau, int p, int bs)
+Factors factor_ilut(Csr &&A, double tau, int p, int bs)
 {
-    Csr B = block_diagonal(A, bs);
+    const int n = A.n;
+    Csr B = block_diagonal(std::move(A), bs);
     Factors F;
-    F.n = A.n;
-    F.L.n = F.U.n = A.n;
+    F.n = n;
+    F.L.n = F.U.n = n;
     F.L.p.push_back(0);
     F.U.p.push_back(0);
-    for (int r0 = 0; r0 < A.n; r0 += bs) ilut_block(B, r0, std::min(A.n, r0 + bs), tau, p, F.L, F.U);
+    for (int r0 = 0; r0 < n; r0 += bs) ilut_block(B, r0, std::min(n, r0 + bs), tau, p, F.L, F.U);
     return F;
 }
 
@@ -393,17 +513,10 @@ namespace lsspg {
 
 // Host half of the GPU factorisation (ilu_gpu.cu): the matrix the numeric phase works on -- A with
 // its diagonal repaired, scattered into the ILU(level) pattern, restricted to the diagonal blocks.
-int ilu_prepare(int n, const int *Ap, const int *Aj, const double *Ax, int level, int bs, std::vector<int> &Mp,
-                std::vector<int> &Mj, std::vector<double> &Mx)
+int ilu_prepare(int n, const int *Ap, const int *Aj, const double *Ax, int level, int bs, IVec &Mp, IVec &Mj, DVec &Mx)
 {
-    Csr A;
-    A.n = n;
-    A.p.assign(Ap, Ap + n + 1);
-    A.j.assign(Aj, Aj + Ap[n]);
-    A.x.assign(Ax, Ax + Ap[n]);
-    sort_rows(A);
-    Csr Ad = with_diagonal(A, kPivotTol);
-    Csr M = (level > 0) ? block_diagonal(iluk_pattern(Ad, level), bs) : block_diagonal(Ad, bs);
+    Csr Ad = ingest(n, Ap, Aj, Ax);
+    Csr M = (level > 0) ? block_diagonal(iluk_pattern(Ad, level), bs) : block_diagonal(std::move(Ad), bs);
     Mp.swap(M.p);
     Mj.swap(M.j);
     Mx.swap(M.x);
@@ -411,14 +524,15 @@ int ilu_prepare(int n, const int *Ap, const int *Aj, const double *Ax, int level
 }
 
 // ... and the split of the factored rows into L (unit diagonal last) and U (diagonal first)
-lsspg_factors *ilu_split(int n, const std::vector<int> &Mp, const std::vector<int> &Mj, const std::vector<double> &Mx)
+lsspg_factors *ilu_split(int n, IVec &Mp, IVec &Mj, DVec &Mx)
 {
     lsspg_factors *F = new lsspg_factors();
     F->f.n = n;
-    F->f.L.n = F->f.U.n = n;
-    F->f.L.p.push_back(0);
-    F->f.U.p.push_back(0);
-    for (int i = 0; i < n; i++) split_row(&Mj[Mp[i]], &Mx[Mp[i]], Mp[i + 1] - Mp[i], i, F->f.L, F->f.U);
+    Csr M;
+    M.n = n;
+    M.p.swap(Mp); M.j.swap(Mj); M.x.swap(Mx);
+    split_all(M, F->f.L, F->f.U);
+    M.p.swap(Mp); M.j.swap(Mj); M.x.swap(Mx);
     return F;
 }
 
@@ -437,24 +551,20 @@ int lsspg_ilu_factor(int kind, int n, const int *hAp, const int *hAj, const doub
         lsspg::set_error("lsspg_ilu_factor: unknown kind %d", kind);
         return 1;
     }
-    Csr A;
-    A.n = n;
-    A.p.assign(hAp, hAp + n + 1);
-    A.j.assign(hAj, hAj + hAp[n]);
-    A.x.assign(hAx, hAx + hAp[n]);
-    sort_rows(A);
-    const int nnz = A.nnz();
-    Csr Ad = with_diagonal(A, kPivotTol);   // reference src/pc-iluk.cxx:573, src/pc-ilut.cxx:448
+    PROF_T0;
+    const int nnz = hAp[n];
+    Csr Ad = ingest(n, hAp, hAj, hAx);
+    PROF("ingest");
     const int bs = (blk_size <= 0 || blk_size > n) ? n : blk_size;
     lsspg_factors *F = new lsspg_factors();
     if (kind == LSSPG_ILUK) {
         if (level < 0) level = 0;               // reference src/pc-iluk.cxx:286-290
-        F->f = factor_iluk(Ad, level, bs);
+        F->f = factor_iluk(std::move(Ad), level, bs);
     }
     else {
         if (p <= 0) p = (nnz + n - 1) / n;      // reference src/pc-ilut.cxx:436-438
         if (tol < 0) tol = 1e-3;                // reference src/pc-ilut.cxx:440-442, src/pc.cxx:4
-        F->f = factor_ilut(Ad, tol, p, bs);
+        F->f = factor_ilut(std::move(Ad), tol, p, bs);
     }
     *out = F;
     return 0;
@@ -471,12 +581,12 @@ int lsspg_factors_sizes(const lsspg_factors *F, int *n, int *nnzL, int *nnzU)
 int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int *Up, int *Uj, double *Ux)
 {
     const Csr &L = F->f.L, &U = F->f.U;
-    memcpy(Lp, L.p.data(), sizeof(int) * L.p.size());
-    memcpy(Lj, L.j.data(), sizeof(int) * L.j.size());
-    memcpy(Lx, L.x.data(), sizeof(double) * L.x.size());
-    memcpy(Up, U.p.data(), sizeof(int) * U.p.size());
-    memcpy(Uj, U.j.data(), sizeof(int) * U.j.size());
-    memcpy(Ux, U.x.data(), sizeof(double) * U.x.size());
+    parallel_copy(Lp, L.p.data(), sizeof(int) * L.p.size());
+    parallel_copy(Lj, L.j.data(), sizeof(int) * L.j.size());
+    parallel_copy(Lx, L.x.data(), sizeof(double) * L.x.size());
+    parallel_copy(Up, U.p.data(), sizeof(int) * U.p.size());
+    parallel_copy(Uj, U.j.data(), sizeof(int) * U.j.size());
+    parallel_copy(Ux, U.x.data(), sizeof(double) * U.x.size());
     return 0;
 }
 

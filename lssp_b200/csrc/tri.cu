@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "blas1.cuh"
 #include "tri.cuh"
 
@@ -320,6 +321,71 @@ int lsspg_debug_tri_walk_layout_host(int which, int n, const int *hTp, const int
     }
     if (num_slices) *num_slices = H.num_slices;
     if (padded_nnz) *padded_nnz = H.padded_nnz;
+    return 0;
+}
+
+// Fingerprint of the device image of a factor's schedule, computed without any CUDA call: the CPU test-suite pins
+// it so that changes to the (threaded) set-up code are known to upload the same bytes.  `kind`: 0 slice schedule,
+// 1 box blobs (CSR), 2 box blobs (ELL, completion flags).  seconds[0] = schedule, [1] = packing.
+static unsigned long long mix_words(unsigned long long h, const void *p, size_t bytes)
+{
+    const unsigned char *b = (const unsigned char *)p;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        unsigned long long w;
+        memcpy(&w, b + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    for (; i < bytes; i++) h = (h ^ b[i]) * 0x100000001B3ull;
+    return h;
+}
+
+int lsspg_debug_tri_pack_host(int which, int n, const int *hTp, const int *hTj, const double *hTx, int *kind,
+                              unsigned long long *fingerprint, long long *bytes, double *seconds /* [2] */)
+{
+    auto now = [] {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    };
+    unsigned long long h = 0xCBF29CE484222325ull;
+    long long total = 0;
+    const double t0 = now();
+    double t1 = t0, t2 = t0;
+    const char *e = getenv("LSSPG_TRI_TILED");
+    TiledHost TH;
+    const int rc = (e && atoi(e) == 0) ? 2 : tri_tiled_build_host(which, n, hTp, hTj, hTx, TH);
+    if (rc == 1) return 1;
+    if (rc == 0) {
+        t1 = now();
+        PackedBoxes P;
+        LSSPG_TRY(tri_tiled_pack_host(TH, P));
+        t2 = now();
+        h = mix_words(h, P.blob.data(), P.blob.size());
+        h = mix_words(h, P.desc_bytes.data(), P.desc_bytes.size());
+        const long long meta[4] = {(long long)P.cap, P.max_ext, P.flags, TH.num_tile_levels};
+        h = mix_words(h, meta, sizeof(meta));
+        total = (long long)(P.blob.size() + P.desc_bytes.size());
+        if (kind) *kind = P.flags ? 2 : 1;
+    }
+    else {
+        TriHost H;
+        LSSPG_TRY(tri_build_host(which, n, hTp, hTj, hTx, true, H));
+        t1 = t2 = now();
+        h = mix_words(h, H.perm.data(), H.perm.size() * sizeof(int));
+        h = mix_words(h, H.diag.data(), H.diag.size() * sizeof(double));
+        h = mix_words(h, H.slice_ptr.data(), H.slice_ptr.size() * sizeof(int));
+        h = mix_words(h, H.slice_need.data(), H.slice_need.size() * sizeof(int));
+        h = mix_words(h, H.col.data(), H.col.size() * sizeof(int));
+        h = mix_words(h, H.val.data(), H.val.size() * sizeof(double));
+        total = (long long)(H.perm.size() * 4 + H.diag.size() * 8 + H.slice_ptr.size() * 4 + H.slice_need.size() * 4 +
+                            H.col.size() * 12);
+        if (kind) *kind = 0;
+    }
+    if (fingerprint) *fingerprint = h;
+    if (bytes) *bytes = total;
+    if (seconds) { seconds[0] = t1 - t0; seconds[1] = t2 - t1; }
     return 0;
 }
 

@@ -68,6 +68,15 @@ struct TiledHost {
 // returns 0 when a tile schedule was built, 2 when the factor is not a structured-grid factor
 // (caller falls back to the slice schedule), 1 on error
 int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const double *Tx, TiledHost &H);
+// The device image of a tile schedule: one 16-byte aligned blob per box plus BoxDesc[num_tiles] (raw bytes here;
+// the struct is private to tri_tiled.cu).  Packed on the host, no CUDA call involved.
+struct PackedBoxes {
+    std::vector<unsigned char> blob, desc_bytes;
+    size_t cap = 0;       // largest blob
+    int max_ext = 0;      // most operands a box reads from other boxes
+    bool flags = false;   // ELL blobs for the completion-flag kernel (acyclic box graphs)
+};
+int tri_tiled_pack_host(const TiledHost &H, PackedBoxes &P);
 int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T);
 void tri_tiled_free(lsspg_tri *T);
 int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded);

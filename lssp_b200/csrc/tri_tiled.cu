@@ -780,9 +780,12 @@ int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double
     return 0;
 }
 
-static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const std::vector<unsigned char> &blob,
-                         const std::vector<BoxDesc> &desc, size_t cap, int max_ext, bool flags)
+static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const PackedBoxes &P)
 {
+    const std::vector<unsigned char> &blob = P.blob, &desc = P.desc_bytes;
+    const size_t cap = P.cap;
+    const int max_ext = P.max_ext;
+    const bool flags = P.flags;
     T->tiled = true;
     T->num_tiles = H.num_tiles; T->max_tile_rows = H.max_tile_rows; T->num_tile_levels = H.num_tile_levels;
     T->blob_cap = (int)cap;
@@ -792,10 +795,10 @@ static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const
     LSSPG_CUDA(cudaMemsetAsync(T->t_flags, 0, sizeof(unsigned int) * std::max(H.num_tiles, 1), ctx->stream));
     for (int k = 0; k < 3; k++) { T->tile_dims[k] = H.tile_dims[k]; T->grid_dims[k] = H.grid_dims[k]; }
     LSSPG_CUDA(cudaMalloc(&T->t_blob, blob.size()));
-    LSSPG_CUDA(cudaMalloc(&T->t_desc, sizeof(BoxDesc) * std::max<size_t>(desc.size(), 1)));
+    LSSPG_CUDA(cudaMalloc(&T->t_desc, std::max<size_t>(desc.size(), sizeof(BoxDesc))));
     LSSPG_CUDA(cudaMemcpyAsync(T->t_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!desc.empty())
-        LSSPG_CUDA(cudaMemcpyAsync(T->t_desc, desc.data(), sizeof(BoxDesc) * desc.size(), cudaMemcpyHostToDevice, ctx->stream));
+        LSSPG_CUDA(cudaMemcpyAsync(T->t_desc, desc.data(), desc.size(), cudaMemcpyHostToDevice, ctx->stream));
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(tri_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -806,8 +809,8 @@ static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const
     return 0;
 }
 
-// acyclic box graph: ELL blobs for tri_box_ell_kernel
-static int upload_ell(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
+// acyclic box graph: ELL blobs for tri_box_ell_kernel.  Host only; 2 = not applicable (a box would not fit).
+static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
 {
     std::vector<BoxDesc> desc(H.num_tiles);
     size_t total = 0, cap = 0;
@@ -876,15 +879,18 @@ static int upload_ell(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
             }
         }
     }
-    return upload_common(ctx, H, T, blob, desc, cap, max_ext, true);
+    P.blob.swap(blob);
+    P.desc_bytes.assign((const unsigned char *)desc.data(), (const unsigned char *)(desc.data() + desc.size()));
+    P.cap = cap; P.max_ext = max_ext; P.flags = true;
+    return 0;
 }
 
-int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
+int tri_tiled_pack_host(const TiledHost &H, PackedBoxes &P)
 {
     {
         const char *e = getenv("LSSPG_TRI_BOX_FLAGS");
         if (H.acyclic && !(e && atoi(e) == 0)) {
-            const int rc = upload_ell(ctx, H, T);
+            const int rc = pack_ell_host(H, P);
             if (rc != 2) return rc;
         }
     }
@@ -933,7 +939,17 @@ int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
             val[e] = H.val[e0 + e];
         }
     }
-    return upload_common(ctx, H, T, blob, desc, cap, max_ext, false);
+    P.blob.swap(blob);
+    P.desc_bytes.assign((const unsigned char *)desc.data(), (const unsigned char *)(desc.data() + desc.size()));
+    P.cap = cap; P.max_ext = max_ext; P.flags = false;
+    return 0;
+}
+
+int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
+{
+    PackedBoxes P;
+    LSSPG_TRY(tri_tiled_pack_host(H, P));
+    return upload_common(ctx, H, T, P);
 }
 
 void tri_tiled_free(lsspg_tri *T)
