@@ -24,6 +24,7 @@
 #include <time.h>
 #include "blas1.cuh"
 #include "tri.cuh"
+#include "host_par.h"
 
 namespace lsspg {
 
@@ -63,46 +64,62 @@ int tri_build_host(int which, int n, const int *Tp, const int *Tj, const double 
     std::vector<int> lstart(nlev + 1, 0);
     for (int i = 0; i < n; i++) lstart[H.level[i] + 1]++;
     for (int l = 0; l < nlev; l++) lstart[l + 1] += lstart[l];
-    std::vector<int> order(n);
+    IVec order((size_t)n);
     {
         std::vector<int> pos(lstart.begin(), lstart.end() - 1);
         for (int i = 0; i < n; i++) order[pos[H.level[i]]++] = i;
     }
-    long long nslices = 0;
-    for (int l = 0; l < nlev; l++) nslices += (lstart[l + 1] - lstart[l] + 31) / 32;
+    // first slice of every level
+    std::vector<long long> sfirst(nlev + 1, 0);
+    for (int l = 0; l < nlev; l++) sfirst[l + 1] = sfirst[l] + (lstart[l + 1] - lstart[l] + 31) / 32;
+    const long long nslices = sfirst[nlev];
     LSSPG_CHECK(nslices * 32 < (1ll << 31), "tri: too many slices");
     H.num_slices = (int)nslices;
-    H.perm.assign((size_t)nslices * 32, -1);
-    H.diag.assign((size_t)nslices * 32, 1.0);
-    H.slice_ptr.assign((size_t)nslices + 1, 0);
-    H.slice_need.assign((size_t)nslices, 0);
-    long long s = 0, wsum = 0;
-    H.offdiag_nnz = 0;
-    long long first_of_prev_level = 0, first_of_this_level = 0;
-    for (int l = 0; l < nlev; l++) {
-        first_of_prev_level = first_of_this_level;
-        first_of_this_level = s;
-        for (int r0 = lstart[l]; r0 < lstart[l + 1]; r0 += 32, s++) {
+    H.perm.resize((size_t)nslices * 32);
+    H.diag.resize((size_t)nslices * 32);
+    H.slice_ptr.resize((size_t)nslices + 1);
+    H.slice_need.resize((size_t)nslices);
+    // slices are filled by the host threads, level by level piece (every slice is written by one thread);
+    // slice_ptr first holds the slice's width, the offsets follow from a scan
+    std::vector<long long> off_part(host_threads() + 1, 0);
+    parallel_ranges(nlev, [&](long long l0, long long l1, int) {
+        for (int l = (int)l0; l < (int)l1; l++) {
+            long long s = sfirst[l];
             // progress hint: start polling the operands once every slice of levels < l-1 is done
-            H.slice_need[s] = (int)first_of_prev_level;
-            const int cnt = std::min(32, lstart[l + 1] - r0);
-            int w = 0;
-            for (int q = 0; q < cnt; q++) {
-                const int i = order[r0 + q];
-                H.perm[s * 32 + q] = i;
-                w = std::max(w, Tp[i + 1] - Tp[i] - 1);
-                H.offdiag_nnz += Tp[i + 1] - Tp[i] - 1;
+            const int need = (int)(l > 0 ? sfirst[l - 1] : 0);
+            for (int r0 = lstart[l]; r0 < lstart[l + 1]; r0 += 32, s++) {
+                H.slice_need[s] = need;
+                const int cnt = std::min(32, lstart[l + 1] - r0);
+                int w = 0;
+                for (int q = 0; q < cnt; q++) {
+                    const int i = order[r0 + q];
+                    H.perm[s * 32 + q] = i;
+                    w = std::max(w, Tp[i + 1] - Tp[i] - 1);
+                }
+                for (int q = cnt; q < 32; q++) H.perm[s * 32 + q] = -1;
+                H.slice_ptr[s] = w;
             }
-            H.slice_ptr[s] = (int)wsum;
-            wsum += w;
-            LSSPG_CHECK(wsum < (1ll << 31) / 32, "tri: padded factor too large for int32 offsets");
         }
+    }, 0, 8);
+    H.offdiag_nnz = n ? (long long)Tp[n] - Tp[0] - n : 0;
+    long long wsum = 0;
+    for (long long s = 0; s < nslices; s++) {
+        const int w = H.slice_ptr[s];
+        H.slice_ptr[s] = (int)wsum;
+        wsum += w;
+        LSSPG_CHECK(wsum < (1ll << 31) / 32, "tri: padded factor too large for int32 offsets");
     }
     H.slice_ptr[nslices] = (int)wsum;
     H.padded_nnz = wsum * 32;
-    H.col.assign((size_t)H.padded_nnz, -1);
-    H.val.assign((size_t)H.padded_nnz, 0.0);
-    for (long long sl = 0; sl < nslices; sl++) {
+    H.col.resize((size_t)H.padded_nnz);
+    H.val.resize((size_t)H.padded_nnz);
+    parallel_ranges(nslices, [&](long long s0, long long s1, int) {
+    for (long long sl = s0; sl < s1; sl++) {
+        const long long base = (long long)H.slice_ptr[sl] * 32, wid = H.slice_ptr[sl + 1] - H.slice_ptr[sl];
+        for (long long e = base; e < base + wid * 32; e++) { H.col[e] = -1; H.val[e] = 0.0; }
+        for (int q = 0; q < 32; q++) H.diag[sl * 32 + q] = 1.0;
+    }
+    for (long long sl = s0; sl < s1; sl++) {
         const long long base = (long long)H.slice_ptr[sl] * 32;
         for (int q = 0; q < 32; q++) {
             const int i = H.perm[sl * 32 + q];
@@ -124,6 +141,7 @@ int tri_build_host(int which, int n, const int *Tp, const int *Tj, const double 
             }
         }
     }
+    }, 0, 256);
     return 0;
 }
 

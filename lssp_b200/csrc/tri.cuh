@@ -2,6 +2,7 @@
 #pragma once
 #include <vector>
 #include "common.cuh"
+#include "host_par.h"
 
 namespace lsspg {
 
@@ -16,12 +17,13 @@ struct TriHost {
     int num_levels = 0, num_slices = 0;
     long long padded_nnz = 0, offdiag_nnz = 0;
     std::vector<int> level;      // [n]
-    std::vector<int> perm;       // [num_slices*32]
-    std::vector<double> diag;    // [num_slices*32] divisor of the row
-    std::vector<int> slice_ptr;  // [num_slices+1]
-    std::vector<int> slice_need; // [num_slices] progress hint: #slices that precede level(slice) - 1
-    std::vector<int> col;        // [padded_nnz]
-    std::vector<double> val;     // [padded_nnz]
+    // filled by the host threads (host_par.h: no serial zero-fill on resize)
+    IVec perm;       // [num_slices*32]
+    DVec diag;       // [num_slices*32] divisor of the row
+    IVec slice_ptr;  // [num_slices+1]
+    IVec slice_need; // [num_slices] progress hint: #slices that precede level(slice) - 1
+    IVec col;        // [padded_nnz]
+    DVec val;        // [padded_nnz]
 };
 
 // returns 0 on success; levels only when want_layout == false
@@ -60,10 +62,11 @@ struct TiledHost {
     int n = 0, which = 0, num_tiles = 0, max_tile_rows = 0, num_tile_levels = 0, num_levels = 0;
     int tile_dims[3] = {0, 0, 0}, grid_dims[3] = {0, 0, 0};
     long long offdiag_nnz = 0;
-    std::vector<int> perm, ptr, col, tile_ptr, lev_off, lev_ptr;
+    IVec perm, ptr, col;               // [n], [n+1], [offdiag_nnz]: filled by the host threads
+    std::vector<int> tile_ptr, lev_off, lev_ptr;
     bool acyclic = false;              // box graph has no cycles: boxes may wait for whole predecessor boxes
     std::vector<int> pred_ptr, pred;   // per box (ticket order): tickets of the boxes it reads from
-    std::vector<double> diag, val;
+    DVec diag, val;
 };
 // returns 0 when a tile schedule was built, 2 when the factor is not a structured-grid factor
 // (caller falls back to the slice schedule), 1 on error
@@ -71,7 +74,8 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
 // The device image of a tile schedule: one 16-byte aligned blob per box plus BoxDesc[num_tiles] (raw bytes here;
 // the struct is private to tri_tiled.cu).  Packed on the host, no CUDA call involved.
 struct PackedBoxes {
-    std::vector<unsigned char> blob, desc_bytes;
+    std::vector<unsigned char, default_init_allocator<unsigned char>> blob;   // zeroed box by box by the packing threads
+    std::vector<unsigned char> desc_bytes;
     size_t cap = 0;       // largest blob
     int max_ext = 0;      // most operands a box reads from other boxes
     bool flags = false;   // ELL blobs for the completion-flag kernel (acyclic box graphs)

@@ -24,23 +24,55 @@
 #include <numeric>
 #include "blas1.cuh"
 #include "tri.cuh"
+#include "host_par.h"
 
 namespace lsspg {
 
 constexpr unsigned long long kSentinelBitsT = 0xFFF8DEADBEEF0001ull;   // same value as tri.cu
 constexpr int kMaxTileRows = 1024;
 
+// Histogram of |column - row| over the off-diagonal entries (at most 16 distinct offsets: stencil factors have
+// a handful).  Pieces of rows are counted by the host threads and merged; counts are order-independent.
+struct OffsetHist {
+    int m = 0;
+    long long off[17], cnt[17];
+    bool add(long long d, long long c)
+    {
+        for (int q = 0; q < m; q++)
+            if (off[q] == d) { cnt[q] += c; return true; }
+        if (m == 16) return false;
+        off[m] = d; cnt[m] = c; m++;
+        return true;
+    }
+};
+
 static bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3])
 {
-    std::map<long long, long long> hist;
-    for (int i = 0; i < n; i++) {
-        for (int k = Tp[i]; k < Tp[i + 1]; k++) {
-            const long long d = llabs((long long)Tj[k] - i);
-            if (d == 0) continue;
-            hist[d]++;
-            if (hist.size() > 16) return false;   // stencil factors have a handful of offsets
+    const int np = host_threads();
+    std::vector<OffsetHist> part(np);
+    std::vector<char> over(np, 0);
+    parallel_ranges(n, [&](long long r0, long long r1, int p) {
+        OffsetHist h;
+        long long last = -1;
+        int lastq = 0;
+        for (int i = (int)r0; i < (int)r1; i++) {
+            for (int k = Tp[i]; k < Tp[i + 1]; k++) {
+                const long long d = llabs((long long)Tj[k] - i);
+                if (d == 0) continue;
+                if (d == last) { h.cnt[lastq]++; continue; }
+                if (!h.add(d, 1)) { over[p] = 1; return; }
+                last = d;
+                for (lastq = 0; h.off[lastq] != d; lastq++) {}
+            }
         }
+        part[p] = h;
+    }, np);
+    std::map<long long, long long> hist;
+    for (int p = 0; p < np; p++) {
+        if (over[p]) return false;
+        for (int q = 0; q < part[p].m; q++) hist[part[p].off[q]] += part[p].cnt[q];
     }
+    if (hist.size() > 16) return false;
     if (hist.size() < 2 || hist.begin()->first != 1) return false;
     const long long s3 = hist.rbegin()->first;
     if (s3 <= 1 || n % s3 != 0) return false;
@@ -61,6 +93,9 @@ static bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3])
     return (long long)dims[0] * dims[1] * dims[2] == n;
 }
 
+// Set-up of the box schedule.  Only the dependency-level recurrence is inherently serial (one O(nnz) pass);
+// everything else runs over the host threads on disjoint outputs, so the image does not depend on their number
+// (tests/test_setup_threads.py pins it).
 int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const double *Tx, TiledHost &H)
 {
     const bool lower = (which == LSSPG_TRI_LOWER);
@@ -75,34 +110,68 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
     if ((long long)t[0] * t[1] * t[2] > kMaxTileRows) return 2;
     const int nt[3] = {(g[0] + t[0] - 1) / t[0], (g[1] + t[1] - 1) / t[1], (g[2] + t[2] - 1) / t[2]};
     const int ntiles = nt[0] * nt[1] * nt[2];
-    std::vector<int> tile_of(n);
-    for (int i = 0; i < n; i++) {
-        const int x = i % g[0], y = (i / g[0]) % g[1], z = i / (g[0] * g[1]);
-        tile_of[i] = ((z / t[2]) * nt[1] + (y / t[1])) * nt[0] + (x / t[0]);
+    IVec tile_of((size_t)n);
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) {
+            const int x = i % g[0], y = (i / g[0]) % g[1], z = i / (g[0] * g[1]);
+            tile_of[i] = ((z / t[2]) * nt[1] + (y / t[1])) * nt[0] + (x / t[0]);
+        }
+    });
+    // validate the triangle (threads) ...
+    {
+        const int np = host_threads();
+        std::vector<char> bad(np, 0);
+        parallel_ranges(n, [&](long long r0, long long r1, int p) {
+            for (int i = (int)r0; i < (int)r1; i++) {
+                const int b = Tp[i], e = Tp[i + 1];
+                if (e <= b) { bad[p] = 1; return; }
+                const int dpos = lower ? e - 1 : b;
+                if (Tj[dpos] != i) { bad[p] = 1; return; }
+                for (int k = b; k < e; k++) {
+                    if (k == dpos) continue;
+                    const int c = Tj[k];
+                    if (lower ? !(c >= 0 && c < i) : !(c > i && c < n)) { bad[p] = 1; return; }
+                }
+            }
+        }, np);
+        for (char b : bad)
+            if (b) return 2;
     }
-    // validate the triangle and compute the dependency level of every row, in solve order.  Rows of
-    // a box are later grouped by this GLOBAL level: the unfinished row of smallest level anywhere is
-    // then always inside its box's current group with all operands produced, so level barriers inside
-    // boxes can never deadlock boxes that depend on each other.
-    std::vector<int> gl(n, 0);
-    std::vector<long long> edges;   // box dependency edges: from * ntiles + to
+    // ... and compute the dependency level of every row, in solve order.  Rows of a box are later grouped by
+    // this GLOBAL level: the unfinished row of smallest level anywhere is then always inside its box's current
+    // group with all operands produced, so level barriers inside boxes can never deadlock boxes that depend
+    // on each other.
+    IVec gl((size_t)n);
     int nlev_global = 0;
     for (int q = 0; q < n; q++) {
         const int i = lower ? q : n - 1 - q;
-        const int b = Tp[i], e = Tp[i + 1];
-        if (e <= b) return 2;
-        const int dpos = lower ? e - 1 : b;
-        if (Tj[dpos] != i) return 2;
+        const int b = lower ? Tp[i] : Tp[i] + 1, e = lower ? Tp[i + 1] - 1 : Tp[i + 1];
         int gg = 0;
-        for (int k = b; k < e; k++) {
-            if (k == dpos) continue;
-            const int c = Tj[k];
-            if (lower ? !(c >= 0 && c < i) : !(c > i && c < n)) return 2;
-            gg = std::max(gg, gl[c] + 1);
-            if (tile_of[c] != tile_of[i]) edges.push_back((long long)tile_of[c] * ntiles + tile_of[i]);
-        }
+        for (int k = b; k < e; k++) gg = std::max(gg, gl[Tj[k]] + 1);
         gl[i] = gg;
         nlev_global = std::max(nlev_global, gg + 1);
+    }
+    // box dependency edges (from * ntiles + to), each piece of rows deduplicated on its own, then merged
+    std::vector<long long> edges;
+    {
+        const int np = host_threads();
+        std::vector<std::vector<long long>> part(np);
+        parallel_ranges(n, [&](long long r0, long long r1, int p) {
+            std::vector<long long> &ev = part[p];
+            long long last = -1;
+            for (int i = (int)r0; i < (int)r1; i++) {
+                const int ti = tile_of[i];
+                for (int k = Tp[i]; k < Tp[i + 1]; k++) {
+                    const int c = Tj[k];
+                    if (c == i || tile_of[c] == ti) continue;
+                    const long long ed = (long long)tile_of[c] * ntiles + ti;
+                    if (ed != last) { ev.push_back(ed); last = ed; }
+                }
+            }
+            std::sort(ev.begin(), ev.end());
+            ev.erase(std::unique(ev.begin(), ev.end()), ev.end());
+        }, np);
+        for (auto &ev : part) edges.insert(edges.end(), ev.begin(), ev.end());
     }
     std::sort(edges.begin(), edges.end());
     edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
@@ -174,19 +243,45 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
     std::vector<int> ticket_of(ntiles);
     for (int k = 0; k < ntiles; k++) ticket_of[torder[k]] = k;
     // slots: rows sorted by (ticket of box, local level, row)
-    std::vector<int> order(n);
+    H.perm.resize((size_t)n);
+    IVec &order = H.perm;
+    H.tile_ptr.assign(ntiles + 1, 0);
+    std::vector<int> &start = H.tile_ptr;
     {
-        std::vector<int> start(ntiles + 1, 0);
         for (int i = 0; i < n; i++) start[ticket_of[tile_of[i]] + 1]++;
         for (int k = 0; k < ntiles; k++) start[k + 1] += start[k];
         std::vector<int> pos(start.begin(), start.end() - 1);
         for (int i = 0; i < n; i++) order[pos[ticket_of[tile_of[i]]]++] = i;   // bucket by box, rows ascending
-        for (int k = 0; k < ntiles; k++)
+    }
+    H.max_tile_rows = 0;
+    for (int k = 0; k < ntiles; k++) H.max_tile_rows = std::max(H.max_tile_rows, start[k + 1] - start[k]);
+    if (H.max_tile_rows > kMaxTileRows) return 2;
+    // per box: rows stably sorted by level; number of level groups and of off-diagonal entries
+    IVec slot_of((size_t)n);
+    H.ptr.resize((size_t)n + 1);
+    H.lev_off.assign(ntiles + 1, 0);
+    parallel_ranges(ntiles, [&](long long k0, long long k1, int) {
+        for (int k = (int)k0; k < (int)k1; k++) {
             std::stable_sort(order.begin() + start[k], order.begin() + start[k + 1],
                              [&](int a, int b) { return gl[a] < gl[b]; });
+            int groups = 0, cur = -1;
+            for (int s = start[k]; s < start[k + 1]; s++) {
+                const int i = order[s];
+                slot_of[i] = s;
+                H.ptr[s] = Tp[i + 1] - Tp[i] - 1;
+                if (gl[i] != cur) { groups++; cur = gl[i]; }
+            }
+            H.lev_off[k] = groups + 1;   // group starts + the closing entry
+        }
+    }, 0, 64);
+    const long long nent_total = parallel_exclusive_scan(H.ptr.data(), n);
+    H.ptr[n] = (int)nent_total;
+    {
+        int run = 0;
+        for (int k = 0; k < ntiles; k++) { const int c = H.lev_off[k]; H.lev_off[k] = run; run += c; }
+        H.lev_off[ntiles] = run;
+        H.lev_ptr.assign((size_t)run, 0);
     }
-    std::vector<int> slot_of(n);
-    for (int s = 0; s < n; s++) slot_of[order[s]] = s;
     H.n = n; H.which = which; H.num_tiles = ntiles; H.num_levels = nlev_global;
     H.num_tile_levels = ntiles ? *std::max_element(tl.begin(), tl.end()) + 1 : 0;
     H.acyclic = (max_scc <= 1);
@@ -199,45 +294,33 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
         for (long long ed : edges) H.pred[pos[ticket_of[ed % ntiles]]++] = ticket_of[ed / ntiles];
     }
     for (int k = 0; k < 3; k++) { H.tile_dims[k] = t[k]; H.grid_dims[k] = g[k]; }
-    H.perm = order;
-    H.diag.resize(n);
-    H.ptr.assign(n + 1, 0);
-    H.tile_ptr.assign(ntiles + 1, 0);
-    H.lev_off.assign(ntiles + 1, 0);
-    H.lev_ptr.clear();
+    H.diag.resize((size_t)n);
     H.offdiag_nnz = (long long)Tp[n] - n;
+    if (nent_total != H.offdiag_nnz) return 2;
     H.col.resize((size_t)H.offdiag_nnz);
     H.val.resize((size_t)H.offdiag_nnz);
-    H.max_tile_rows = 0;
-    int s = 0, ent = 0;
-    for (int k = 0; k < ntiles; k++) {
-        const int s0 = s;
-        H.tile_ptr[k] = s0;
-        H.lev_off[k] = (int)H.lev_ptr.size();
-        int cur = -1;
-        while (s < n && ticket_of[tile_of[order[s]]] == k) {
-            const int i = order[s];
-            if (gl[i] != cur) { H.lev_ptr.push_back(s); cur = gl[i]; }
-            const int b = Tp[i], e = Tp[i + 1];
-            H.ptr[s] = ent;
-            H.diag[s] = lower ? Tx[e - 1] : Tx[b];
-            // application order: lower ascending storage order, upper descending
-            for (int q = 0; q < e - b - 1; q++) {
-                const int kk = lower ? b + q : e - 1 - q;
-                const int c = Tj[kk];
-                H.col[ent] = (tile_of[c] == tile_of[i]) ? -(slot_of[c] - s0 + 1) : c;
-                H.val[ent] = Tx[kk];
-                ent++;
+    parallel_ranges(ntiles, [&](long long k0, long long k1, int) {
+        for (int k = (int)k0; k < (int)k1; k++) {
+            const int s0 = start[k], s1 = start[k + 1];
+            int lp = H.lev_off[k], cur = -1;
+            for (int s = s0; s < s1; s++) {
+                const int i = order[s];
+                if (gl[i] != cur) { H.lev_ptr[lp++] = s; cur = gl[i]; }
+                const int b = Tp[i], e = Tp[i + 1];
+                int ent = H.ptr[s];
+                H.diag[s] = lower ? Tx[e - 1] : Tx[b];
+                // application order: lower ascending storage order, upper descending
+                for (int q = 0; q < e - b - 1; q++) {
+                    const int kk = lower ? b + q : e - 1 - q;
+                    const int c = Tj[kk];
+                    H.col[ent] = (tile_of[c] == tile_of[i]) ? -(slot_of[c] - s0 + 1) : c;
+                    H.val[ent] = Tx[kk];
+                    ent++;
+                }
             }
-            s++;
+            H.lev_ptr[lp] = s1;
         }
-        H.lev_ptr.push_back(s);
-        H.max_tile_rows = std::max(H.max_tile_rows, s - s0);
-    }
-    H.tile_ptr[ntiles] = n;
-    H.lev_off[ntiles] = (int)H.lev_ptr.size();
-    H.ptr[n] = ent;
-    if (s != n || H.max_tile_rows > kMaxTileRows) return 2;
+    }, 0, 64);
     return 0;
 }
 
@@ -782,7 +865,8 @@ int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double
 
 static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const PackedBoxes &P)
 {
-    const std::vector<unsigned char> &blob = P.blob, &desc = P.desc_bytes;
+    const auto &blob = P.blob;
+    const std::vector<unsigned char> &desc = P.desc_bytes;
     const size_t cap = P.cap;
     const int max_ext = P.max_ext;
     const bool flags = P.flags;
@@ -810,76 +894,91 @@ static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const
 }
 
 // acyclic box graph: ELL blobs for tri_box_ell_kernel.  Host only; 2 = not applicable (a box would not fit).
+// Boxes are sized, laid out and filled by the host threads (a box's blob is written by exactly one thread).
 static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
 {
-    std::vector<BoxDesc> desc(H.num_tiles);
+    const int nb = H.num_tiles;
+    std::vector<BoxDesc> desc(nb);
+    parallel_ranges(nb, [&](long long k0, long long k1, int) {
+        for (int k = (int)k0; k < (int)k1; k++) {
+            const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
+            BoxDesc &d = desc[k];
+            d.nrows = s1 - s0;
+            d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
+            d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
+            d.next = 0;
+            int w = 0;
+            for (int s = s0; s < s1; s++) w = std::max(w, H.ptr[s + 1] - H.ptr[s]);
+            for (int e = H.ptr[s0]; e < H.ptr[s1]; e++) d.next += (H.col[e] >= 0);
+            d.nent = w;   // ELL width
+            d.bytes = (int)ell_layout(d.nrows, w, d.nlev, d.next, d.npred).total;
+        }
+    }, 0, 64);
     size_t total = 0, cap = 0;
     int max_ext = 0;
-    for (int k = 0; k < H.num_tiles; k++) {
-        const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
-        BoxDesc &d = desc[k];
-        d.nrows = s1 - s0;
-        d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
-        d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
-        d.next = 0;
-        int w = 0;
-        for (int s = s0; s < s1; s++) w = std::max(w, H.ptr[s + 1] - H.ptr[s]);
-        for (int e = H.ptr[s0]; e < H.ptr[s1]; e++) d.next += (H.col[e] >= 0);
-        d.nent = w;   // ELL width
-        max_ext = std::max(max_ext, d.next);
-        const EllLayout lay = ell_layout(d.nrows, w, d.nlev, d.next, d.npred);
-        d.off = (long long)total;
-        d.bytes = (int)lay.total;
-        total += lay.total;
-        cap = std::max(cap, lay.total);
+    for (int k = 0; k < nb; k++) {
+        desc[k].off = (long long)total;
+        total += (size_t)desc[k].bytes;
+        cap = std::max(cap, (size_t)desc[k].bytes);
+        max_ext = std::max(max_ext, desc[k].next);
     }
     if (16 + cap + 8 * ((size_t)H.max_tile_rows + max_ext + 2) > (size_t)200 * 1024) return 2;
-    std::vector<unsigned char> blob(std::max<size_t>(total, 16), 0);
-    std::vector<int> pos_of_row(H.n, 0);   // row -> position in box-major order
-    for (int s = 0; s < H.n; s++) pos_of_row[H.perm[s]] = s;
-    for (int k = 0; k < H.num_tiles; k++) {
-        const int s0 = H.tile_ptr[k];
-        const BoxDesc &d = desc[k];
-        const int w = d.nent, nr = d.nrows;
-        const EllLayout lay = ell_layout(nr, w, d.nlev, d.next, d.npred);
-        unsigned char *b = blob.data() + d.off;
-        int *lev = (int *)(b + lay.lev), *perm = (int *)(b + lay.perm), *ext = (int *)(b + lay.ext), *pred = (int *)(b + lay.pred);
-        int *ecol = (int *)(b + lay.ecol);
-        double *diag = (double *)(b + lay.diag), *eval = (double *)(b + lay.eval);
-        for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
-        // gate operand per predecessor box: of the rows this box reads from it, the one that box stores last
-        for (int q = 0; q < d.npred; q++) {
-            const int p = H.pred[H.pred_ptr[k] + q];
-            int best = -1;
-            for (int e = H.ptr[s0]; e < H.ptr[s0 + nr]; e++) {
-                const int c = H.col[e];
-                if (c < 0) continue;
-                const int pos = pos_of_row[c];
-                if (pos >= H.tile_ptr[p] && pos < H.tile_ptr[p + 1] && (best < 0 || pos > pos_of_row[best])) best = c;
-            }
-            if (best < 0) return 1;   // a predecessor without operands: the schedule is inconsistent
-            pred[q] = best;
-        }
-        int q = 0;
-        for (int s = 0; s < nr; s++) {
-            perm[s] = H.perm[s0 + s];
-            diag[s] = H.diag[s0 + s];
-            const int e0 = H.ptr[s0 + s], len = H.ptr[s0 + s + 1] - e0;
-            for (int j = 0; j < w; j++) {
-                if (j < len) {
-                    const int c = H.col[e0 + j];
-                    if (c >= 0) { ext[q] = c; ecol[j * nr + s] = nr + q; q++; }
-                    else ecol[j * nr + s] = -c - 1;
-                    eval[j * nr + s] = H.val[e0 + j];
+    P.blob.resize(std::max<size_t>(total, 16));
+    if (total < 16) memset(P.blob.data(), 0, 16);
+    unsigned char *blob = P.blob.data();
+    IVec pos_of_row((size_t)H.n);   // row -> position in box-major order
+    parallel_ranges(H.n, [&](long long a, long long b, int) {
+        for (int s = (int)a; s < (int)b; s++) pos_of_row[H.perm[s]] = s;
+    });
+    const int np = host_threads();
+    std::vector<char> bad(np, 0);
+    parallel_ranges(nb, [&](long long k0, long long k1, int piece) {
+        for (int k = (int)k0; k < (int)k1; k++) {
+            const int s0 = H.tile_ptr[k];
+            const BoxDesc &d = desc[k];
+            const int w = d.nent, nr = d.nrows;
+            const EllLayout lay = ell_layout(nr, w, d.nlev, d.next, d.npred);
+            unsigned char *b = blob + d.off;
+            memset(b, 0, (size_t)d.bytes);
+            int *lev = (int *)(b + lay.lev), *perm = (int *)(b + lay.perm), *ext = (int *)(b + lay.ext), *pred = (int *)(b + lay.pred);
+            int *ecol = (int *)(b + lay.ecol);
+            double *diag = (double *)(b + lay.diag), *eval = (double *)(b + lay.eval);
+            for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
+            // gate operand per predecessor box: of the rows this box reads from it, the one that box stores last
+            for (int q = 0; q < d.npred; q++) {
+                const int p = H.pred[H.pred_ptr[k] + q];
+                int best = -1;
+                for (int e = H.ptr[s0]; e < H.ptr[s0 + nr]; e++) {
+                    const int c = H.col[e];
+                    if (c < 0) continue;
+                    const int pos = pos_of_row[c];
+                    if (pos >= H.tile_ptr[p] && pos < H.tile_ptr[p + 1] && (best < 0 || pos > pos_of_row[best])) best = c;
                 }
-                else {
-                    ecol[j * nr + s] = nr + d.next;   // the box's private +0.0 operand
-                    eval[j * nr + s] = 0.0;
+                if (best < 0) { bad[piece] = 1; return; }   // a predecessor without operands: the schedule is inconsistent
+                pred[q] = best;
+            }
+            int q = 0;
+            for (int s = 0; s < nr; s++) {
+                perm[s] = H.perm[s0 + s];
+                diag[s] = H.diag[s0 + s];
+                const int e0 = H.ptr[s0 + s], len = H.ptr[s0 + s + 1] - e0;
+                for (int j = 0; j < w; j++) {
+                    if (j < len) {
+                        const int c = H.col[e0 + j];
+                        if (c >= 0) { ext[q] = c; ecol[j * nr + s] = nr + q; q++; }
+                        else ecol[j * nr + s] = -c - 1;
+                        eval[j * nr + s] = H.val[e0 + j];
+                    }
+                    else {
+                        ecol[j * nr + s] = nr + d.next;   // the box's private +0.0 operand
+                        eval[j * nr + s] = 0.0;
+                    }
                 }
             }
         }
-    }
-    P.blob.swap(blob);
+    }, np, 1);
+    for (char b : bad)
+        if (b) return 1;
     P.desc_bytes.assign((const unsigned char *)desc.data(), (const unsigned char *)(desc.data() + desc.size()));
     P.cap = cap; P.max_ext = max_ext; P.flags = true;
     return 0;
@@ -894,52 +993,60 @@ int tri_tiled_pack_host(const TiledHost &H, PackedBoxes &P)
             if (rc != 2) return rc;
         }
     }
-    // pack the boxes
-    std::vector<BoxDesc> desc(H.num_tiles);
+    // pack the boxes (CSR blobs for tri_box_kernel)
+    const int nb = H.num_tiles;
+    std::vector<BoxDesc> desc(nb);
+    parallel_ranges(nb, [&](long long k0, long long k1, int) {
+        for (int k = (int)k0; k < (int)k1; k++) {
+            const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
+            BoxDesc &d = desc[k];
+            d.nrows = s1 - s0;
+            d.nent = H.ptr[s1] - H.ptr[s0];
+            d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
+            d.next = 0;
+            d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
+            for (int e = H.ptr[s0]; e < H.ptr[s1]; e++) d.next += (H.col[e] >= 0);
+            d.bytes = (int)box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred).total;
+        }
+    }, 0, 64);
     size_t total = 0, cap = 0;
     int max_ext = 0;
-    for (int k = 0; k < H.num_tiles; k++) {
-        const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
-        BoxDesc &d = desc[k];
-        d.nrows = s1 - s0;
-        d.nent = H.ptr[s1] - H.ptr[s0];
-        d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
-        d.next = 0;
-        d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
-        for (int e = H.ptr[s0]; e < H.ptr[s1]; e++) d.next += (H.col[e] >= 0);
-        max_ext = std::max(max_ext, d.next);
-        const BoxLayout lay = box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred);
-        d.off = (long long)total;
-        d.bytes = (int)lay.total;
-        total += lay.total;
-        cap = std::max(cap, lay.total);
+    for (int k = 0; k < nb; k++) {
+        desc[k].off = (long long)total;
+        total += (size_t)desc[k].bytes;
+        cap = std::max(cap, (size_t)desc[k].bytes);
+        max_ext = std::max(max_ext, desc[k].next);
     }
     if (16 + cap + 16 * (size_t)H.max_tile_rows + 8 * (size_t)max_ext > (size_t)200 * 1024) {
         set_error("tri_tiled: a box needs more shared memory than one SM has");
         return 1;
     }
-    std::vector<unsigned char> blob(std::max<size_t>(total, 16), 0);
-    for (int k = 0; k < H.num_tiles; k++) {
-        const int s0 = H.tile_ptr[k];
-        const BoxDesc &d = desc[k];
-        const BoxLayout lay = box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred);
-        unsigned char *b = blob.data() + d.off;
-        int *lev = (int *)(b + lay.lev), *ptr = (int *)(b + lay.ptr), *perm = (int *)(b + lay.perm), *col = (int *)(b + lay.col);
-        int *ext = (int *)(b + lay.ext), *pred = (int *)(b + lay.pred);
-        for (int q = 0; q < d.npred; q++) pred[q] = H.pred[H.pred_ptr[k] + q];
-        double *diag = (double *)(b + lay.diag), *val = (double *)(b + lay.val);
-        for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
-        const int e0 = H.ptr[s0];
-        for (int s = 0; s <= d.nrows; s++) ptr[s] = H.ptr[s0 + s] - e0;
-        for (int s = 0; s < d.nrows; s++) { perm[s] = H.perm[s0 + s]; diag[s] = H.diag[s0 + s]; }
-        for (int e = 0, q = 0; e < d.nent; e++) {
-            const int c = H.col[e0 + e];
-            if (c >= 0) { ext[q] = c; col[e] = q++; }
-            else col[e] = c;
-            val[e] = H.val[e0 + e];
+    P.blob.resize(std::max<size_t>(total, 16));
+    if (total < 16) memset(P.blob.data(), 0, 16);
+    unsigned char *blob = P.blob.data();
+    parallel_ranges(nb, [&](long long k0, long long k1, int) {
+        for (int k = (int)k0; k < (int)k1; k++) {
+            const int s0 = H.tile_ptr[k];
+            const BoxDesc &d = desc[k];
+            const BoxLayout lay = box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred);
+            unsigned char *b = blob + d.off;
+            memset(b, 0, (size_t)d.bytes);
+            int *lev = (int *)(b + lay.lev), *ptr = (int *)(b + lay.ptr), *perm = (int *)(b + lay.perm), *col = (int *)(b + lay.col);
+            int *ext = (int *)(b + lay.ext), *pred = (int *)(b + lay.pred);
+            for (int q = 0; q < d.npred; q++) pred[q] = H.pred[H.pred_ptr[k] + q];
+            double *diag = (double *)(b + lay.diag), *val = (double *)(b + lay.val);
+            for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
+            const int e0 = H.ptr[s0];
+            for (int s = 0; s <= d.nrows; s++) ptr[s] = H.ptr[s0 + s] - e0;
+            for (int s = 0; s < d.nrows; s++) { perm[s] = H.perm[s0 + s]; diag[s] = H.diag[s0 + s]; }
+            for (int e = 0, q = 0; e < d.nent; e++) {
+                const int c = H.col[e0 + e];
+                if (c >= 0) { ext[q] = c; col[e] = q++; }
+                else col[e] = c;
+                val[e] = H.val[e0 + e];
+            }
         }
-    }
-    P.blob.swap(blob);
+    }, 0, 64);
     P.desc_bytes.assign((const unsigned char *)desc.data(), (const unsigned char *)(desc.data() + desc.size()));
     P.cap = cap; P.max_ext = max_ext; P.flags = false;
     return 0;

@@ -1,0 +1,93 @@
+"""The threaded host set-up (ilu_host.cpp, tri.cu, tri_tiled.cu over host_par.h) must produce exactly the bytes the
+serial code produced: factors equal to the reference's, schedule images equal to the fingerprints pinned in
+tests/golden/pack_golden.json (generated with LSSPG_HOST_THREADS=1 before the set-up was threaded), for any
+number of host threads.  No GPU involved: lsspg_debug_tri_pack_host builds the image lsspg_tri_analyse uploads."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from lssp_b200 import api, generators as g
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_pack_golden as mpg  # noqa: E402
+
+with open(os.path.join(ROOT, "tests", "golden", "pack_golden.json")) as f:
+    PACK = json.load(f)
+
+
+def fingerprints(name):
+    make, kw = mpg.CASES[name]
+    L, U = api.ilu_factor(make(), **kw)
+    out = {}
+    for which, T, tag in ((0, L, "L"), (1, U, "U")):
+        r = api.tri_pack_host(which, T)
+        out[name + "/" + tag] = dict(kind=r["kind"], bytes=r["bytes"], fingerprint="%016x" % r["fingerprint"])
+    return out
+
+
+@pytest.mark.parametrize("name", list(mpg.CASES))
+def test_schedule_images_match_the_pinned_serial_ones(name):
+    for key, got in fingerprints(name).items():
+        assert got == PACK[key], key
+
+
+@pytest.mark.parametrize("threads", [1, 3, 7])
+def test_schedule_images_do_not_depend_on_the_thread_count(threads):
+    # the thread count is read once per process: run the comparison in a child
+    code = ("import json, sys; sys.path[:0] = [%r, %r]; import test_setup_threads as t; "
+            "print(json.dumps({k: v for n in ('lap3d_48/iluk0_bj3', 'cd3d_40/ilut', 'lap2d_300/iluk0') "
+            "for k, v in t.fingerprints(n).items()}))" % (ROOT, os.path.join(ROOT, "tests")))
+    env = dict(os.environ, LSSPG_HOST_THREADS=str(threads))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    got = json.loads(out.stdout.strip().splitlines()[-1])
+    assert got and all(PACK[k] == v for k, v in got.items())
+
+
+def _same(F, G):
+    return all(np.array_equal(a, b) for X, Y in zip(F, G) for a, b in zip(X, Y))
+
+
+def test_threaded_factorisation_equals_the_reference_at_sizes_that_use_threads(ref):
+    # n = 110 592 rows: every threaded loop of the set-up really runs on several threads
+    A = g.cd3d(48)
+    n = len(A[0]) - 1
+    for kw in (dict(kind="iluk", level=0), dict(kind="iluk", level=1), dict(kind="iluk", level=2, blk_size=(n + 2) // 3),
+               dict(kind="ilut", p=5, tol=1e-3, blk_size=(n + 1) // 2)):
+        assert _same(api.ilu_factor(A, **kw), ref.ilu(A, **kw)), kw
+
+
+def test_unsorted_rows_and_missing_diagonals_take_the_repair_path(ref):
+    Ap, Aj, Ax = g.cd3d(40)
+    Aj, Ax = Aj.copy(), Ax.copy()
+    n = len(Ap) - 1
+    rng = np.random.default_rng(5)
+    for i in rng.choice(n, 2000, replace=False):      # shuffle some rows: sorted by the set-up (src/lssp.cxx:173)
+        b, e = Ap[i], Ap[i + 1]
+        p = rng.permutation(e - b)
+        Aj[b:e], Ax[b:e] = Aj[b:e][p], Ax[b:e][p]
+    B = (Ap, Aj, Ax)
+    for kw in (dict(kind="iluk", level=0), dict(kind="iluk", level=1, blk_size=(n + 3) // 4)):
+        assert _same(api.ilu_factor(B, **kw), ref.ilu(B, **kw)), kw
+    # Missing diagonals: src/matrix-utils.cxx:483-587 inserts (i, tol = 1e-10) in sorted position.  The reference
+    # leaves num_nnzs of the repaired matrix stale (:485 copies the struct, the count is never updated), so its own
+    # factorisation of such a matrix reads short / crashes -- the pin is the documented semantics instead: the
+    # factors equal those of the matrix with the entries written out.
+    Ap, Aj, Ax = g.cd3d(40)
+    drop = np.zeros(len(Aj), bool)
+    rows = np.sort(rng.choice(n, 500, replace=False))
+    for i in rows:
+        b, e = Ap[i], Ap[i + 1]
+        drop[b:e] |= Aj[b:e] == i
+    cnt = np.add.reduceat((~drop).astype(np.int64), Ap[:-1])
+    Bp = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    B = (Bp, Aj[~drop], Ax[~drop])
+    Cx = Ax.copy()
+    Cx[drop] = 1e-10
+    for kw in (dict(kind="iluk", level=0), dict(kind="iluk", level=1), dict(kind="ilut", p=5, tol=1e-3)):
+        assert _same(api.ilu_factor(B, **kw), api.ilu_factor((Ap, Aj, Cx), **kw)), kw
