@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <thread>
 #include <utility>
@@ -104,5 +105,130 @@ long long parallel_exclusive_scan(T *counts, long long n)
     }, np);
     return part[np];
 }
+
+// Rows whose dependencies are only discovered while they are computed (ILU(k) symbolic phase, ILUT): a row may
+// need any FINISHED row of smaller index.  Chunks of consecutive rows are handed out in natural order; a thread
+// runs the rows of its chunk in order and, before reading row r of an earlier chunk, waits until that chunk's
+// progress counter has passed r.  Waits only ever target chunks handed out earlier, and the lowest chunk in
+// flight never waits, so the scheme cannot deadlock; every row sees exactly the finished rows the serial loop
+// would show it, so results do not depend on the number of threads or on timing.  With the chunk length equal to
+// the innermost grid dimension of a stencil matrix, a thread trails the owner of the previous grid line by one row.
+class RowPipeline {
+public:
+    RowPipeline(int n, int chunk) : n_(n), chunk_(std::max(1, chunk)), nchunks_((n + chunk_ - 1) / chunk_),
+                                    progress_(new Counter[(size_t)std::max(nchunks_, 1)]), ticket_(0)
+    {
+        for (int c = 0; c < nchunks_; c++) progress_[c].v.store(0, std::memory_order_relaxed);
+    }
+    // row r (smaller than the caller's current row) is finished on return
+    void wait(int r, int my_chunk_begin) const
+    {
+        if (r >= my_chunk_begin) return;   // the caller finished it itself
+        const int c = r / chunk_, need = r - c * chunk_ + 1;
+        int spins = 0;
+        while (progress_[c].v.load(std::memory_order_acquire) < need)
+            if (++spins > 4000) { std::this_thread::yield(); spins = 0; }
+    }
+    // body(thread, row, chunk_begin)
+    template <class F>
+    void run(int threads, F body)
+    {
+        auto worker = [&](int t) {
+            for (;;) {
+                const int c = ticket_.fetch_add(1, std::memory_order_relaxed);
+                if (c >= nchunks_) return;
+                const int b = c * chunk_, e = std::min(n_, b + chunk_);
+                for (int r = b; r < e; r++) {
+                    body(t, r, b);
+                    // published every few rows (and at the end): the followers' polling costs the owner a cache miss
+                    if (((r - b) & 3) == 3 || r == e - 1) progress_[c].v.store(r - b + 1, std::memory_order_release);
+                }
+            }
+        };
+        if (threads <= 1) {
+            worker(0);
+            return;
+        }
+        std::vector<std::thread> th;
+        for (int t = 1; t < threads; t++) th.emplace_back(worker, t);
+        worker(0);
+        for (auto &x : th) x.join();
+    }
+
+private:
+    struct alignas(64) Counter {
+        std::atomic<int> v;
+    };
+    int n_, chunk_, nchunks_;
+    std::unique_ptr<Counter[]> progress_;
+    std::atomic<int> ticket_;
+};
+
+// Blocks of ints/doubles that never move once handed out (rows publish pointers into them).
+template <class T>
+class BlockArena {
+public:
+    T *take(size_t count)
+    {
+        if (count > left_) {
+            const size_t cap = std::max(count, (size_t)1 << 18);
+            blocks_.emplace_back(new T[cap]);
+            cur_ = blocks_.back().get();
+            left_ = cap;
+        }
+        T *p = cur_;
+        cur_ += count;
+        left_ -= count;
+        return p;
+    }
+
+private:
+    std::vector<std::unique_ptr<T[]>> blocks_;
+    T *cur_ = nullptr;
+    size_t left_ = 0;
+};
+
+// Rows grouped by dependency level, run level after level by a team of host threads (spinning barrier between
+// levels; the rows of one level are cut into contiguous pieces, one per thread).  fn(row) may read everything
+// rows of EARLIER levels wrote and must write only what belongs to its own row -- results are then independent
+// of the number of threads.
+class LevelTeam {
+public:
+    template <class F>
+    static void run(int nlev, const int *start, const int *order, F fn)
+    {
+        const int nt = host_threads();
+        long long rows = nlev > 0 ? (long long)start[nlev] - start[0] : 0;
+        if (nt <= 1 || rows < (1 << 15) || rows / std::max(nlev, 1) < 4 * nt) {
+            for (int l = 0; l < nlev; l++)
+                for (int q = start[l]; q < start[l + 1]; q++) fn(order[q]);
+            return;
+        }
+        std::atomic<int> arrived(0), sense(0);
+        auto worker = [&](int t) {
+            int local = 0;
+            for (int l = 0; l < nlev; l++) {
+                const long long b = start[l], cnt = start[l + 1] - b;
+                const long long q0 = b + cnt * t / nt, q1 = b + cnt * (t + 1) / nt;
+                for (long long q = q0; q < q1; q++) fn(order[q]);
+                // sense-reversing barrier
+                local ^= 1;
+                if (arrived.fetch_add(1, std::memory_order_acq_rel) == nt - 1) {
+                    arrived.store(0, std::memory_order_relaxed);
+                    sense.store(local, std::memory_order_release);
+                }
+                else {
+                    int spins = 0;
+                    while (sense.load(std::memory_order_acquire) != local)
+                        if (++spins > 2000) std::this_thread::yield();
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(worker, t);
+        worker(0);
+        for (auto &x : th) x.join();
+    }
+};
 
 }  // namespace lsspg

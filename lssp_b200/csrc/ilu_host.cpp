@@ -203,7 +203,7 @@ Csr ingest(int n, const int *Ap, const int *Aj, const double *Ax)
 // lev(i,k) + lev(k,c) + 1; candidates above `level` are ignored; an entry that
 // is ALREADY in the row has its level RAISED to the candidate's when that is
 // larger (the reference's non-textbook rule).
-Csr iluk_pattern(const Csr &A, int level)
+Csr iluk_pattern_general(const Csr &A, int level)
 {
     const int n = A.n;
     std::vector<std::vector<int>> ucol(n), ulev(n);   // strict upper part of every finished row
@@ -265,6 +265,142 @@ Csr iluk_pattern(const Csr &A, int level)
     return M;
 }
 
+// Chunk length for RowPipeline: the smallest sub-diagonal offset i - c > 1 that at least a quarter of the sampled
+// rows have (the innermost grid dimension of a stencil matrix: a chunk is then one grid line, whose rows chain
+// through i - 1 inside the chunk and meet the previous line one row behind), else 256.
+int pipeline_chunk(const Csr &A)
+{
+    if (const char *e = getenv("LSSPG_PIPE_CHUNK"))
+        if (atoi(e) > 0) return atoi(e);
+    const int n = A.n, rows = std::min(n, 1 << 16), r0 = (n - rows) / 2;
+    std::vector<std::pair<int, int>> hist;   // (offset, count)
+    for (int i = r0; i < r0 + rows; i++) {
+        for (int k = A.p[i]; k < A.p[i + 1]; k++) {
+            const int d = i - A.j[k];
+            if (d <= 1 || d > 8192) continue;
+            size_t q = 0;
+            for (; q < hist.size() && hist[q].first != d; q++) {}
+            if (q == hist.size()) {
+                if (hist.size() >= 64) continue;
+                hist.emplace_back(d, 0);
+            }
+            hist[q].second++;
+        }
+    }
+    int best = 0;
+    for (auto &h : hist)
+        if (h.second >= rows / 4 && (best == 0 || h.first < best)) best = h.first;
+    return best ? std::max(best, 16) : 256;
+}
+
+// The same symbolic phase for the usual input (strictly ascending columns): the upper parts of the finished rows
+// live in one flat array instead of two heap vectors per row, the rows of the pattern are appended to M.j directly,
+// and the values (A's where present, 0 on fill) are merged in afterwards by the host threads.  The row recurrence
+// itself -- pivots in ascending order, candidates in the order the pivot row discovered them, the level-raising
+// rule -- is the one of iluk_pattern_general, statement for statement.
+Csr iluk_pattern(const Csr &A, int level)
+{
+    const int n = A.n;
+    {
+        const int np = lsspg::host_threads();
+        std::vector<char> loose(np, 0);
+        parallel_ranges(n, [&](long long r0, long long r1, int p) {
+            for (int i = (int)r0; i < (int)r1; i++)
+                for (int k = A.p[i] + 1; k < A.p[i + 1]; k++)
+                    if (A.j[k - 1] >= A.j[k]) { loose[p] = 1; return; }
+        }, np);
+        if (std::find(loose.begin(), loose.end(), (char)1) != loose.end()) return iluk_pattern_general(A, level);
+    }
+    // per finished row one arena record [sorted pattern (len) | upper columns (nu) | their levels (nu)], upper part in
+    // discovery order; published through the pipeline's progress counters
+    PROF_T0;
+    std::vector<const int *> rec((size_t)n);
+    IVec len((size_t)n + 1), nup((size_t)n);
+    const int nt = lsspg::host_threads();
+    lsspg::RowPipeline pipe(n, pipeline_chunk(A));
+    struct Scratch {
+        std::vector<int> where, lc, ll, uc, ul, cols;
+        lsspg::BlockArena<int> arena;
+    };
+    std::vector<Scratch> scratch(nt);
+    pipe.run(nt, [&](int t, int i, int chunk_begin) {
+        Scratch &S = scratch[t];
+        if (S.where.empty()) S.where.assign(n, -1);   // column -> index in the row's work lists
+        std::vector<int> &where = S.where, &lc = S.lc, &ll = S.ll, &uc = S.uc, &ul = S.ul, &cols = S.cols;
+        lc.clear(); ll.clear(); uc.clear(); ul.clear();
+        for (int k = A.p[i]; k < A.p[i + 1]; k++) {
+            const int c = A.j[k];
+            if (c < i) { where[c] = (int)lc.size(); lc.push_back(c); ll.push_back(0); }
+            else if (c > i) { where[c] = n + (int)uc.size(); uc.push_back(c); ul.push_back(0); }
+        }
+        for (size_t tt = 0; tt < lc.size(); tt++) {
+            // next pivot = smallest not-yet-used lower column (fill may have appended more)
+            size_t m = tt;
+            for (size_t q = tt + 1; q < lc.size(); q++)
+                if (lc[q] < lc[m]) m = q;
+            if (m != tt) {
+                std::swap(lc[tt], lc[m]);
+                std::swap(ll[tt], ll[m]);
+                where[lc[tt]] = (int)tt;
+                where[lc[m]] = (int)m;
+            }
+            const int piv = lc[tt], lt = ll[tt];
+            pipe.wait(piv, chunk_begin);
+            const int pn = nup[piv];
+            const int *pc = rec[piv] + len[piv], *pl = pc + pn;
+            for (int q = 0; q < pn; q++) {
+                const int c = pc[q];
+                const int cand = pl[q] + lt + 1;
+                if (cand > level) continue;
+                const int w = where[c];
+                if (w < 0) {
+                    if (c < i) { where[c] = (int)lc.size(); lc.push_back(c); ll.push_back(cand); }
+                    else if (c > i) { where[c] = n + (int)uc.size(); uc.push_back(c); ul.push_back(cand); }
+                }
+                else if (w >= n) { if (ul[w - n] < cand) ul[w - n] = cand; }
+                else { if (ll[w] < cand) ll[w] = cand; }
+            }
+        }
+        for (int c : lc) where[c] = -1;
+        for (int c : uc) where[c] = -1;
+        cols.assign(lc.begin(), lc.end());
+        cols.push_back(i);
+        cols.insert(cols.end(), uc.begin(), uc.end());
+        std::sort(cols.begin(), cols.end());
+        int *r = S.arena.take(cols.size() + 2 * uc.size());
+        std::copy(cols.begin(), cols.end(), r);
+        std::copy(uc.begin(), uc.end(), r + cols.size());
+        std::copy(ul.begin(), ul.end(), r + cols.size() + uc.size());
+        len[i] = (int)cols.size();
+        nup[i] = (int)uc.size();
+        rec[i] = r;
+    });
+    PROF("  symbolic rows");
+    Csr M;
+    M.n = n;
+    M.p.resize((size_t)n + 1);
+    parallel_copy(M.p.data(), len.data(), sizeof(int) * (size_t)n);
+    const long long total = parallel_exclusive_scan(M.p.data(), n);
+    M.p[n] = (int)total;
+    M.j.resize((size_t)total);
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) std::copy(rec[i], rec[i] + len[i], M.j.data() + M.p[i]);
+    });
+    M.x.resize(M.j.size());
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) {
+            int a = A.p[i];
+            const int ae = A.p[i + 1];
+            for (int k = M.p[i]; k < M.p[i + 1]; k++) {
+                const int c = M.j[k];
+                while (a < ae && A.j[a] < c) a++;
+                M.x[k] = (a < ae && A.j[a] == c) ? A.x[a] : 0.0;
+            }
+        }
+    });
+    return M;
+}
+
 inline double repaired_pivot_signed(double d)
 {
     if (fabs(d) < kPivotTol) return d > 0 ? kPivotValue : -kPivotValue;
@@ -299,6 +435,78 @@ void ilu0_block(Csr &M, int r0, int r1, std::vector<double> &wk, std::vector<dou
         }
         inv[i] = 1. / d;
     }
+}
+
+// The same factorisation, level-scheduled over the host threads: row i needs the FINISHED rows of its strictly
+// lower columns, so rows are grouped by the level of that dependency graph (one serial O(nnz) pass) and the rows of
+// a level are independent.  A row scales each lower entry by the pivot's inverse and subtracts a_ik * a_kj from
+// the entries it shares with row k -- found by a two-pointer merge of the sorted column lists instead of the
+// dense scatter of ilu0_block; same operations, same order, so the factors are bit-identical (the GPU numeric
+// phase, ilu_gpu.cu, does the same).  Rows with repeated columns would not merge like the scatter: the serial loop
+// handles such a matrix.
+void ilu0_levels(Csr &M, int bs)
+{
+    const int n = M.n;
+    const int *P = M.p.data();
+    const int *C = M.j.data();
+    double *X = M.x.data();
+    const int np = lsspg::host_threads();
+    std::vector<char> loose(np, 0);
+    parallel_ranges(n, [&](long long r0, long long r1, int p) {
+        for (int i = (int)r0; i < (int)r1; i++)
+            for (int k = P[i] + 1; k < P[i + 1]; k++)
+                if (C[k - 1] >= C[k]) { loose[p] = 1; return; }
+    }, np);
+    if (np <= 1 || std::find(loose.begin(), loose.end(), (char)1) != loose.end()) {
+        std::vector<double> wk(n, 0.0), inv(n, 0.0);
+        for (int r0 = 0; r0 < n; r0 += bs) ilu0_block(M, r0, std::min(n, r0 + bs), wk, inv);
+        return;
+    }
+    IVec lev((size_t)n);
+    std::vector<int> start(1, 0);
+    for (int i = 0; i < n; i++) {
+        int l = 0;
+        for (int k = P[i]; C[k] < i; k++) l = std::max(l, lev[C[k]] + 1);
+        lev[i] = l;
+        if ((int)start.size() < l + 2) start.resize(l + 2, 0);
+        start[l + 1]++;
+    }
+    const int nlev = (int)start.size() - 1;
+    IVec order((size_t)n);
+    for (int l = 0; l < nlev; l++) start[l + 1] += start[l];
+    {
+        std::vector<int> pos(start.begin(), start.end() - 1);
+        for (int i = 0; i < n; i++) order[pos[lev[i]]++] = i;
+    }
+    DVec inv((size_t)n);
+    lsspg::LevelTeam::run(nlev, start.data(), order.data(), [&](int i) {
+        const int e = P[i + 1];
+        int k = P[i];
+        if (i % bs == 0) {   // first row of a block, as in ilu0_block
+            inv[i] = 1. / repaired_pivot_signed(X[k]);
+            return;
+        }
+        for (; C[k] < i; k++) {
+            const int pr = C[k];
+            const double a_ik = X[k] = X[k] * inv[pr];
+            int pq = P[pr];
+            const int pe = P[pr + 1];
+            for (int q = k + 1; q < e; q++) {
+                const int c = C[q];
+                while (pq < pe && C[pq] < c) pq++;
+                if (pq < pe && C[pq] == c) {
+                    const double w = X[pq];
+                    if (w != 0.) X[q] = X[q] - a_ik * w;
+                }
+            }
+        }
+        double d = kPivotValue;
+        if (C[k] == i) {
+            if (fabs(X[k]) < kPivotTol) X[k] = kPivotValue;
+            d = X[k];
+        }
+        inv[i] = 1. / d;
+    });
 }
 
 struct Factors {
@@ -368,8 +576,7 @@ Factors factor_iluk(Csr &&A, int level, int bs)
     const int n = A.n;
     Csr M = (level > 0) ? block_diagonal(iluk_pattern(A, level), bs) : block_diagonal(std::move(A), bs);
     PROF("pattern+block_diagonal");
-    std::vector<double> wk(n, 0.0), inv(n, 0.0);
-    for (int r0 = 0; r0 < n; r0 += bs) ilu0_block(M, r0, std::min(n, r0 + bs), wk, inv);
+    ilu0_levels(M, bs);
     PROF("numeric");
     Factors F;
     F.n = n;
@@ -490,16 +697,176 @@ void ilut_block(const Csr &B, int r0, int r1, double tau, int p, Csr &L, Csr &U)
     }
 }
 
+// ILUT over the host threads.  Row i needs the finished rows of the lower entries it keeps while it is eliminated
+// -- known only as the elimination proceeds -- so the rows go through a RowPipeline (host_par.h): each thread runs
+// whole chunks of consecutive rows and waits for a pivot row of an earlier chunk until its owner has published it.
+// A row performs exactly the statements of ilut_block in the same order (the work row is kept as two compact
+// arrays, lower part and upper part, instead of one array indexed [0, nl) / (i, i + nu]; positions inside the two
+// parts, which is all select_largest and the stored order depend on, are the same), so L and U are bit-identical
+// for any number of threads.  Rows with repeated columns take the serial path.
+Factors factor_ilut_rows(const Csr &B, double tau, int p, int bs)
+{
+    const int n = B.n;
+    const int nt = lsspg::host_threads();
+    std::vector<const int *> rcol((size_t)n);
+    std::vector<const double *> rval((size_t)n);
+    IVec rlen((size_t)n);
+    DVec diag((size_t)n);
+    struct Scratch {
+        std::vector<int> jr, jwl, jwu;
+        std::vector<double> wl, wu;
+        lsspg::BlockArena<int> ia;
+        lsspg::BlockArena<double> da;
+    };
+    std::vector<Scratch> scratch(nt);
+    constexpr int kUp = 1 << 30, kDiag = -2;   // jr: -1 absent, kDiag the diagonal, < kUp lower position, >= kUp upper position
+    lsspg::RowPipeline pipe(n, pipeline_chunk(B));
+    pipe.run(nt, [&](int t, int i, int chunk_begin) {
+        Scratch &S = scratch[t];
+        if (S.jr.empty()) S.jr.assign(n, -1);
+        std::vector<int> &jr = S.jr, &jwl = S.jwl, &jwu = S.jwu;
+        std::vector<double> &wl = S.wl, &wu = S.wu;
+        const int b = B.p[i], e = B.p[i + 1];
+        if (i % bs == 0) {
+            // first row of a block: copied verbatim; its leading entry is the pivot
+            int *c = S.ia.take(e - b);
+            double *v = S.da.take(e - b);
+            std::copy(B.j.begin() + b, B.j.begin() + e, c);
+            std::copy(B.x.begin() + b, B.x.begin() + e, v);
+            rcol[i] = c; rval[i] = v; rlen[i] = e - b;
+            diag[i] = repaired_pivot_signed(B.x[b]);
+            return;
+        }
+        double norm = 0.0;
+        for (int k = b; k < e; k++) norm += fabs(B.x[k]);
+        norm /= (double)(e - b);
+        const double drop = tau * norm;
+        int nl = 0, nu = 0;
+        double wd = 0.0;
+        jwl.clear(); wl.clear(); jwu.clear(); wu.clear();
+        jr[i] = kDiag;
+        for (int k = b; k < e; k++) {
+            const int c = B.j[k];
+            if (c < i) { jr[c] = nl; jwl.push_back(c); wl.push_back(B.x[k]); nl++; }
+            else if (c == i) wd = B.x[k];
+            else { jr[c] = kUp + nu; jwu.push_back(c); wu.push_back(B.x[k]); nu++; }
+        }
+        for (int tt = 0; tt < nl; tt++) {
+            int piv = jwl[tt], at = tt;
+            for (int q = tt + 1; q < nl; q++)
+                if (jwl[q] < piv) { piv = jwl[q]; at = q; }
+            if (at != tt) {
+                const int c = jwl[tt];
+                jwl[tt] = jwl[at];
+                jwl[at] = c;
+                jr[piv] = tt;
+                jr[c] = at;
+                std::swap(wl[tt], wl[at]);
+            }
+            jr[piv] = -1;
+            pipe.wait(piv, chunk_begin);
+            const double a_ik = wl[tt] = wl[tt] / diag[piv];
+            const int *pc = rcol[piv];
+            const double *pv = rval[piv];
+            for (int q = 0, qe = rlen[piv]; q < qe; q++) {
+                const int c = pc[q];
+                if (c <= piv) continue;
+                const int at2 = jr[c];
+                const double mx = -a_ik * pv[q];
+                if (at2 == -1 && fabs(mx) < drop) continue;   // only NEW fill is dropped
+                if (at2 == kDiag) wd += mx;
+                else if (at2 >= kUp) wu[at2 - kUp] += mx;
+                else if (at2 >= 0) wl[at2] += mx;
+                else if (c < i) { jr[c] = nl; jwl.push_back(c); wl.push_back(mx); nl++; }
+                else { jr[c] = kUp + nu; jwu.push_back(c); wu.push_back(mx); nu++; }
+            }
+        }
+        jr[i] = -1;
+        for (int q = 0; q < nl; q++) jr[jwl[q]] = -1;
+        for (int q = 0; q < nu; q++) jr[jwu[q]] = -1;
+        const double d = repaired_pivot_signed(wd);
+        const int keepl = std::min(nl, p), keepu = std::min(nu, p);
+        select_largest(wl.data(), jwl.data(), nl, keepl);
+        select_largest(wu.data(), jwu.data(), nu, keepu);
+        const int len = keepl + 1 + keepu;
+        int *c = S.ia.take(len);
+        double *v = S.da.take(len);
+        std::copy(jwl.begin(), jwl.begin() + keepl, c);
+        std::copy(wl.begin(), wl.begin() + keepl, v);
+        c[keepl] = i;
+        v[keepl] = d;
+        std::copy(jwu.begin(), jwu.begin() + keepu, c + keepl + 1);
+        std::copy(wu.begin(), wu.begin() + keepu, v + keepl + 1);
+        rcol[i] = c; rval[i] = v; rlen[i] = len;
+        diag[i] = d;
+    });
+    // L (entries left of the diagonal in stored order, unit diagonal LAST) and U (diagonal FIRST, then the rest)
+    Factors F;
+    F.n = n;
+    Csr &L = F.L, &U = F.U;
+    L.n = U.n = n;
+    L.p.resize((size_t)n + 1);
+    U.p.resize((size_t)n + 1);
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) {
+            int cl = 0, cu = 0;
+            for (int q = 0; q < rlen[i]; q++) {
+                cl += (rcol[i][q] <= i);
+                cu += (rcol[i][q] >= i);
+            }
+            L.p[i] = cl;
+            U.p[i] = cu;
+        }
+    });
+    const long long tl = parallel_exclusive_scan(L.p.data(), n), tu = parallel_exclusive_scan(U.p.data(), n);
+    L.p[n] = (int)tl;
+    U.p[n] = (int)tu;
+    L.j.resize((size_t)tl); L.x.resize((size_t)tl);
+    U.j.resize((size_t)tu); U.x.resize((size_t)tu);
+    parallel_ranges(n, [&](long long r0, long long r1, int) {
+        for (int i = (int)r0; i < (int)r1; i++) {
+            int ol = L.p[i], ou = U.p[i];
+            for (int q = 0; q < rlen[i]; q++) {
+                const int c = rcol[i][q];
+                const double v = rval[i][q];
+                if (c < i) { L.j[ol] = c; L.x[ol] = v; ol++; }
+                else if (c == i) {
+                    L.j[ol] = i; L.x[ol] = 1; ol++;
+                    U.j[ou] = i; U.x[ou] = v; ou++;
+                }
+                else { U.j[ou] = c; U.x[ou] = v; ou++; }
+            }
+        }
+    });
+    return F;
+}
+
 Factors factor_ilut(Csr &&A, double tau, int p, int bs)
 {
+    PROF_T0;
     const int n = A.n;
     Csr B = block_diagonal(std::move(A), bs);
+    {
+        const int np = lsspg::host_threads();
+        std::vector<char> loose(np, 0);
+        parallel_ranges(n, [&](long long r0, long long r1, int q) {
+            for (int i = (int)r0; i < (int)r1; i++)
+                for (int k = B.p[i] + 1; k < B.p[i + 1]; k++)
+                    if (B.j[k - 1] >= B.j[k]) { loose[q] = 1; return; }
+        }, np);
+        if (std::find(loose.begin(), loose.end(), (char)1) == loose.end()) {
+            Factors F = factor_ilut_rows(B, tau, p, bs);
+            PROF("ilut rows (pipelined)");
+            return F;
+        }
+    }
     Factors F;
     F.n = n;
     F.L.n = F.U.n = n;
     F.L.p.push_back(0);
     F.U.p.push_back(0);
     for (int r0 = 0; r0 < n; r0 += bs) ilut_block(B, r0, std::min(n, r0 + bs), tau, p, F.L, F.U);
+    PROF("ilut rows (serial)");
     return F;
 }
 

@@ -36,13 +36,15 @@ def test_schedule_images_match_the_pinned_serial_ones(name):
         assert got == PACK[key], key
 
 
-@pytest.mark.parametrize("threads", [1, 3, 7])
-def test_schedule_images_do_not_depend_on_the_thread_count(threads):
-    # the thread count is read once per process: run the comparison in a child
+@pytest.mark.parametrize("threads,chunk", [(1, 0), (3, 0), (7, 5), (4, 1000), (8, 1)])
+def test_schedule_images_do_not_depend_on_the_thread_count(threads, chunk):
+    # the thread count (and the RowPipeline chunk length) is read once per process: run the comparison in a child
     code = ("import json, sys; sys.path[:0] = [%r, %r]; import test_setup_threads as t; "
-            "print(json.dumps({k: v for n in ('lap3d_48/iluk0_bj3', 'cd3d_40/ilut', 'lap2d_300/iluk0') "
+            "print(json.dumps({k: v for n in ('lap3d_48/iluk0_bj3', 'cd3d_40/ilut', 'cd3d_32/iluk1', 'lap2d_300/iluk0') "
             "for k, v in t.fingerprints(n).items()}))" % (ROOT, os.path.join(ROOT, "tests")))
     env = dict(os.environ, LSSPG_HOST_THREADS=str(threads))
+    if chunk:
+        env["LSSPG_PIPE_CHUNK"] = str(chunk)
     out = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     got = json.loads(out.stdout.strip().splitlines()[-1])
