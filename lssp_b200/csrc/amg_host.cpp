@@ -16,7 +16,9 @@
 // the CPU for the test-suite (lsspg_debug_amg_walk_gs_host) -- a layout check, not a fallback.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <thread>
 #include <vector>
@@ -590,19 +592,38 @@ int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hA
         L.Ax.assign(hAx, hAx + hAp[n]);
     }
     int rc = 0;
+    const bool prof = getenv("LSSPG_SETUP_PROF") && atoi(getenv("LSSPG_SETUP_PROF")) != 0;
+    auto now = [] {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    };
+    double tp = now();
+    auto PROF = [&](const char *what) {
+        if (!prof) return;
+        const double t = now();
+        fprintf(stderr, "[amg setup] level %d %-22s %.3f s\n", (int)H->levels.size() - 1, what, t - tp);
+        tp = t;
+    };
     while ((int)H->levels.size() < pr.max_levels && H->levels.back().n > pr.coarse_dof) {
         AmgLevelHost &L = H->levels.back();
         Graph S, T;
         strong_couplings(L, pr, S);
+        PROF("strong couplings");
         transpose_graph(L.n, S, T);
+        PROF("transpose graph");
         const int nc = cf_split(L.n, S, T, L.cf);
+        PROF("C/F split");
         if (nc == 0 || nc >= L.n) {   // coarsening stalled: this level is the last one
             L.cf.clear();
             break;
         }
         direct_interpolation(L, S, pr);
+        PROF("interpolation");
         visiting_ranks(L, pr.cf_order);
+        PROF("visiting ranks");
         transpose_csr(L.n, L.nc, L.Pp, L.Pj, L.Px, L.Rp, L.Rj, L.Rx);
+        PROF("restriction");
         std::vector<int> Tp, Tj;
         std::vector<double> Tx;
         AmgLevelHost C;
@@ -610,6 +631,7 @@ int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hA
         rc = spgemm(L.n, L.nc, L.Ap, L.Aj, L.Ax, L.Pp, L.Pj, L.Px, Tp, Tj, Tx);
         if (!rc) rc = spgemm(L.nc, L.nc, L.Rp, L.Rj, L.Rx, Tp, Tj, Tx, C.Ap, C.Aj, C.Ax);
         if (rc) break;
+        PROF("Galerkin products");
         if (pr.verb > 0)
             printf("amg: level %d: n = %d, nnz = %d, C points = %d\n", (int)H->levels.size() - 1, L.n, L.Ap[L.n], L.nc);
         H->levels.push_back(std::move(C));

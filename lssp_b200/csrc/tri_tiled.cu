@@ -46,7 +46,7 @@ struct OffsetHist {
     }
 };
 
-static bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3])
+static bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3], std::vector<long long> &offsets)
 {
     const int np = host_threads();
     std::vector<OffsetHist> part(np);
@@ -73,6 +73,8 @@ static bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3])
         for (int q = 0; q < part[p].m; q++) hist[part[p].off[q]] += part[p].cnt[q];
     }
     if (hist.size() > 16) return false;
+    offsets.clear();
+    for (auto &kv : hist) offsets.push_back(kv.first);
     if (hist.size() < 2 || hist.begin()->first != 1) return false;
     const long long s3 = hist.rbegin()->first;
     if (s3 <= 1 || n % s3 != 0) return false;
@@ -100,7 +102,8 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
 {
     const bool lower = (which == LSSPG_TRI_LOWER);
     int g[3];
-    if (n < 4096 || !detect_lattice(n, Tp, Tj, g)) return 2;
+    std::vector<long long> offsets;
+    if (n < 4096 || !detect_lattice(n, Tp, Tj, g, offsets)) return 2;
     int t[3] = {8, 8, 8};
     if (g[2] == 1) { t[0] = 16; t[1] = 16; t[2] = 1; }
     if (const char *e = getenv("LSSPG_TRI_TILE")) {
@@ -108,15 +111,64 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
         if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { t[0] = a; t[1] = b; t[2] = c; }
     }
     if ((long long)t[0] * t[1] * t[2] > kMaxTileRows) return 2;
-    const int nt[3] = {(g[0] + t[0] - 1) / t[0], (g[1] + t[1] - 1) / t[1], (g[2] + t[2] - 1) / t[2]};
-    const int ntiles = nt[0] * nt[1] * nt[2];
+    // Skewed boxes (LSSPG_TRI_SKEW=1).  An entry at offset d = dz nx ny + dy nx + dx couples grid point p with
+    // p - (dx, dy, dz) (lower factor) or p + (dx, dy, dz) (upper).  With fill (ILU(1): offsets nx - 1, nx ny - nx,
+    // nx ny - 1) some dx or dy are negative, neighbouring axis-aligned boxes then need each other and the box graph
+    // is cyclic.  Boxes cut along u = x + s1 y + t1 z, v = y + s2 z, w = z instead, with the smallest s1, s2, t1 >= 0
+    // that make u, v, w non-decreasing along every offset, are only ever coupled one way: the graph is acyclic by
+    // construction (and verified below like any other).  s1 = s2 = t1 = 0 is the plain box grid.
+    int sk[3] = {0, 0, 0};   // s1, s2, t1
+    if (const char *e = getenv("LSSPG_TRI_SKEW")) {
+        if (atoi(e) != 0) {
+            struct V { long long x, y, z; };
+            std::vector<V> vs;
+            for (long long d : offsets) {
+                long long dz = d / ((long long)g[0] * g[1]), r = d % ((long long)g[0] * g[1]);
+                long long dy = r / g[0], dx = r % g[0];
+                if (dx > g[0] / 2) { dx -= g[0]; dy += 1; }
+                if (dy > g[1] / 2 && g[2] > 1) { dy -= g[1]; dz += 1; }
+                vs.push_back({dx, dy, dz});
+            }
+            auto ceil_div = [](long long a, long long b) { return (a + b - 1) / b; };   // a >= 0, b > 0
+            long long s1 = 0, s2 = 0, t1 = 0;
+            for (const V &v : vs) {
+                if (v.z == 0 && v.y > 0 && v.x < 0) s1 = std::max(s1, ceil_div(-v.x, v.y));
+                if (v.z > 0 && v.y < 0) s2 = std::max(s2, ceil_div(-v.y, v.z));
+            }
+            for (const V &v : vs)
+                if (v.z > 0 && v.x + s1 * v.y < 0) t1 = std::max(t1, ceil_div(-(v.x + s1 * v.y), v.z));
+            if (s1 <= 4 && s2 <= 4 && t1 <= 8) { sk[0] = (int)s1; sk[1] = (int)s2; sk[2] = (int)t1; }
+        }
+    }
+    const long long ext[3] = {(long long)g[0] + (long long)sk[0] * (g[1] - 1) + (long long)sk[2] * (g[2] - 1),
+                              (long long)g[1] + (long long)sk[1] * (g[2] - 1), g[2]};
+    const long long ntl[3] = {(ext[0] + t[0] - 1) / t[0], (ext[1] + t[1] - 1) / t[1], (ext[2] + t[2] - 1) / t[2]};
+    if (ntl[0] * ntl[1] * ntl[2] > (1ll << 28)) return 2;
+    const int nt[3] = {(int)ntl[0], (int)ntl[1], (int)ntl[2]};
+    int ntiles = nt[0] * nt[1] * nt[2];
     IVec tile_of((size_t)n);
     parallel_ranges(n, [&](long long r0, long long r1, int) {
         for (int i = (int)r0; i < (int)r1; i++) {
             const int x = i % g[0], y = (i / g[0]) % g[1], z = i / (g[0] * g[1]);
-            tile_of[i] = ((z / t[2]) * nt[1] + (y / t[1])) * nt[0] + (x / t[0]);
+            const int u = x + sk[0] * y + sk[2] * z, v = y + sk[1] * z;
+            tile_of[i] = ((z / t[2]) * nt[1] + (v / t[1])) * nt[0] + (u / t[0]);
         }
     });
+    if (sk[0] || sk[1] || sk[2]) {
+        // skewed boxes that lie outside the grid are empty: renumber the others, order kept
+        std::vector<int> newid((size_t)ntiles, 0);
+        for (int i = 0; i < n; i++) newid[tile_of[i]] = 1;
+        int cnt = 0;
+        for (int k = 0; k < ntiles; k++) {
+            const int has = newid[k];
+            newid[k] = cnt;
+            cnt += has;
+        }
+        parallel_ranges(n, [&](long long r0, long long r1, int) {
+            for (int i = (int)r0; i < (int)r1; i++) tile_of[i] = newid[tile_of[i]];
+        });
+        ntiles = cnt;
+    }
     // validate the triangle (threads) ...
     {
         const int np = host_threads();
@@ -782,6 +834,8 @@ __global__ void __launch_bounds__(32, 8) tri_box_ell_kernel(const TiledArgs a)  
             case 2: box_levels<2, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
             case 3: box_levels<3, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
             case 4: box_levels<4, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+            case 5: box_levels<5, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;   // ILU(1)
+            case 6: box_levels<6, 2>(slev, d.nlev, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;   // fill
             default:
                 for (int L = 0; L < d.nlev; L++) {
                     const int sa = slev[L], sb = slev[L + 1];

@@ -93,3 +93,28 @@ def test_unsorted_rows_and_missing_diagonals_take_the_repair_path(ref):
     Cx[drop] = 1e-10
     for kw in (dict(kind="iluk", level=0), dict(kind="iluk", level=1), dict(kind="ilut", p=5, tol=1e-3)):
         assert _same(api.ilu_factor(B, **kw), api.ilu_factor((Ap, Aj, Cx), **kw)), kw
+
+
+@pytest.mark.parametrize("case", ["cd3d_32/iluk1", "cd3d_24/iluk2", "lap2d_150/iluk1", "cd3d_40/iluk1_bj2"])
+def test_skewed_boxes_give_fill_factors_an_acyclic_box_schedule(case, port, monkeypatch):
+    # ILU(1)/(2) fill couples axis-aligned neighbour boxes both ways (cyclic box graph -> slice schedule).  Boxes cut
+    # along x + s1 y + t1 z, y + s2 z, z (LSSPG_TRI_SKEW=1, tri_tiled.cu) are coupled one way only: the factor gets
+    # the completion-flag box schedule (kind 2), and walking it box by box reproduces the serial sweeps bit for bit.
+    A, kw = {"cd3d_32/iluk1": (g.cd3d(32), dict(kind="iluk", level=1)),
+             "cd3d_24/iluk2": (g.cd3d(24), dict(kind="iluk", level=2)),
+             "lap2d_150/iluk1": (g.laplacian_5pt(150), dict(kind="iluk", level=1)),
+             "cd3d_40/iluk1_bj2": (g.cd3d(40), dict(kind="iluk", level=1, blk_size=32000))}[case]
+    n = len(A[0]) - 1
+    L, U = api.ilu_factor(A, **kw)
+    rhs = np.sin(np.arange(n) * 0.37) + 0.3
+    assert api.tri_pack_host(0, L)["kind"] == 0 and api.tri_walk_tiled_host(0, L, rhs)[1] is None
+    monkeypatch.setenv("LSSPG_TRI_SKEW", "1")
+    assert api.tri_pack_host(0, L)["kind"] == 2 and api.tri_pack_host(1, U)["kind"] == 2
+    y, info = api.tri_walk_tiled_host(0, L, rhs)
+    x, info_u = api.tri_walk_tiled_host(1, U, y)
+    assert info["max_box_rows"] <= 512 and info["box_levels"] < info["row_levels"] / 3
+    assert np.array_equal(x, port.ilu_apply(L, U, rhs))
+    # the plain box grid of ILU(0) factors is the zero-skew case: same image as pinned
+    L0, U0 = api.ilu_factor(g.lap3d(32), kind="iluk", level=0)
+    r = api.tri_pack_host(0, L0)
+    assert "%016x" % r["fingerprint"] == PACK["lap3d_32/iluk0/L"]["fingerprint"]
