@@ -111,15 +111,16 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
         if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { t[0] = a; t[1] = b; t[2] = c; }
     }
     if ((long long)t[0] * t[1] * t[2] > kMaxTileRows) return 2;
-    // Skewed boxes (LSSPG_TRI_SKEW=1).  An entry at offset d = dz nx ny + dy nx + dx couples grid point p with
+    // Skewed boxes (default; LSSPG_TRI_SKEW=0 keeps the plain grid).  An entry at offset d = dz nx ny + dy nx + dx couples grid point p with
     // p - (dx, dy, dz) (lower factor) or p + (dx, dy, dz) (upper).  With fill (ILU(1): offsets nx - 1, nx ny - nx,
     // nx ny - 1) some dx or dy are negative, neighbouring axis-aligned boxes then need each other and the box graph
     // is cyclic.  Boxes cut along u = x + s1 y + t1 z, v = y + s2 z, w = z instead, with the smallest s1, s2, t1 >= 0
     // that make u, v, w non-decreasing along every offset, are only ever coupled one way: the graph is acyclic by
     // construction (and verified below like any other).  s1 = s2 = t1 = 0 is the plain box grid.
     int sk[3] = {0, 0, 0};   // s1, s2, t1
-    if (const char *e = getenv("LSSPG_TRI_SKEW")) {
-        if (atoi(e) != 0) {
+    {
+        const char *e = getenv("LSSPG_TRI_SKEW");
+        if (!(e && atoi(e) == 0)) {
             struct V { long long x, y, z; };
             std::vector<V> vs;
             for (long long d : offsets) {

@@ -263,16 +263,22 @@ def test_both_tri_schedules_are_exercised(ctx, checker):
         L, U = api.ilu_factor(A, "iluk", level=level)
         rhs = tvec(n, 4)
         want = checker.tri_lower(L, rhs)
-        # ILU(0): acyclic box graph -> box schedule by default.  ILU(1): boxes depend on each other
-        # both ways -> slice schedule by default, polling box schedule only on request.
+        # ILU(0): the plain 8x8x8 box grid is acyclic -> box schedule.  ILU(1): axis-aligned boxes depend on each other
+        # both ways; by default the boxes are skewed (acyclic again, completion-flag kernel); with LSSPG_TRI_SKEW=0
+        # the factor takes the slice schedule, or the polling box kernel on request (LSSPG_TRI_TILED_CYCLIC=1).
         os.environ["LSSPG_TRI_TILED_CYCLIC"] = "1"
+        os.environ["LSSPG_TRI_SKEW"] = "0"
         try:
             T = api.Tri(ctx, 0, L)
-        finally:
             del os.environ["LSSPG_TRI_TILED_CYCLIC"]
+            Tn = api.Tri(ctx, 0, L)
+        finally:
+            os.environ.pop("LSSPG_TRI_TILED_CYCLIC", None)
+            del os.environ["LSSPG_TRI_SKEW"]
         assert T.schedule()["tiled"] and T.schedule()["boxes"] == 64
+        assert Tn.schedule()["tiled"] == (level == 0)
         Td = api.Tri(ctx, 0, L)
-        assert Td.schedule()["tiled"] == (level == 0)
+        assert Td.schedule()["tiled"] and Td.schedule()["boxes"] == (64 if level == 0 else 100)
         os.environ["LSSPG_TRI_TILED"] = "0"
         try:
             T0 = api.Tri(ctx, 0, L)
@@ -280,7 +286,7 @@ def test_both_tri_schedules_are_exercised(ctx, checker):
             del os.environ["LSSPG_TRI_TILED"]
         assert not T0.schedule()["tiled"]
         drhs, dx = ctx.upload(rhs), ctx.empty(n)
-        for t in (T, Td, T0):
+        for t in (T, Tn, Td, T0):
             t.solve(dx, drhs)
             assert np.array_equal(dx.get(), want)
             t.solve(dx, drhs)      # a second sweep reuses flags / counters (epoch bump, ticket wrap)

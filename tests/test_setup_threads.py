@@ -20,14 +20,7 @@ with open(os.path.join(ROOT, "tests", "golden", "pack_golden.json")) as f:
     PACK = json.load(f)
 
 
-def fingerprints(name):
-    make, kw = mpg.CASES[name]
-    L, U = api.ilu_factor(make(), **kw)
-    out = {}
-    for which, T, tag in ((0, L, "L"), (1, U, "U")):
-        r = api.tri_pack_host(which, T)
-        out[name + "/" + tag] = dict(kind=r["kind"], bytes=r["bytes"], fingerprint="%016x" % r["fingerprint"])
-    return out
+fingerprints = mpg.fingerprints
 
 
 @pytest.mark.parametrize("name", list(mpg.CASES))
@@ -40,7 +33,7 @@ def test_schedule_images_match_the_pinned_serial_ones(name):
 def test_schedule_images_do_not_depend_on_the_thread_count(threads, chunk):
     # the thread count (and the RowPipeline chunk length) is read once per process: run the comparison in a child
     code = ("import json, sys; sys.path[:0] = [%r, %r]; import test_setup_threads as t; "
-            "print(json.dumps({k: v for n in ('lap3d_48/iluk0_bj3', 'cd3d_40/ilut', 'cd3d_32/iluk1', 'lap2d_300/iluk0') "
+            "print(json.dumps({k: v for n in ('lap3d_48/iluk0_bj3', 'cd3d_40/ilut', 'cd3d_32/iluk1', 'cd3d_32/iluk1_slices', 'lap2d_300/iluk0') "
             "for k, v in t.fingerprints(n).items()}))" % (ROOT, os.path.join(ROOT, "tests")))
     env = dict(os.environ, LSSPG_HOST_THREADS=str(threads))
     if chunk:
@@ -98,7 +91,7 @@ def test_unsorted_rows_and_missing_diagonals_take_the_repair_path(ref):
 @pytest.mark.parametrize("case", ["cd3d_32/iluk1", "cd3d_24/iluk2", "lap2d_150/iluk1", "cd3d_40/iluk1_bj2"])
 def test_skewed_boxes_give_fill_factors_an_acyclic_box_schedule(case, port, monkeypatch):
     # ILU(1)/(2) fill couples axis-aligned neighbour boxes both ways (cyclic box graph -> slice schedule).  Boxes cut
-    # along x + s1 y + t1 z, y + s2 z, z (LSSPG_TRI_SKEW=1, tri_tiled.cu) are coupled one way only: the factor gets
+    # along x + s1 y + t1 z, y + s2 z, z (the default; LSSPG_TRI_SKEW=0 disables, tri_tiled.cu) are coupled one way only: the factor gets
     # the completion-flag box schedule (kind 2), and walking it box by box reproduces the serial sweeps bit for bit.
     A, kw = {"cd3d_32/iluk1": (g.cd3d(32), dict(kind="iluk", level=1)),
              "cd3d_24/iluk2": (g.cd3d(24), dict(kind="iluk", level=2)),
@@ -107,8 +100,9 @@ def test_skewed_boxes_give_fill_factors_an_acyclic_box_schedule(case, port, monk
     n = len(A[0]) - 1
     L, U = api.ilu_factor(A, **kw)
     rhs = np.sin(np.arange(n) * 0.37) + 0.3
+    monkeypatch.setenv("LSSPG_TRI_SKEW", "0")
     assert api.tri_pack_host(0, L)["kind"] == 0 and api.tri_walk_tiled_host(0, L, rhs)[1] is None
-    monkeypatch.setenv("LSSPG_TRI_SKEW", "1")
+    monkeypatch.delenv("LSSPG_TRI_SKEW")
     assert api.tri_pack_host(0, L)["kind"] == 2 and api.tri_pack_host(1, U)["kind"] == 2
     y, info = api.tri_walk_tiled_host(0, L, rhs)
     x, info_u = api.tri_walk_tiled_host(1, U, y)
