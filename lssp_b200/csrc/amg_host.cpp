@@ -312,8 +312,18 @@ int spgemm(int nrows, int ncolsB, const std::vector<int> &Ap, const std::vector<
         const int r0 = (int)((long long)nrows * t / nt), r1 = (int)((long long)nrows * (t + 1) / nt);
         Piece &P = pieces[t];
         P.len.assign(r1 - r0, 0);
-        std::vector<int> where(ncolsB, -1), cols;
-        std::vector<double> acc(ncolsB, 0.0);
+        // accumulator of one row: open-addressed table keyed by column (grown when half full).  A column's
+        // products are added in the order the row-by-row loop meets them, exactly as a dense accumulator
+        // would -- without two ncolsB-sized arrays per thread to allocate and touch.
+        size_t cap = 256;
+        std::vector<int> keys(cap, -1), cols;
+        std::vector<double> acc(cap, 0.0);
+        std::vector<size_t> slots;
+        auto slot_of = [&](int c) {
+            size_t h = ((size_t)(unsigned)c * 2654435761u) & (cap - 1);
+            while (keys[h] != -1 && keys[h] != c) h = (h + 1) & (cap - 1);
+            return h;
+        };
         for (int i = r0; i < r1; i++) {
             cols.clear();
             for (int k = Ap[i]; k < Ap[i + 1]; k++) {
@@ -321,19 +331,39 @@ int spgemm(int nrows, int ncolsB, const std::vector<int> &Ap, const std::vector<
                 const double a = Ax[k];
                 for (int q = Bp[m]; q < Bp[m + 1]; q++) {
                     const int c = Bj[q];
-                    if (where[c] != i) {
-                        where[c] = i;
-                        acc[c] = 0.0;
+                    size_t h = slot_of(c);
+                    if (keys[h] == -1) {
+                        if (2 * (cols.size() + 1) > cap) {   // grow: move the partial sums, nothing is re-added
+                            std::vector<int> okeys(2 * cap, -1);
+                            std::vector<double> oacc(2 * cap, 0.0);
+                            okeys.swap(keys);
+                            oacc.swap(acc);
+                            cap *= 2;
+                            for (int cc : cols) {
+                                size_t ho = ((size_t)(unsigned)cc * 2654435761u) & (cap / 2 - 1);
+                                while (okeys[ho] != cc) ho = (ho + 1) & (cap / 2 - 1);
+                                const size_t hn = slot_of(cc);
+                                keys[hn] = cc;
+                                acc[hn] = oacc[ho];
+                            }
+                            h = slot_of(c);
+                        }
+                        keys[h] = c;
+                        acc[h] = 0.0;
                         cols.push_back(c);
                     }
-                    acc[c] += a * Bx[q];
+                    acc[h] += a * Bx[q];
                 }
             }
             std::sort(cols.begin(), cols.end());
+            slots.clear();
             for (int c : cols) {
+                const size_t h = slot_of(c);
                 P.j.push_back(c);
-                P.x.push_back(acc[c]);
+                P.x.push_back(acc[h]);
+                slots.push_back(h);
             }
+            for (size_t h : slots) keys[h] = -1;   // only after every look-up of the row (probe chains stay intact)
             P.len[i - r0] = (int)cols.size();
         }
     };

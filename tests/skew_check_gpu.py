@@ -29,7 +29,35 @@ def timed(ctx, fn, reps=20, warm=3):
     return t.value / reps
 
 
+def tile_sweep(N, shapes):
+    """box shapes for the skewed schedule: ms per ILUK(1) application at N^3 (SKEW_TILES="16,8,4;8,8,8" N)"""
+    ctx = api.Context(0)
+    A = g.cd3d(N)
+    n = len(A[0]) - 1
+    L, U = api.ilu_factor(A, kind="iluk", level=1)
+    rhs = np.sin(np.arange(n) * 0.37) + 0.3
+    first = None
+    for shape in shapes:
+        os.environ["LSSPG_TRI_TILE"] = shape
+        try:
+            pc = api.Preconditioner(ctx, "ilu", n, L, U)
+        finally:
+            del os.environ["LSSPG_TRI_TILE"]
+        x, b = ctx.zeros(n), ctx.upload(rhs)
+        pc.apply(x, b)
+        got = x.get()
+        if first is None:
+            first = got
+        ms = timed(ctx, lambda: pc.apply(x, b), reps=10, warm=2)
+        print(json.dumps({"case": "cd3d_%d ILUK(1) box shape" % N, "shape": shape, "apply_ms": ms,
+                          "same_bits_as_first_shape": bool(np.array_equal(got, first))}), flush=True)
+        pc.free()
+    ctx.close()
+
+
 def main():
+    if os.environ.get("SKEW_TILES"):
+        return tile_sweep(int(sys.argv[1]) if len(sys.argv) > 1 else 256, os.environ["SKEW_TILES"].split(";"))
     sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 256]
     ctx = api.Context(0)
     import oracle
