@@ -312,6 +312,12 @@ int spgemm(int nrows, int ncolsB, const std::vector<int> &Ap, const std::vector<
         const int r0 = (int)((long long)nrows * t / nt), r1 = (int)((long long)nrows * (t + 1) / nt);
         Piece &P = pieces[t];
         P.len.assign(r1 - r0, 0);
+        {   // the number of products bounds the piece's entries: reserve once (untouched pages cost nothing)
+            size_t bound = 0;
+            for (int k = Ap[r0]; k < Ap[r1]; k++) bound += (size_t)(Bp[Aj[k] + 1] - Bp[Aj[k]]);
+            P.j.reserve(bound);
+            P.x.reserve(bound);
+        }
         // accumulator of one row: open-addressed table keyed by column (grown when half full).  A column's
         // products are added in the order the row-by-row loop meets them, exactly as a dense accumulator
         // would -- without two ncolsB-sized arrays per thread to allocate and touch.
@@ -367,28 +373,43 @@ int spgemm(int nrows, int ncolsB, const std::vector<int> &Ap, const std::vector<
             P.len[i - r0] = (int)cols.size();
         }
     };
+    timespec ts0, ts1;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
     if (nt == 1) work(0);
     else {
         std::vector<std::thread> th;
         for (int t = 0; t < nt; t++) th.emplace_back(work, t);
         for (auto &q : th) q.join();
     }
+    clock_gettime(CLOCK_MONOTONIC, &ts1);
+    if (getenv("LSSPG_SETUP_PROF")) fprintf(stderr, "[spgemm] rows %d threads part %.3f s\n", nrows, (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec));
     size_t total = 0;
     for (const Piece &P : pieces) total += P.j.size();
     AMG_CHECK(total < (size_t)0x7fffffff, "amg: coarse operator exceeds int32 indexing");
     Cp.assign(nrows + 1, 0);
     Cj.resize(total);
     Cx.resize(total);
-    size_t off = 0;
-    int row = 0;
-    for (const Piece &P : pieces) {
-        std::copy(P.j.begin(), P.j.end(), Cj.begin() + off);
-        std::copy(P.x.begin(), P.x.end(), Cx.begin() + off);
-        off += P.j.size();
-        for (int l : P.len) {
-            Cp[row + 1] = Cp[row] + l;
-            row++;
+    std::vector<size_t> off(nt + 1, 0);
+    std::vector<int> row0(nt + 1, 0);
+    for (int t = 0; t < nt; t++) {
+        off[t + 1] = off[t] + pieces[t].j.size();
+        row0[t + 1] = row0[t] + (int)pieces[t].len.size();
+    }
+    auto gather = [&](int t) {
+        const Piece &P = pieces[t];
+        std::copy(P.j.begin(), P.j.end(), Cj.begin() + off[t]);
+        std::copy(P.x.begin(), P.x.end(), Cx.begin() + off[t]);
+        size_t run = off[t];
+        for (size_t q = 0; q < P.len.size(); q++) {
+            run += (size_t)P.len[q];
+            Cp[row0[t] + q + 1] = (int)run;
         }
+    };
+    if (nt == 1) gather(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(gather, t);
+        for (auto &q : th) q.join();
     }
     return 0;
 }

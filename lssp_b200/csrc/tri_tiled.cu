@@ -106,9 +106,10 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
     if (n < 4096 || !detect_lattice(n, Tp, Tj, g, offsets)) return 2;
     int t[3] = {8, 8, 8};
     if (g[2] == 1) { t[0] = 16; t[1] = 16; t[2] = 1; }
+    bool shape_given = false;
     if (const char *e = getenv("LSSPG_TRI_TILE")) {
         int a, b, c;
-        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { t[0] = a; t[1] = b; t[2] = c; }
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && b > 0 && c > 0) { t[0] = a; t[1] = b; t[2] = c; shape_given = true; }
     }
     if ((long long)t[0] * t[1] * t[2] > kMaxTileRows) return 2;
     // Skewed boxes (default; LSSPG_TRI_SKEW=0 keeps the plain grid).  An entry at offset d = dz nx ny + dy nx + dx couples grid point p with
@@ -141,6 +142,9 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
             if (s1 <= 4 && s2 <= 4 && t1 <= 8) { sk[0] = (int)s1; sk[1] = (int)s2; sk[2] = (int)t1; }
         }
     }
+    // skewed 3-D boxes: u spans (1 + s1 + t1) nx, so boxes longer in u and flatter in w shorten the chain of boxes;
+    // measured for ILUK(1) at 256^3 (profiles/r01_skew_tiles.log): 12x8x5 3.88 ms, 8x8x8 4.12, 16x8x4 4.14, 8x4x8 4.46
+    if (!shape_given && g[2] > 1 && (sk[0] || sk[1] || sk[2])) { t[0] = 12; t[1] = 8; t[2] = 5; }
     const long long ext[3] = {(long long)g[0] + (long long)sk[0] * (g[1] - 1) + (long long)sk[2] * (g[2] - 1),
                               (long long)g[1] + (long long)sk[1] * (g[2] - 1), g[2]};
     const long long ntl[3] = {(ext[0] + t[0] - 1) / t[0], (ext[1] + t[1] - 1) / t[1], (ext[2] + t[2] - 1) / t[2]};
