@@ -1,13 +1,14 @@
 /* config.h -- build configuration of the B200-native LSSP facade.  Every third-party
  * adapter of the reference (include/config.h.in:18-34) is off: they are CPU libraries outside
- * the accelerated path.  USE_GPU marks this build. */
+ * the accelerated path.  USE_GPU marks this build.  USE_BLAS / USE_LAPACK only switch on what the
+ * reference guards with them -- LSSP_PC_BILUK -- which this build implements itself. */
 #ifndef LSSP_CONFIG_H
 #define LSSP_CONFIG_H
 #define LSSP_VER_MAJOR 1
 #define LSSP_VER_MINOR 0
 #define USE_GPU     1
-#define USE_BLAS    0
-#define USE_LAPACK  0
+#define USE_BLAS    1   /* block ILU(k) (pc-biluk.h) is built in: the dense block kernels are the library's own, */
+#define USE_LAPACK  1   /* no BLAS / LAPACK is linked (reference include/type-defs.h:70-74, src/pc-biluk.cxx:3-4) */
 #define USE_LASPACK 0
 #define USE_SSPARSE 0
 #define USE_MUMPS   0

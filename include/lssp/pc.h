@@ -4,6 +4,7 @@
 
 #include "pc-iluk.h"
 #include "pc-ilut.h"
+#include "pc-biluk.h"
 #include "pc-sxamg.h"
 
 void lssp_pc_create(LSSP_PC &pc, LSSP_PC_TYPE type);

@@ -48,6 +48,11 @@ typedef enum LSSP_PC_TYPE_ {
     LSSP_PC_NON,
     LSSP_PC_ILUK,
     LSSP_PC_ILUT,
+#if USE_BLAS
+#if USE_LAPACK
+    LSSP_PC_BILUK,              /* block-wise ILUK (reference include/type-defs.h:70-74) */
+#endif
+#endif
 #if USE_SXAMG
     LSSP_PC_SXAMG,              /* AMG, SX-AMG style (reference include/type-defs.h:92-94) */
 #endif

@@ -171,6 +171,20 @@ int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int 
                       double *Ux);
 int lsspg_factors_destroy(lsspg_factors *F);
 
+/* Block ILU(k) set-up (reference lssp_pc_biluk_assemble / _assemble_mat, src/pc-biluk.cxx:377-431; there only
+ * `#if USE_BLAS && USE_LAPACK`): blocks of n / num_blks rows (s.num_blks, src/pc-biluk.cxx:427), CSR -> BCSR
+ * (src/matrix-utils.cxx:62-162), level-of-fill symbolic phase on the block graph, block IKJ with dense block
+ * products and inverted pivot blocks.  Result: L (strict lower blocks, unit diagonal last), D (block diagonal of
+ * the inverted pivot blocks), U (inverse pivot times the upper blocks, unit diagonal first) -- the operands of
+ * lsspg_pc_create_bilu.  The dense kernels are the netlib reference DGEMM / DGETF2 / DGETRI (unblocked). */
+typedef struct lsspg_bfactors lsspg_bfactors;
+int lsspg_bilu_factor(int n, const int *hAp, const int *hAj, const double *hAx, int num_blks,
+                      int level, lsspg_bfactors **out);
+int lsspg_bfactors_sizes(const lsspg_bfactors *F, int *n, int *nnzL, int *nnzD, int *nnzU);
+int lsspg_bfactors_get(const lsspg_bfactors *F, int *Lp, int *Lj, double *Lx, int *Dp, int *Dj,
+                       double *Dx, int *Up, int *Uj, double *Ux);
+int lsspg_bfactors_destroy(lsspg_bfactors *F);
+
 /* ---- preconditioner application (replaces LSSP_PC.solve,
  *      include/type-defs.h:104,144) ------------------------------------------ */
 #define LSSPG_PC_NON   0   /* x = rhs                          src/pc.cxx:67-70            */

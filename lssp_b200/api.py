@@ -328,6 +328,22 @@ def ilu_factor(A, kind="iluk", level=0, p=-1, tol=1e-3, blk_size=0, ctx=None):
     return (Lp, Lj, Lx), (Up, Uj, Ux)
 
 
+def bilu_factor(A, num_blks, level=0):
+    """Block ILU(k) set-up (reference src/pc-biluk.cxx:377-431): blocks of n / num_blks rows.  Returns (L, D, U) CSR
+    triples -- unit diagonal last in L and first in U, D the block diagonal of the inverted pivot blocks."""
+    Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
+    n = len(Ap) - 1
+    h = C.c_void_p()
+    check(lib().lsspg_bilu_factor(n, _p(Ap), _p(Aj), _p(Ax), int(num_blks), int(level), C.byref(h)))
+    nn, nl, nd, nu = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lib().lsspg_bfactors_sizes(h, C.byref(nn), C.byref(nl), C.byref(nd), C.byref(nu))
+    out = [(np.empty(n + 1, np.int32), np.empty(z.value, np.int32), np.empty(z.value)) for z in (nl, nd, nu)]
+    (Lp, Lj, Lx), (Dp, Dj, Dx), (Up, Uj, Ux) = out
+    lib().lsspg_bfactors_get(h, _p(Lp), _p(Lj), _p(Lx), _p(Dp), _p(Dj), _p(Dx), _p(Up), _p(Uj), _p(Ux))
+    lib().lsspg_bfactors_destroy(h)
+    return out
+
+
 class Preconditioner:
     """Device-side preconditioner application (the `pc.solve` seam, reference
     include/type-defs.h:104,144)."""
@@ -360,6 +376,12 @@ class Preconditioner:
         """lssp_pc_iluk_assemble (reference src/pc-iluk.cxx:566-581); default level 1 (src/pc.cxx:3)"""
         L, U = ilu_factor(A, "iluk", level=level, blk_size=blk_size)
         return cls(ctx, "ilu", len(L[0]) - 1, L, U)
+
+    @classmethod
+    def biluk(cls, ctx, A, num_blks, level=1):
+        """lssp_pc_biluk_assemble (reference src/pc-biluk.cxx:416-431); default level 1 (src/pc.cxx:3)"""
+        L, D, U = bilu_factor(A, num_blks, level=level)
+        return cls(ctx, "bilu", len(L[0]) - 1, L, U, D)
 
     @classmethod
     def ilut(cls, ctx, A, p=-1, tol=1e-3, blk_size=0):

@@ -535,6 +535,91 @@ void lssp_pc_ilut_assemble(LSSP_PC &pc, LSSP_SOLVER s)
 void lssp_pc_ilut_set_drop_tol(LSSP_PC &pc, double tol) { pc.ilut_tol = fabs(tol); }
 void lssp_pc_ilut_set_p(LSSP_PC &pc, int p) { pc.ilut_p = p; }
 
+// ---- block ILU(k) (reference src/pc-biluk.cxx) ------------------------------------------------------------
+// pc.solve: x = U^-1 D L^-1 rhs (src/pc-biluk.cxx:22-60) with the factors resident on the device
+void lssp_pc_bilu_solve(LSSP_PC *pc, lssp_vec x, lssp_vec rhs)
+{
+    assert(pc->gpu != NULL);
+    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc->gpu, x.d, rhs.d));
+}
+
+void lssp_pc_biluk_destroy(LSSP_PC *pc)   // src/pc-biluk.cxx:303-313
+{
+    assert(pc->assembled);
+    lssp_mat_destroy(pc->L);
+    lssp_mat_destroy(pc->U);
+    lssp_mat_destroy(pc->D);
+    lssp_free<double>(pc->cache);
+    release_device_pc(pc);
+    pc->assembled = false;
+}
+
+static void adopt_block_factors(LSSP_PC &pc, lsspg_bfactors *F)
+{
+    int n, nl, nd, nu;
+    lsspg_bfactors_sizes(F, &n, &nl, &nd, &nu);
+    lssp_mat_csr *M[3] = {&pc.L, &pc.D, &pc.U};
+    const int nz[3] = {nl, nd, nu};
+    for (int q = 0; q < 3; q++) {
+        M[q]->num_rows = M[q]->num_cols = n;
+        M[q]->num_nnzs = nz[q];
+        M[q]->Ap = lssp_malloc<int>(n + 1);
+        M[q]->Aj = lssp_malloc<int>(nz[q]);
+        M[q]->Ax = lssp_malloc<double>(nz[q]);
+    }
+    lsspg_bfactors_get(F, pc.L.Ap, pc.L.Aj, pc.L.Ax, pc.D.Ap, pc.D.Aj, pc.D.Ax, pc.U.Ap, pc.U.Aj, pc.U.Ax);
+    lsspg_bfactors_destroy(F);
+    lsspg_pc *d = NULL;
+    GPU(lsspg_pc_create_bilu(ctx(), n, pc.L.Ap, pc.L.Aj, pc.L.Ax, pc.D.Ap, pc.D.Aj, pc.D.Ax, pc.U.Ap, pc.U.Aj, pc.U.Ax, &d));
+    pc.gpu = d;
+    pc.cache = lssp_malloc<double>(2 * n);   // src/pc-biluk.cxx:406
+    pc.solve = lssp_pc_bilu_solve;
+    pc.destroy = lssp_pc_biluk_destroy;
+}
+
+// src/pc-biluk.cxx:377-414.  The block matrix is expanded to CSR (every entry of every block, stored zeros included:
+// the factors keep them, src/pc-biluk.cxx:129-171) and handed to the same set-up as lssp_pc_biluk_assemble; block
+// rows need not be sorted.
+void lssp_pc_biluk_assemble_mat(LSSP_PC &pc, lssp_mat_bcsr A)
+{
+    double time = lssp_get_time();
+    const int bs = A.blk_size, bs2 = bs * bs;
+    assert(bs > 0 && A.num_rows == A.num_cols && A.num_rows > 0);
+    const int n = A.num_rows * bs;
+    const int nnz = A.Ap[A.num_rows] * bs2;
+    int *Ap = lssp_malloc<int>(n + 1), *Aj = lssp_malloc<int>(nnz);
+    double *Ax = lssp_malloc<double>(nnz);
+    int o = 0;
+    Ap[0] = 0;
+    for (int i = 0; i < A.num_rows; i++)
+        for (int a = 0; a < bs; a++) {
+            for (int k = A.Ap[i]; k < A.Ap[i + 1]; k++)
+                for (int b = 0; b < bs; b++, o++) {
+                    Aj[o] = A.Aj[k] * bs + b;
+                    Ax[o] = A.Ax[(size_t)k * bs2 + b * bs + a];
+                }
+            Ap[i * bs + a + 1] = o;
+        }
+    lsspg_bfactors *F = NULL;
+    GPU(lsspg_bilu_factor(n, Ap, Aj, Ax, A.num_rows, pc.iluk_level, &F));
+    lssp_free(Ap); lssp_free(Aj); lssp_free(Ax);
+    adopt_block_factors(pc, F);
+    if (pc.verb > 0) lssp_printf("pc: BILUK assemble time: %f\n", lssp_get_time() - time);
+}
+
+void lssp_pc_biluk_assemble(LSSP_PC &pc, LSSP_SOLVER s)   // src/pc-biluk.cxx:416-431
+{
+    assert(s.A.num_rows == s.A.num_cols);
+    assert(s.A.num_rows > 0 && s.A.num_nnzs > 0);
+    assert(s.num_blks > 0);
+    assert(s.A.num_rows % s.num_blks == 0);
+    double time = lssp_get_time();
+    lsspg_bfactors *F = NULL;
+    GPU(lsspg_bilu_factor(s.A.num_rows, s.A.Ap, s.A.Aj, s.A.Ax, s.num_blks, pc.iluk_level, &F));
+    adopt_block_factors(pc, F);
+    if (pc.verb > 0) lssp_printf("pc: BILUK assemble time: %f\n", lssp_get_time() - time);
+}
+
 // user-defined preconditioner: its pc.solve works on host vectors
 static void user_pc_trampoline(void *user, double *hx, const double *hrhs, int n)
 {
@@ -575,6 +660,10 @@ void lssp_pc_assemble(LSSP_PC &pc, LSSP_SOLVER s)
         case LSSP_PC_ILUT:
             if (pc.verb >= 0) lssp_printf("pc: type: ILUT\n");
             lssp_pc_ilut_assemble(pc, s);
+            break;
+        case LSSP_PC_BILUK:   // src/pc.cxx:124-135
+            if (pc.verb >= 0) lssp_printf("pc: type: block version ILUK\n");
+            lssp_pc_biluk_assemble(pc, s);
             break;
 #if USE_SXAMG
         case LSSP_PC_SXAMG:   // src/pc.cxx:208-217

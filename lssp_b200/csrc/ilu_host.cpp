@@ -21,6 +21,7 @@
 #include <string.h>
 #include <time.h>
 #include <algorithm>
+#include <limits>
 #include <numeric>
 #include <vector>
 #include "../../include/lsspg.h"
@@ -870,10 +871,237 @@ Factors factor_ilut(Csr &&A, double tau, int p, int bs)
     return F;
 }
 
+// ---- block ILU(k) (reference src/pc-biluk.cxx:62-431, compiled there only with BLAS + LAPACK) ---------------
+// Dense bs x bs blocks, column-major.  The three dense kernels restate the PUBLISHED netlib reference algorithms the
+// reference reaches through dgemm_/dgetrf_/dgetri_ (src/pc-biluk.cxx:10-16): reference-BLAS DGEMM 'N','N', LAPACK's
+// unblocked DGETF2 (partial pivoting) and DGETRI's unblocked path (DTRTI2, then the column sweep).  With an
+// optimised BLAS the reference's own factors differ from these in the last bits -- the order of the dense sums is
+// the BLAS's, not LSSP's.
+
+// C = alpha A B + beta C  (src/pc-biluk.cxx:86-103, n == 1 handled as there)
+void block_gemm(const double *A, const double *B, double alpha, double *C, double beta, int n)
+{
+    if (n == 1) {
+        C[0] = A[0] * B[0] * alpha + beta * C[0];
+        return;
+    }
+    for (int j = 0; j < n; j++) {
+        if (beta == 0.0) for (int i = 0; i < n; i++) C[i + j * n] = 0.0;
+        else if (beta != 1.0) for (int i = 0; i < n; i++) C[i + j * n] = beta * C[i + j * n];
+        for (int l = 0; l < n; l++) {
+            const double temp = alpha * B[l + j * n];
+            for (int i = 0; i < n; i++) C[i + j * n] = C[i + j * n] + temp * A[i + l * n];
+        }
+    }
+}
+
+// A <- A^-1 in place (src/pc-biluk.cxx:62-84); != 0: singular
+int block_inverse(double *A, int n, double *work, int *ipiv)
+{
+    if (n == 1) {
+        if (A[0] == 0.0) return 1;
+        A[0] = 1.0 / A[0];
+        return 0;
+    }
+    int info = 0;
+    for (int j = 0; j < n; j++) {   // DGETF2
+        int jp = j;
+        double big = fabs(A[j + j * n]);
+        for (int i = j + 1; i < n; i++)
+            if (fabs(A[i + j * n]) > big) { big = fabs(A[i + j * n]); jp = i; }
+        ipiv[j] = jp;
+        if (A[jp + j * n] != 0.0) {
+            if (jp != j)
+                for (int c = 0; c < n; c++) std::swap(A[j + c * n], A[jp + c * n]);
+            if (j < n - 1) {
+                if (fabs(A[j + j * n]) >= std::numeric_limits<double>::min()) {
+                    const double r = 1.0 / A[j + j * n];
+                    for (int i = j + 1; i < n; i++) A[i + j * n] = r * A[i + j * n];
+                }
+                else for (int i = j + 1; i < n; i++) A[i + j * n] = A[i + j * n] / A[j + j * n];
+            }
+        }
+        else if (info == 0) info = j + 1;
+        if (j < n - 1)
+            for (int c = j + 1; c < n; c++) {
+                if (A[j + c * n] == 0.0) continue;
+                const double temp = -A[j + c * n];
+                for (int i = j + 1; i < n; i++) A[i + c * n] = A[i + c * n] + A[i + j * n] * temp;
+            }
+    }
+    if (info) return info;
+    for (int j = 0; j < n; j++)
+        if (A[j + j * n] == 0.0) return j + 1;
+    for (int j = 0; j < n; j++) {   // DTRTI2: inverse of the upper triangle
+        A[j + j * n] = 1.0 / A[j + j * n];
+        const double ajj = -A[j + j * n];
+        for (int c = 0; c < j; c++) {
+            if (A[c + j * n] == 0.0) continue;
+            const double temp = A[c + j * n];
+            for (int i = 0; i < c; i++) A[i + j * n] = A[i + j * n] + temp * A[i + c * n];
+            A[c + j * n] = A[c + j * n] * A[c + c * n];
+        }
+        for (int i = 0; i < j; i++) A[i + j * n] = ajj * A[i + j * n];
+    }
+    for (int j = n - 1; j >= 0; j--) {   // inv(A) L = inv(U)
+        for (int i = j + 1; i < n; i++) { work[i] = A[i + j * n]; A[i + j * n] = 0.0; }
+        for (int c = j + 1; c < n; c++) {
+            const double temp = -work[c];
+            for (int i = 0; i < n; i++) A[i + j * n] = A[i + j * n] + temp * A[i + c * n];
+        }
+    }
+    for (int j = n - 2; j >= 0; j--)
+        if (ipiv[j] != j)
+            for (int i = 0; i < n; i++) std::swap(A[i + j * n], A[i + ipiv[j] * n]);
+    return 0;
+}
+
+struct BFactors {
+    int n = 0;
+    Csr L, D, U;
+};
+
+// A: rows sorted by column.  bs x bs blocks; L = strict lower blocks + unit diagonal (last), D = inverted pivot
+// blocks, U = inv(pivot) * upper blocks behind a unit diagonal (first): x = U^-1 D L^-1 rhs (src/pc-biluk.cxx:22-60).
+int factor_biluk(const Csr &A, int bs, int level, BFactors &F)
+{
+    const int n = A.n, nb = n / bs, bs2 = bs * bs;
+    // CSR -> BCSR (src/matrix-utils.cxx:62-162): block columns of a block row ascending, blocks column-major
+    Csr B;   // block graph; x unused
+    B.n = nb;
+    B.p.assign((size_t)nb + 1, 0);
+    {
+        std::vector<int> mark(nb, -1), cols;
+        for (int i = 0; i < nb; i++) {
+            cols.clear();
+            for (int r = i * bs; r < (i + 1) * bs; r++)
+                for (int k = A.p[r]; k < A.p[r + 1]; k++) {
+                    const int c = A.j[k] / bs;
+                    if (mark[c] != i) { mark[c] = i; cols.push_back(c); }
+                }
+            std::sort(cols.begin(), cols.end());
+            B.j.insert(B.j.end(), cols.begin(), cols.end());
+            B.p[i + 1] = (int)B.j.size();
+        }
+    }
+    for (int i = 0; i < nb; i++)
+        if (!std::binary_search(B.j.begin() + B.p[i], B.j.begin() + B.p[i + 1], i)) {
+            lsspg::set_error("biluk: block row %d has no diagonal block", i);
+            return 1;
+        }
+    // symbolic phase on the block graph (src/pc-biluk.cxx:316-375): level 0 keeps the pattern
+    Csr T;
+    if (level > 0) {
+        B.x.assign(B.j.size(), 0.0);
+        T = iluk_pattern(B, level);
+    }
+    else {
+        T.n = nb;
+        T.p = B.p;
+        T.j = B.j;
+    }
+    const int *Tp = T.p.data(), *Tj = T.j.data();
+    DVec X((size_t)Tp[nb] * bs2);
+    std::fill(X.begin(), X.end(), 0.0);
+    {
+        std::vector<int> where(nb, -1);
+        for (int i = 0; i < nb; i++) {
+            for (int k = Tp[i]; k < Tp[i + 1]; k++) where[Tj[k]] = k;
+            for (int r = i * bs; r < (i + 1) * bs; r++)
+                for (int k = A.p[r]; k < A.p[r + 1]; k++) {
+                    const int c = A.j[k];
+                    X[(size_t)where[c / bs] * bs2 + (size_t)(c % bs) * bs + (r % bs)] = A.x[k];
+                }
+        }
+    }
+    // numeric phase (src/pc-biluk.cxx:198-277): block IKJ; inv[i] = inverse of the pivot block
+    DVec inv((size_t)nb * bs2);
+    std::vector<double> blk(bs2), work(10 * (size_t)bs);
+    std::vector<int> ipiv(bs);
+    for (int i = 0; i < nb; i++) {
+        const int e = Tp[i + 1];
+        int k = Tp[i];
+        for (; k < e && Tj[k] < i; k++) {
+            const int pr = Tj[k];
+            double *a_ik = &X[(size_t)k * bs2];
+            std::copy(a_ik, a_ik + bs2, blk.begin());
+            block_gemm(blk.data(), &inv[(size_t)pr * bs2], 1., a_ik, 0., bs);
+            int pq = Tp[pr];
+            const int pe = Tp[pr + 1];
+            for (int j = k + 1; j < e; j++) {
+                const int c = Tj[j];
+                while (pq < pe && Tj[pq] < c) pq++;
+                if (pq < pe && Tj[pq] == c) block_gemm(a_ik, &X[(size_t)pq * bs2], -1., &X[(size_t)j * bs2], 1., bs);
+            }
+        }
+        std::copy(&X[(size_t)k * bs2], &X[(size_t)k * bs2] + bs2, &inv[(size_t)i * bs2]);   // k: the diagonal block
+        if (block_inverse(&inv[(size_t)i * bs2], bs, work.data(), ipiv.data())) {
+            lsspg::set_error("lssp: bilu(0) singular diagonal submatrix.");   // src/pc-biluk.cxx:262
+            return 1;
+        }
+    }
+    // L, U, D as CSR (src/pc-biluk.cxx:105-196, :279-314): rows end up sorted by column
+    F.n = n;
+    Csr &L = F.L, &U = F.U, &D = F.D;
+    L.n = U.n = D.n = n;
+    L.p.assign((size_t)n + 1, 0);
+    U.p.assign((size_t)n + 1, 0);
+    D.p.assign((size_t)n + 1, 0);
+    for (int i = 0; i < nb; i++) {
+        int nl = 0, nu = 0;
+        for (int k = Tp[i]; k < Tp[i + 1]; k++) {
+            nl += (Tj[k] < i);
+            nu += (Tj[k] > i);
+        }
+        for (int a = 0; a < bs; a++) {
+            const int r = i * bs + a;
+            L.p[r + 1] = L.p[r] + nl * bs + 1;
+            U.p[r + 1] = U.p[r] + nu * bs + 1;
+            D.p[r + 1] = D.p[r] + bs;
+        }
+    }
+    L.j.resize((size_t)L.p[n]); L.x.resize((size_t)L.p[n]);
+    U.j.resize((size_t)U.p[n]); U.x.resize((size_t)U.p[n]);
+    D.j.resize((size_t)D.p[n]); D.x.resize((size_t)D.p[n]);
+    std::vector<double> cache(bs2, 0.0);
+    for (int i = 0; i < nb; i++) {
+        std::vector<int> ol(bs), ou(bs);
+        for (int a = 0; a < bs; a++) {
+            const int r = i * bs + a;
+            ol[a] = L.p[r];
+            ou[a] = U.p[r];
+            U.j[ou[a]] = r; U.x[ou[a]] = 1.; ou[a]++;
+            for (int b = 0; b < bs; b++) {
+                D.j[D.p[r] + b] = i * bs + b;
+                D.x[D.p[r] + b] = inv[(size_t)i * bs2 + (size_t)b * bs + a];
+            }
+        }
+        for (int k = Tp[i]; k < Tp[i + 1]; k++) {
+            const int c = Tj[k];
+            const double *d = &X[(size_t)k * bs2];
+            if (c < i) {
+                for (int a = 0; a < bs; a++)
+                    for (int b = 0; b < bs; b++) { L.j[ol[a]] = c * bs + b; L.x[ol[a]] = d[b * bs + a]; ol[a]++; }
+            }
+            else if (c > i) {
+                block_gemm(&inv[(size_t)i * bs2], d, 1., cache.data(), 0., bs);
+                for (int a = 0; a < bs; a++)
+                    for (int b = 0; b < bs; b++) { U.j[ou[a]] = c * bs + b; U.x[ou[a]] = cache[b * bs + a]; ou[a]++; }
+            }
+        }
+        for (int a = 0; a < bs; a++) { L.j[ol[a]] = i * bs + a; L.x[ol[a]] = 1.; }
+    }
+    return 0;
+}
+
 }  // namespace
 
 struct lsspg_factors {
     Factors f;
+};
+
+struct lsspg_bfactors {
+    BFactors f;
 };
 
 namespace lsspg {
@@ -958,6 +1186,62 @@ int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int 
 }
 
 int lsspg_factors_destroy(lsspg_factors *F)
+{
+    delete F;
+    return 0;
+}
+
+// Block ILU(k) set-up (reference lssp_pc_biluk_assemble, src/pc-biluk.cxx:416-431): blocks of n / num_blks rows.
+int lsspg_bilu_factor(int n, const int *hAp, const int *hAj, const double *hAx, int num_blks, int level, lsspg_bfactors **out)
+{
+    if (!out || !hAp || !hAj || !hAx || n <= 0 || num_blks <= 0) {
+        lsspg::set_error("lsspg_bilu_factor: bad argument");
+        return 1;
+    }
+    if (n % num_blks != 0) {
+        lsspg::set_error("lsspg_bilu_factor: num_rows %d is not a multiple of the number of blocks %d", n, num_blks);
+        return 1;
+    }
+    Csr A;
+    A.n = n;
+    A.p.assign(hAp, hAp + n + 1);
+    A.j.assign(hAj, hAj + hAp[n]);
+    A.x.assign(hAx, hAx + hAp[n]);
+    sort_rows(A);   // src/lssp.cxx:173
+    if (level < 0) level = 0;
+    lsspg_bfactors *F = new lsspg_bfactors();
+    if (factor_biluk(A, n / num_blks, level, F->f)) {
+        delete F;
+        return 1;
+    }
+    *out = F;
+    return 0;
+}
+
+int lsspg_bfactors_sizes(const lsspg_bfactors *F, int *n, int *nnzL, int *nnzD, int *nnzU)
+{
+    if (n) *n = F->f.n;
+    if (nnzL) *nnzL = F->f.L.nnz();
+    if (nnzD) *nnzD = F->f.D.nnz();
+    if (nnzU) *nnzU = F->f.U.nnz();
+    return 0;
+}
+
+int lsspg_bfactors_get(const lsspg_bfactors *F, int *Lp, int *Lj, double *Lx, int *Dp, int *Dj, double *Dx, int *Up,
+                       int *Uj, double *Ux)
+{
+    const Csr *M[3] = {&F->f.L, &F->f.D, &F->f.U};
+    int *P[3] = {Lp, Dp, Up}, *J[3] = {Lj, Dj, Uj};
+    double *X[3] = {Lx, Dx, Ux};
+    for (int q = 0; q < 3; q++) {
+        memcpy(P[q], M[q]->p.data(), sizeof(int) * M[q]->p.size());
+        memcpy(J[q], M[q]->j.data(), sizeof(int) * M[q]->j.size());
+        memcpy(X[q], M[q]->x.data(), sizeof(double) * M[q]->x.size());
+    }
+    return 0;
+}
+
+int lsspg_bfactors_destroy(lsspg_bfactors *F)
 {
     delete F;
     return 0;

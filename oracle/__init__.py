@@ -158,6 +158,52 @@ class Ref:
         return np.array(hist)
 
 
+class RefB:
+    """The unmodified reference built with USE_BLAS = USE_LAPACK = 1 against oracle/blas_standin.c: its block
+    ILU(k) set-up (src/pc-biluk.cxx), through oracle/ref_bilu_shim.cxx."""
+
+    def __init__(self):
+        self.path = os.path.join(HERE, "_ref", "liblssp_refb.so")
+        self.lib = C.CDLL(self.path)
+        self.lib.refb_bilu_create.restype = C.c_void_p
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "liblssp_refb.so"))
+
+    def bilu(self, A, num_blks, level=0, rhs=None):
+        """(L, D, U) CSR triples of the reference's BILUK(level) with block size n / num_blks; with rhs also
+        x = U^-1 D L^-1 rhs from the reference's own apply"""
+        Ap, Aj, Ax = A
+        n = len(Ap) - 1
+        h = C.c_void_p(self.lib.refb_bilu_create(n, _ptr(Ap), _ptr(Aj), _ptr(Ax), int(num_blks), int(level)))
+        nl, nd, nu = C.c_int(), C.c_int(), C.c_int()
+        self.lib.refb_bilu_sizes(h, C.byref(nl), C.byref(nd), C.byref(nu))
+        out = []
+        for nz in (nl.value, nd.value, nu.value):
+            out.append((np.empty(n + 1, np.int32), np.empty(nz, np.int32), np.empty(nz)))
+        (Lp, Lj, Lx), (Dp, Dj, Dx), (Up, Uj, Ux) = out
+        self.lib.refb_bilu_get(h, _ptr(Lp), _ptr(Lj), _ptr(Lx), _ptr(Dp), _ptr(Dj), _ptr(Dx), _ptr(Up), _ptr(Uj), _ptr(Ux))
+        x = None
+        if rhs is not None:
+            x = np.zeros(n)
+            r = np.ascontiguousarray(rhs, dtype=np.float64)
+            self.lib.refb_bilu_apply(h, n, _ptr(x), _ptr(r))
+        self.lib.refb_bilu_destroy(h)
+        return out if rhs is None else (out, x)
+
+    def solve_biluk(self, solver, A, b, num_blks, level=1, rtol=1e-7, maxit=1000, restart=50, x0=None):
+        """lssp_solver_create/assemble/solve with LSSP_PC_BILUK (s.num_blks = num_blks): dict(nits, residual, x)"""
+        Ap, Aj, Ax = A
+        n = len(Ap) - 1
+        x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64)
+        out = np.zeros(1)
+        nits = self.lib.refb_solve_biluk(SOLVERS[solver], n, _ptr(Ap), _ptr(Aj), _ptr(Ax),
+                                         _ptr(np.ascontiguousarray(b, dtype=np.float64)), _ptr(x), int(num_blks),
+                                         int(level), C.c_double(rtol), int(maxit), int(restart), _ptr(out))
+        return dict(nits=nits, residual=out[0], x=x)
+
+
 class OrcPC(C.Structure):
     _fields_ = [("kind", C.c_int), ("Lp", C.c_void_p), ("Lj", C.c_void_p), ("Lx", C.c_void_p),
                 ("Up", C.c_void_p), ("Uj", C.c_void_p), ("Ux", C.c_void_p), ("cache", C.c_void_p),
