@@ -46,6 +46,7 @@ int main(int argc, char **argv)
     if (pname == "non") pt = LSSP_PC_NON;
     if (pname == "ilut") pt = LSSP_PC_ILUT;
     if (pname == "sxamg") pt = LSSP_PC_SXAMG;          // one V-cycle per application
+    if (pname == "biluk") pt = LSSP_PC_BILUK;          // block ILU(k); 5th argument: block size (default 2)
 
     lssp_mat_csr A = poisson2d(N);
     const int n = A.num_rows;
@@ -66,6 +67,7 @@ int main(int argc, char **argv)
         pars.zero_guess = atoi(argv[4]);
         lssp_pc_sxamg_set_pars(pc, &pars);
     }
+    if (pt == LSSP_PC_BILUK) solver.num_blks = n / (argc > 4 ? atoi(argv[4]) : 2);   // block size = n / num_blks
     lssp_solver_assemble(solver, A, x, b, pc);
     const int nits = lssp_solver_solve(solver, pc);
 

@@ -72,6 +72,17 @@ def test_facade_symbols_are_link_compatible_with_the_reference():
     assert not (hot - ours), sorted(hot - ours)
 
 
+def test_block_ilu_symbols_are_link_compatible_with_a_blas_build_of_the_reference():
+    """LSSP_PC_BILUK exists in the reference only `#if USE_BLAS && USE_LAPACK` (include/pc-biluk.h:10-19): compare with
+    the oracle build that has them on (oracle/_ref/liblssp_refb.so)."""
+    refb = os.path.join(ROOT, "oracle", "_ref", "liblssp_refb.so")
+    if not os.path.exists(refb):
+        pytest.skip("oracle/_ref/liblssp_refb.so not built")
+    want = {m for m in mangled(refb) if re.match(r"_Z\d+lssp_pc_bilu", m)}
+    assert len(want) == 4, want     # bilu_solve, biluk_destroy, biluk_assemble_mat, biluk_assemble
+    assert not (want - mangled(LIB)), sorted(want - mangled(LIB))
+
+
 @pytest.mark.gpu
 def test_exam_program_with_the_amg_preconditioner_and_the_amg_solver(port):
     """LSSP_PC_SXAMG / LSSP_SOLVER_SXAMG through the C++ API; expected counts from the restated

@@ -50,3 +50,20 @@ def test_gpu_drivers_with_block_ilu_equal_the_reference_in_sequential_mode(key):
     pc.free()
     dA.free()
     c.close()
+
+
+@pytest.mark.gpu
+def test_exam_program_with_the_block_ilu_preconditioner():
+    """LSSP_PC_BILUK through the C++ API (lssp_solver_create / s.num_blks / lssp_solver_assemble): the exam.cxx
+    matrix with 2 x 2 blocks, level 1 -- the reference needs 32 CG iterations (fixture lap2d_100/bs2/k1/cg)."""
+    import re
+    import subprocess
+    exam = os.path.join(ROOT, "examples", "exam")
+    e = GOLD["solves"]["lap2d_100/bs2/k1/cg"]
+    out = subprocess.run([exam, "100", "cg", "biluk", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"iterations: (\d+), solver residual: (\S+)", out.stdout)
+    k = re.search(r"solution L2 norm: (\S+) residual: (\S+)", out.stdout)
+    assert abs(int(m.group(1)) - e["nits"]) <= 1, out.stdout
+    assert abs(float(k.group(1)) - e["xnorm"]) <= 1e-6 * e["xnorm"]
+    assert abs(float(k.group(2)) - float(m.group(2))) <= 1e-3 * float(m.group(2)) + 1e-9
