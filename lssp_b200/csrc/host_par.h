@@ -2,8 +2,9 @@
 //
 // Every use hands DISJOINT output ranges to the threads and computes each output element exactly as
 // the serial code does, so results never depend on the number of threads (LSSPG_HOST_THREADS, default:
-// the hardware concurrency, at most 32; 1 = run inline).
+// the cores of the process' affinity mask divided by LOCAL_WORLD_SIZE, at most 32; 1 = run inline).
 #pragma once
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -41,7 +42,13 @@ inline int host_threads()
     static const int nt = [] {
         int v = 0;
         if (const char *e = getenv("LSSPG_HOST_THREADS")) v = atoi(e);
-        if (v <= 0) v = (int)std::thread::hardware_concurrency();
+        if (v <= 0) {
+            // the cores this process may run on, shared with the other ranks of a torchrun launch on this node
+            cpu_set_t set;
+            v = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+            if (const char *w = getenv("LOCAL_WORLD_SIZE"))
+                if (atoi(w) > 1) v /= atoi(w);
+        }
         return std::max(1, std::min(v, 32));
     }();
     return nt;
