@@ -88,7 +88,8 @@ def test_unsorted_rows_and_missing_diagonals_take_the_repair_path(ref):
         assert _same(api.ilu_factor(B, **kw), api.ilu_factor((Ap, Aj, Cx), **kw)), kw
 
 
-@pytest.mark.parametrize("case", ["cd3d_32/iluk1", "cd3d_24/iluk2", "lap2d_150/iluk1", "cd3d_40/iluk1_bj2"])
+@pytest.mark.parametrize("case", ["cd3d_32/iluk1", "cd3d_24/iluk2", "lap2d_150/iluk1", "cd3d_40/iluk1_bj2", "grid_20x48x12/iluk1",
+                                  "grid_12x20x48/iluk2"])
 def test_skewed_boxes_give_fill_factors_an_acyclic_box_schedule(case, port, monkeypatch):
     # ILU(1)/(2) fill couples axis-aligned neighbour boxes both ways (cyclic box graph -> slice schedule).  Boxes cut
     # along x + s1 y + t1 z, y + s2 z, z (the default; LSSPG_TRI_SKEW=0 disables, tri_tiled.cu) are coupled one way only: the factor gets
@@ -96,7 +97,9 @@ def test_skewed_boxes_give_fill_factors_an_acyclic_box_schedule(case, port, monk
     A, kw = {"cd3d_32/iluk1": (g.cd3d(32), dict(kind="iluk", level=1)),
              "cd3d_24/iluk2": (g.cd3d(24), dict(kind="iluk", level=2)),
              "lap2d_150/iluk1": (g.laplacian_5pt(150), dict(kind="iluk", level=1)),
-             "cd3d_40/iluk1_bj2": (g.cd3d(40), dict(kind="iluk", level=1, blk_size=32000))}[case]
+             "cd3d_40/iluk1_bj2": (g.cd3d(40), dict(kind="iluk", level=1, blk_size=32000)),
+             "grid_20x48x12/iluk1": (g.stencil_7pt_rows((20, 48, 12), 0, 11520, conv=(0.3, 0.2, 0.1)), dict(kind="iluk", level=1)),
+             "grid_12x20x48/iluk2": (g.stencil_7pt_rows((12, 20, 48), 0, 11520, conv=(0.3, 0.2, 0.1)), dict(kind="iluk", level=2))}[case]
     n = len(A[0]) - 1
     L, U = api.ilu_factor(A, **kw)
     rhs = np.sin(np.arange(n) * 0.37) + 0.3
@@ -107,6 +110,7 @@ def test_skewed_boxes_give_fill_factors_an_acyclic_box_schedule(case, port, monk
     y, info = api.tri_walk_tiled_host(0, L, rhs)
     x, info_u = api.tri_walk_tiled_host(1, U, y)
     assert info["max_box_rows"] <= 512 and info["box_levels"] < info["row_levels"] / 3
+    assert info["nx"] * info["ny"] * info["nz"] == n
     assert np.array_equal(x, port.ilu_apply(L, U, rhs))
     # the plain box grid of ILU(0) factors is the zero-skew case: same image as pinned
     L0, U0 = api.ilu_factor(g.lap3d(32), kind="iluk", level=0)
