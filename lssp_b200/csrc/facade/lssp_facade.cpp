@@ -11,6 +11,7 @@
 #include <numeric>
 #include <vector>
 
+#include "../host_par.h"
 #include "lssp.h"
 #include "lsspg.h"
 
@@ -730,9 +731,12 @@ void lssp_solver_assemble(LSSP_SOLVER &s, lssp_mat_csr &Ax, lssp_vec x, lssp_vec
     A.num_rows = Ax.num_rows;
     A.num_cols = Ax.num_cols;
     A.num_nnzs = Ax.num_nnzs;
-    A.Ap = lssp_copy_on<int>(Ax.Ap, Ax.num_rows + 1);            // deep copy, :169-171
-    A.Aj = lssp_copy_on<int>(Ax.Aj, Ax.num_nnzs);
-    A.Ax = lssp_copy_on<double>(Ax.Ax, Ax.num_nnzs);
+    A.Ap = lssp_malloc<int>(Ax.num_rows + 1);                    // deep copy, :169-171 (by the host threads)
+    A.Aj = lssp_malloc<int>(Ax.num_nnzs);
+    A.Ax = lssp_malloc<double>(Ax.num_nnzs);
+    lsspg::parallel_copy(A.Ap, Ax.Ap, sizeof(int) * ((size_t)Ax.num_rows + 1));
+    lsspg::parallel_copy(A.Aj, Ax.Aj, sizeof(int) * (size_t)Ax.num_nnzs);
+    lsspg::parallel_copy(A.Ax, Ax.Ax, sizeof(double) * (size_t)Ax.num_nnzs);
     if (!lssp_mat_csr_is_sorted(A)) lssp_mat_sort_column(A);    // :173
     s.rhs = b;                                                  // aliases, :175-176
     s.x = x;
