@@ -153,6 +153,226 @@ void lssp_mat_sort_column(lssp_mat_csr &A)
     }
 }
 
+bool lssp_mat_bcsr_is_sorted(const lssp_mat_bcsr A)   // src/matrix-utils.cxx:217-247
+{
+    assert(A.num_rows > 0 && A.num_cols > 0 && A.blk_size > 0);
+    if (A.num_nnzs <= 0) return true;
+    for (int i = 0; i < A.num_rows; i++)
+        for (int k = A.Ap[i] + 1; k < A.Ap[i + 1]; k++)
+            if (A.Aj[k - 1] > A.Aj[k]) return false;
+    return true;
+}
+
+// ---- format converters and matrix utilities (reference src/matrix-utils.cxx:62-215, :281-380, :483-765): host-side
+//      data formats either side of the solve loop, written fresh with the reference's results ------------------------
+lssp_mat_coo lssp_mat_csr_to_coo(const lssp_mat_csr csr)   // :302-322
+{
+    lssp_mat_coo A;
+    lssp_mat_init(A);
+    A.num_rows = csr.num_rows;
+    A.num_cols = csr.num_cols;
+    A.num_nnzs = csr.num_nnzs;
+    if (csr.num_nnzs <= 0) return A;
+    A.Ai = lssp_malloc<int>(csr.num_nnzs);
+    A.Aj = lssp_copy_on<int>(csr.Aj, csr.num_nnzs);
+    A.Ax = lssp_copy_on<double>(csr.Ax, csr.num_nnzs);
+    for (int i = 0; i < csr.num_rows; i++)
+        for (int k = csr.Ap[i]; k < csr.Ap[i + 1]; k++) A.Ai[k] = i;
+    return A;
+}
+
+lssp_mat_csr lssp_mat_coo_to_csr(const lssp_mat_coo A)   // :324-380: entries of a row keep their COO order
+{
+    lssp_mat_csr csr;
+    lssp_mat_init(csr);
+    csr.num_rows = A.num_rows;
+    csr.num_cols = A.num_cols;
+    csr.num_nnzs = A.num_nnzs;
+    if (A.num_nnzs <= 0) return csr;
+    csr.Ap = lssp_malloc<int>(csr.num_rows + 1);
+    csr.Aj = lssp_malloc<int>(csr.num_nnzs);
+    csr.Ax = lssp_malloc<double>(csr.num_nnzs);
+    std::vector<int> pos(A.num_rows + 1, 0);
+    for (int k = 0; k < A.num_nnzs; k++) pos[A.Ai[k] + 1]++;
+    for (int i = 0; i < A.num_rows; i++) pos[i + 1] += pos[i];
+    memcpy(csr.Ap, pos.data(), sizeof(int) * (A.num_rows + 1));
+    for (int k = 0; k < A.num_nnzs; k++) {
+        const int at = pos[A.Ai[k]]++;
+        csr.Aj[at] = A.Aj[k];
+        csr.Ax[at] = A.Ax[k];
+    }
+    return csr;
+}
+
+// :62-162.  Blocks column-major; the block columns of a block row ascending; entries absent from A are stored as 0.
+lssp_mat_bcsr lssp_mat_csr_to_bcsr(const lssp_mat_csr A, int bs)
+{
+    assert(A.num_rows > 0 && A.num_rows == A.num_cols && A.num_nnzs > 0);
+    assert(bs > 0);
+    if (A.num_rows % bs != 0) lssp_error(1, "num_rows is not a multiple of block size: %d\n", bs);
+    lssp_mat_bcsr B;
+    lssp_mat_init(B);
+    const int nb = A.num_rows / bs, bs2 = bs * bs;
+    B.num_rows = B.num_cols = nb;
+    B.blk_size = bs;
+    B.Ap = lssp_malloc<int>(nb + 1);
+    std::vector<int> mark(nb, -1), cols, all;
+    B.Ap[0] = 0;
+    for (int i = 0; i < nb; i++) {
+        cols.clear();
+        for (int r = i * bs; r < (i + 1) * bs; r++)
+            for (int k = A.Ap[r]; k < A.Ap[r + 1]; k++) {
+                const int c = A.Aj[k] / bs;
+                if (mark[c] != i) { mark[c] = i; cols.push_back(c); }
+            }
+        std::sort(cols.begin(), cols.end());
+        all.insert(all.end(), cols.begin(), cols.end());
+        B.Ap[i + 1] = (int)all.size();
+    }
+    B.num_nnzs = B.Ap[nb];
+    B.Aj = lssp_copy_on<int>(all.data(), B.num_nnzs);
+    B.Ax = lssp_malloc<double>(B.num_nnzs * bs2);
+    for (long long k = 0; k < (long long)B.num_nnzs * bs2; k++) B.Ax[k] = 0.;
+    std::vector<int> where(nb, -1);
+    for (int i = 0; i < nb; i++) {
+        for (int k = B.Ap[i]; k < B.Ap[i + 1]; k++) where[B.Aj[k]] = k;
+        for (int r = i * bs; r < (i + 1) * bs; r++)
+            for (int k = A.Ap[r]; k < A.Ap[r + 1]; k++) {
+                const int c = A.Aj[k];
+                B.Ax[(size_t)where[c / bs] * bs2 + (size_t)(c % bs) * bs + (r % bs)] = A.Ax[k];
+            }
+    }
+    return B;
+}
+
+// :164-215.  Stored zeros of the blocks are dropped; rows sorted by column.
+lssp_mat_csr lssp_mat_bcsr_to_csr(const lssp_mat_bcsr A)
+{
+    const int bs = A.blk_size, bs2 = bs * bs, n = A.num_rows * bs;
+    lssp_mat_csr B;
+    lssp_mat_init(B);
+    B.num_rows = n;
+    B.num_cols = A.num_cols * bs;
+    std::vector<int> cnt(n + 1, 0);
+    for (int i = 0; i < A.num_rows; i++)
+        for (int k = A.Ap[i]; k < A.Ap[i + 1]; k++)
+            for (int q = 0; q < bs2; q++)
+                if (fabs(A.Ax[(size_t)k * bs2 + q]) > 0.) cnt[i * bs + q % bs + 1]++;
+    for (int r = 0; r < n; r++) cnt[r + 1] += cnt[r];
+    B.num_nnzs = cnt[n];
+    if (B.num_nnzs <= 0) return B;   // as lssp_mat_coo_to_csr on an empty matrix (:369)
+    B.Ap = lssp_copy_on<int>(cnt.data(), n + 1);
+    B.Aj = lssp_malloc<int>(B.num_nnzs);
+    B.Ax = lssp_malloc<double>(B.num_nnzs);
+    for (int i = 0; i < A.num_rows; i++)
+        for (int k = A.Ap[i]; k < A.Ap[i + 1]; k++)
+            for (int q = 0; q < bs2; q++) {
+                const double v = A.Ax[(size_t)k * bs2 + q];
+                if (fabs(v) > 0.) {
+                    const int at = cnt[i * bs + q % bs]++;
+                    B.Aj[at] = A.Aj[k] * bs + q / bs;
+                    B.Ax[at] = v;
+                }
+            }
+    lssp_mat_sort_column(B);
+    return B;
+}
+
+// :483-587: a row without a stored diagonal receives (i, tol), slid into sorted position.  (The reference returns the
+// result with the INPUT's num_nnzs, :485 -- its callers then under-allocate; here the count is the result's.)
+lssp_mat_csr lssp_mat_adjust_zero_diag(const lssp_mat_csr A, double tol)
+{
+    const int n = A.num_rows;
+    lssp_mat_csr M = A;
+    std::vector<char> has(n, 0);
+    int missing = 0;
+    for (int i = 0; i < n; i++) {
+        for (int k = A.Ap[i]; k < A.Ap[i + 1]; k++)
+            if (A.Aj[k] == i) has[i] = 1;
+        missing += !has[i];
+    }
+    M.num_nnzs = A.Ap[n] + missing;
+    M.Ap = lssp_malloc<int>(n + 1);
+    M.Aj = lssp_malloc<int>(M.num_nnzs);
+    M.Ax = lssp_malloc<double>(M.num_nnzs);
+    M.Ap[0] = 0;
+    for (int i = 0; i < n; i++) {
+        int o = M.Ap[i];
+        for (int k = A.Ap[i]; k < A.Ap[i + 1]; k++, o++) { M.Aj[o] = A.Aj[k]; M.Ax[o] = A.Ax[k]; }
+        if (!has[i]) {
+            M.Aj[o] = i;
+            M.Ax[o] = 1 * tol;
+            for (int q = o; q > M.Ap[i] && M.Aj[q - 1] > M.Aj[q]; q--) {
+                std::swap(M.Aj[q - 1], M.Aj[q]);
+                std::swap(M.Ax[q - 1], M.Ax[q]);
+            }
+            o++;
+        }
+        M.Ap[i + 1] = o;
+    }
+    return M;
+}
+
+// :589-698: entries outside the row's own diagonal block (blocks of blk_size rows, the last one shorter) are
+// discarded; a row left empty becomes the unit row.  This is the block-Jacobi restriction used when sharding.
+lssp_mat_csr lssp_mat_get_block_diag(const lssp_mat_csr A, int blk_size)
+{
+    assert(A.num_nnzs > 0 && A.num_rows > 0 && A.num_cols > 0 && A.num_rows == A.num_cols && blk_size > 0);
+    const int n = A.num_rows;
+    lssp_mat_csr M = A;
+    if (blk_size == n) {
+        M.Ap = lssp_copy_on<int>(A.Ap, n + 1);
+        M.Aj = lssp_copy_on<int>(A.Aj, A.num_nnzs);
+        M.Ax = lssp_copy_on<double>(A.Ax, A.num_nnzs);
+        return M;
+    }
+    M.Ap = lssp_malloc<int>(n + 1);
+    M.Ap[0] = 0;
+    for (int i = 0; i < n; i++) {
+        const int lo = (i / blk_size) * blk_size, hi = std::min(n, lo + blk_size);
+        int kept = 0;
+        for (int k = A.Ap[i]; k < A.Ap[i + 1]; k++) kept += (A.Aj[k] >= lo && A.Aj[k] < hi);
+        M.Ap[i + 1] = M.Ap[i] + (kept ? kept : 1);
+    }
+    M.num_nnzs = M.Ap[n];
+    M.Aj = lssp_malloc<int>(M.num_nnzs);
+    M.Ax = lssp_malloc<double>(M.num_nnzs);
+    for (int i = 0; i < n; i++) {
+        const int lo = (i / blk_size) * blk_size, hi = std::min(n, lo + blk_size);
+        int o = M.Ap[i];
+        for (int k = A.Ap[i]; k < A.Ap[i + 1]; k++)
+            if (A.Aj[k] >= lo && A.Aj[k] < hi) { M.Aj[o] = A.Aj[k]; M.Ax[o] = A.Ax[k]; o++; }
+        if (o == M.Ap[i]) { M.Aj[o] = i; M.Ax[o] = 1; }
+    }
+    return M;
+}
+
+lssp_mat_csr lssp_mat_transpose(const lssp_mat_csr A)   // :700-765: rows of the result ordered by source row
+{
+    assert(A.num_rows > 0 && A.num_cols > 0);
+    lssp_mat_csr T;
+    lssp_mat_init(T);
+    T.num_rows = A.num_cols;
+    T.num_cols = A.num_rows;
+    T.num_nnzs = A.num_nnzs;
+    if (A.num_nnzs <= 0) return T;
+    const int nnz = A.Ap[A.num_rows];
+    T.Ap = lssp_malloc<int>(T.num_rows + 1);
+    T.Aj = lssp_malloc<int>(A.num_nnzs);
+    T.Ax = lssp_malloc<double>(A.num_nnzs);
+    std::vector<int> pos(T.num_rows + 1, 0);
+    for (int k = 0; k < nnz; k++) pos[A.Aj[k] + 1]++;
+    for (int c = 0; c < T.num_rows; c++) pos[c + 1] += pos[c];
+    memcpy(T.Ap, pos.data(), sizeof(int) * (T.num_rows + 1));
+    for (int i = 0; i < A.num_rows; i++)
+        for (int k = A.Ap[i]; k < A.Ap[i + 1]; k++) {
+            const int at = pos[A.Aj[k]]++;
+            T.Aj[at] = i;
+            T.Ax[at] = A.Ax[k];
+        }
+    return T;
+}
+
 // ---- vector (reference src/vector.cxx) ------------------------------------------------------------
 lssp_vec lssp_vec_create(int n)
 {

@@ -72,6 +72,19 @@ def test_facade_symbols_are_link_compatible_with_the_reference():
     assert not (hot - ours), sorted(hot - ours)
 
 
+def test_matrix_utilities_give_the_reference_results_through_the_same_binary_interface(tmp_path):
+    """tests/cxx/mat_utils_abi_check.cpp: ONE caller binary fetches the ten lssp_mat_* utilities by their mangled names
+    from the compiled reference and from liblssp.so and compares the results bit for bit (CSR <-> COO <-> BCSR,
+    sortedness, column sort, diagonal repair, block-Jacobi restriction, transpose)."""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref not built")
+    exe = str(tmp_path / "mat_abi")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cxx", "mat_utils_abi_check.cpp"), "-ldl"],
+                   check=True)
+    out = subprocess.run([exe, REF, LIB], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "0 mismatches" in out.stdout, out.stdout + out.stderr
+
+
 def test_block_ilu_symbols_are_link_compatible_with_a_blas_build_of_the_reference():
     """LSSP_PC_BILUK exists in the reference only `#if USE_BLAS && USE_LAPACK` (include/pc-biluk.h:10-19): compare with
     the oracle build that has them on (oracle/_ref/liblssp_refb.so)."""
