@@ -145,6 +145,21 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
     // skewed 3-D boxes: u spans (1 + s1 + t1) nx, so boxes longer in u and flatter in w shorten the chain of boxes;
     // measured for ILUK(1) at 256^3 (profiles/r01_skew_tiles.log): 12x8x5 3.88 ms, 8x8x8 4.12, 16x8x4 4.14, 8x4x8 4.46
     if (!shape_given && g[2] > 1 && (sk[0] || sk[1] || sk[2])) { t[0] = 12; t[1] = 8; t[2] = 5; }
+    if (sk[0] || sk[1] || sk[2]) {
+        // rows wider than the unrolled in-box code paths (ELL width <= 6: ILU(1) of 5-/7-point stencils) have only been
+        // verified on the host walk so far, not on a GPU: they keep the slice schedule unless LSSPG_TRI_SKEW=2 asks
+        const char *e = getenv("LSSPG_TRI_SKEW");
+        if (!(e && atoi(e) >= 2)) {
+            const int np = host_threads();
+            std::vector<int> widest(np, 0);
+            parallel_ranges(n, [&](long long r0, long long r1, int p) {
+                int w = 0;
+                for (int i = (int)r0; i < (int)r1; i++) w = std::max(w, Tp[i + 1] - Tp[i] - 1);
+                widest[p] = w;
+            }, np);
+            if (*std::max_element(widest.begin(), widest.end()) > 6) return 2;
+        }
+    }
     const long long ext[3] = {(long long)g[0] + (long long)sk[0] * (g[1] - 1) + (long long)sk[2] * (g[2] - 1),
                               (long long)g[1] + (long long)sk[1] * (g[2] - 1), g[2]};
     const long long ntl[3] = {(ext[0] + t[0] - 1) / t[0], (ext[1] + t[1] - 1) / t[1], (ext[2] + t[2] - 1) / t[2]};
