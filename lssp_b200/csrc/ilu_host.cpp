@@ -966,59 +966,96 @@ struct BFactors {
 int factor_biluk(const Csr &A, int bs, int level, BFactors &F)
 {
     const int n = A.n, nb = n / bs, bs2 = bs * bs;
-    // CSR -> BCSR (src/matrix-utils.cxx:62-162): block columns of a block row ascending, blocks column-major
+    // CSR -> BCSR (src/matrix-utils.cxx:62-162): block columns of a block row ascending, blocks column-major.
+    // Block rows are independent: counted, scanned and filled by the host threads.
     Csr B;   // block graph; x unused
     B.n = nb;
-    B.p.assign((size_t)nb + 1, 0);
-    {
-        std::vector<int> mark(nb, -1), cols;
+    B.p.resize((size_t)nb + 1);
+    auto block_cols = [&](int i, std::vector<int> &cols) {
+        cols.clear();
+        for (int r = i * bs; r < (i + 1) * bs; r++)
+            for (int k = A.p[r]; k < A.p[r + 1]; k++) cols.push_back(A.j[k] / bs);
+        std::sort(cols.begin(), cols.end());
+        cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+    };
+    const int np = lsspg::host_threads();
+    std::vector<char> nodiag(np, 0);
+    parallel_ranges(nb, [&](long long b0, long long b1, int piece) {
+        std::vector<int> cols;
+        for (int i = (int)b0; i < (int)b1; i++) {
+            block_cols(i, cols);
+            B.p[i] = (int)cols.size();
+            if (!std::binary_search(cols.begin(), cols.end(), i)) nodiag[piece] = 1;
+        }
+    }, np, 1);
+    if (std::find(nodiag.begin(), nodiag.end(), (char)1) != nodiag.end()) {
         for (int i = 0; i < nb; i++) {
-            cols.clear();
-            for (int r = i * bs; r < (i + 1) * bs; r++)
-                for (int k = A.p[r]; k < A.p[r + 1]; k++) {
-                    const int c = A.j[k] / bs;
-                    if (mark[c] != i) { mark[c] = i; cols.push_back(c); }
-                }
-            std::sort(cols.begin(), cols.end());
-            B.j.insert(B.j.end(), cols.begin(), cols.end());
-            B.p[i + 1] = (int)B.j.size();
+            std::vector<int> cols;
+            block_cols(i, cols);
+            if (!std::binary_search(cols.begin(), cols.end(), i)) {
+                lsspg::set_error("biluk: block row %d has no diagonal block", i);
+                return 1;
+            }
         }
     }
-    for (int i = 0; i < nb; i++)
-        if (!std::binary_search(B.j.begin() + B.p[i], B.j.begin() + B.p[i + 1], i)) {
-            lsspg::set_error("biluk: block row %d has no diagonal block", i);
-            return 1;
+    const long long nblk = parallel_exclusive_scan(B.p.data(), nb);
+    B.p[nb] = (int)nblk;
+    B.j.resize((size_t)nblk);
+    parallel_ranges(nb, [&](long long b0, long long b1, int) {
+        std::vector<int> cols;
+        for (int i = (int)b0; i < (int)b1; i++) {
+            block_cols(i, cols);
+            std::copy(cols.begin(), cols.end(), B.j.begin() + B.p[i]);
         }
+    }, 0, 1024);
     // symbolic phase on the block graph (src/pc-biluk.cxx:316-375): level 0 keeps the pattern
     Csr T;
     if (level > 0) {
-        B.x.assign(B.j.size(), 0.0);
+        B.x.resize(B.j.size());
         T = iluk_pattern(B, level);
     }
     else {
         T.n = nb;
-        T.p = B.p;
-        T.j = B.j;
+        T.p.swap(B.p);
+        T.j.swap(B.j);
     }
     const int *Tp = T.p.data(), *Tj = T.j.data();
     DVec X((size_t)Tp[nb] * bs2);
-    std::fill(X.begin(), X.end(), 0.0);
-    {
-        std::vector<int> where(nb, -1);
-        for (int i = 0; i < nb; i++) {
-            for (int k = Tp[i]; k < Tp[i + 1]; k++) where[Tj[k]] = k;
+    parallel_ranges(nb, [&](long long b0, long long b1, int) {
+        for (int i = (int)b0; i < (int)b1; i++) {
+            std::fill(X.begin() + (size_t)Tp[i] * bs2, X.begin() + (size_t)Tp[i + 1] * bs2, 0.0);
             for (int r = i * bs; r < (i + 1) * bs; r++)
                 for (int k = A.p[r]; k < A.p[r + 1]; k++) {
                     const int c = A.j[k];
-                    X[(size_t)where[c / bs] * bs2 + (size_t)(c % bs) * bs + (r % bs)] = A.x[k];
+                    const int at = (int)(std::lower_bound(Tj + Tp[i], Tj + Tp[i + 1], c / bs) - Tj);
+                    X[(size_t)at * bs2 + (size_t)(c % bs) * bs + (r % bs)] = A.x[k];
                 }
         }
-    }
-    // numeric phase (src/pc-biluk.cxx:198-277): block IKJ; inv[i] = inverse of the pivot block
+    }, 0, 1024);
+    // numeric phase (src/pc-biluk.cxx:198-277): block IKJ; inv[i] = inverse of the pivot block.  Block row i needs the
+    // finished block rows of its lower block columns: rows grouped by the level of that dependency graph, the rows of a
+    // level run by the host threads (as ilu0_levels); every block operation is the serial loop's.
     DVec inv((size_t)nb * bs2);
-    std::vector<double> blk(bs2), work(10 * (size_t)bs);
-    std::vector<int> ipiv(bs);
+    IVec lev((size_t)nb), order((size_t)nb);
+    std::vector<int> start(1, 0);
     for (int i = 0; i < nb; i++) {
+        int l = 0;
+        for (int k = Tp[i]; k < Tp[i + 1] && Tj[k] < i; k++) l = std::max(l, lev[Tj[k]] + 1);
+        lev[i] = l;
+        if ((int)start.size() < l + 2) start.resize(l + 2, 0);
+        start[l + 1]++;
+    }
+    const int nlev = (int)start.size() - 1;
+    for (int l = 0; l < nlev; l++) start[l + 1] += start[l];
+    {
+        std::vector<int> pos(start.begin(), start.end() - 1);
+        for (int i = 0; i < nb; i++) order[pos[lev[i]]++] = i;
+    }
+    std::atomic<int> singular(0);
+    lsspg::LevelTeam::run(nlev, start.data(), order.data(), [&](int i) {
+        thread_local std::vector<double> blk, work;
+        thread_local std::vector<int> ipiv;
+        blk.resize(bs2); work.resize(10 * (size_t)bs); ipiv.resize(bs);
         const int e = Tp[i + 1];
         int k = Tp[i];
         for (; k < e && Tj[k] < i; k++) {
@@ -1035,62 +1072,73 @@ int factor_biluk(const Csr &A, int bs, int level, BFactors &F)
             }
         }
         std::copy(&X[(size_t)k * bs2], &X[(size_t)k * bs2] + bs2, &inv[(size_t)i * bs2]);   // k: the diagonal block
-        if (block_inverse(&inv[(size_t)i * bs2], bs, work.data(), ipiv.data())) {
-            lsspg::set_error("lssp: bilu(0) singular diagonal submatrix.");   // src/pc-biluk.cxx:262
-            return 1;
-        }
+        if (block_inverse(&inv[(size_t)i * bs2], bs, work.data(), ipiv.data())) singular.store(1);
+    });
+    if (singular.load()) {
+        lsspg::set_error("lssp: bilu(0) singular diagonal submatrix.");   // src/pc-biluk.cxx:262
+        return 1;
     }
-    // L, U, D as CSR (src/pc-biluk.cxx:105-196, :279-314): rows end up sorted by column
+    // L, U, D as CSR (src/pc-biluk.cxx:105-196, :279-314): rows end up sorted by column; block rows written by the threads
     F.n = n;
     Csr &L = F.L, &U = F.U, &D = F.D;
     L.n = U.n = D.n = n;
-    L.p.assign((size_t)n + 1, 0);
-    U.p.assign((size_t)n + 1, 0);
-    D.p.assign((size_t)n + 1, 0);
-    for (int i = 0; i < nb; i++) {
-        int nl = 0, nu = 0;
-        for (int k = Tp[i]; k < Tp[i + 1]; k++) {
-            nl += (Tj[k] < i);
-            nu += (Tj[k] > i);
+    L.p.resize((size_t)n + 1);
+    U.p.resize((size_t)n + 1);
+    D.p.resize((size_t)n + 1);
+    parallel_ranges(nb, [&](long long b0, long long b1, int) {
+        for (int i = (int)b0; i < (int)b1; i++) {
+            int nl = 0, nu = 0;
+            for (int k = Tp[i]; k < Tp[i + 1]; k++) {
+                nl += (Tj[k] < i);
+                nu += (Tj[k] > i);
+            }
+            for (int a = 0; a < bs; a++) {
+                L.p[i * bs + a] = nl * bs + 1;
+                U.p[i * bs + a] = nu * bs + 1;
+                D.p[i * bs + a] = bs;
+            }
         }
-        for (int a = 0; a < bs; a++) {
-            const int r = i * bs + a;
-            L.p[r + 1] = L.p[r] + nl * bs + 1;
-            U.p[r + 1] = U.p[r] + nu * bs + 1;
-            D.p[r + 1] = D.p[r] + bs;
-        }
+    }, 0, 1024);
+    const long long tl = parallel_exclusive_scan(L.p.data(), n), tu = parallel_exclusive_scan(U.p.data(), n),
+                    td = parallel_exclusive_scan(D.p.data(), n);
+    if (tl > 0x7fffffffll || tu > 0x7fffffffll) {
+        lsspg::set_error("biluk: factors exceed int32 indexing");
+        return 1;
     }
-    L.j.resize((size_t)L.p[n]); L.x.resize((size_t)L.p[n]);
-    U.j.resize((size_t)U.p[n]); U.x.resize((size_t)U.p[n]);
-    D.j.resize((size_t)D.p[n]); D.x.resize((size_t)D.p[n]);
-    std::vector<double> cache(bs2, 0.0);
-    for (int i = 0; i < nb; i++) {
+    L.p[n] = (int)tl; U.p[n] = (int)tu; D.p[n] = (int)td;
+    L.j.resize((size_t)tl); L.x.resize((size_t)tl);
+    U.j.resize((size_t)tu); U.x.resize((size_t)tu);
+    D.j.resize((size_t)td); D.x.resize((size_t)td);
+    parallel_ranges(nb, [&](long long b0, long long b1, int) {
+        std::vector<double> cache(bs2, 0.0);
         std::vector<int> ol(bs), ou(bs);
-        for (int a = 0; a < bs; a++) {
-            const int r = i * bs + a;
-            ol[a] = L.p[r];
-            ou[a] = U.p[r];
-            U.j[ou[a]] = r; U.x[ou[a]] = 1.; ou[a]++;
-            for (int b = 0; b < bs; b++) {
-                D.j[D.p[r] + b] = i * bs + b;
-                D.x[D.p[r] + b] = inv[(size_t)i * bs2 + (size_t)b * bs + a];
+        for (int i = (int)b0; i < (int)b1; i++) {
+            for (int a = 0; a < bs; a++) {
+                const int r = i * bs + a;
+                ol[a] = L.p[r];
+                ou[a] = U.p[r];
+                U.j[ou[a]] = r; U.x[ou[a]] = 1.; ou[a]++;
+                for (int b = 0; b < bs; b++) {
+                    D.j[D.p[r] + b] = i * bs + b;
+                    D.x[D.p[r] + b] = inv[(size_t)i * bs2 + (size_t)b * bs + a];
+                }
             }
+            for (int k = Tp[i]; k < Tp[i + 1]; k++) {
+                const int c = Tj[k];
+                const double *d = &X[(size_t)k * bs2];
+                if (c < i) {
+                    for (int a = 0; a < bs; a++)
+                        for (int b = 0; b < bs; b++) { L.j[ol[a]] = c * bs + b; L.x[ol[a]] = d[b * bs + a]; ol[a]++; }
+                }
+                else if (c > i) {
+                    block_gemm(&inv[(size_t)i * bs2], d, 1., cache.data(), 0., bs);
+                    for (int a = 0; a < bs; a++)
+                        for (int b = 0; b < bs; b++) { U.j[ou[a]] = c * bs + b; U.x[ou[a]] = cache[b * bs + a]; ou[a]++; }
+                }
+            }
+            for (int a = 0; a < bs; a++) { L.j[ol[a]] = i * bs + a; L.x[ol[a]] = 1.; }
         }
-        for (int k = Tp[i]; k < Tp[i + 1]; k++) {
-            const int c = Tj[k];
-            const double *d = &X[(size_t)k * bs2];
-            if (c < i) {
-                for (int a = 0; a < bs; a++)
-                    for (int b = 0; b < bs; b++) { L.j[ol[a]] = c * bs + b; L.x[ol[a]] = d[b * bs + a]; ol[a]++; }
-            }
-            else if (c > i) {
-                block_gemm(&inv[(size_t)i * bs2], d, 1., cache.data(), 0., bs);
-                for (int a = 0; a < bs; a++)
-                    for (int b = 0; b < bs; b++) { U.j[ou[a]] = c * bs + b; U.x[ou[a]] = cache[b * bs + a]; ou[a]++; }
-            }
-        }
-        for (int a = 0; a < bs; a++) { L.j[ol[a]] = i * bs + a; L.x[ol[a]] = 1.; }
-    }
+    }, 0, 1024);
     return 0;
 }
 
@@ -1204,9 +1252,12 @@ int lsspg_bilu_factor(int n, const int *hAp, const int *hAj, const double *hAx, 
     }
     Csr A;
     A.n = n;
-    A.p.assign(hAp, hAp + n + 1);
-    A.j.assign(hAj, hAj + hAp[n]);
-    A.x.assign(hAx, hAx + hAp[n]);
+    A.p.resize((size_t)n + 1);
+    A.j.resize((size_t)hAp[n]);
+    A.x.resize((size_t)hAp[n]);
+    parallel_copy(A.p.data(), hAp, sizeof(int) * ((size_t)n + 1));
+    parallel_copy(A.j.data(), hAj, sizeof(int) * (size_t)hAp[n]);
+    parallel_copy(A.x.data(), hAx, sizeof(double) * (size_t)hAp[n]);
     sort_rows(A);   // src/lssp.cxx:173
     if (level < 0) level = 0;
     lsspg_bfactors *F = new lsspg_bfactors();
@@ -1234,9 +1285,9 @@ int lsspg_bfactors_get(const lsspg_bfactors *F, int *Lp, int *Lj, double *Lx, in
     int *P[3] = {Lp, Dp, Up}, *J[3] = {Lj, Dj, Uj};
     double *X[3] = {Lx, Dx, Ux};
     for (int q = 0; q < 3; q++) {
-        memcpy(P[q], M[q]->p.data(), sizeof(int) * M[q]->p.size());
-        memcpy(J[q], M[q]->j.data(), sizeof(int) * M[q]->j.size());
-        memcpy(X[q], M[q]->x.data(), sizeof(double) * M[q]->x.size());
+        parallel_copy(P[q], M[q]->p.data(), sizeof(int) * M[q]->p.size());
+        parallel_copy(J[q], M[q]->j.data(), sizeof(int) * M[q]->j.size());
+        parallel_copy(X[q], M[q]->x.data(), sizeof(double) * M[q]->x.size());
     }
     return 0;
 }

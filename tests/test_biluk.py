@@ -53,6 +53,11 @@ def test_block_factors_equal_the_compiled_reference(refb):
                 continue
             for level in (0, 1, 3):
                 assert same(api.bilu_factor(A, n // bs, level), refb.bilu(A, n // bs, level)), (n, bs, level)
+    # sizes at which the level-scheduled numeric phase and the threaded assembly really use several threads
+    A = g.cd3d(48)
+    n = len(A[0]) - 1
+    for bs, level in ((2, 1), (1, 2), (3, 0)):
+        assert same(api.bilu_factor(A, n // bs, level), refb.bilu(A, n // bs, level)), (n, bs, level)
     # unsorted rows are sorted first (src/lssp.cxx:173)
     Ap, Aj, Ax = g.cd3d(8)
     Aj, Ax = Aj.copy(), Ax.copy()
