@@ -382,7 +382,7 @@ int spgemm(int nrows, int ncolsB, const std::vector<int> &Ap, const std::vector<
         for (auto &q : th) q.join();
     }
     clock_gettime(CLOCK_MONOTONIC, &ts1);
-    if (getenv("LSSPG_SETUP_PROF")) fprintf(stderr, "[spgemm] rows %d threads part %.3f s\n", nrows, (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec));
+    if (getenv("LSSPG_SETUP_PROF") && atoi(getenv("LSSPG_SETUP_PROF")) != 0) fprintf(stderr, "[spgemm] rows %d threads part %.3f s\n", nrows, (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec));
     size_t total = 0;
     for (const Piece &P : pieces) total += P.j.size();
     AMG_CHECK(total < (size_t)0x7fffffff, "amg: coarse operator exceeds int32 indexing");

@@ -317,7 +317,8 @@ Csr iluk_pattern(const Csr &A, int level)
     PROF_T0;
     std::vector<const int *> rec((size_t)n);
     IVec len((size_t)n + 1), nup((size_t)n);
-    const int nt = lsspg::host_threads();
+    // every pipeline thread owns a column map of n ints: at most ~4 GB of them
+    const int nt = (int)std::max<long long>(1, std::min<long long>(lsspg::host_threads(), (1ll << 30) / std::max(n, 1)));
     lsspg::RowPipeline pipe(n, pipeline_chunk(A));
     struct Scratch {
         std::vector<int> where, lc, ll, uc, ul, cols;
@@ -708,7 +709,8 @@ void ilut_block(const Csr &B, int r0, int r1, double tau, int p, Csr &L, Csr &U)
 Factors factor_ilut_rows(const Csr &B, double tau, int p, int bs)
 {
     const int n = B.n;
-    const int nt = lsspg::host_threads();
+    // every pipeline thread owns a column map of n ints: at most ~4 GB of them
+    const int nt = (int)std::max<long long>(1, std::min<long long>(lsspg::host_threads(), (1ll << 30) / std::max(n, 1)));
     std::vector<const int *> rcol((size_t)n);
     std::vector<const double *> rval((size_t)n);
     IVec rlen((size_t)n);
