@@ -473,7 +473,12 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
     // rows in visiting order of their block (ranks are distinct inside a block)
     std::vector<int> by_rank(n);
     for (int i = 0; i < n; i++) by_rank[i] = i;
-    if (rank) std::sort(by_rank.begin(), by_rank.end(), [&](int a, int b) { return rank[a] < rank[b] || (rank[a] == rank[b] && a < b); });
+    if (rank) {
+        bool ascending = true;   // visiting by index (cf_order 0 / 1): already in order
+        for (int i = 1; i < n && ascending; i++) ascending = rank[i - 1] <= rank[i];
+        if (!ascending)
+            std::sort(by_rank.begin(), by_rank.end(), [&](int a, int b) { return rank[a] < rank[b] || (rank[a] == rank[b] && a < b); });
+    }
     std::vector<int> lev(n, 0);
     int nlev[2] = {0, 0};   // [0] F block, [1] C block
     for (int t = 0; t < n; t++) {
@@ -522,22 +527,30 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
         G.padded_nnz = G.offdiag_nnz;
         G.col.resize((size_t)G.offdiag_nnz);
         G.val.resize((size_t)G.offdiag_nnz);
-        int k = 0;
-        for (int p = 0; p < n; p++) {
-            const int i = order[p];
-            G.slice_ptr[p] = k;
-            for (int q = Ap[i]; q < Ap[i + 1]; q++) {
-                const int c = Aj[q];
-                if (c == i) {
-                    G.diag[p] = Ax[q];
-                    continue;
-                }
-                G.col[k] = encode(i, c);
-                G.val[k] = Ax[q];
-                k++;
+        {
+            int k = 0;
+            for (int p = 0; p < n; p++) {
+                G.slice_ptr[p] = k;
+                k += Ap[order[p] + 1] - Ap[order[p]] - 1;
             }
+            G.slice_ptr[n] = k;
         }
-        G.slice_ptr[n] = k;
+        lsspg::parallel_ranges(n, [&](long long p0, long long p1, int) {
+            for (int p = (int)p0; p < (int)p1; p++) {
+                const int i = order[p];
+                int k = G.slice_ptr[p];
+                for (int q = Ap[i]; q < Ap[i + 1]; q++) {
+                    const int c = Aj[q];
+                    if (c == i) {
+                        G.diag[p] = Ax[q];
+                        continue;
+                    }
+                    G.col[k] = encode(i, c);
+                    G.val[k] = Ax[q];
+                    k++;
+                }
+            }
+        });
         return 0;
     }
     long long nslices = 0, cslices = 0;
@@ -573,10 +586,12 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
     }
     G.slice_ptr[nslices] = (int)wsum;
     G.padded_nnz = wsum * 32;
-    G.col.assign((size_t)G.padded_nnz, -1);
-    G.val.assign((size_t)G.padded_nnz, 0.0);
-    for (long long sl = 0; sl < nslices; sl++) {
-        const long long base = (long long)G.slice_ptr[sl] * 32;
+    G.col.resize((size_t)G.padded_nnz);
+    G.val.resize((size_t)G.padded_nnz);
+    lsspg::parallel_ranges(nslices, [&](long long sl0, long long sl1, int) {
+    for (long long sl = sl0; sl < sl1; sl++) {
+        const long long base = (long long)G.slice_ptr[sl] * 32, wid = G.slice_ptr[sl + 1] - G.slice_ptr[sl];
+        for (long long e = base; e < base + wid * 32; e++) { G.col[e] = -1; G.val[e] = 0.0; }
         for (int q = 0; q < 32; q++) {
             const int i = G.perm[sl * 32 + q];
             if (i < 0) continue;
@@ -593,6 +608,7 @@ int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const i
             }
         }
     }
+    }, 0, 256);
     return 0;
 }
 

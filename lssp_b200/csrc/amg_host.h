@@ -1,6 +1,7 @@
 // amg_host.h -- host image of the SX-AMG-style hierarchy and of the Gauss-Seidel smoother layout.
 #pragma once
 #include <vector>
+#include "host_par.h"
 #include "../../include/lsspg.h"
 
 namespace lsspg {
@@ -35,8 +36,8 @@ struct GsHost {
     std::vector<double> diag;     // [num_slices*32]
     std::vector<int> slice_ptr;   // [num_slices+1]
     std::vector<int> level_ptr;   // mode 0: first slice of every dependency level, C levels then F levels (+ end)
-    std::vector<int> col;
-    std::vector<double> val;
+    lsspg::IVec col;     // filled by the host threads (host_par.h)
+    lsspg::DVec val;
 };
 
 // cf == NULL: every row in the C block (natural-order sweep)

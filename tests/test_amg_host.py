@@ -236,3 +236,18 @@ def test_setup_and_restated_cycle_match_the_committed_fixtures(hier, port, amg_g
         mz = port.amg(H.levels, coarse_inv=H.coarse_inv, cf_order=order, zero_guess=1)
         r = port.solve("cg", matrix(name), np.ones(n), amg=mz, maxit=100)
         assert r["nits"] == e["pcg_zero_guess_nits"] and r["residual"] == e["pcg_zero_guess_residual"]
+
+
+@pytest.mark.parametrize("cf_order", [1, 2])
+def test_smoother_layout_built_by_several_threads_walks_like_the_serial_sweep(port, cf_order):
+    """64 000 rows: the slices of the fine levels are filled by several host threads (amg_host.cpp, gs_build_host);
+    walking the image must still give the serial in-place sweep bit for bit, in all three layouts."""
+    from lssp_b200 import generators as g
+    H = api.AmgHierarchy(g.lap3d(40), cf_order=cf_order)
+    for l in (0, 1):
+        L = H.levels[l]
+        b, x0 = tvec(L["n"], l), tvec(L["n"], l + 5)
+        for post in (0, 1):
+            xo = port.gs_sweep(L["A"], L["cf"], post, b, x0, rank=L["rank"])
+            for mode in (0, 1, 2):
+                assert np.array_equal(H.walk_gs_host(l, post, b, x0, mode=mode)[0], xo)
