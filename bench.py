@@ -383,7 +383,7 @@ def main():
                              % (dA.spmv_bytes / 1e9)},
             "ms_per_iteration": ms_per_it, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
             "roofline": roof, "roofline_spmv": roof_spmv,
-            "setup_s": {"generate": t_gen, "pc_host_setup_and_upload": t_pc}}
+            "setup_s": {"generate": t_gen, "pc_host_setup_and_upload": t_pc, "host_threads": int(L.lsspg_host_threads())}}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, A, solver, pckind, pc)
     print(json.dumps(line))

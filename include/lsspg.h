@@ -185,6 +185,10 @@ int lsspg_bfactors_get(const lsspg_bfactors *F, int *Lp, int *Lj, double *Lx, in
                        double *Dx, int *Up, int *Uj, double *Ux);
 int lsspg_bfactors_destroy(lsspg_bfactors *F);
 
+/* Number of host threads the set-up code (factorisations, schedules, packing) runs on: LSSPG_HOST_THREADS, default
+ * the cores of the process' affinity mask divided by LOCAL_WORLD_SIZE, at most 32.  Results do not depend on it. */
+int lsspg_host_threads(void);
+
 /* ---- preconditioner application (replaces LSSP_PC.solve,
  *      include/type-defs.h:104,144) ------------------------------------------ */
 #define LSSPG_PC_NON   0   /* x = rhs                          src/pc.cxx:67-70            */

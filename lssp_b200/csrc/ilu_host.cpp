@@ -1300,4 +1300,7 @@ int lsspg_bfactors_destroy(lsspg_bfactors *F)
     return 0;
 }
 
+// host threads the set-up uses (LSSPG_HOST_THREADS; default: the cores of the affinity mask / LOCAL_WORLD_SIZE, <= 32)
+int lsspg_host_threads(void) { return lsspg::host_threads(); }
+
 }  // extern "C"
