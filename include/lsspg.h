@@ -147,6 +147,11 @@ int lsspg_debug_tri_walk_tiled_host(int which, int n, const int *hTp, const int 
 int lsspg_debug_tri_pack_host(int which, int n, const int *hTp, const int *hTj, const double *hTx,
                               int *kind, unsigned long long *fingerprint, long long *bytes,
                               double *seconds);
+/* CPU emulation of the ELL box kernels from the PACKED blobs (the bytes the device reads), boxes advancing one
+ * chunk per round: x must equal the serial sweep; info[4] = rounds (longest chain of hand-offs), chunks per box,
+ * boxes, levels of the box graph.  Test-suite only (also verifies the experimental LSSPG_TRI_CHUNKS schedule). */
+int lsspg_debug_tri_walk_packed_host(int which, int n, const int *hTp, const int *hTj, const double *hTx,
+                                     double *hx, const double *hrhs, int *applicable, int *info);
 /* schedule of a device-resident factor: tiled != 0 when the box schedule is in use */
 int lsspg_tri_schedule(const lsspg_tri *T, int *tiled, int *num_tiles, int *num_tile_levels,
                        int *max_tile_rows);

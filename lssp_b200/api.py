@@ -272,6 +272,19 @@ def tri_pack_host(which, T):
     return dict(kind=kind.value, fingerprint=fp.value, bytes=nb.value, schedule_s=sec[0], pack_s=sec[1])
 
 
+def tri_walk_packed_host(which, T, rhs):
+    """Emulation of the ELL box kernels from the packed blobs (tests only).  Returns (x, dict(rounds, chunks, boxes,
+    box_levels)) or (None, None) when the factor has no such schedule."""
+    Tp, Tj, Tx = _i32(T[0]), _i32(T[1]), _f64(T[2])
+    n = len(Tp) - 1
+    x = np.zeros(n)
+    ok, info = C.c_int(), (C.c_int * 4)()
+    check(lib().lsspg_debug_tri_walk_packed_host(which, n, _p(Tp), _p(Tj), _p(Tx), _p(x), _p(_f64(rhs)), C.byref(ok), info))
+    if not ok.value:
+        return None, None
+    return x, dict(zip(("rounds", "chunks", "boxes", "box_levels"), list(info)))
+
+
 class Tri:
     """Device-resident triangular factor in level order (lsspg_tri)."""
 

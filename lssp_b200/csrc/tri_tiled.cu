@@ -888,6 +888,134 @@ __global__ void __launch_bounds__(32, 8) tri_box_ell_kernel(const TiledArgs a)  
     }
 }
 
+// EXPERIMENT (opt-in, LSSPG_TRI_CHUNKS=2..8; never the default; not yet run on a GPU -- see ROADMAP.md).  The same box
+// blobs with a chunk table in place of the predecessor list: the in-box levels are cut into C chunks; before chunk c the
+// warp gates on (and fetches) only the operands of other boxes that the rows of chunk c read, and after chunk c it
+// publishes the rows of chunk c.  A downstream box then starts after ~1/C of its predecessor instead of all of it:
+// the chain of boxes costs (t + 3t/C) in-box levels per box instead of 3t (model in ROADMAP.md).
+//   pred section: [C][cl: C+1 level boundaries][xp: C+1 operand boundaries][gp: C+1 gate boundaries][gate rows]
+__global__ void __launch_bounds__(32, 8) tri_box_chunk_kernel(const TiledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (a.stop && *a.stop) return;
+    const int lane = threadIdx.x;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
+    unsigned char *sblob = smem + 16;
+    double *sx = reinterpret_cast<double *>(sblob + a.blob_cap);
+    const unsigned int bar_s = smem_u32(bar), blob_s = smem_u32(sblob);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned int phase = 0;
+    const unsigned int total = (unsigned int)a.num_tiles + gridDim.x;
+    for (;;) {
+        unsigned int tk = 0;
+        if (lane == 0) tk = atomicInc(a.counter, total - 1);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= (unsigned int)a.num_tiles) break;
+        const BoxDesc d = a.desc[tk];   // d.nent: ELL width; d.npred: ints in the chunk table
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"((unsigned int)d.bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(blob_s), "l"(a.blob + d.off), "r"((unsigned int)d.bytes), "r"(bar_s) : "memory");
+        }
+        {
+            unsigned int ok = 0;
+            while (!ok) {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(bar_s), "r"(phase) : "memory");
+            }
+            phase ^= 1;
+        }
+        const int nrows = d.nrows, w = d.nent;
+        const EllLayout lay = ell_layout(nrows, w, d.nlev, d.next, d.npred);
+        const int *slev = reinterpret_cast<const int *>(sblob + lay.lev);
+        const int *sperm = reinterpret_cast<const int *>(sblob + lay.perm);
+        const int *sext = reinterpret_cast<const int *>(sblob + lay.ext);
+        const int *stab = reinterpret_cast<const int *>(sblob + lay.pred);
+        const double *sdiag = reinterpret_cast<const double *>(sblob + lay.diag);
+        const int *ecol = reinterpret_cast<const int *>(sblob + lay.ecol);
+        const double *eval = reinterpret_cast<const double *>(sblob + lay.eval);
+        const int C = stab[0];
+        const int *cl = stab + 1, *xp = cl + (C + 1), *gp = xp + (C + 1), *gates = gp + (C + 1);
+        for (int s0 = 0; s0 < nrows; s0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * 32 + lane;
+                v[u] = (s < nrows) ? __ldg(a.rhs + sperm[s]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * 32 + lane;
+                if (s < nrows) sx[s] = v[u];
+            }
+        }
+        if (lane == 0) sx[nrows + d.next] = 0.0;
+        for (int c = 0; c < C; c++) {
+            // gate: one lane per (predecessor box, chunk) polls the operand of it that is stored last
+            for (int q = gp[c] + lane; q < gp[c + 1]; q += 32) {
+                const double *f = a.x + gates[q];
+                int spins = 0;
+                while ((unsigned long long)__double_as_longlong(ldx_relaxed(f)) == kSentinelBitsT) {
+                    if (++spins > 16) __nanosleep(40);
+                    if (spins > (1 << 21)) { *a.err = 1; break; }
+                }
+            }
+            __syncwarp();
+            for (int q0 = xp[c]; q0 < xp[c + 1]; q0 += 256) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int q = q0 + u * 32 + lane;
+                    v[u] = (q < xp[c + 1]) ? ldx_relaxed(a.x + sext[q]) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int q = q0 + u * 32 + lane;
+                    if (q < xp[c + 1]) {
+                        int spins = 0;
+                        while ((unsigned long long)__double_as_longlong(v[u]) == kSentinelBitsT) {
+                            v[u] = ldx_relaxed(a.x + sext[q]);
+                            if (++spins > (1 << 21)) { *a.err = 1; break; }
+                        }
+                        sx[nrows + q] = v[u];
+                    }
+                }
+            }
+            __syncwarp();
+            const int *clev = slev + cl[c];
+            const int cn = cl[c + 1] - cl[c];
+            switch (w) {
+                case 1: box_levels<1, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+                case 2: box_levels<2, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+                case 3: box_levels<3, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+                case 4: box_levels<4, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+                case 5: box_levels<5, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+                case 6: box_levels<6, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
+                default:
+                    for (int L = 0; L < cn; L++) {
+                        const int sa = clev[L], sb = clev[L + 1];
+                        for (int slot = sa + lane; slot < sb; slot += 32) {
+                            double r = sx[slot];
+                            for (int k = 0; k < w; k++) r = r - eval[k * nrows + slot] * sx[ecol[k * nrows + slot]];
+                            const double dg = sdiag[slot];
+                            if (dg != 1.0) r = r / dg;
+                            sx[slot] = r;
+                        }
+                        __syncwarp();
+                    }
+            }
+            // publish the rows of this chunk (the values are their own ready flags)
+            for (int s = slev[cl[c]] + lane; s < slev[cl[c + 1]]; s += 32)
+                asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(a.x + sperm[s]), "d"(sx[s]) : "memory");
+        }
+    }
+}
+
 int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded)
 {
     double sentinel;
@@ -922,7 +1050,8 @@ int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double
         if (prof_on) { cudaMalloc(&d_prof, 64); cudaMemset(d_prof, 0, 64); }
     }
     a.prof = prof_on ? d_prof : nullptr;
-    if (T->box_flags) LSSPG_LAUNCH(ctx, tri_box_ell_kernel, grid, 32, smem, a);
+    if (T->box_flags && T->box_chunks > 1) LSSPG_LAUNCH(ctx, tri_box_chunk_kernel, grid, 32, smem, a);
+    else if (T->box_flags) LSSPG_LAUNCH(ctx, tri_box_ell_kernel, grid, 32, smem, a);
     else LSSPG_LAUNCH(ctx, tri_box_kernel, grid, 32, smem, a);
     if (prof_on) {
         unsigned long long h[8];
@@ -949,6 +1078,7 @@ static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const
     T->blob_cap = (int)cap;
     T->max_ext = max_ext;
     T->box_flags = flags;
+    T->box_chunks = P.chunks;
     LSSPG_CUDA(cudaMalloc(&T->t_flags, sizeof(unsigned int) * std::max(H.num_tiles, 1)));
     LSSPG_CUDA(cudaMemsetAsync(T->t_flags, 0, sizeof(unsigned int) * std::max(H.num_tiles, 1), ctx->stream));
     for (int k = 0; k < 3; k++) { T->tile_dims[k] = H.tile_dims[k]; T->grid_dims[k] = H.grid_dims[k]; }
@@ -961,6 +1091,7 @@ static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const
     if (!attr_done) {
         cudaFuncSetAttribute(tri_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(tri_box_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(tri_box_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
     LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -973,6 +1104,55 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
 {
     const int nb = H.num_tiles;
     std::vector<BoxDesc> desc(nb);
+    // experimental chunked hand-off (tri_box_chunk_kernel): LSSPG_TRI_CHUNKS = 2..8
+    int chunks = 1;
+    if (const char *e = getenv("LSSPG_TRI_CHUNKS")) chunks = std::max(1, std::min(atoi(e), 8));
+    IVec pos_of_row((size_t)H.n);   // row -> position in box-major order
+    parallel_ranges(H.n, [&](long long a, long long b, int) {
+        for (int s = (int)a; s < (int)b; s++) pos_of_row[H.perm[s]] = s;
+    });
+    // chunk table of box k: [C][cl: C+1][xp: C+1][gp: C+1][gate rows] (see tri_box_chunk_kernel)
+    std::vector<std::vector<int>> tables(chunks > 1 ? nb : 0);
+    auto chunk_table = [&](int k, std::vector<int> &tab) {
+        const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
+        const int nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
+        const int C = std::max(1, std::min(chunks, nlev));
+        std::vector<int> cl(C + 1), xp(C + 1, 0), gp(C + 1, 0), gates;
+        for (int c = 0; c <= C; c++) cl[c] = (int)((long long)c * nlev / C);
+        std::vector<std::pair<int, int>> best;   // (predecessor ticket, latest position read from it) of the current chunk
+        int L = 0, c = 0, q = 0;
+        auto close_chunk = [&] {
+            for (auto &pb : best) gates.push_back(H.perm[pb.second]);
+            best.clear();
+        };
+        for (int s = s0; s < s1; s++) {
+            while (L + 1 < nlev && s >= H.lev_ptr[H.lev_off[k] + L + 1]) L++;
+            while (c + 1 < C && L >= cl[c + 1]) {
+                close_chunk();
+                c++;
+                xp[c] = q;
+                gp[c] = (int)gates.size();
+            }
+            for (int e = H.ptr[s]; e < H.ptr[s + 1]; e++) {
+                if (H.col[e] < 0) continue;
+                const int pos = pos_of_row[H.col[e]];
+                const int p = (int)(std::upper_bound(H.tile_ptr.begin(), H.tile_ptr.end(), pos) - H.tile_ptr.begin()) - 1;
+                size_t m = 0;
+                for (; m < best.size() && best[m].first != p; m++) {}
+                if (m == best.size()) best.emplace_back(p, pos);
+                else if (pos > best[m].second) best[m].second = pos;
+                q++;
+            }
+        }
+        close_chunk();
+        for (int cc = c + 1; cc <= C; cc++) { xp[cc] = q; gp[cc] = (int)gates.size(); }
+        tab.clear();
+        tab.push_back(C);
+        tab.insert(tab.end(), cl.begin(), cl.end());
+        tab.insert(tab.end(), xp.begin(), xp.end());
+        tab.insert(tab.end(), gp.begin(), gp.end());
+        tab.insert(tab.end(), gates.begin(), gates.end());
+    };
     parallel_ranges(nb, [&](long long k0, long long k1, int) {
         for (int k = (int)k0; k < (int)k1; k++) {
             const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
@@ -980,6 +1160,10 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
             d.nrows = s1 - s0;
             d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
             d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
+            if (chunks > 1) {
+                chunk_table(k, tables[k]);
+                d.npred = (int)tables[k].size();
+            }
             d.next = 0;
             int w = 0;
             for (int s = s0; s < s1; s++) w = std::max(w, H.ptr[s + 1] - H.ptr[s]);
@@ -1000,10 +1184,6 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
     P.blob.resize(std::max<size_t>(total, 16));
     if (total < 16) memset(P.blob.data(), 0, 16);
     unsigned char *blob = P.blob.data();
-    IVec pos_of_row((size_t)H.n);   // row -> position in box-major order
-    parallel_ranges(H.n, [&](long long a, long long b, int) {
-        for (int s = (int)a; s < (int)b; s++) pos_of_row[H.perm[s]] = s;
-    });
     const int np = host_threads();
     std::vector<char> bad(np, 0);
     parallel_ranges(nb, [&](long long k0, long long k1, int piece) {
@@ -1018,8 +1198,9 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
             int *ecol = (int *)(b + lay.ecol);
             double *diag = (double *)(b + lay.diag), *eval = (double *)(b + lay.eval);
             for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
+            if (chunks > 1) std::copy(tables[k].begin(), tables[k].end(), pred);
             // gate operand per predecessor box: of the rows this box reads from it, the one that box stores last
-            for (int q = 0; q < d.npred; q++) {
+            for (int q = 0; chunks <= 1 && q < d.npred; q++) {
                 const int p = H.pred[H.pred_ptr[k] + q];
                 int best = -1;
                 for (int e = H.ptr[s0]; e < H.ptr[s0 + nr]; e++) {
@@ -1054,7 +1235,7 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
     for (char b : bad)
         if (b) return 1;
     P.desc_bytes.assign((const unsigned char *)desc.data(), (const unsigned char *)(desc.data() + desc.size()));
-    P.cap = cap; P.max_ext = max_ext; P.flags = true;
+    P.cap = cap; P.max_ext = max_ext; P.flags = true; P.chunks = chunks;
     return 0;
 }
 
@@ -1122,7 +1303,7 @@ int tri_tiled_pack_host(const TiledHost &H, PackedBoxes &P)
         }
     }, 0, 64);
     P.desc_bytes.assign((const unsigned char *)desc.data(), (const unsigned char *)(desc.data() + desc.size()));
-    P.cap = cap; P.max_ext = max_ext; P.flags = false;
+    P.cap = cap; P.max_ext = max_ext; P.flags = false; P.chunks = 1;
     return 0;
 }
 
@@ -1213,6 +1394,88 @@ int lsspg_debug_tri_walk_tiled_host(int which, int n, const int *hTp, const int 
         info[0] = H.num_tiles; info[1] = H.num_tile_levels; info[2] = H.max_tile_rows; info[3] = H.num_levels;
         info[4] = H.grid_dims[0]; info[5] = H.grid_dims[1]; info[6] = H.grid_dims[2]; info[7] = H.tile_dims[0];
     }
+    return 0;
+}
+
+// CPU emulation of the ELL box kernels FROM THE PACKED BLOBS (what the device reads), for the test-suite: boxes are
+// visited round-robin in ticket order and a box advances by at most ONE chunk per round (the whole box when the blobs
+// carry no chunk table), only when its gate rows and every operand of the chunk have been published.  x equals the serial
+// sweep bit for bit when the image is right; info[0] = rounds needed = length of the longest chain of hand-offs,
+// info[1] = chunks per box, info[2] = boxes, info[3] = levels of the box graph.  Never called by a product path.
+int lsspg_debug_tri_walk_packed_host(int which, int n, const int *hTp, const int *hTj, const double *hTx, double *hx,
+                                     const double *hrhs, int *applicable, int *info /* [4] */)
+{
+    TiledHost H;
+    const int rc = tri_tiled_build_host(which, n, hTp, hTj, hTx, H);
+    if (applicable) *applicable = 0;
+    if (rc == 1) return 1;
+    if (rc == 2) return 0;
+    PackedBoxes P;
+    LSSPG_TRY(tri_tiled_pack_host(H, P));
+    if (!P.flags) return 0;   // CSR blobs of the polling kernel: not emulated here
+    if (applicable) *applicable = 1;
+    const BoxDesc *desc = (const BoxDesc *)P.desc_bytes.data();
+    const double poison = strtod("nan", nullptr);
+    for (int i = 0; i < n; i++) hx[i] = poison;
+    const int nb = H.num_tiles;
+    std::vector<std::vector<double>> sx(nb);
+    std::vector<int> next_chunk(nb, 0);
+    int remaining = nb, rounds = 0, max_chunks = 1;
+    while (remaining > 0) {
+        rounds++;
+        int advanced = 0;
+        std::vector<std::pair<int, double>> published;   // visible to the other boxes from the NEXT round on
+        for (int tk = 0; tk < nb; tk++) {
+            const BoxDesc &d = desc[tk];
+            const unsigned char *b = P.blob.data() + d.off;
+            const int nr = d.nrows, w = d.nent;
+            const EllLayout lay = ell_layout(nr, w, d.nlev, d.next, d.npred);
+            const int *lev = (const int *)(b + lay.lev), *perm = (const int *)(b + lay.perm), *ext = (const int *)(b + lay.ext);
+            const int *tab = (const int *)(b + lay.pred), *ecol = (const int *)(b + lay.ecol);
+            const double *diag = (const double *)(b + lay.diag), *eval = (const double *)(b + lay.eval);
+            int C = 1;
+            std::vector<int> cl = {0, d.nlev}, xp = {0, d.next}, gp = {0, d.npred};
+            const int *gates = tab;
+            if (P.chunks > 1) {
+                C = tab[0];
+                cl.assign(tab + 1, tab + 2 + C);
+                xp.assign(tab + 2 + C, tab + 3 + 2 * C);
+                gp.assign(tab + 3 + 2 * C, tab + 4 + 3 * C);
+                gates = tab + 4 + 3 * C;
+            }
+            max_chunks = std::max(max_chunks, C);
+            const int c = next_chunk[tk];
+            if (c >= C) continue;
+            bool ready = true;
+            for (int q = gp[c]; q < gp[c + 1] && ready; q++) ready = hx[gates[q]] == hx[gates[q]];
+            for (int q = xp[c]; q < xp[c + 1] && ready; q++) ready = hx[ext[q]] == hx[ext[q]];
+            if (!ready) continue;
+            std::vector<double> &x = sx[tk];
+            if (c == 0) {
+                x.assign((size_t)nr + d.next + 2, poison);
+                for (int s = 0; s < nr; s++) x[s] = hrhs[perm[s]];
+                x[nr + d.next] = 0.0;
+            }
+            for (int q = xp[c]; q < xp[c + 1]; q++) x[nr + q] = hx[ext[q]];
+            for (int L = cl[c]; L < cl[c + 1]; L++)
+                for (int slot = lev[L]; slot < lev[L + 1]; slot++) {
+                    double r = x[slot];
+                    for (int k = 0; k < w; k++) r = r - eval[k * nr + slot] * x[ecol[k * nr + slot]];
+                    if (diag[slot] != 1.0) r = r / diag[slot];
+                    x[slot] = r;
+                }
+            for (int s = lev[cl[c]]; s < lev[cl[c + 1]]; s++) published.emplace_back(perm[s], x[s]);
+            next_chunk[tk] = c + 1;
+            advanced++;
+            if (c + 1 == C) remaining--;
+        }
+        for (auto &pv : published) hx[pv.first] = pv.second;
+        if (!advanced) {
+            lsspg::set_error("packed walk: no progress (the schedule would deadlock)");
+            return 1;
+        }
+    }
+    if (info) { info[0] = rounds; info[1] = max_chunks; info[2] = nb; info[3] = H.num_tile_levels; }
     return 0;
 }
 
