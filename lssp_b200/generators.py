@@ -38,8 +38,8 @@ def stencil_7pt(N, conv=(0.0, 0.0, 0.0), chunk_planes=16):
     stencil = np.array([-1.0 - cz, -1.0 - cy, -1.0 - cx, 6.0, -1.0 + cx, -1.0 + cy, -1.0 + cz])
     offs = np.array([-N * N, -N, -1, 0, 1, N, N * N], dtype=np.int64)
     Ap = np.zeros(n + 1, dtype=np.int64)
-    Aj_parts, Ax_parts = [], []
-    for z0 in range(0, N, chunk_planes):
+
+    def planes(z0):   # rows of the planes [z0, z0 + chunk_planes): independent of every other chunk
         z1 = min(N, z0 + chunk_planes)
         idx = np.arange(z0 * N * N, z1 * N * N, dtype=np.int64)
         x, y, z = idx % N, (idx // N) % N, idx // (N * N)
@@ -47,11 +47,19 @@ def stencil_7pt(N, conv=(0.0, 0.0, 0.0), chunk_planes=16):
                          z < N - 1], axis=1)
         cols = idx[:, None] + offs[None, :]
         Ap[idx + 1] = mask.sum(axis=1)
-        Aj_parts.append(cols[mask].astype(np.int32))
-        Ax_parts.append(np.broadcast_to(stencil, mask.shape)[mask])
+        return cols[mask].astype(np.int32), np.broadcast_to(stencil, mask.shape)[mask]
+
+    starts = list(range(0, N, chunk_planes))
+    if len(starts) > 1:   # chunks on a thread pool (numpy releases the GIL in its kernels), concatenated in order
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max(1, min(16, os.cpu_count() or 1))) as ex:
+            parts = list(ex.map(planes, starts))
+    else:
+        parts = [planes(z0) for z0 in starts]
     np.cumsum(Ap, out=Ap)
     assert Ap[-1] < 2 ** 31
-    return Ap.astype(np.int32), np.concatenate(Aj_parts), np.concatenate(Ax_parts)
+    return Ap.astype(np.int32), np.concatenate([q[0] for q in parts]), np.concatenate([q[1] for q in parts])
 
 
 def stencil_7pt_rows(dims, r0, r1, conv=(0.0, 0.0, 0.0), chunk=1 << 20):
@@ -102,6 +110,9 @@ def _u01(h):
     return ((h >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
 
 
+_PL_BLOCK = 1 << 18   # rows per generator block
+
+
 def powerlaw(n, seed=20261018, lmin=5, gamma=2.3, lmax=4096, window=65536, local=0.9):
     """Irregular CSR with power-law row lengths and column locality (SURVEY.md 8d,
     C5): l_i = clamp(floor(lmin * u^(-1/(gamma-1))), 1, lmax) off-diagonal draws,
@@ -109,7 +120,24 @@ def powerlaw(n, seed=20261018, lmin=5, gamma=2.3, lmax=4096, window=65536, local
     (-1,0), duplicates merged (summed), diagonal = 1 + sum |off| (strictly
     diagonally dominant, nonsymmetric).  Counter-based splitmix64 hashing of
     (seed, row, k) makes the matrix reproducible anywhere."""
-    return powerlaw_rows(n, 0, n, seed, lmin, gamma, lmax, window, local)
+    if n <= _PL_BLOCK:
+        return powerlaw_rows(n, 0, n, seed, lmin, gamma, lmax, window, local)
+    # every row is a function of (seed, row) only: row blocks on a thread pool (numpy releases the GIL in its
+    # kernels), concatenated -- the same arrays as one call over all rows
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    starts = list(range(0, n, _PL_BLOCK))
+    with ThreadPoolExecutor(max(1, min(16, os.cpu_count() or 1))) as ex:
+        parts = list(ex.map(lambda r0: powerlaw_rows(n, r0, min(n, r0 + _PL_BLOCK), seed, lmin, gamma, lmax, window, local),
+                            starts))
+    Ap = np.zeros(n + 1, dtype=np.int64)
+    off = 0
+    for r0, (p, _, _) in zip(starts, parts):
+        Ap[r0 + 1:r0 + len(p)] = off + p[1:].astype(np.int64)
+        off += int(p[-1])
+    if off >= 2 ** 31:
+        raise ValueError("powerlaw: more than 2^31 - 1 entries (int32 CSR)")
+    return Ap.astype(np.int32), np.concatenate([q[1] for q in parts]), np.concatenate([q[2] for q in parts])
 
 
 def powerlaw_rows(n, r0, r1, seed=20261018, lmin=5, gamma=2.3, lmax=4096, window=65536, local=0.9):

@@ -102,9 +102,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true", help="small grids (smoke run of this script)")
     ap.add_argument("--only", default="")
+    ap.add_argument("--pl-rows", type=int, default=4000000,
+                    help="rows of the power-law case C5 (BASELINE.json configs[4] is 50 000 000: ~1 G entries, 12 GB CSR; "
+                         "the generator runs row blocks on a thread pool, about a minute on 16 cores)")
     a = ap.parse_args()
     only = set(a.only.split(",")) if a.only else None
-    N3, N2, NP = (48, 200, 100000) if a.quick else (256, 1000, 4000000)
+    N3, N2, NP = (48, 200, 100000) if a.quick else (256, 1000, a.pl_rows)
     ctx = api.Context(0)
     cases = [
         ("C1", "lap2d_%d CG unpreconditioned (exam.cxx operator)" % N2, lambda: g.laplacian_5pt(N2), "cg", "non", {}),
