@@ -181,3 +181,15 @@ def test_generators_are_deterministic_and_sorted():
     from lssp_b200 import generators as g
     B = g.lap3d(8)
     assert int(B[0][-1]) == 7 * 512 - 6 * 64
+
+
+def test_generators_blocked_on_the_thread_pool_give_the_same_arrays(monkeypatch):
+    from lssp_b200 import generators as g
+    monkeypatch.setattr(g, "_PL_BLOCK", 700)
+    A = g.powerlaw(4000, window=300)
+    B = g.powerlaw_rows(4000, 0, 4000, window=300)
+    assert all(np.array_equal(a, b) for a, b in zip(A, B)) and A[0].dtype == np.int32
+    assert sha(*A) == sha(*matrix("powerlaw_4000"))
+    C = g.stencil_7pt(20, conv=(0.3, 0.2, 0.1), chunk_planes=3)      # 7 chunks on the pool
+    D = g.stencil_7pt(20, conv=(0.3, 0.2, 0.1), chunk_planes=20)     # one chunk, inline
+    assert all(np.array_equal(a, b) for a, b in zip(C, D))
