@@ -142,6 +142,12 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
             if (s1 <= 4 && s2 <= 4 && t1 <= 8) { sk[0] = (int)s1; sk[1] = (int)s2; sk[2] = (int)t1; }
         }
     }
+    if (const char *e = getenv("LSSPG_TRI_SKEW_FORCE")) {   // experiments: any skew at least as large as the needed one
+        int a, b, c;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= sk[0] && b >= sk[1] && c >= sk[2] && a <= 8 && b <= 8 && c <= 16) {
+            sk[0] = a; sk[1] = b; sk[2] = c;
+        }
+    }
     // skewed 3-D boxes: u spans (1 + s1 + t1) nx, so boxes longer in u and flatter in w shorten the chain of boxes;
     // measured for ILUK(1) at 256^3 (profiles/r01_skew_tiles.log): 12x8x5 3.88 ms, 8x8x8 4.12, 16x8x4 4.14, 8x4x8 4.46
     if (!shape_given && g[2] > 1 && (sk[0] || sk[1] || sk[2])) { t[0] = 12; t[1] = 8; t[2] = 5; }
