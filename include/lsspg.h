@@ -152,7 +152,16 @@ int lsspg_debug_tri_pack_host(int which, int n, const int *hTp, const int *hTj, 
  * boxes, levels of the box graph.  Test-suite only (also verifies the experimental LSSPG_TRI_CHUNKS schedule). */
 int lsspg_debug_tri_walk_packed_host(int which, int n, const int *hTp, const int *hTj, const double *hTx,
                                      double *hx, const double *hrhs, int *applicable, int *info);
-/* schedule of a device-resident factor: tiled != 0 when the box schedule is in use */
+/* CPU replay of the PENCIL schedule (tri_pencil.cu) from the image the device reads: value stream, line
+ * descriptors, ghost lanes, mailboxes.  x must equal the serial sweep of src/solver-tri.cxx:4-46 bit for bit.
+ * info[8]: pencils, threads per pencil, most ghost lines, largest operand distance, slots per row, values per
+ * row, most steps, skew.  Test-suite only. */
+int lsspg_debug_tri_walk_pencil_host(int which, int n, const int *hTp, const int *hTj, const double *hTx,
+                                     double *hx, const double *hrhs, int *applicable, int *info);
+/* LSSPG_TRI_PROF=1: per-pencil timers of the last sweep (8 words per pencil, ticket order: start ns, end ns, cycles
+ * total / waiting for ghost lanes / in the step barrier, steps, CTA, SM); returns the number of pencils copied */
+int lsspg_debug_tri_pencil_prof(lsspg_ctx *ctx, const lsspg_tri *T, unsigned long long *out, int max_pencils);
+/* schedule of a device-resident factor: tiled = 2 pencil schedule, 1 box schedule, 0 slice schedule */
 int lsspg_tri_schedule(const lsspg_tri *T, int *tiled, int *num_tiles, int *num_tile_levels,
                        int *max_tile_rows);
 

@@ -285,6 +285,20 @@ def tri_walk_packed_host(which, T, rhs):
     return x, dict(zip(("rounds", "chunks", "boxes", "box_levels"), list(info)))
 
 
+def tri_walk_pencil_host(which, T, rhs):
+    """Replay of the pencil schedule (tri_pencil.cu) from the image the device reads (tests only).  Returns
+    (x, info) or (None, None) when the factor is not a lattice factor."""
+    Tp, Tj, Tx = _i32(T[0]), _i32(T[1]), _f64(T[2])
+    n = len(Tp) - 1
+    x = np.zeros(n)
+    ok, info = C.c_int(), (C.c_int * 8)()
+    check(lib().lsspg_debug_tri_walk_pencil_host(which, n, _p(Tp), _p(Tj), _p(Tx), _p(x), _p(_f64(rhs)), C.byref(ok), info))
+    if not ok.value:
+        return None, None
+    keys = ("pencils", "threads", "max_ghost", "max_dk", "slots", "values_per_row", "max_steps", "skew")
+    return x, dict(zip(keys, list(info)))
+
+
 class Tri:
     """Device-resident triangular factor in level order (lsspg_tri)."""
 

@@ -427,6 +427,7 @@ int read_scalars(lsspg_ctx *ctx, int first, int count, bool with_flags)
     LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (with_flags && ctx->h_flags[FLAG_TRI_TIMEOUT]) {
         cudaMemsetAsync(ctx->d_flags + FLAG_TRI_TIMEOUT, 0, sizeof(int), ctx->stream);
+        ctx->tri_timeouts++;
         set_error("triangular solve watchdog: a row waited for a dependency that never arrived");
         return 1;
     }

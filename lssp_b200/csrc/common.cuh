@@ -75,6 +75,7 @@ struct lsspg_ctx {
     size_t stage_len = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t tev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    int tri_timeouts = 0;   // sweeps aborted by the watchdog so far (pencil schedules then empty their mailboxes)
     void *comm = nullptr;   // multi-GPU communicator (comm.cu), NULL on a single GPU
     // work-vector pool: the drivers allocate their vectors per solve as the reference does, but
     // cudaMalloc/cudaFree cost milliseconds, so released vectors are kept here for the next solve

@@ -274,6 +274,7 @@ int tri_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs
     LSSPG_CHECK(T && dx && drhs, "tri_solve: NULL operand");
     LSSPG_CHECK(dx != drhs, "tri_solve: x and rhs must not alias");
     if (T->n == 0) return 0;
+    if (T->pencil) return tri_pencil_solve(ctx, T, dx, drhs, guarded);
     if (T->tiled) return tri_tiled_solve(ctx, T, dx, drhs, guarded);
     double sentinel;
     const unsigned long long bits = kSentinelBits;
@@ -413,6 +414,24 @@ int lsspg_tri_analyse(lsspg_ctx *ctx, int which, int n, const int *hTp, const in
     LSSPG_CHECK(ctx && out, "lsspg_tri_analyse: NULL argument");
     LSSPG_CHECK(n == 0 || hTx, "lsspg_tri_analyse: NULL values");
     LSSPG_CUDA(cudaSetDevice(ctx->device));
+    {   // lattice factor: pencil schedule (tri_pencil.cu); LSSPG_TRI_PENCIL=0 disables it
+        const char *e = getenv("LSSPG_TRI_PENCIL");
+        if (!(e && atoi(e) == 0 && !strchr(e, ','))) {
+            PencilHost PH;
+            const int rc = tri_pencil_build_host(which, n, hTp, hTj, hTx, ctx->num_sms, PH);
+            if (rc == 1) return 1;
+            if (rc == 0) {
+                lsspg_tri *T = new lsspg_tri();
+                T->n = n; T->which = which; T->num_levels = PH.num_levels; T->offdiag_nnz = PH.offdiag_nnz;
+                T->padded_nnz = PH.offdiag_nnz;
+                LSSPG_CUDA(cudaMalloc(&T->d_counter, sizeof(unsigned int) * 64));
+                LSSPG_CUDA(cudaMemsetAsync(T->d_counter, 0, sizeof(unsigned int) * 64, ctx->stream));
+                LSSPG_TRY(tri_pencil_upload(ctx, PH, T));
+                *out = T;
+                return 0;
+            }
+        }
+    }
     {   // structured-grid factor: tile schedule (tri_tiled.cu); LSSPG_TRI_TILED=0 disables it
         const char *e = getenv("LSSPG_TRI_TILED");
         if (!(e && atoi(e) == 0)) {
@@ -475,6 +494,7 @@ int lsspg_tri_destroy(lsspg_ctx *ctx, lsspg_tri *T)
     cudaFree(T->d_val);
     cudaFree(T->d_counter);
     if (T->tiled) tri_tiled_free(T);
+    if (T->pencil) tri_pencil_free(T);
     delete T;
     return 0;
 }
@@ -494,7 +514,7 @@ int lsspg_tri_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double
 
 int lsspg_tri_schedule(const lsspg_tri *T, int *tiled, int *num_tiles, int *num_tile_levels, int *max_tile_rows)
 {
-    if (tiled) *tiled = T->tiled ? 1 : 0;
+    if (tiled) *tiled = T->pencil ? 2 : (T->tiled ? 1 : 0);
     if (num_tiles) *num_tiles = T->num_tiles;
     if (num_tile_levels) *num_tile_levels = T->num_tile_levels;
     if (max_tile_rows) *max_tile_rows = T->max_tile_rows;

@@ -54,6 +54,14 @@ struct lsspg_tri {
     int box_chunks = 0;                // > 1: experimental chunked hand-off (tri_box_chunk_kernel)
     unsigned int *t_flags = nullptr;   // [num_tiles] epoch of the last sweep that finished the box
     unsigned int epoch = 0;
+    // pencil schedule (tri_pencil.cu): lattice factors; num_tiles = pencils, tile_dims = pencil cross-section
+    bool pencil = false;
+    void *p_hdr = nullptr, *p_thr = nullptr, *p_ghost = nullptr;
+    double *p_vals = nullptr, *p_mail = nullptr;
+    long long p_mail_len = 0;
+    int p_T = 0, p_RS = 0, p_W = 0, p_diag = 0, p_dir = 1, p_pv = 0, p_pw = 0;
+    int p_seen_timeouts = 0;
+    unsigned long long *p_prof = nullptr;
 };
 
 namespace lsspg {
@@ -86,6 +94,47 @@ int tri_tiled_pack_host(const TiledHost &H, PackedBoxes &P);
 int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T);
 void tri_tiled_free(lsspg_tri *T);
 int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded);
+// lattice test shared by the box and the pencil schedules: grid dimensions and the distinct |column - row| offsets
+bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3], std::vector<long long> &offsets);
+
+// ---- pencil schedule (tri_pencil.cu) ----
+constexpr int kPenMaxW = 8;          // off-diagonal entries per row
+constexpr int kPenMaxOut = 4;        // mailboxes one line feeds
+constexpr int kPenRing = 16;         // hyperplanes kept in shared memory
+constexpr int kPenMaxDk = 7;         // largest distance (in steps) between a row and an operand
+constexpr int kPenMaxGhost = 96;     // ghost lines per pencil
+constexpr int kPenMaxThreads = 256;  // lines per pencil
+struct PencilHdr {      // one per pencil, ticket order (32 bytes)
+    long long val_off;  // first value of the pencil in the value stream: vals[val_off + ((k * NV + w) * T + t)]
+    int nsteps, nghost, thr_off, ghost_off;
+    int pad[2];         // pad[0]: last virtual step + 1 the ghost prefetcher handles
+};
+struct PencilThread {   // one per (pencil, thread) = per line (64 bytes)
+    int kstart, kend;   // the line is active in steps [kstart, kend)
+    int row0;           // row of step k: row0 + dir * k
+    int pad;
+    int op[kPenMaxW];   // per slot: (distance in steps << 16) | ring lane  (lanes >= T: ghost lines)
+    int out[kPenMaxOut];// mailbox position of step 0 (INT_MIN: none): the value of step k also goes to mail[out + k]
+};
+struct PencilGhost {    // one per (pencil, ghost line): virtual step kg in [kg0, kg1) is mail[mail0 + kg]
+    int mail0, kg0, kg1, pad;
+};
+struct PencilHost {
+    int n = 0, which = 0, W = 0, nv = 0, T = 0, pv = 0, pw = 0, dir = 1;
+    int num_pencils = 0, max_ghost = 0, max_dk = 0, max_steps = 0, num_levels = 0;
+    int grid_dims[3] = {0, 0, 0}, skew[3] = {0, 0, 0};
+    long long mail_len = 0, offdiag_nnz = 0;
+    std::vector<PencilHdr> hdr;
+    std::vector<PencilThread> thr;
+    std::vector<PencilGhost> ghost;
+    DVec vals;
+};
+// 0: built; 2: not a lattice factor (caller falls back); 1: error
+int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const double *Tx, int num_sms, PencilHost &H);
+int tri_pencil_walk_host(const PencilHost &H, double *x, const double *rhs, int *info);
+int tri_pencil_upload(lsspg_ctx *ctx, const PencilHost &H, lsspg_tri *T);
+void tri_pencil_free(lsspg_tri *T);
+int tri_pencil_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded);
 // x = T^-1 rhs; `guarded`: skip when ctx->d_flags[FLAG_STOP] is set
 int tri_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded);
 }  // namespace lsspg

@@ -46,7 +46,7 @@ struct OffsetHist {
     }
 };
 
-static bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3], std::vector<long long> &offsets)
+bool detect_lattice(int n, const int *Tp, const int *Tj, int dims[3], std::vector<long long> &offsets)
 {
     const int np = host_threads();
     std::vector<OffsetHist> part(np);
