@@ -59,7 +59,7 @@ struct lsspg_tri {
     void *p_hdr = nullptr, *p_thr = nullptr, *p_ghost = nullptr;
     double *p_vals = nullptr, *p_mail = nullptr;
     long long p_mail_len = 0;
-    int p_T = 0, p_RS = 0, p_W = 0, p_diag = 0, p_dir = 1, p_pv = 0, p_pw = 0;
+    int p_T = 0, p_RS = 0, p_W = 0, p_diag = 0, p_dir = 1, p_pv = 0, p_pw = 0, p_holes = 0;
     int p_seen_timeouts = 0;
     unsigned long long *p_prof = nullptr;
 };
@@ -104,6 +104,9 @@ constexpr int kPenRing = 16;         // hyperplanes kept in shared memory
 constexpr int kPenMaxDk = 7;         // largest distance (in steps) between a row and an operand
 constexpr int kPenMaxGhost = 96;     // ghost lines per pencil
 constexpr int kPenMaxThreads = 256;  // lines per pencil
+constexpr int kPenZeroLane = 0xffff; // operand descriptor of a neighbour that does not exist: the ring lane holding +0.0
+// ring lanes per hyperplane: own lines, ghost lines, the +0.0 lane (last)
+inline int pencil_ring_stride(int T, int max_ghost) { return T + ((max_ghost + 1 + 15) / 16) * 16; }
 struct PencilHdr {      // one per pencil, ticket order (32 bytes)
     long long val_off;  // first value of the pencil in the value stream: vals[val_off + ((k * NV + w) * T + t)]
     int nsteps, nghost, thr_off, ghost_off;
@@ -121,6 +124,7 @@ struct PencilGhost {    // one per (pencil, ghost line): virtual step kg in [kg0
 };
 struct PencilHost {
     int n = 0, which = 0, W = 0, nv = 0, T = 0, pv = 0, pw = 0, dir = 1;
+    bool holes = false;   // rows lack entries whose neighbour exists: the value stream marks missing entries
     int num_pencils = 0, max_ghost = 0, max_dk = 0, max_steps = 0, num_levels = 0;
     int grid_dims[3] = {0, 0, 0}, skew[3] = {0, 0, 0};
     long long mail_len = 0, offdiag_nnz = 0;

@@ -93,7 +93,7 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
     // every row: diagonal where the reference expects it, entries in application order = strictly increasing slot,
     // every entry a true lattice neighbour (no wrap-around across a grid line)
     const int np = host_threads();
-    std::vector<char> bad(np, 0), nonunit(np, 0);
+    std::vector<char> bad(np, 0), nonunit(np, 0), hole(np, 0);
     auto canon = [&](int i, int &cx, int &cy, int &cz) {
         const int x = i % g[0], y = (i / g[0]) % g[1], z = i / (g[0] * g[1]);
         if (lower) { cx = x; cy = y; cz = z; }
@@ -108,22 +108,35 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
             if (Tx[dpos] != 1.0) nonunit[p] = 1;
             int cx, cy, cz, last = -1;
             canon(i, cx, cy, cz);
+            auto inside = [&](int w) {
+                return cx - dx[w] >= 0 && cx - dx[w] < g[0] && cy - dy[w] >= 0 && cy - dy[w] < g[1] && cz - dz[w] >= 0 &&
+                       cz - dz[w] < g[2];
+            };
             for (int q = 0; q < e - b - 1; q++) {
                 const int k = lower ? b + q : e - 1 - q;   // src/solver-tri.cxx:17 / :39
                 const long long d = lower ? (long long)i - Tj[k] : (long long)Tj[k] - i;
                 int w = last + 1;
-                while (w < W && offsets[w] != d) w++;
+                while (w < W && offsets[w] != d) {
+                    if (inside(w)) hole[p] = 1;   // the lattice neighbour exists but the row has no entry for it
+                    w++;
+                }
                 if (d <= 0 || w >= W) { bad[p] = 1; return; }
-                if (cx - dx[w] < 0 || cx - dx[w] >= g[0] || cy - dy[w] < 0 || cy - dy[w] >= g[1] || cz - dz[w] < 0 ||
-                    cz - dz[w] >= g[2]) { bad[p] = 1; return; }
+                if (!inside(w)) { bad[p] = 1; return; }
                 last = w;
             }
+            for (int w = last + 1; w < W; w++)
+                if (inside(w)) hole[p] = 1;
         }
     }, np);
     for (char b : bad)
         if (b) return 2;
-    bool hasdiag = false;
+    bool hasdiag = false, holes = false;
     for (char b : nonunit) hasdiag = hasdiag || b;
+    // HOLES: some row lacks an entry although the neighbour exists (not the case for ILU(k) factors of uniform
+    // stencils, where entries are only missing at the domain boundary).  Without holes a missing entry is stored as
+    // +0.0 and its operand is +0.0 by construction (see the kernel): no test in the step loop.
+    for (char b : hole) holes = holes || b;
+    if (getenv("LSSPG_TRI_PENCIL_HOLES") && atoi(getenv("LSSPG_TRI_PENCIL_HOLES")) != 0) holes = true;
     // pencil cross-section
     int pv = 16, pw = 16;
     if (g[2] == 1) { pw = 1; pv = (g[1] >= 512) ? 64 : 32; }
@@ -196,7 +209,7 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
     for (size_t q = 0; q < H.thr.size(); q++) {
         PencilThread &d = H.thr[q];
         d.kstart = 0; d.kend = 0; d.row0 = 0; d.pad = 0;
-        for (int w = 0; w < kPenMaxW; w++) d.op[w] = (1 << 16) | (int)(q % T);
+        for (int w = 0; w < kPenMaxW; w++) d.op[w] = (1 << 16) | kPenZeroLane;   // no such neighbour: the +0.0 lane
         for (int o = 0; o < kPenMaxOut; o++) d.out[o] = kPenNoOut;
     }
     // thread descriptors, ghost streams (consumer side)
@@ -289,7 +302,7 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
     // the value stream
     H.vals.resize((size_t)val_total);
     {
-        const double missing = bits_to_double(kPenMissingBits);
+        const double missing = holes ? bits_to_double(kPenMissingBits) : 0.0;
         double *vals = H.vals.data();
         parallel_ranges(val_total, [&](long long a, long long b, int) {
             for (long long q = a; q < b; q++) vals[q] = missing;
@@ -315,6 +328,7 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
         });
     }
     H.n = n; H.which = which; H.W = W; H.nv = NV; H.T = T; H.pv = pv; H.pw = pw; H.dir = lower ? 1 : -1;
+    H.holes = holes;
     H.num_pencils = npen; H.max_ghost = max_ghost; H.max_dk = max_dk; H.max_steps = max_steps; H.mail_len = mail_len;
     H.offdiag_nnz = (long long)Tp[n] - n;
     for (int k = 0; k < 3; k++) H.grid_dims[k] = g[k];
@@ -337,7 +351,7 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
 // an empty mailbox or from a ring slot that was overwritten poisons the result.
 int tri_pencil_walk_host(const PencilHost &H, double *x, const double *rhs, int *info)
 {
-    const int T = H.T, W = H.W, NV = H.nv, RD = kPenRing, RS = T + std::max(H.max_ghost, 1);
+    const int T = H.T, W = H.W, NV = H.nv, RD = kPenRing, RS = pencil_ring_stride(T, H.max_ghost);
     const double empty = bits_to_double(kPenEmptyBits), poison = strtod("nan", nullptr);
     std::vector<double> mail((size_t)std::max<long long>(H.mail_len, 1), empty);
     std::vector<double> ring((size_t)RD * RS);
@@ -348,7 +362,7 @@ int tri_pencil_walk_host(const PencilHost &H, double *x, const double *rhs, int 
         const PencilHdr &h = H.hdr[p];
         const PencilThread *thr = H.thr.data() + h.thr_off;
         const PencilGhost *gh = H.ghost.data() + h.ghost_off;
-        std::fill(ring.begin(), ring.end(), poison);
+        std::fill(ring.begin(), ring.end(), 0.0);          // the kernel zeroes the ring of every pencil
         std::fill(ring_step.begin(), ring_step.end(), LLONG_MIN);
         std::vector<double> out(T);
         int ghost_ready = kPenG0;
@@ -358,12 +372,12 @@ int tri_pencil_walk_host(const PencilHost &H, double *x, const double *rhs, int 
             while (ghost_ready < ((k == h.nsteps - 1) ? h.pad[0] : std::min(k + RD - kPenMaxDk, h.pad[0]))) {
                 const int kg = ghost_ready;
                 for (int e = 0; e < h.nghost; e++) {
-                    if (kg < gh[e].kg0 || kg >= gh[e].kg1) continue;
+                    const size_t slot = (size_t)(kg & (RD - 1)) * RS + T + e;
+                    if (kg < gh[e].kg0 || kg >= gh[e].kg1) { ring[slot] = 0.0; ring_step[slot] = LLONG_MIN; continue; }
                     double &m = mail[(size_t)gh[e].mail0 + kg];
                     unsigned long long mb;
                     memcpy(&mb, &m, 8);
                     if (mb == kPenEmptyBits) { set_error("pencil walk: mailbox empty (ticket order is not topological)"); return 1; }
-                    const size_t slot = (size_t)(kg & (RD - 1)) * RS + T + e;
                     ring[slot] = m; ring_step[slot] = kg;
                     m = empty;
                 }
@@ -377,18 +391,24 @@ int tri_pencil_walk_host(const PencilHost &H, double *x, const double *rhs, int 
                     const double *v = H.vals.data() + h.val_off + (size_t)k * NV * T + t;
                     r = rhs[d.row0 + H.dir * k];
                     for (int w = 0; w < W; w++) {
-                        double a = v[(size_t)w * T];
+                        const double a = v[(size_t)w * T];
                         unsigned long long ab;
                         memcpy(&ab, &a, 8);
-                        double xv = 0.0;
-                        if (ab == kPenMissingBits) a = 0.0;
+                        const int lane = (d.op[w] & 0xffff) == kPenZeroLane ? RS - 1 : (d.op[w] & 0xffff), dk = d.op[w] >> 16;
+                        const size_t slot = (size_t)((k - dk) & (RD - 1)) * RS + lane;
+                        double pr;
+                        if (H.holes && ab == kPenMissingBits) pr = 0.0;
                         else {
-                            const int lane = d.op[w] & 0xffff, dk = d.op[w] >> 16;
-                            const size_t slot = (size_t)((k - dk) & (RD - 1)) * RS + lane;
-                            if (ring_step[slot] != k - dk) bad_operands++;
-                            xv = ring[slot];
+                            // a stored +0.0 in a hole-free factor is a missing entry: its operand must be +0.0 exactly
+                            if (!H.holes && ab == 0 && lane != RS - 1 && ring_step[slot] != k - dk) {
+                                unsigned long long xb;
+                                memcpy(&xb, &ring[slot], 8);
+                                if (xb != 0) bad_operands++;
+                            }
+                            else if (!(ab == 0 && !H.holes) && ring_step[slot] != k - dk) bad_operands++;
+                            pr = a * ring[slot];
                         }
-                        r = r - a * xv;   // src/solver-tri.cxx:18 / :40
+                        r = r - pr;   // src/solver-tri.cxx:18 / :40
                     }
                     if (NV > W) r = r / v[(size_t)W * T];   // :22 / :44
                 }
@@ -397,7 +417,8 @@ int tri_pencil_walk_host(const PencilHost &H, double *x, const double *rhs, int 
             for (int t = 0; t < T; t++) {
                 const PencilThread &d = thr[t];
                 const size_t slot = (size_t)(k & (RD - 1)) * RS + t;
-                ring[slot] = out[t]; ring_step[slot] = k;
+                ring[slot] = out[t];
+                ring_step[slot] = (k >= d.kstart && k < d.kend) ? k : LLONG_MIN;
                 if (k >= d.kstart && k < d.kend) {
                     x[d.row0 + H.dir * k] = out[t];
                     for (int o = 0; o < kPenMaxOut; o++)
@@ -413,7 +434,7 @@ int tri_pencil_walk_host(const PencilHost &H, double *x, const double *rhs, int 
         memcpy(&mb, &mail[(size_t)q], 8);
         if (mb != kPenEmptyBits) { set_error("pencil walk: mailbox %lld not emptied", q); return 1; }
     }
-    if (info) { info[0] = H.num_pencils; info[1] = H.T; info[2] = H.max_ghost; info[3] = H.max_dk; info[4] = H.W; info[5] = H.nv; info[6] = H.max_steps; info[7] = H.skew[0] * 100 + H.skew[1] * 10 + H.skew[2]; }
+    if (info) { info[0] = H.num_pencils; info[1] = H.T; info[2] = H.max_ghost; info[3] = H.max_dk; info[4] = H.W; info[5] = H.nv; info[6] = H.max_steps; info[7] = H.skew[0] * 100 + H.skew[1] * 10 + H.skew[2] + (H.holes ? 1000 : 0); }
     return 0;
 }
 
@@ -430,6 +451,7 @@ struct PencilArgs {
     const double *rhs;
     const int *stop;
     int *err;
+    int dbg;                    // LSSPG_TRI_PENCIL_DBG: timing experiments only (skips work, wrong results)
     unsigned long long *prof;   // LSSPG_TRI_PROF=1: 8 words per pencil (start ns, end ns, cycles: total, ghost wait, barrier; steps)
 };
 
@@ -484,7 +506,7 @@ __device__ __forceinline__ void pen_st_flag(int *p, int v)
 // steps ahead into registers, with an L2 prefetch further ahead.
 constexpr int kPenChunk = 16;   // steps per rhs / x tile
 constexpr int kPenNB = 3;       // rhs tiles in flight
-constexpr int kPenP = 4;        // steps the value stream is fetched ahead
+constexpr int kPenP = 2;        // steps the value stream is fetched ahead into registers
 constexpr int kPenL2Ahead = 32; // steps the value stream is prefetched into L2
 
 __host__ __device__ inline size_t pencil_smem_bytes(int T, int RS)
@@ -492,22 +514,25 @@ __host__ __device__ inline size_t pencil_smem_bytes(int T, int RS)
     return sizeof(double) * ((size_t)kPenRing * RS + (size_t)(kPenNB + 2) * T * (kPenChunk + 1)) + sizeof(int) * 2 * (size_t)T;
 }
 
-template <int W, int DIAG>
+template <int W, int DIAG, bool HOLES, bool PROF>
 __global__ void __launch_bounds__(kPenMaxThreads + 32) tri_pencil_kernel(const PencilArgs a)
 {
     extern __shared__ __align__(16) double smem_d[];
     __shared__ int s_ctl[4];                          // ticket, ghost_ready, steps_done, abort
-    constexpr int NV = W + DIAG, RD = kPenRing, C = kPenChunk, CP = kPenChunk + 1, P = kPenP;
+    constexpr int NV = W + DIAG, RD = kPenRing, C = kPenChunk, CP = kPenChunk + 1;
+    // Steps the value stream is fetched ahead into registers.  Deliberately shallow: a warp has 6 scoreboards, so with
+    // 8 steps x 3 loads in flight a wait for one step's values also waits for much younger loads (measured: long-
+    // scoreboard stalls on unrelated instructions, ~750 cycles per step).  The helper warp pulls the stream into L2
+    // kPenL2Ahead steps ahead instead, and the 2-deep register fetch then hits L2.
+    constexpr int P = kPenP;
     const int T = a.T, RS = a.RS, tid = threadIdx.x;
-    double *ring = smem_d;                            // [RD][RS]: lanes [0, T) own lines, [T, RS) ghost lines
+    double *ring = smem_d;                            // [RD][RS]: lanes [0, T) own lines, then ghost lines, last: +0.0
     double *rhsT = ring + (size_t)RD * RS;            // [kPenNB][T][C + 1]
     double *outT = rhsT + (size_t)kPenNB * T * CP;    // [2][T][C + 1]
-    int *s_row0 = reinterpret_cast<int *>(outT + (size_t)2 * T * CP);
-    int *s_kske = s_row0 + T;                         // kstart | kend << 16
+    int2 *s_line = reinterpret_cast<int2 *>(outT + (size_t)2 * T * CP);   // per line: row0, kstart | length << 16
     if (a.stop && *a.stop) return;
     if (tid == 0) s_ctl[3] = 0;
     const unsigned int total = (unsigned int)a.num_pencils + gridDim.x;
-    const double missing = __longlong_as_double((long long)kPenMissingBits);
     for (;;) {
         __syncthreads();
         if (tid == 0) {
@@ -515,135 +540,161 @@ __global__ void __launch_bounds__(kPenMaxThreads + 32) tri_pencil_kernel(const P
             s_ctl[1] = kPenG0;
             s_ctl[2] = 0;
         }
+        // Operands of rows that do not exist (line starts, domain boundary, virtual steps a ghost line does not have)
+        // are read from ring slots nobody writes: they must hold +0.0 so that the +0.0 stored for the missing entry
+        // gives the product +0.0 and r - (+0.0) == r bit for bit.
+        for (int q = tid; q < RD * RS; q += blockDim.x) ring[q] = 0.0;
         __syncthreads();
         const unsigned int tk = (unsigned int)s_ctl[0];
         if (tk >= (unsigned int)a.num_pencils || s_ctl[3]) break;
         const PencilHdr h = a.hdr[tk];
         if (tid < T) {
-            // ---- compute threads: one line each ----
+            // ---- compute threads: one line each.  Everything in the step loop is incremental (pointers and ring
+            // offsets advance by constants): the first version spent ~230 instructions per warp and step, mostly on
+            // 64-bit address arithmetic and masks, and was issue-bound at ~1000 cycles per step.
             const int4 *dp = reinterpret_cast<const int4 *>(a.thr + h.thr_off + tid);
             const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2), d3 = __ldg(dp + 3);
-            const int kstart = d0.x, kend = d0.y;
+            const int kstart = d0.x, klen = d0.y - d0.x;
             const int opw[8] = {d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
-            const int outw[4] = {d3.x, d3.y, d3.z, d3.w};
-            int olane[W], odk[W];
+            const unsigned int RS8 = (unsigned int)RS * 8u, ring_bytes = (unsigned int)RD * RS8;
+            char *ringb = reinterpret_cast<char *>(ring);
+            unsigned int rop[W];   // byte offset in the ring of slot w's operand for the current step
 #pragma unroll
-            for (int w = 0; w < W; w++) { olane[w] = opw[w] & 0xffff; odk[w] = opw[w] >> 16; }
-            bool feeds = false;
-#pragma unroll
-            for (int o = 0; o < kPenMaxOut; o++) feeds = feeds || (outw[o] != kPenNoOut);
-            s_row0[tid] = d0.z;
-            s_kske[tid] = kstart | (kend << 16);
-            const double *vp = a.vals + h.val_off + tid;
+            for (int w = 0; w < W; w++) {
+                const int lane = ((opw[w] & 0xffff) == kPenZeroLane) ? RS - 1 : (opw[w] & 0xffff);
+                rop[w] = (unsigned int)((0 - (opw[w] >> 16)) & (RD - 1)) * RS8 + (unsigned int)lane * 8u;
+            }
+            unsigned int rown = (unsigned int)tid * 8u;   // own slot of the current step
+            // mailboxes this line feeds (filled in order by the builder); pointers advance with the step
+            double *mp0 = a.mail + (long long)d3.x, *mp1 = a.mail + (long long)d3.y, *mp2 = a.mail + (long long)d3.z,
+                   *mp3 = a.mail + (long long)d3.w;
+            const int nout = (d3.x != kPenNoOut) + (d3.y != kPenNoOut) + (d3.z != kPenNoOut) + (d3.w != kPenNoOut);
+            s_line[tid] = make_int2(d0.z, kstart | (klen << 16));
             const long long dir = a.dir;
             const int nchunks = (h.nsteps + C - 1) / C;
             const int jj = tid & (C - 1), lbase = tid >> 4, lstep = T >> 4;   // this thread's column of the rhs / x tiles
             asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
             double v[P][NV];
-            auto fetch = [&](int j, int k) {
-                const bool act = k >= kstart && k < kend;
 #pragma unroll
-                for (int w = 0; w < NV; w++) {
-                    v[j][w] = missing;
-                    if (act) v[j][w] = pen_ld_stream(vp + ((size_t)k * NV + w) * T);
-                }
-                if (DIAG && !act) v[j][W] = 1.0;
-                // one lane per 128-byte line pulls the values of a later step into L2
-                if ((tid & 15) == 0 && k + kPenL2Ahead < h.nsteps) {
+            for (int j = 0; j < P; j++)
 #pragma unroll
-                    for (int w = 0; w < NV; w++)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + ((size_t)(k + kPenL2Ahead) * NV + w) * T));
+                for (int w = 0; w < NV; w++) v[j][w] = (w == W) ? 1.0 : 0.0;
+            const size_t vstride = (size_t)NV * T;                   // doubles per step in the value stream
+            const double *vq = a.vals + h.val_off + tid;             // values of the step fetched next ...
+            unsigned int kf = (unsigned int)(0 - kstart);            // ... which is step kf + kstart
+            auto fetch = [&](int j) {
+                if (kf < (unsigned int)klen && !(PROF && (a.dbg & 4))) {   // an inactive step keeps stale values: its result is discarded
+#pragma unroll
+                    for (int w = 0; w < NV; w++) v[j][w] = pen_ld_stream(vq + (size_t)w * T);
                 }
+                vq += vstride;
+                kf++;
             };
             // right-hand side of (chunk, step j): element (line lbase + j lstep, column jj) of the tile
             auto issue_rhs = [&](int chunk, int j, int buf) {
                 const int line = lbase + j * lstep, kk = chunk * C + jj;
-                const int ke2 = s_kske[line], r0 = s_row0[line];
-                const bool act = chunk < nchunks && kk >= (ke2 & 0xffff) && kk < (ke2 >> 16);
-                const double *src = act ? a.rhs + ((long long)r0 + dir * kk) : a.rhs;
+                const int2 ln = s_line[line];
+                const bool act = chunk < nchunks && (unsigned int)(kk - (ln.y & 0xffff)) < (unsigned int)(ln.y >> 16);
+                const double *src = act ? a.rhs + ((long long)ln.x + dir * kk) : a.rhs;
                 const unsigned int dst = (unsigned int)__cvta_generic_to_shared(rhsT + ((size_t)buf * T + line) * CP + jj);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(act ? 8 : 0) : "memory");
             };
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < C; j++) issue_rhs(0, j, 0);
             asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < C; j++) issue_rhs(1, j, 1);
             asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < P; j++) fetch(j, j);
+            for (int j = 0; j < P; j++) fetch(j);
             bool aborted = false;
             unsigned long long p_t0 = 0, p_c0 = 0, p_wait = 0, p_bar = 0;
-            const bool prof = a.prof != nullptr && tid == 0;
+            const bool prof = PROF && a.prof != nullptr && tid == 0;
             if (prof) { p_t0 = pen_globaltimer(); p_c0 = clock64(); }
-            if (h.nghost) {
-                while (pen_ld_flag(&s_ctl[1]) < 0)
+            if (h.nghost) {   // steps 0..3 read virtual steps <= 2: the batches up to [0, 4)
+                const int want = min(kPenBatch, h.nsteps);
+                while (pen_ld_flag(&s_ctl[1]) < want)
                     if (*(volatile int *)&s_ctl[3]) { aborted = true; break; }
             }
             asm volatile("cp.async.wait_group 1;" ::: "memory");
             asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
-            int buf = 0;
+            int buf = 0, k = 0;
             for (int c = 0; c < nchunks && !aborted; c++) {
                 const int buf2 = (buf + 2 >= kPenNB) ? buf + 2 - kPenNB : buf + 2;
                 const double *rt = rhsT + ((size_t)buf * T + tid) * CP;
                 double *ot = outT + ((size_t)(c & 1) * T + tid) * CP;
-                const double *otprev = outT + (size_t)((c & 1) ^ 1) * T * CP;
+                // staging of this chunk's steps: x of chunk c - 1 out of otprev, rhs of chunk c + 2 into buffer buf2
+                const double *otprev = outT + (size_t)((c & 1) ^ 1) * T * CP + jj;
+                const unsigned int nxt = (unsigned int)__cvta_generic_to_shared(rhsT + (size_t)buf2 * T * CP + jj);
+                const int kprev = (c - 1) * C + jj;          // step of the element written out (same column for all lines)
+                const bool have_next = c + 2 < nchunks;
+                int line = lbase;
 #pragma unroll 1
                 for (int jo = 0; jo < C; jo += P) {
 #pragma unroll
-                for (int ji = 0; ji < P; ji++) {
-                    const int j = jo + ji;
-                    const int k = c * C + j, kk = k & (RD - 1);
-                    double acc = rt[j];
+                    for (int ji = 0; ji < P; ji++) {
+                        double acc = rt[jo + ji];
 #pragma unroll
-                    for (int w = 0; w < W; w++) {
-                        double xv = ring[((kk - odk[w]) & (RD - 1)) * RS + olane[w]];
-                        double av = v[ji][w];
-                        const bool miss = ((unsigned long long)__double_as_longlong(av) == kPenMissingBits);
-                        av = miss ? 0.0 : av;
-                        xv = miss ? 0.0 : xv;
-                        acc = acc - av * xv;               // src/solver-tri.cxx:18 / :40
+                        for (int w = 0; w < W; w++) {
+                            const double xv = (PROF && (a.dbg & 16)) ? 1.0 : *reinterpret_cast<const double *>(ringb + rop[w]);
+                            rop[w] += RS8;
+                            if (rop[w] >= ring_bytes) rop[w] -= ring_bytes;
+                            const double av = v[ji][w];
+                            double pr = av * xv;
+                            if (HOLES && __double2hiint(av) == (int)(kPenMissingBits >> 32)) pr = 0.0;   // r - (+0.0) == r
+                            acc = acc - pr;                    // src/solver-tri.cxx:18 / :40
+                        }
+                        if (DIAG) acc = acc / v[ji][W];        // :22 / :44
+                        const bool act = (unsigned int)(k - kstart) < (unsigned int)klen;
+                        const double out = act ? acc : 0.0;
+                        *reinterpret_cast<double *>(ringb + rown) = out;
+                        rown += RS8;
+                        if (rown >= ring_bytes) rown -= ring_bytes;
+                        ot[jo + ji] = out;
+                        if (nout > 0 && act && !(PROF && (a.dbg & 8))) {
+                            pen_st_relaxed(mp0 + k, out);
+                            if (nout > 1) {
+                                pen_st_relaxed(mp1 + k, out);
+                                if (nout > 2) {
+                                    pen_st_relaxed(mp2 + k, out);
+                                    if (nout > 3) pen_st_relaxed(mp3 + k, out);
+                                }
+                            }
+                        }
+                        {   // element (line, jj) of the x tile of chunk c - 1 and of the rhs tile of chunk c + 2
+                            const int2 ln = s_line[line];
+                            const unsigned int tp = (unsigned int)(kprev - (ln.y & 0xffff)), len = (unsigned int)(ln.y >> 16);
+                            const long long idx = (long long)ln.x + dir * kprev;
+                            if (tp < len && !(PROF && (a.dbg & 1))) a.x[idx] = otprev[(size_t)line * CP];
+                            const bool actn = have_next && (tp + 3 * C) < len;
+                            const double *src = actn ? a.rhs + (idx + dir * (3 * C)) : a.rhs;
+                            if (!(PROF && (a.dbg & 2)))
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(nxt + (unsigned int)(line * CP * 8)), "l"(src), "r"(actn ? 8 : 0) : "memory");
+                            line += lstep;
+                        }
+                        fetch(ji);
+                        k++;
+                        if (((jo + ji) & (kPenBatch - 1)) == kPenBatch - 1) {
+                            // every kPenBatch steps: the ghost lanes of the next kPenBatch steps must have arrived
+                            // (the helper publishes whole batches), and the helper learns how far this pencil is
+                            unsigned long long p_a = 0, p_b = 0;
+                            if (prof) p_a = clock64();
+                            if (h.nghost) {
+                                const int want = min(k + kPenBatch, h.nsteps);
+                                while (pen_ld_flag(&s_ctl[1]) < want)
+                                    if (*(volatile int *)&s_ctl[3]) { aborted = true; break; }
+                            }
+                            if (prof) p_b = clock64();
+                            asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
+                            if (prof) { p_wait += p_b - p_a; p_bar += clock64() - p_b; }
+                            if (tid == 0) pen_st_flag(&s_ctl[2], k);
+                        }
+                        else asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
                     }
-                    if (DIAG) acc = acc / v[ji][W];   // :22 / :44
-                    const bool act = k >= kstart && k < kend;
-                    const double out = act ? acc : 0.0;
-                    ring[kk * RS + tid] = out;
-                    ot[j] = out;
-                    if (act && feeds) {
-#pragma unroll
-                        for (int o = 0; o < kPenMaxOut; o++)
-                            if (outw[o] != kPenNoOut) pen_st_relaxed(a.mail + ((long long)outw[o] + k), out);
-                    }
-                    {   // x of the previous chunk and rhs of the chunk after the next one: element (line, jj) each
-                        const int line = lbase + j * lstep;
-                        const int ke2 = s_kske[line], r0 = s_row0[line];
-                        const int kprev = (c - 1) * C + jj;
-                        if (c > 0 && kprev >= (ke2 & 0xffff) && kprev < (ke2 >> 16))
-                            a.x[(long long)r0 + dir * kprev] = otprev[(size_t)line * CP + jj];
-                        const int knext = (c + 2) * C + jj;
-                        const bool actn = c + 2 < nchunks && knext >= (ke2 & 0xffff) && knext < (ke2 >> 16);
-                        const double *src = actn ? a.rhs + ((long long)r0 + dir * knext) : a.rhs;
-                        const unsigned int dst = (unsigned int)__cvta_generic_to_shared(rhsT + ((size_t)buf2 * T + line) * CP + jj);
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(actn ? 8 : 0) : "memory");
-                    }
-                    fetch(ji, k + P);
-                    if (j == C - 1) {
-                        asm volatile("cp.async.commit_group;" ::: "memory");
-                        asm volatile("cp.async.wait_group 1;" ::: "memory");   // the next chunk's tile has landed
-                    }
-                    unsigned long long p_a = 0, p_b = 0;
-                    if (prof) p_a = clock64();
-                    if (h.nghost) {   // the ghost lanes the NEXT step reads (virtual steps <= k) must have arrived
-                        const int want = min(k + 1, h.nsteps);
-                        while (pen_ld_flag(&s_ctl[1]) < want)
-                            if (*(volatile int *)&s_ctl[3]) { aborted = true; break; }
-                    }
-                    if (prof) p_b = clock64();
-                    asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
-                    if (prof) { p_wait += p_b - p_a; p_bar += clock64() - p_b; }
-                    if (tid == 0) pen_st_flag(&s_ctl[2], k + 1);
                 }
-                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 1;" ::: "memory");   // the next chunk's tile has landed ...
+                asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");   // ... for every thread
                 buf = (buf + 1 >= kPenNB) ? 0 : buf + 1;
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -657,21 +708,26 @@ __global__ void __launch_bounds__(kPenMaxThreads + 32) tri_pencil_kernel(const P
             }
             if (!aborted) {   // results of the last chunk
                 const int c = nchunks - 1;
-                const double *otlast = outT + (size_t)(c & 1) * T * CP;
-#pragma unroll 4
+                const double *otlast = outT + (size_t)(c & 1) * T * CP + jj;
+                const int kl = c * C + jj;
+#pragma unroll 1
                 for (int j = 0; j < C; j++) {
                     const int line = lbase + j * lstep;
-                    const int ke2 = s_kske[line], r0 = s_row0[line];
-                    const int kl = c * C + jj;
-                    if (kl >= (ke2 & 0xffff) && kl < (ke2 >> 16)) a.x[(long long)r0 + dir * kl] = otlast[(size_t)line * CP + jj];
+                    const int2 ln = s_line[line];
+                    if ((unsigned int)(kl - (ln.y & 0xffff)) < (unsigned int)(ln.y >> 16))
+                        a.x[(long long)ln.x + dir * kl] = otlast[(size_t)line * CP];
                 }
             }
         }
-        else if (h.nghost) {
-            // ---- helper warp: mailboxes -> ghost lanes, kPenBatch virtual steps per round ----
+        else {
+            // ---- helper warp: value stream -> L2, mailboxes -> ghost lanes; kPenBatch (virtual) steps per round ----
             const int lane = tid - T;
             const PencilGhost *gh = a.ghost + h.ghost_off;
             bool aborted = false;
+            const char *vbase = reinterpret_cast<const char *>(a.vals + h.val_off);
+            const long long step_bytes = (long long)NV * T * 8, vend = step_bytes * h.nsteps;
+            for (long long b = (long long)lane * 128; b < step_bytes * kPenL2Ahead && b < vend; b += 32 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + b));
             for (int g = kPenG0; g < h.pad[0] && !aborted; g += kPenBatch) {
                 // a ghost slot is reused every RD virtual steps and read up to kPenMaxDk steps after it was written
                 {
@@ -680,6 +736,11 @@ __global__ void __launch_bounds__(kPenMaxThreads + 32) tri_pencil_kernel(const P
                         __nanosleep(20);
                         if (++spins > (1 << 24)) { aborted = true; break; }
                     }
+                }
+                if (g >= 0) {   // the values of steps [g + kPenL2Ahead, + kPenBatch) on their way to L2
+                    const long long b0 = step_bytes * (g + kPenL2Ahead), b1 = min(b0 + step_bytes * kPenBatch, vend);
+                    for (long long b = b0 + (long long)lane * 128; b < b1; b += 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + b));
                 }
                 for (int e = lane; e < h.nghost && !aborted; e += 32) {
                     const PencilGhost gd = gh[e];
@@ -701,11 +762,11 @@ __global__ void __launch_bounds__(kPenMaxThreads + 32) tri_pencil_kernel(const P
                     }
                     if (aborted) break;
 #pragma unroll
-                    for (int j = 0; j < kPenBatch; j++)
-                        if (need[j]) {
-                            ring[((g + j) & (RD - 1)) * RS + T + e] = val[j];
+                    for (int j = 0; j < kPenBatch; j++) {
+                        ring[((g + j) & (RD - 1)) * RS + T + e] = val[j];   // +0.0 where the ghost line has no row
+                        if (need[j])
                             pen_st_relaxed(a.mail + ((long long)gd.mail0 + g + j), __longlong_as_double((long long)kPenEmptyBits));
-                        }
+                    }
                 }
                 aborted = __any_sync(0xffffffffu, aborted);
                 if (aborted) {
@@ -720,10 +781,10 @@ __global__ void __launch_bounds__(kPenMaxThreads + 32) tri_pencil_kernel(const P
     }
 }
 
-template <int W, int DIAG>
+template <int W, int DIAG, bool HOLES, bool PROF>
 static int pencil_launch(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &a)
 {
-    auto kern = tri_pencil_kernel<W, DIAG>;
+    auto kern = tri_pencil_kernel<W, DIAG, HOLES, PROF>;
     const size_t smem = pencil_smem_bytes(a.T, a.RS);
     const int block = a.T + 32;
     static size_t attr_smem = 0;
@@ -746,6 +807,14 @@ static int pencil_launch(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &
     return 0;
 }
 
+template <int W>
+static int pencil_dispatch(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &a)
+{
+    if (a.prof && W == 3 && !Tr->p_holes)   // the profiling build exists for the 7-point ILU(0) shapes only
+        return Tr->p_diag ? pencil_launch<W, 1, false, (W == 3)>(ctx, Tr, a) : pencil_launch<W, 0, false, (W == 3)>(ctx, Tr, a);
+    if (Tr->p_holes) return Tr->p_diag ? pencil_launch<W, 1, true, false>(ctx, Tr, a) : pencil_launch<W, 0, true, false>(ctx, Tr, a);
+    return Tr->p_diag ? pencil_launch<W, 1, false, false>(ctx, Tr, a) : pencil_launch<W, 0, false, false>(ctx, Tr, a);
+}
 
 int tri_pencil_solve(lsspg_ctx *ctx, const lsspg_tri *Tr, double *dx, const double *drhs, bool guarded)
 {
@@ -766,13 +835,13 @@ int tri_pencil_solve(lsspg_ctx *ctx, const lsspg_tri *Tr, double *dx, const doub
     static int prof_on = -1;
     if (prof_on < 0) prof_on = getenv("LSSPG_TRI_PROF") ? 1 : 0;
     a.prof = nullptr;
+    a.dbg = getenv("LSSPG_TRI_PENCIL_DBG") ? atoi(getenv("LSSPG_TRI_PENCIL_DBG")) : 0;
     if (prof_on) {
         if (!Tm->p_prof) LSSPG_CUDA(cudaMalloc(&Tm->p_prof, 64 * (size_t)std::max(Tr->num_tiles, 1)));
         a.prof = Tm->p_prof;
     }
-#define PEN_CASE(w)                                                                   \
-    case w:                                                                           \
-        return Tr->p_diag ? pencil_launch<w, 1>(ctx, Tr, a) : pencil_launch<w, 0>(ctx, Tr, a);
+#define PEN_CASE(w) \
+    case w: return pencil_dispatch<w>(ctx, Tr, a);
     switch (Tr->p_W) {
         PEN_CASE(1) PEN_CASE(2) PEN_CASE(3) PEN_CASE(4) PEN_CASE(5) PEN_CASE(6) PEN_CASE(7) PEN_CASE(8)
     }
@@ -786,7 +855,8 @@ int tri_pencil_upload(lsspg_ctx *ctx, const PencilHost &H, lsspg_tri *T)
     T->pencil = true;
     T->num_tiles = H.num_pencils;
     T->p_T = H.T; T->p_W = H.W; T->p_diag = (H.nv > H.W) ? 1 : 0; T->p_dir = H.dir;
-    T->p_RS = H.T + ((std::max(H.max_ghost, 1) + 15) / 16) * 16;
+    T->p_RS = pencil_ring_stride(H.T, H.max_ghost);
+    T->p_holes = H.holes ? 1 : 0;
     T->p_mail_len = H.mail_len;
     T->p_seen_timeouts = ctx->tri_timeouts;
     T->p_pv = H.pv; T->p_pw = H.pw;
