@@ -56,10 +56,10 @@ struct lsspg_tri {
     unsigned int epoch = 0;
     // pencil schedule (tri_pencil.cu): lattice factors; num_tiles = pencils, tile_dims = pencil cross-section
     bool pencil = false;
-    void *p_hdr = nullptr, *p_thr = nullptr, *p_ghost = nullptr;
+    void *p_hdr = nullptr, *p_thr = nullptr, *p_ghost = nullptr, *p_outs = nullptr;
     double *p_vals = nullptr, *p_mail = nullptr;
     long long p_mail_len = 0;
-    int p_T = 0, p_RS = 0, p_W = 0, p_diag = 0, p_dir = 1, p_pv = 0, p_pw = 0, p_holes = 0;
+    int p_T = 0, p_RS = 0, p_W = 0, p_diag = 0, p_dir = 1, p_pv = 0, p_pw = 0, p_holes = 0, p_own_last = 0;
     int p_seen_timeouts = 0;
     unsigned long long *p_prof = nullptr;
 };
@@ -106,11 +106,17 @@ constexpr int kPenMaxGhost = 96;     // ghost lines per pencil
 constexpr int kPenMaxThreads = 256;  // lines per pencil
 constexpr int kPenZeroLane = 0xffff; // operand descriptor of a neighbour that does not exist: the ring lane holding +0.0
 // ring lanes per hyperplane: own lines, ghost lines, the +0.0 lane (last)
-inline int pencil_ring_stride(int T, int max_ghost) { return T + ((max_ghost + 1 + 15) / 16) * 16; }
-struct PencilHdr {      // one per pencil, ticket order (32 bytes)
+// (odd, so that a column of the ring -- one lane over consecutive steps -- spreads over the banks)
+inline int pencil_ring_stride(int T, int max_ghost) { return T + ((max_ghost + 1 + 15) / 16) * 16 + 1; }
+struct PencilHdr {      // one per pencil, ticket order (48 bytes)
     long long val_off;  // first value of the pencil in the value stream: vals[val_off + ((k * NV + w) * T + t)]
     int nsteps, nghost, thr_off, ghost_off;
-    int pad[2];         // pad[0]: last virtual step + 1 the ghost prefetcher handles
+    int kgend;          // last virtual step + 1 the ghost prefetcher handles
+    int nout, out_off;  // mailboxes the pencil feeds: PencilOut[out_off, out_off + nout)
+    int pad[3];
+};
+struct PencilOut {      // one per (pencil, fed mailbox): steps [kstart, kend) of ring lane `lane` go to mail[mail0 + k]
+    int lane, mail0, kstart, kend;
 };
 struct PencilThread {   // one per (pencil, thread) = per line (64 bytes)
     int kstart, kend;   // the line is active in steps [kstart, kend)
@@ -131,6 +137,8 @@ struct PencilHost {
     std::vector<PencilHdr> hdr;
     std::vector<PencilThread> thr;
     std::vector<PencilGhost> ghost;
+    std::vector<PencilOut> outs;
+    bool own_last = false;   // the last slot of every row is the row's predecessor on its own line (kept in a register)
     DVec vals;
 };
 // 0: built; 2: not a lattice factor (caller falls back); 1: error

@@ -44,6 +44,21 @@ constexpr unsigned long long kPenEmptyBits = 0xFFF8DEADBEEF0001ull;     // empty
 constexpr int kPenG0 = -8;        // first virtual step the ghost prefetcher handles (ghost dk <= 8)
 constexpr int kPenBatch = 4;      // virtual steps per prefetch round
 constexpr int kPenNoOut = INT_MIN;
+// shared-memory geometry of the kernel (see "the kernel" below)
+constexpr int kPenChunk = 8;       // steps per rhs / x tile
+constexpr int kPenNB = 3;          // rhs tiles
+constexpr int kPenVRing = 8;       // steps of values in shared memory (even)
+constexpr int kPenStagers = 128;   // threads
+constexpr int kPenValuers = 64;    // threads
+constexpr int kPenExtra = kPenStagers + kPenValuers + 32 + 32;   // + mailer + helper
+constexpr int kPenL2Ahead = 32;    // steps the value stream is prefetched into L2
+
+__host__ __device__ inline size_t pencil_smem_bytes(int T, int RS, int NV, int nb = kPenNB, int vr = kPenVRing)
+{
+    return sizeof(double) * ((size_t)kPenRing * RS + (size_t)nb * T * (kPenChunk + 1) + (size_t)vr * NV * T) +
+           sizeof(int) * 2 * (size_t)T;
+}
+
 
 static inline double bits_to_double(unsigned long long b)
 {
@@ -153,6 +168,11 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
         if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0 && (a * b) % 32 == 0 && a * b <= kPenMaxThreads) { pv = a; pw = b; }
     }
     if (g[2] == 1) pw = 1;
+    // the pencil must fit one SM: ring + rhs / x tiles + value ring (wide rows: fewer lines per pencil)
+    while (pv * pw > 32 && pencil_smem_bytes(pv * pw, pencil_ring_stride(pv * pw, kPenMaxGhost), W + (hasdiag ? 1 : 0)) > (size_t)220 * 1024) {
+        if (pw > 1 && pw >= pv / 2) pw /= 2;
+        else pv /= 2;
+    }
     const int T = pv * pw;
     if (T % 32 != 0 || T > kPenMaxThreads) return 2;
     const int NV = W + (hasdiag ? 1 : 0);
@@ -257,8 +277,8 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
             }
             if (mail_len > (long long)INT_MAX - (1 << 20)) return 2;
             h.nghost = (int)mine.size();
-            h.pad[0] = h.nsteps;   // kgend: the prefetcher empties every mailbox position, also those no row reads
-            for (int q = h.ghost_off; q < (int)H.ghost.size(); q++) h.pad[0] = std::max(h.pad[0], H.ghost[q].kg1);
+            h.kgend = h.nsteps;   // kgend: the prefetcher empties every mailbox position, also those no row reads
+            for (int q = h.ghost_off; q < (int)H.ghost.size(); q++) h.kgend = std::max(h.kgend, H.ghost[q].kg1);
             max_ghost = std::max(max_ghost, h.nghost);
             // pass 2: descriptors
             for (int l : lines_of[p]) {
@@ -299,6 +319,22 @@ int tri_pencil_build_host(int which, int n, const int *Tp, const int *Tj, const 
         if (o == kPenMaxOut) return 2;
         d.out[o] = (int)(s.mailbase - d.kstart);
     }
+    // mailboxes per pencil (what the mailer warp walks), and whether the last slot is always the own line's predecessor
+    H.outs.clear();
+    bool own_last = true;
+    for (int p = 0; p < npen; p++) {
+        PencilHdr &h = H.hdr[p];
+        h.out_off = (int)H.outs.size();
+        for (int t = 0; t < T; t++) {
+            const PencilThread &d = H.thr[(size_t)p * T + t];
+            for (int o = 0; o < kPenMaxOut; o++)
+                if (d.out[o] != kPenNoOut) H.outs.push_back({t, d.out[o], d.kstart, d.kend});
+            if (d.kend > d.kstart && d.op[W - 1] != ((1 << 16) | t)) own_last = false;
+        }
+        h.nout = (int)H.outs.size() - h.out_off;
+    }
+    if (getenv("LSSPG_TRI_PENCIL_OWNLAST") && atoi(getenv("LSSPG_TRI_PENCIL_OWNLAST")) == 0) own_last = false;
+    H.own_last = own_last;
     // the value stream
     H.vals.resize((size_t)val_total);
     {
@@ -369,7 +405,7 @@ int tri_pencil_walk_host(const PencilHost &H, double *x, const double *rhs, int 
         for (int k = 0; k < h.nsteps; k++) {
             // the prefetcher is at least up to virtual step k - 1 and at most kPenRing - kPenMaxDk - 1 ahead; replay the
             // furthest-ahead case, which is the one that can overwrite slots still in use
-            while (ghost_ready < ((k == h.nsteps - 1) ? h.pad[0] : std::min(k + RD - kPenMaxDk, h.pad[0]))) {
+            while (ghost_ready < ((k == h.nsteps - 1) ? h.kgend : std::min(k + RD - kPenMaxDk, h.kgend))) {
                 const int kg = ghost_ready;
                 for (int e = 0; e < h.nghost; e++) {
                     const size_t slot = (size_t)(kg & (RD - 1)) * RS + T + e;
@@ -443,10 +479,12 @@ struct PencilArgs {
     const PencilHdr *hdr;
     const PencilThread *thr;
     const PencilGhost *ghost;
+    const PencilOut *outs;
     const double *vals;
     double *mail;
     unsigned int *counter;
     int num_pencils, T, RS, dir;
+    int nb, vr;                 // rhs tiles and steps of values kept in shared memory
     double *x;
     const double *rhs;
     const int *stop;
@@ -495,246 +533,302 @@ __device__ __forceinline__ void pen_st_flag(int *p, int v)
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
-// W: off-diagonal slots per row; DIAG: rows carry a divisor (1 more value per row).
-//
-// Memory traffic of one step is 256 rows on 256 DIFFERENT grid lines (2 KB apart): a per-thread load of rhs or store of
-// x would touch 32 cache lines per warp request (~66 cycles of L1 replays each, B300_MICROARCH.md "L1tex wavefront
-// queue"; measured here: 0.95 ms per sweep).  rhs and x are therefore staged through shared memory in chunks of
-// kPenChunk = 16 steps, [line][16 + 1] tiles: while chunk c is computed, every thread issues per step ONE 8-byte
-// cp.async of chunk c + 2's right-hand side and ONE store of chunk c - 1's results, consecutive threads along x
-// (128-byte pieces of a line).  The value stream is already coalesced ([step][slot][thread]) and is fetched kPenP
-// steps ahead into registers, with an L2 prefetch further ahead.
-constexpr int kPenChunk = 16;   // steps per rhs / x tile
-constexpr int kPenNB = 3;       // rhs tiles in flight
-constexpr int kPenP = 2;        // steps the value stream is fetched ahead into registers
-constexpr int kPenL2Ahead = 32; // steps the value stream is prefetched into L2
+// ---- the kernel ------------------------------------------------------------------------------------------------------
+// One step of a pencil is 256 rows on 256 DIFFERENT grid lines (2 KB apart).  What was measured on the way here
+// (256^3, L sweep; profiles/r02_pencil_*.txt, scripts/ubench/step.cu):
+//   * per-thread rhs loads / x stores touch 32 cache lines per warp request (~66 cycles of L1 replays): 0.95 ms;
+//   * rhs / x staged through shared memory by the compute threads themselves: a dependent stream of ~100 instructions
+//     per warp and step, values fetched into registers aliasing on the warp's 6 scoreboards: 0.59 ms;
+//   * a step is bound by SHARED-MEMORY BANDWIDTH AND LATENCY: every 64-bit LDS / STS of the 8 compute warps costs ~16
+//     cycles (128 B/clk), an exposed poll of a progress word ~80, a mailbox store by two lanes of a warp ~40.
+// Hence WARP SPECIALISATION with as few shared-memory accesses as possible on the compute warps, which keep only
+//     LDS operands -> products -> subtractions (-> divide) -> STS -> bar.sync
+// while everything that moves data runs beside them, synchronised through progress words in shared memory (polled one
+// step ahead of their use, so that no poll latency is exposed):
+//   * stagers (4 warps): rhs tiles in ([line][8 + 1] doubles, cp.async, consecutive threads along x = 64-byte pieces of
+//     a line); x out, read straight from the ring of hyperplanes;
+//   * valuers (2 warps): the value stream [step][slot][thread] into a ring of kPenVRing steps, 16-byte cp.async;
+//   * mailer (1 warp): face values from the ring to the mailboxes of the pencils that read them;
+//   * helper (1 warp): mailboxes -> ghost lanes, and prefetch.global.L2 of the value stream kPenL2Ahead steps ahead.
+enum { CTL_TICKET = 0, CTL_GHOST = 1, CTL_STEPS = 2, CTL_ABORT = 3, CTL_RHS = 4, CTL_VALS = 5, CTL_MAILED = 6, CTL_XOUT = 7 };
 
-__host__ __device__ inline size_t pencil_smem_bytes(int T, int RS)
+// spin until *flag >= want (progress words only grow); a raised abort flag ends every wait so that all roles run to
+// the end of the pencil with matching barrier counts (the sweep is then wrong and FLAG_TRI_TIMEOUT says so)
+__device__ __forceinline__ void pen_wait(const int *flag, int want, const int *abort_flag)
 {
-    return sizeof(double) * ((size_t)kPenRing * RS + (size_t)(kPenNB + 2) * T * (kPenChunk + 1)) + sizeof(int) * 2 * (size_t)T;
+    while (pen_ld_flag(flag) < want)
+        if (pen_ld_flag(abort_flag)) break;
+}
+// the same for the data-moving roles: they sleep between polls so that their spinning neither takes issue slots from
+// the compute warps on the same scheduler nor fills the shared-memory pipe with polls
+__device__ __forceinline__ void pen_wait_sleep(const int *flag, int want, const int *abort_flag)
+{
+    while (pen_ld_flag(flag) < want) {
+        if (pen_ld_flag(abort_flag)) break;
+        __nanosleep(64);
+    }
 }
 
-template <int W, int DIAG, bool HOLES, bool PROF>
-__global__ void __launch_bounds__(kPenMaxThreads + 32) tri_pencil_kernel(const PencilArgs a)
+template <int W, int DIAG, bool HOLES, bool OWN, bool PROF>
+__global__ void __launch_bounds__(kPenMaxThreads + kPenExtra, 2) tri_pencil_kernel(const PencilArgs a)
 {
     extern __shared__ __align__(16) double smem_d[];
-    __shared__ int s_ctl[4];                          // ticket, ghost_ready, steps_done, abort
+    __shared__ int s_ctl[8];
     constexpr int NV = W + DIAG, RD = kPenRing, C = kPenChunk, CP = kPenChunk + 1;
-    // Steps the value stream is fetched ahead into registers.  Deliberately shallow: a warp has 6 scoreboards, so with
-    // 8 steps x 3 loads in flight a wait for one step's values also waits for much younger loads (measured: long-
-    // scoreboard stalls on unrelated instructions, ~750 cycles per step).  The helper warp pulls the stream into L2
-    // kPenL2Ahead steps ahead instead, and the 2-deep register fetch then hits L2.
-    constexpr int P = kPenP;
+    const int VR = a.vr, NB = a.nb;
+    constexpr int WR = OWN ? W - 1 : W;               // operands read from the ring
     const int T = a.T, RS = a.RS, tid = threadIdx.x;
-    double *ring = smem_d;                            // [RD][RS]: lanes [0, T) own lines, then ghost lines, last: +0.0
-    double *rhsT = ring + (size_t)RD * RS;            // [kPenNB][T][C + 1]
-    double *outT = rhsT + (size_t)kPenNB * T * CP;    // [2][T][C + 1]
-    int2 *s_line = reinterpret_cast<int2 *>(outT + (size_t)2 * T * CP);   // per line: row0, kstart | length << 16
+    double *vring = smem_d;                           // [VR][NV][T] (first: 16-byte aligned for cp.async)
+    double *rhsT = vring + (size_t)VR * NV * T;       // [kPenNB][T][C + 1]
+    double *ring = rhsT + (size_t)NB * T * CP;        // [RD][RS]: lanes [0, T) own lines, then ghost lines, last: +0.0
+    int2 *s_line = reinterpret_cast<int2 *>(ring + (size_t)RD * RS);   // per line: row0, kstart | length << 16
     if (a.stop && *a.stop) return;
-    if (tid == 0) s_ctl[3] = 0;
+    if (tid == 0) s_ctl[CTL_ABORT] = 0;
     const unsigned int total = (unsigned int)a.num_pencils + gridDim.x;
+    const long long dir = a.dir;
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            s_ctl[0] = (int)atomicInc(a.counter, total - 1);
-            s_ctl[1] = kPenG0;
-            s_ctl[2] = 0;
+            s_ctl[CTL_TICKET] = (int)atomicInc(a.counter, total - 1);
+            s_ctl[CTL_GHOST] = kPenG0;
+            s_ctl[CTL_STEPS] = 0;
+            s_ctl[CTL_RHS] = 0;
+            s_ctl[CTL_VALS] = 0;
+            s_ctl[CTL_MAILED] = 0;
+            s_ctl[CTL_XOUT] = 0;
         }
         // Operands of rows that do not exist (line starts, domain boundary, virtual steps a ghost line does not have)
         // are read from ring slots nobody writes: they must hold +0.0 so that the +0.0 stored for the missing entry
         // gives the product +0.0 and r - (+0.0) == r bit for bit.
         for (int q = tid; q < RD * RS; q += blockDim.x) ring[q] = 0.0;
         __syncthreads();
-        const unsigned int tk = (unsigned int)s_ctl[0];
-        if (tk >= (unsigned int)a.num_pencils || s_ctl[3]) break;
+        const unsigned int tk = (unsigned int)s_ctl[CTL_TICKET];
+        if (tk >= (unsigned int)a.num_pencils || s_ctl[CTL_ABORT]) break;
         const PencilHdr h = a.hdr[tk];
+        const int nchunks = (h.nsteps + C - 1) / C;
+        int4 d0 = make_int4(0, 0, 0, 0), d1 = d0, d2 = d0;
         if (tid < T) {
-            // ---- compute threads: one line each.  Everything in the step loop is incremental (pointers and ring
-            // offsets advance by constants): the first version spent ~230 instructions per warp and step, mostly on
-            // 64-bit address arithmetic and masks, and was issue-bound at ~1000 cycles per step.
             const int4 *dp = reinterpret_cast<const int4 *>(a.thr + h.thr_off + tid);
-            const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2), d3 = __ldg(dp + 3);
+            d0 = __ldg(dp); d1 = __ldg(dp + 1); d2 = __ldg(dp + 2);
+            s_line[tid] = make_int2(d0.z, d0.x | ((d0.y - d0.x) << 16));
+        }
+        __syncthreads();   // the line table is there for the stagers
+        if (tid < T) {
+            // ---- compute threads: one line each ----
             const int kstart = d0.x, klen = d0.y - d0.x;
             const int opw[8] = {d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
             const unsigned int RS8 = (unsigned int)RS * 8u, ring_bytes = (unsigned int)RD * RS8;
             char *ringb = reinterpret_cast<char *>(ring);
-            unsigned int rop[W];   // byte offset in the ring of slot w's operand for the current step
+            unsigned int rop[WR > 0 ? WR : 1];   // byte offset in the ring of slot w's operand for the current step
 #pragma unroll
-            for (int w = 0; w < W; w++) {
+            for (int w = 0; w < WR; w++) {
                 const int lane = ((opw[w] & 0xffff) == kPenZeroLane) ? RS - 1 : (opw[w] & 0xffff);
                 rop[w] = (unsigned int)((0 - (opw[w] >> 16)) & (RD - 1)) * RS8 + (unsigned int)lane * 8u;
             }
             unsigned int rown = (unsigned int)tid * 8u;   // own slot of the current step
-            // mailboxes this line feeds (filled in order by the builder); pointers advance with the step
-            double *mp0 = a.mail + (long long)d3.x, *mp1 = a.mail + (long long)d3.y, *mp2 = a.mail + (long long)d3.z,
-                   *mp3 = a.mail + (long long)d3.w;
-            const int nout = (d3.x != kPenNoOut) + (d3.y != kPenNoOut) + (d3.z != kPenNoOut) + (d3.w != kPenNoOut);
-            s_line[tid] = make_int2(d0.z, kstart | (klen << 16));
-            const long long dir = a.dir;
-            const int nchunks = (h.nsteps + C - 1) / C;
-            const int jj = tid & (C - 1), lbase = tid >> 4, lstep = T >> 4;   // this thread's column of the rhs / x tiles
-            asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
-            double v[P][NV];
-#pragma unroll
-            for (int j = 0; j < P; j++)
-#pragma unroll
-                for (int w = 0; w < NV; w++) v[j][w] = (w == W) ? 1.0 : 0.0;
-            const size_t vstride = (size_t)NV * T;                   // doubles per step in the value stream
-            const double *vq = a.vals + h.val_off + tid;             // values of the step fetched next ...
-            unsigned int kf = (unsigned int)(0 - kstart);            // ... which is step kf + kstart
-            auto fetch = [&](int j) {
-                if (kf < (unsigned int)klen && !(PROF && (a.dbg & 4))) {   // an inactive step keeps stale values: its result is discarded
-#pragma unroll
-                    for (int w = 0; w < NV; w++) v[j][w] = pen_ld_stream(vq + (size_t)w * T);
-                }
-                vq += vstride;
-                kf++;
-            };
-            // right-hand side of (chunk, step j): element (line lbase + j lstep, column jj) of the tile
-            auto issue_rhs = [&](int chunk, int j, int buf) {
-                const int line = lbase + j * lstep, kk = chunk * C + jj;
-                const int2 ln = s_line[line];
-                const bool act = chunk < nchunks && (unsigned int)(kk - (ln.y & 0xffff)) < (unsigned int)(ln.y >> 16);
-                const double *src = act ? a.rhs + ((long long)ln.x + dir * kk) : a.rhs;
-                const unsigned int dst = (unsigned int)__cvta_generic_to_shared(rhsT + ((size_t)buf * T + line) * CP + jj);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(act ? 8 : 0) : "memory");
-            };
-#pragma unroll 1
-            for (int j = 0; j < C; j++) issue_rhs(0, j, 0);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll 1
-            for (int j = 0; j < C; j++) issue_rhs(1, j, 1);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < P; j++) fetch(j);
-            bool aborted = false;
-            unsigned long long p_t0 = 0, p_c0 = 0, p_wait = 0, p_bar = 0;
+            const unsigned int vstep = (unsigned int)NV * T * 8u, vring_bytes = (unsigned int)VR * vstep;
+            const char *vb = reinterpret_cast<const char *>(vring + tid);
+            unsigned int voff = 0;                          // byte offset of the current step in the value ring
+            unsigned long long p_t0 = 0, p_c0 = 0, p_wait = 0, p_bar = 0, p_wv = 0, p_wr = 0;
             const bool prof = PROF && a.prof != nullptr && tid == 0;
             if (prof) { p_t0 = pen_globaltimer(); p_c0 = clock64(); }
-            if (h.nghost) {   // steps 0..3 read virtual steps <= 2: the batches up to [0, 4)
-                const int want = min(kPenBatch, h.nsteps);
-                while (pen_ld_flag(&s_ctl[1]) < want)
-                    if (*(volatile int *)&s_ctl[3]) { aborted = true; break; }
-            }
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
-            int buf = 0, k = 0;
-            for (int c = 0; c < nchunks && !aborted; c++) {
-                const int buf2 = (buf + 2 >= kPenNB) ? buf + 2 - kPenNB : buf + 2;
-                const double *rt = rhsT + ((size_t)buf * T + tid) * CP;
-                double *ot = outT + ((size_t)(c & 1) * T + tid) * CP;
-                // staging of this chunk's steps: x of chunk c - 1 out of otprev, rhs of chunk c + 2 into buffer buf2
-                const double *otprev = outT + (size_t)((c & 1) ^ 1) * T * CP + jj;
-                const unsigned int nxt = (unsigned int)__cvta_generic_to_shared(rhsT + (size_t)buf2 * T * CP + jj);
-                const int kprev = (c - 1) * C + jj;          // step of the element written out (same column for all lines)
-                const bool have_next = c + 2 < nchunks;
-                int line = lbase;
-#pragma unroll 1
-                for (int jo = 0; jo < C; jo += P) {
-#pragma unroll
-                    for (int ji = 0; ji < P; ji++) {
-                        double acc = rt[jo + ji];
-#pragma unroll
-                        for (int w = 0; w < W; w++) {
-                            const double xv = (PROF && (a.dbg & 16)) ? 1.0 : *reinterpret_cast<const double *>(ringb + rop[w]);
-                            rop[w] += RS8;
-                            if (rop[w] >= ring_bytes) rop[w] -= ring_bytes;
-                            const double av = v[ji][w];
-                            double pr = av * xv;
-                            if (HOLES && __double2hiint(av) == (int)(kPenMissingBits >> 32)) pr = 0.0;   // r - (+0.0) == r
-                            acc = acc - pr;                    // src/solver-tri.cxx:18 / :40
-                        }
-                        if (DIAG) acc = acc / v[ji][W];        // :22 / :44
-                        const bool act = (unsigned int)(k - kstart) < (unsigned int)klen;
-                        const double out = act ? acc : 0.0;
-                        *reinterpret_cast<double *>(ringb + rown) = out;
-                        rown += RS8;
-                        if (rown >= ring_bytes) rown -= ring_bytes;
-                        ot[jo + ji] = out;
-                        if (nout > 0 && act && !(PROF && (a.dbg & 8))) {
-                            pen_st_relaxed(mp0 + k, out);
-                            if (nout > 1) {
-                                pen_st_relaxed(mp1 + k, out);
-                                if (nout > 2) {
-                                    pen_st_relaxed(mp2 + k, out);
-                                    if (nout > 3) pen_st_relaxed(mp3 + k, out);
-                                }
-                            }
-                        }
-                        {   // element (line, jj) of the x tile of chunk c - 1 and of the rhs tile of chunk c + 2
-                            const int2 ln = s_line[line];
-                            const unsigned int tp = (unsigned int)(kprev - (ln.y & 0xffff)), len = (unsigned int)(ln.y >> 16);
-                            const long long idx = (long long)ln.x + dir * kprev;
-                            if (tp < len && !(PROF && (a.dbg & 1))) a.x[idx] = otprev[(size_t)line * CP];
-                            const bool actn = have_next && (tp + 3 * C) < len;
-                            const double *src = actn ? a.rhs + (idx + dir * (3 * C)) : a.rhs;
-                            if (!(PROF && (a.dbg & 2)))
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(nxt + (unsigned int)(line * CP * 8)), "l"(src), "r"(actn ? 8 : 0) : "memory");
-                            line += lstep;
-                        }
-                        fetch(ji);
-                        k++;
-                        if (((jo + ji) & (kPenBatch - 1)) == kPenBatch - 1) {
-                            // every kPenBatch steps: the ghost lanes of the next kPenBatch steps must have arrived
-                            // (the helper publishes whole batches), and the helper learns how far this pencil is
-                            unsigned long long p_a = 0, p_b = 0;
-                            if (prof) p_a = clock64();
-                            if (h.nghost) {
-                                const int want = min(k + kPenBatch, h.nsteps);
-                                while (pen_ld_flag(&s_ctl[1]) < want)
-                                    if (*(volatile int *)&s_ctl[3]) { aborted = true; break; }
-                            }
-                            if (prof) p_b = clock64();
-                            asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
-                            if (prof) { p_wait += p_b - p_a; p_bar += clock64() - p_b; }
-                            if (tid == 0) pen_st_flag(&s_ctl[2], k);
-                        }
-                        else asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
-                    }
+            // Progress words are read one poll period BEFORE they are needed (they only grow, so a stale value that
+            // already suffices is good); only a value that does not suffice is polled again, in a loop.
+            int f_vals = 0, f_ghost = kPenG0, f_rhs = 0, f_mail = 0, f_xout = 0;
+            double prev = 0.0;                              // OWN: the row's predecessor on its own line
+            int k = 0, buf = 0;
+            for (int c = 0; c < nchunks; c++) {
+                {   // chunk c needs its rhs tile; its ring rows are those of chunk c - 2: mailed and written out
+                    unsigned long long t = 0;
+                    if (prof) t = clock64();
+                    if (f_rhs < c + 1) pen_wait(&s_ctl[CTL_RHS], c + 1, &s_ctl[CTL_ABORT]);
+                    if (f_xout < c - 1) pen_wait(&s_ctl[CTL_XOUT], c - 1, &s_ctl[CTL_ABORT]);
+                    if (h.nout && f_mail < (c - 1) * C) pen_wait(&s_ctl[CTL_MAILED], (c - 1) * C, &s_ctl[CTL_ABORT]);
+                    if (prof) p_wr += clock64() - t;
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 1;" ::: "memory");   // the next chunk's tile has landed ...
-                asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");   // ... for every thread
-                buf = (buf + 1 >= kPenNB) ? 0 : buf + 1;
+                const double *rt = rhsT + ((size_t)buf * T + tid) * CP;
+#pragma unroll
+                for (int j = 0; j < C; j++) {
+                    if ((j & 1) == 0) {   // values of steps k, k + 1
+                        const int want = min(k + 2, h.nsteps);
+                        if (f_vals < want) {
+                            unsigned long long t = 0;
+                            if (prof) t = clock64();
+                            pen_wait(&s_ctl[CTL_VALS], want, &s_ctl[CTL_ABORT]);
+                            if (prof) p_wv += clock64() - t;
+                        }
+                        f_vals = pen_ld_flag(&s_ctl[CTL_VALS]);   // consumed two steps from now
+                    }
+                    if ((j & (kPenBatch - 1)) == 0 && h.nghost) {   // ghost lanes of steps k .. k + 3: virtual steps < k + 4
+                        const int want = min(k + kPenBatch, h.nsteps);
+                        if (f_ghost < want) {
+                            unsigned long long t = 0;
+                            if (prof) t = clock64();
+                            pen_wait(&s_ctl[CTL_GHOST], want, &s_ctl[CTL_ABORT]);
+                            if (prof) p_wait += clock64() - t;
+                        }
+                        f_ghost = pen_ld_flag(&s_ctl[CTL_GHOST]);
+                    }
+                    if (j == C - 2) { f_rhs = pen_ld_flag(&s_ctl[CTL_RHS]); f_mail = pen_ld_flag(&s_ctl[CTL_MAILED]); f_xout = pen_ld_flag(&s_ctl[CTL_XOUT]); }
+                    double acc = rt[j];
+                    double av[NV];
+#pragma unroll
+                    for (int w = 0; w < NV; w++) av[w] = *reinterpret_cast<const double *>(vb + voff + (unsigned int)w * (unsigned int)T * 8u);
+                    voff += vstep;
+                    if (voff >= vring_bytes) voff = 0;
+#pragma unroll
+                    for (int w = 0; w < W; w++) {
+                        double xv;
+                        if (OWN && w == W - 1) xv = prev;
+                        else {
+                            xv = *reinterpret_cast<const double *>(ringb + rop[w < WR ? w : 0]);
+                            rop[w < WR ? w : 0] += RS8;
+                            if (rop[w < WR ? w : 0] >= ring_bytes) rop[w < WR ? w : 0] -= ring_bytes;
+                        }
+                        double pr = av[w] * xv;
+                        if (HOLES && __double2hiint(av[w]) == (int)(kPenMissingBits >> 32)) pr = 0.0;   // r - (+0.0) == r
+                        acc = acc - pr;                    // src/solver-tri.cxx:18 / :40
+                    }
+                    if (DIAG) acc = acc / av[NV - 1];      // :22 / :44
+                    const bool act = (unsigned int)(k - kstart) < (unsigned int)klen;
+                    const double out = act ? acc : 0.0;
+                    prev = out;
+                    *reinterpret_cast<double *>(ringb + rown) = out;
+                    rown += RS8;
+                    if (rown >= ring_bytes) rown -= ring_bytes;
+                    k++;
+                    {   // (one bar.sync for the whole warp: the aligned barrier must not be executed divergently)
+                        unsigned long long t = 0;
+                        if (PROF && prof) t = clock64();
+                        asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
+                        if (PROF && prof) p_bar += clock64() - t;
+                    }
+                    if (tid == 0) pen_st_flag(&s_ctl[CTL_STEPS], k);
+                }
+                buf = (buf + 1 >= NB) ? 0 : buf + 1;
             }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
             if (prof) {
                 unsigned long long *q = a.prof + 8 * (size_t)tk;
                 q[0] = p_t0; q[1] = pen_globaltimer(); q[2] = clock64() - p_c0; q[3] = p_wait; q[4] = p_bar; q[5] = (unsigned long long)h.nsteps;
-                q[6] = blockIdx.x;
-                unsigned int smid;
-                asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-                q[7] = smid;
+                q[6] = p_wv; q[7] = p_wr;
             }
-            if (!aborted) {   // results of the last chunk
-                const int c = nchunks - 1;
-                const double *otlast = outT + (size_t)(c & 1) * T * CP + jj;
-                const int kl = c * C + jj;
-#pragma unroll 1
-                for (int j = 0; j < C; j++) {
-                    const int line = lbase + j * lstep;
+        }
+        else if (tid < T + kPenStagers) {
+            // ---- stagers: rhs tiles in (cp.async), x out of the ring.  Element e of a chunk: line e / 8, column e % 8 ----
+            const int sid = tid - T, per = T * C / kPenStagers;
+            auto rhs_in = [&](int chunk, int buf) {
+                const unsigned int tile = (unsigned int)__cvta_generic_to_shared(rhsT + (size_t)buf * T * CP);
+#pragma unroll 4
+                for (int i = 0; i < per; i++) {
+                    const int e = i * kPenStagers + sid, line = e >> 3, col = e & 7, kk = chunk * C + col;
                     const int2 ln = s_line[line];
-                    if ((unsigned int)(kl - (ln.y & 0xffff)) < (unsigned int)(ln.y >> 16))
-                        a.x[(long long)ln.x + dir * kl] = otlast[(size_t)line * CP];
+                    const bool act = (unsigned int)(kk - (ln.y & 0xffff)) < (unsigned int)(ln.y >> 16);
+                    const double *src = act ? a.rhs + ((long long)ln.x + dir * kk) : a.rhs;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(tile + (unsigned int)((line * CP + col) * 8)), "l"(src), "r"(act ? 8 : 0) : "memory");
                 }
+            };
+            for (int c0 = 0; c0 < NB && c0 < nchunks; c0++) rhs_in(c0, c0);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(kPenStagers) : "memory");
+            if (sid == 0) pen_st_flag(&s_ctl[CTL_RHS], NB);
+            for (int i = 1; i <= nchunks; i++) {
+                // Chunk i - 1 has been computed.  (1) The tiles requested so far (up to chunk i + NB - 2) have landed: publish.
+                // (2) The tile chunk i - 1 used is free: request chunk i + NB - 1 into it.  (3) x of chunk i - 1 goes out of
+                // the ring (rows (i - 1) C .. + 7, which chunk i + 1 will reuse: the compute threads wait for CTL_XOUT >= i).
+                pen_wait_sleep(&s_ctl[CTL_STEPS], i * C, &s_ctl[CTL_ABORT]);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(kPenStagers) : "memory");
+                if (sid == 0) pen_st_flag(&s_ctl[CTL_RHS], i + NB - 1);
+                if (i + NB - 1 < nchunks) rhs_in(i + NB - 1, (i - 1) % NB);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                for (int q0 = 0; q0 < per; q0 += 8) {   // 8 elements in flight per thread
+                    int2 ln[8];
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) ln[u] = s_line[min((q0 + u) * kPenStagers + sid, T * C - 1) >> 3];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int e = min((q0 + u) * kPenStagers + sid, T * C - 1), kk = (i - 1) * C + (e & 7);
+                        v[u] = ring[(kk & (RD - 1)) * RS + (e >> 3)];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int e = (q0 + u) * kPenStagers + sid, kk = (i - 1) * C + (e & 7);
+                        if (q0 + u < per && (unsigned int)(kk - (ln[u].y & 0xffff)) < (unsigned int)(ln[u].y >> 16))
+                            a.x[(long long)ln[u].x + dir * kk] = v[u];
+                    }
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(kPenStagers) : "memory");
+                if (sid == 0) pen_st_flag(&s_ctl[CTL_XOUT], i);
+            }
+        }
+        else if (tid < T + kPenStagers + kPenValuers) {
+            // ---- valuers: the value stream into the ring, two steps (one contiguous piece) per round ----
+            const int vid = tid - T - kPenStagers;
+            const int npairs = (h.nsteps + 1) / 2;
+            const int pieces = NV * T;                       // 16-byte pieces per pair
+            const char *src0 = reinterpret_cast<const char *>(a.vals + h.val_off);
+            const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(vring);
+            const unsigned int pair_bytes = 2u * NV * T * 8u;
+            // pair q is published `lag` rounds after it was requested; lag < VR / 2, or the request of pair q + lag (which
+            // waits for the slot of pair q + lag - VR / 2 to be consumed) would stand before the publication it waits for
+            const int lag = (VR >= 8) ? 2 : 1;
+            for (int q = 0; q < npairs + lag; q++) {
+                if (q < npairs) {
+                    pen_wait_sleep(&s_ctl[CTL_STEPS], 2 * q - (VR - 2), &s_ctl[CTL_ABORT]);   // the ring slot of pair q is free
+                    const char *src = src0 + (size_t)q * pair_bytes;
+                    const unsigned int dst = ring_s + (unsigned int)(q % (VR / 2)) * pair_bytes;
+                    for (int i = vid; i < pieces; i += kPenValuers) {
+                        const unsigned int o = (unsigned int)i * 16u;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (lag == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");   // pair q - lag has landed (this thread's pieces)
+                else asm volatile("cp.async.wait_group 1;" ::: "memory");
+                asm volatile("bar.sync 3, %0;" ::"n"(kPenValuers) : "memory");      // ... and everybody's
+                if (vid == 0 && q >= lag) pen_st_flag(&s_ctl[CTL_VALS], 2 * (q - lag) + 2);
+            }
+        }
+        else if (tid < T + kPenStagers + kPenValuers + 32) {
+            // ---- mailer: the face values of every finished step go to the mailboxes of the pencils that read them ----
+            const int lane = tid - T - kPenStagers - kPenValuers;
+            const PencilOut *po = a.outs + h.out_off;
+            int done = 0;
+            while (done < h.nsteps && h.nout) {
+                int sd;
+                while ((sd = pen_ld_flag(&s_ctl[CTL_STEPS])) <= done) {
+                    if (pen_ld_flag(&s_ctl[CTL_ABORT])) { sd = h.nsteps; break; }
+                    __nanosleep(32);
+                }
+                sd = min(sd, h.nsteps);
+                for (int e = lane; e < h.nout; e += 32) {
+                    const PencilOut o = po[e];
+                    for (int kk = max(done, o.kstart); kk < min(sd, o.kend); kk++)
+                        pen_st_relaxed(a.mail + ((long long)o.mail0 + kk), ring[(kk & (RD - 1)) * RS + o.lane]);
+                }
+                done = sd;
+                __syncwarp();
+                if (lane == 0) pen_st_flag(&s_ctl[CTL_MAILED], done);
             }
         }
         else {
             // ---- helper warp: value stream -> L2, mailboxes -> ghost lanes; kPenBatch (virtual) steps per round ----
-            const int lane = tid - T;
+            const int lane = tid - T - kPenStagers - kPenValuers - 32;
             const PencilGhost *gh = a.ghost + h.ghost_off;
             bool aborted = false;
             const char *vbase = reinterpret_cast<const char *>(a.vals + h.val_off);
             const long long step_bytes = (long long)NV * T * 8, vend = step_bytes * h.nsteps;
             for (long long b = (long long)lane * 128; b < step_bytes * kPenL2Ahead && b < vend; b += 32 * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + b));
-            for (int g = kPenG0; g < h.pad[0] && !aborted; g += kPenBatch) {
+            for (int g = kPenG0; g < h.kgend; g += kPenBatch) {
                 // a ghost slot is reused every RD virtual steps and read up to kPenMaxDk steps after it was written
                 {
-                    int spins = 0, sd;
-                    while ((sd = pen_ld_flag(&s_ctl[2])) < h.nsteps && sd + (RD - kPenMaxDk) < g + kPenBatch) {
-                        __nanosleep(20);
-                        if (++spins > (1 << 24)) { aborted = true; break; }
+                    int sd;
+                    while ((sd = pen_ld_flag(&s_ctl[CTL_STEPS])) < h.nsteps && sd + (RD - kPenMaxDk) < g + kPenBatch) {
+                        if (pen_ld_flag(&s_ctl[CTL_ABORT])) break;
+                        __nanosleep(64);
                     }
                 }
                 if (g >= 0) {   // the values of steps [g + kPenL2Ahead, + kPenBatch) on their way to L2
@@ -742,51 +836,58 @@ __global__ void __launch_bounds__(kPenMaxThreads + 32) tri_pencil_kernel(const P
                     for (long long b = b0 + (long long)lane * 128; b < b1; b += 32 * 128)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + b));
                 }
-                for (int e = lane; e < h.nghost && !aborted; e += 32) {
+                for (int e = lane; e < h.nghost; e += 32) {
                     const PencilGhost gd = gh[e];
                     double val[kPenBatch];
                     bool need[kPenBatch];
 #pragma unroll
                     for (int j = 0; j < kPenBatch; j++) {
-                        need[j] = (g + j >= gd.kg0) && (g + j < gd.kg1);
+                        need[j] = (g + j >= gd.kg0) && (g + j < gd.kg1) && !aborted;
                         val[j] = need[j] ? pen_ld_relaxed(a.mail + ((long long)gd.mail0 + g + j)) : 0.0;
                     }
 #pragma unroll
                     for (int j = 0; j < kPenBatch; j++) {
                         int spins = 0;
-                        while (need[j] && (unsigned long long)__double_as_longlong(val[j]) == kPenEmptyBits) {
+                        while (need[j] && !aborted && (unsigned long long)__double_as_longlong(val[j]) == kPenEmptyBits) {
                             if (++spins > 8) __nanosleep(spins > 64 ? 200 : 40);
-                            if (spins > (1 << 21)) { aborted = true; break; }
+                            if (spins > (1 << 21) || pen_ld_flag(&s_ctl[CTL_ABORT])) { aborted = true; break; }
                             val[j] = pen_ld_relaxed(a.mail + ((long long)gd.mail0 + g + j));
                         }
                     }
-                    if (aborted) break;
 #pragma unroll
                     for (int j = 0; j < kPenBatch; j++) {
                         ring[((g + j) & (RD - 1)) * RS + T + e] = val[j];   // +0.0 where the ghost line has no row
-                        if (need[j])
+                        if (need[j] && !aborted)
                             pen_st_relaxed(a.mail + ((long long)gd.mail0 + g + j), __longlong_as_double((long long)kPenEmptyBits));
                     }
                 }
-                aborted = __any_sync(0xffffffffu, aborted);
-                if (aborted) {
-                    if (lane == 0) { *a.err = 1; *(volatile int *)&s_ctl[3] = 1; }
-                    break;
+                if (__any_sync(0xffffffffu, aborted) && !pen_ld_flag(&s_ctl[CTL_ABORT])) {
+                    aborted = true;
+                    if (lane == 0) { *a.err = 1; pen_st_flag(&s_ctl[CTL_ABORT], 1); }
                 }
                 __syncwarp();
                 __threadfence_block();
-                if (lane == 0) pen_st_flag(&s_ctl[1], g + kPenBatch);
+                if (lane == 0) pen_st_flag(&s_ctl[CTL_GHOST], g + kPenBatch);
             }
         }
     }
 }
 
-template <int W, int DIAG, bool HOLES, bool PROF>
-static int pencil_launch(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &a)
+template <int W, int DIAG, bool HOLES, bool OWN, bool PROF>
+static int pencil_launch(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &a_in)
 {
-    auto kern = tri_pencil_kernel<W, DIAG, HOLES, PROF>;
-    const size_t smem = pencil_smem_bytes(a.T, a.RS);
-    const int block = a.T + 32;
+    auto kern = tri_pencil_kernel<W, DIAG, HOLES, OWN, PROF>;
+    PencilArgs a = a_in;
+    // LSSPG_TRI_PENCIL_LEAN=1: two pencils per SM with shallower buffers (2 rhs tiles, 4 steps of values), so that pencils
+    // waiting for their predecessors share an SM with pencils that work.  Measured at 256^3 (all 256 pencils resident):
+    // SLOWER, 0.69 / 0.84 ms instead of 0.49 / 0.55 -- the shallow value ring stalls every step; off by default.
+    static int env_lean = -1;
+    if (env_lean < 0) env_lean = getenv("LSSPG_TRI_PENCIL_LEAN") ? atoi(getenv("LSSPG_TRI_PENCIL_LEAN")) : 0;
+    a.nb = kPenNB; a.vr = kPenVRing;
+    if (env_lean && pencil_smem_bytes(a.T, a.RS, W + DIAG, 2, 4) <= (size_t)112 * 1024 &&
+        pencil_smem_bytes(a.T, a.RS, W + DIAG) > (size_t)112 * 1024 && Tr->num_tiles > ctx->num_sms) { a.nb = 2; a.vr = 4; }
+    const size_t smem = pencil_smem_bytes(a.T, a.RS, W + DIAG, a.nb, a.vr);
+    const int block = a.T + kPenExtra;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         LSSPG_CHECK(smem <= (size_t)226 * 1024, "tri_pencil: %zu bytes of shared memory per pencil exceed one SM", smem);
@@ -807,13 +908,19 @@ static int pencil_launch(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &
     return 0;
 }
 
+template <int W, int DIAG>
+static int pencil_dispatch2(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &a)
+{
+    if (Tr->p_holes) return pencil_launch<W, DIAG, true, false, false>(ctx, Tr, a);
+    if (!Tr->p_own_last) return pencil_launch<W, DIAG, false, false, false>(ctx, Tr, a);
+    if (a.prof && W == 3) return pencil_launch<W, DIAG, false, true, (W == 3)>(ctx, Tr, a);   // profiling build: 7-point ILU(0) shapes only
+    return pencil_launch<W, DIAG, false, true, false>(ctx, Tr, a);
+}
+
 template <int W>
 static int pencil_dispatch(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &a)
 {
-    if (a.prof && W == 3 && !Tr->p_holes)   // the profiling build exists for the 7-point ILU(0) shapes only
-        return Tr->p_diag ? pencil_launch<W, 1, false, (W == 3)>(ctx, Tr, a) : pencil_launch<W, 0, false, (W == 3)>(ctx, Tr, a);
-    if (Tr->p_holes) return Tr->p_diag ? pencil_launch<W, 1, true, false>(ctx, Tr, a) : pencil_launch<W, 0, true, false>(ctx, Tr, a);
-    return Tr->p_diag ? pencil_launch<W, 1, false, false>(ctx, Tr, a) : pencil_launch<W, 0, false, false>(ctx, Tr, a);
+    return Tr->p_diag ? pencil_dispatch2<W, 1>(ctx, Tr, a) : pencil_dispatch2<W, 0>(ctx, Tr, a);
 }
 
 int tri_pencil_solve(lsspg_ctx *ctx, const lsspg_tri *Tr, double *dx, const double *drhs, bool guarded)
@@ -826,7 +933,7 @@ int tri_pencil_solve(lsspg_ctx *ctx, const lsspg_tri *Tr, double *dx, const doub
         Tm->p_seen_timeouts = ctx->tri_timeouts;
     }
     PencilArgs a;
-    a.hdr = (const PencilHdr *)Tr->p_hdr; a.thr = (const PencilThread *)Tr->p_thr; a.ghost = (const PencilGhost *)Tr->p_ghost;
+    a.hdr = (const PencilHdr *)Tr->p_hdr; a.thr = (const PencilThread *)Tr->p_thr; a.ghost = (const PencilGhost *)Tr->p_ghost; a.outs = (const PencilOut *)Tr->p_outs;
     a.vals = Tr->p_vals; a.mail = Tr->p_mail; a.counter = Tr->d_counter;
     a.num_pencils = Tr->num_tiles; a.T = Tr->p_T; a.RS = Tr->p_RS; a.dir = Tr->p_dir;
     a.x = dx; a.rhs = drhs;
@@ -866,6 +973,10 @@ int tri_pencil_upload(lsspg_ctx *ctx, const PencilHost &H, lsspg_tri *T)
     LSSPG_CUDA(cudaMalloc(&T->p_hdr, sizeof(PencilHdr) * std::max<size_t>(H.hdr.size(), 1)));
     LSSPG_CUDA(cudaMalloc(&T->p_thr, sizeof(PencilThread) * std::max<size_t>(H.thr.size(), 1)));
     LSSPG_CUDA(cudaMalloc(&T->p_ghost, sizeof(PencilGhost) * std::max<size_t>(H.ghost.size(), 1)));
+    LSSPG_CUDA(cudaMalloc(&T->p_outs, sizeof(PencilOut) * std::max<size_t>(H.outs.size(), 1)));
+    if (!H.outs.empty())
+        LSSPG_CUDA(cudaMemcpyAsync(T->p_outs, H.outs.data(), sizeof(PencilOut) * H.outs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    T->p_own_last = H.own_last ? 1 : 0;
     LSSPG_CUDA(cudaMalloc(&T->p_vals, sizeof(double) * std::max<size_t>(H.vals.size(), 1)));
     LSSPG_CUDA(cudaMalloc(&T->p_mail, sizeof(double) * (size_t)std::max<long long>(H.mail_len, 1)));
     LSSPG_CUDA(cudaMemcpyAsync(T->p_hdr, H.hdr.data(), sizeof(PencilHdr) * H.hdr.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -883,6 +994,7 @@ void tri_pencil_free(lsspg_tri *T)
     cudaFree(T->p_hdr);
     cudaFree(T->p_thr);
     cudaFree(T->p_ghost);
+    cudaFree(T->p_outs);
     cudaFree(T->p_vals);
     cudaFree(T->p_mail);
     cudaFree(T->p_prof);

@@ -49,14 +49,14 @@ def main():
                 t0 = p[:, 0].min()
                 start, end = (p[:, 0] - t0) / 1e3, (p[:, 1] - t0) / 1e3
                 steps = p[:, 5]
-                print("  pencils %d  kernel span %.1f us;  per step (cycles): total %.0f, ghost wait %.0f, barrier %.0f" %
-                      (got, end.max(), (p[:, 2] / steps).mean(), (p[:, 3] / steps).mean(), (p[:, 4] / steps).mean()))
-                print("  pencil duration us: min %.1f mean %.1f max %.1f; distinct SMs %d" %
-                      ((end - start).min(), (end - start).mean(), (end - start).max(), len(set(p[:, 7]))))
+                print("  pencils %d  kernel span %.1f us;  per step (cycles): total %.0f, ghost wait %.0f, barrier %.0f, values wait %.0f, rhs wait %.0f" %
+                      (got, end.max(), (p[:, 2] / steps).mean(), (p[:, 3] / steps).mean(), (p[:, 4] / steps).mean(),
+                       (p[:, 6] / steps).mean(), (p[:, 7] / steps).mean()))
+                print("  pencil duration us: min %.1f mean %.1f max %.1f" % ((end - start).min(), (end - start).mean(), (end - start).max()))
                 idx = np.linspace(0, got - 1, min(got, 24)).astype(int)
                 for i in idx:
-                    print("   ticket %4d: start %7.1f us end %7.1f us  steps %4d  cyc/step %5.0f  wait %5.0f  bar %5.0f  sm %3d" %
-                          (i, start[i], end[i], steps[i], p[i, 2] / steps[i], p[i, 3] / steps[i], p[i, 4] / steps[i], p[i, 7]))
+                    print("   ticket %4d: start %7.1f us end %7.1f us  steps %4d  cyc/step %5.0f  ghost %5.0f  bar %5.0f  vals %5.0f  rhs %5.0f" %
+                          (i, start[i], end[i], steps[i], p[i, 2] / steps[i], p[i, 3] / steps[i], p[i, 4] / steps[i], p[i, 6] / steps[i], p[i, 7] / steps[i]))
         tri.free()
 
 
