@@ -355,11 +355,13 @@ def main():
         pc_gbs = pc.bytes / ms_pcap / 1e6
         # per launch: one application = 2 launches of the sweep kernel (L, then U) of equal algorithmic bytes
         roof = {"bound": "hbm", "achieved": pc_gbs, "peak": peak, "unit": "GB/s", "frac": pc_gbs / peak,
-                "traffic": ncu_traffic("tri_box_ell_kernel@lap3d_%d" % args.grid) if args.workload == "cg_ilu0" else None,
-                "kernel": "triangular sweep (tri_box_ell_kernel on structured-grid factors, tri_solve_kernel otherwise); "
-                          "2 launches per ILU application", "ms": ms_pcap / 2,
+                "traffic": ncu_traffic("tri_pencil_kernel@lap3d_%d" % args.grid) if args.workload == "cg_ilu0" else None,
+                "kernel": "triangular sweep (tri_pencil_kernel on lattice factors, tri_box_ell_kernel / tri_solve_kernel "
+                          "otherwise); 2 launches per ILU application (L, U), average of the two", "ms": ms_pcap / 2,
                 "bytes": pc.bytes / 2, "share_of_iteration": ms_pcap / ms_per_it, "peak_kind": peak_kind,
-                "note": "latency-bound by %d dependency levels per sweep, not by HBM" % pc.info()["levels_L"]}
+                "note": "algorithmic bytes = SURVEY.md 8d (12 nnz(T) + 20 n per sweep); the pencil kernel streams the VALUES "
+                        "only (no column indices, no permutation): traffic < bytes.  Bound by the dependency chain "
+                        "(3N-2 hyperplanes), not by HBM"}
         info = pc.info()
     elif pckind == "amg":
         ms_pcap = timed(lambda: pc.apply(y, b), 10)

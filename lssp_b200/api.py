@@ -317,7 +317,8 @@ class Tri:
     def schedule(self):
         a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         check(lib().lsspg_tri_schedule(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return dict(tiled=bool(a.value), boxes=b.value, box_levels=c.value, max_box_rows=d.value)
+        # kind: 2 pencil schedule (boxes = pencils, box_levels = steps), 1 box schedule, 0 slice schedule
+        return dict(tiled=bool(a.value), kind=a.value, boxes=b.value, box_levels=c.value, max_box_rows=d.value)
 
     def solve(self, x, rhs):
         check(lib().lsspg_tri_solve(self.ctx.h, self.h, x.ptr, rhs.ptr))

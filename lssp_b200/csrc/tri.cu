@@ -374,12 +374,15 @@ int lsspg_debug_tri_pack_host(int which, int n, const int *hTp, const int *hTj, 
     double t1 = t0, t2 = t0;
     const char *e = getenv("LSSPG_TRI_TILED");
     TiledHost TH;
-    const int rc = (e && atoi(e) == 0) ? 2 : tri_tiled_build_host(which, n, hTp, hTj, hTx, TH);
+    int rc = (e && atoi(e) == 0) ? 2 : tri_tiled_build_host(which, n, hTp, hTj, hTx, TH);
     if (rc == 1) return 1;
+    PackedBoxes P;
     if (rc == 0) {
         t1 = now();
-        PackedBoxes P;
-        LSSPG_TRY(tri_tiled_pack_host(TH, P));
+        rc = tri_tiled_pack_host(TH, P);
+        if (rc == 1) return 1;
+    }
+    if (rc == 0) {
         t2 = now();
         h = mix_words(h, P.blob.data(), P.blob.size());
         h = mix_words(h, P.desc_bytes.data(), P.desc_bytes.size());
@@ -444,9 +447,11 @@ int lsspg_tri_analyse(lsspg_ctx *ctx, int which, int n, const int *hTp, const in
                 T->padded_nnz = TH.offdiag_nnz;
                 LSSPG_CUDA(cudaMalloc(&T->d_counter, sizeof(unsigned int) * 64));
                 LSSPG_CUDA(cudaMemsetAsync(T->d_counter, 0, sizeof(unsigned int) * 64, ctx->stream));
-                LSSPG_TRY(tri_tiled_upload(ctx, TH, T));
-                *out = T;
-                return 0;
+                const int urc = tri_tiled_upload(ctx, TH, T);
+                if (urc == 0) { *out = T; return 0; }
+                cudaFree(T->d_counter);
+                delete T;
+                if (urc == 1) return 1;   // 2: the boxes do not fit: slice schedule below
             }
         }
     }

@@ -51,7 +51,6 @@ struct lsspg_tri {
     int blob_cap = 0;                  // largest blob (bytes)
     int max_ext = 0;                   // most operands a box reads from other boxes
     bool box_flags = false;            // acyclic box graph: wait on per-box completion flags
-    int box_chunks = 0;                // > 1: experimental chunked hand-off (tri_box_chunk_kernel)
     unsigned int *t_flags = nullptr;   // [num_tiles] epoch of the last sweep that finished the box
     unsigned int epoch = 0;
     // pencil schedule (tri_pencil.cu): lattice factors; num_tiles = pencils, tile_dims = pencil cross-section
@@ -88,7 +87,6 @@ struct PackedBoxes {
     size_t cap = 0;       // largest blob
     int max_ext = 0;      // most operands a box reads from other boxes
     bool flags = false;   // ELL blobs for the completion-flag kernel (acyclic box graphs)
-    int chunks = 0;       // > 1: ELL blobs with a chunk table (experimental chunked hand-off)
 };
 int tri_tiled_pack_host(const TiledHost &H, PackedBoxes &P);
 int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T);

@@ -142,30 +142,11 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
             if (s1 <= 4 && s2 <= 4 && t1 <= 8) { sk[0] = (int)s1; sk[1] = (int)s2; sk[2] = (int)t1; }
         }
     }
-    if (const char *e = getenv("LSSPG_TRI_SKEW_FORCE")) {   // experiments: any skew at least as large as the needed one
-        int a, b, c;
-        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= sk[0] && b >= sk[1] && c >= sk[2] && a <= 8 && b <= 8 && c <= 16) {
-            sk[0] = a; sk[1] = b; sk[2] = c;
-        }
-    }
     // skewed 3-D boxes: u spans (1 + s1 + t1) nx, so boxes longer in u and flatter in w shorten the chain of boxes;
     // measured for ILUK(1) at 256^3 (profiles/r01_skew_tiles.log): 12x8x5 3.88 ms, 8x8x8 4.12, 16x8x4 4.14, 8x4x8 4.46
     if (!shape_given && g[2] > 1 && (sk[0] || sk[1] || sk[2])) { t[0] = 12; t[1] = 8; t[2] = 5; }
-    if (sk[0] || sk[1] || sk[2]) {
-        // rows wider than the unrolled in-box code paths (ELL width <= 6: ILU(1) of 5-/7-point stencils) have only been
-        // verified on the host walk so far, not on a GPU: they keep the slice schedule unless LSSPG_TRI_SKEW=2 asks
-        const char *e = getenv("LSSPG_TRI_SKEW");
-        if (!(e && atoi(e) >= 2)) {
-            const int np = host_threads();
-            std::vector<int> widest(np, 0);
-            parallel_ranges(n, [&](long long r0, long long r1, int p) {
-                int w = 0;
-                for (int i = (int)r0; i < (int)r1; i++) w = std::max(w, Tp[i + 1] - Tp[i] - 1);
-                widest[p] = w;
-            }, np);
-            if (*std::max_element(widest.begin(), widest.end()) > 6) return 2;
-        }
-    }
+    // (rows wider than the unrolled in-box code paths, ILU(2) and up, take the generic loop of the kernel: verified
+    // bit-exact on a B200 in round 2, profiles/r02_experimental_variants.txt)
     const long long ext[3] = {(long long)g[0] + (long long)sk[0] * (g[1] - 1) + (long long)sk[2] * (g[2] - 1),
                               (long long)g[1] + (long long)sk[1] * (g[2] - 1), g[2]};
     const long long ntl[3] = {(ext[0] + t[0] - 1) / t[0], (ext[1] + t[1] - 1) / t[1], (ext[2] + t[2] - 1) / t[2]};
@@ -292,9 +273,9 @@ int tri_tiled_build_host(int which, int n, const int *Tp, const int *Tj, const d
         }
     }
     if (max_scc > 128) return 2;
-    // Boxes that depend on each other both ways (ILU(1)/(2) fill) can only be run with per-operand
-    // polling, which measured slower than the slice schedule; opt-in for experiments.
-    if (max_scc > 1 && !(getenv("LSSPG_TRI_TILED_CYCLIC") && atoi(getenv("LSSPG_TRI_TILED_CYCLIC")) != 0)) return 2;
+    // Boxes that depend on each other both ways could only be run with per-operand polling, which measured slower
+    // than the slice schedule (round 1; that kernel is gone): such factors take the slice schedule.
+    if (max_scc > 1) return 2;
     // producers-first rank of every component and its longest-path level in the condensation
     std::vector<int> rank_of(ntiles), tlc(ncomp, 0), byrank(ntiles), rstart(ncomp + 1, 0);
     for (int k = 0; k < ntiles; k++) { rank_of[k] = ncomp - 1 - comp[k]; rstart[rank_of[k] + 1]++; }
@@ -466,177 +447,6 @@ __device__ __forceinline__ void stx_relaxed(double *p, double v)
 }
 
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
-
-// One warp (= one CTA) per box.
-__global__ void __launch_bounds__(32) tri_box_kernel(const TiledArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    if (a.stop && *a.stop) return;
-    const int lane = threadIdx.x;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
-    unsigned char *sblob = smem + 16;
-    double *srhs = reinterpret_cast<double *>(sblob + a.blob_cap);
-    double *sxs = srhs + a.max_tile_rows;
-    double *sxe = sxs + a.max_tile_rows;   // operands owned by other boxes, fetched once per box
-    const unsigned int bar_s = smem_u32(bar), blob_s = smem_u32(sblob);
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    unsigned int phase = 0;
-    const unsigned int total = (unsigned int)a.num_tiles + gridDim.x;
-    for (;;) {
-        unsigned int tk = 0;
-        long long t0 = a.prof ? clock64() : 0, t_poll = 0;
-        if (lane == 0) tk = atomicInc(a.counter, total - 1);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk >= (unsigned int)a.num_tiles) break;
-        const BoxDesc d = a.desc[tk];
-        long long t1 = a.prof ? clock64() : 0;
-        if (lane == 0) {
-            // the previous box's generic-proxy reads of the buffer precede this async-proxy write
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"((unsigned int)d.bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(blob_s), "l"(a.blob + d.off), "r"((unsigned int)d.bytes), "r"(bar_s) : "memory");
-        }
-        {   // wait for the bytes to land
-            unsigned int ok = 0;
-            while (!ok) {
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(ok) : "r"(bar_s), "r"(phase) : "memory");
-            }
-            phase ^= 1;
-        }
-        long long t2 = a.prof ? clock64() : 0;
-        const BoxLayout lay = box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred);
-        const int *slev = reinterpret_cast<const int *>(sblob + lay.lev);
-        const int *sptr = reinterpret_cast<const int *>(sblob + lay.ptr);
-        const int *sperm = reinterpret_cast<const int *>(sblob + lay.perm);
-        const int *sext = reinterpret_cast<const int *>(sblob + lay.ext);
-        const double *sdiag = reinterpret_cast<const double *>(sblob + lay.diag);
-        const int *scol = reinterpret_cast<const int *>(sblob + lay.col);
-        const double *sval = reinterpret_cast<const double *>(sblob + lay.val);
-        // gather the right-hand side, eight independent loads in flight per lane
-        for (int s0 = 0; s0 < d.nrows; s0 += 256) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int s = s0 + u * 32 + lane;
-                v[u] = (s < d.nrows) ? __ldg(a.rhs + sperm[s]) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int s = s0 + u * 32 + lane;
-                if (s < d.nrows) srhs[s] = v[u];
-            }
-        }
-        if (a.flags) {
-            // acyclic box graph: wait until every box this one reads from has finished (one flag per box)
-            const int *spred = reinterpret_cast<const int *>(sblob + lay.pred);
-            for (int q = lane; q < d.npred; q += 32) {
-                const unsigned int *f = a.flags + spred[q];
-                int spins = 0;
-                unsigned int got;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(f) : "memory");
-                    if (got != a.epoch && ++spins > 4) __nanosleep(spins > 64 ? 400 : 64);
-                    if (spins > (1 << 21)) { *a.err = 1; break; }
-                } while (got != a.epoch);
-            }
-            __syncwarp();
-        }
-        // one pass over the operands owned by other boxes (all present when flags are used; otherwise
-        // most are, and a sentinel is resolved later, where it is used)
-        for (int q0 = 0; q0 < d.next; q0 += 256) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int q = q0 + u * 32 + lane;
-                v[u] = (q < d.next) ? ldx_relaxed(a.x + sext[q]) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int q = q0 + u * 32 + lane;
-                if (q < d.next) sxe[q] = v[u];
-            }
-        }
-        __syncwarp();
-        long long t3 = a.prof ? clock64() : 0;
-        for (int L = 0; L < d.nlev; L++) {
-            const int sa = slev[L], sb = slev[L + 1];
-            for (int slot = sa + lane; slot < sb; slot += 32) {
-                int e = sptr[slot];
-                const int e1 = sptr[slot + 1];
-                double r = srhs[slot];
-                const double dg = sdiag[slot];
-                const int row = sperm[slot];
-                while (e < e1) {
-                    // four entries at a time: all shared-memory loads first, then the sequential subtractions
-                    int c[4];
-                    double v[4], xv[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const bool on = (e + j < e1);
-                        c[j] = on ? scol[e + j] : 0x7fffffff;
-                        v[j] = on ? sval[e + j] : 0.0;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        xv[j] = (c[j] == 0x7fffffff) ? 0.0 : (c[j] < 0 ? sxs[-c[j] - 1] : sxe[c[j]]);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (c[j] >= 0 && c[j] != 0x7fffffff &&
-                            (unsigned long long)__double_as_longlong(xv[j]) == kSentinelBitsT) {
-                            // operand of another box that had not been produced when this box started
-                            const double *src = a.x + sext[c[j]];
-                            int spins = 0;
-                            const long long tp = a.prof ? clock64() : 0;
-                            do {
-                                xv[j] = ldx_relaxed(src);
-                                if (++spins > 8) __nanosleep(spins > 128 ? 200 : 32);
-                                if (spins > (1 << 21)) { *a.err = 1; break; }
-                            } while ((unsigned long long)__double_as_longlong(xv[j]) == kSentinelBitsT);
-                            if (a.prof) t_poll += clock64() - tp;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (c[j] != 0x7fffffff) r = r - v[j] * xv[j];   // reference src/solver-tri.cxx:18 / :40
-                    e += 4;
-                }
-                const double out = (dg == 1.0) ? r : r / dg;   // :22 / :44 (x / 1.0 == x exactly)
-                sxs[slot] = out;
-                // boxes that other boxes poll (cyclic box graphs) publish every row at once; with
-                // completion flags the rows leave together when the box is done, which keeps global
-                // stores (and the barrier's wait for them) out of the group loop
-                if (!a.flags) stx_relaxed(a.x + row, out);
-            }
-            __syncwarp();   // the group's x values are visible to the whole warp before the next group
-        }
-        if (a.flags) {   // publish: every lane's x stores first, then the box's completion flag
-            for (int s = lane; s < d.nrows; s += 32) a.x[sperm[s]] = sxs[s];
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flags + tk), "r"(a.epoch) : "memory");
-        }
-        if (a.prof) {
-            const long long t4 = clock64();
-            // per-box maximum over lanes of the time spent polling
-            for (int o = 16; o > 0; o >>= 1) t_poll = max(t_poll, __shfl_xor_sync(0xffffffffu, t_poll, o));
-            if (lane == 0) {
-                atomicAdd(a.prof + 0, (unsigned long long)(t1 - t0));
-                atomicAdd(a.prof + 1, (unsigned long long)(t2 - t1));
-                atomicAdd(a.prof + 2, (unsigned long long)(t3 - t2));
-                atomicAdd(a.prof + 3, (unsigned long long)(t4 - t3));
-                atomicAdd(a.prof + 4, (unsigned long long)t_poll);
-                atomicAdd(a.prof + 5, 1ull);
-            }
-        }
-    }
-}
-
 
 // ---- acyclic box graphs: lean kernel -----------------------------------------------------
 // When no two boxes depend on each other (ILU(0)-type factors) a box simply waits for the
@@ -894,134 +704,6 @@ __global__ void __launch_bounds__(32, 8) tri_box_ell_kernel(const TiledArgs a)  
     }
 }
 
-// EXPERIMENT (opt-in, LSSPG_TRI_CHUNKS=2..8; never the default; not yet run on a GPU -- see ROADMAP.md).  The same box
-// blobs with a chunk table in place of the predecessor list: the in-box levels are cut into C chunks; before chunk c the
-// warp gates on (and fetches) only the operands of other boxes that the rows of chunk c read, and after chunk c it
-// publishes the rows of chunk c.  A downstream box then starts after ~1/C of its predecessor instead of all of it:
-// the chain of boxes costs (t + 3t/C) in-box levels per box instead of 3t (model in ROADMAP.md).
-//   pred section: [C][cl: C+1 level boundaries][xp: C+1 operand boundaries][gp: C+1 gate boundaries][gate rows]
-__global__ void __launch_bounds__(32, 8) tri_box_chunk_kernel(const TiledArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    if (a.stop && *a.stop) return;
-    const int lane = threadIdx.x;
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
-    unsigned char *sblob = smem + 16;
-    double *sx = reinterpret_cast<double *>(sblob + a.blob_cap);
-    const unsigned int bar_s = smem_u32(bar), blob_s = smem_u32(sblob);
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    unsigned int phase = 0;
-    const unsigned int total = (unsigned int)a.num_tiles + gridDim.x;
-    for (;;) {
-        unsigned int tk = 0;
-        if (lane == 0) tk = atomicInc(a.counter, total - 1);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk >= (unsigned int)a.num_tiles) break;
-        const BoxDesc d = a.desc[tk];   // d.nent: ELL width; d.npred: ints in the chunk table
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"((unsigned int)d.bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(blob_s), "l"(a.blob + d.off), "r"((unsigned int)d.bytes), "r"(bar_s) : "memory");
-        }
-        {
-            unsigned int ok = 0;
-            while (!ok) {
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(ok) : "r"(bar_s), "r"(phase) : "memory");
-            }
-            phase ^= 1;
-        }
-        const int nrows = d.nrows, w = d.nent;
-        const EllLayout lay = ell_layout(nrows, w, d.nlev, d.next, d.npred);
-        const int *slev = reinterpret_cast<const int *>(sblob + lay.lev);
-        const int *sperm = reinterpret_cast<const int *>(sblob + lay.perm);
-        const int *sext = reinterpret_cast<const int *>(sblob + lay.ext);
-        const int *stab = reinterpret_cast<const int *>(sblob + lay.pred);
-        const double *sdiag = reinterpret_cast<const double *>(sblob + lay.diag);
-        const int *ecol = reinterpret_cast<const int *>(sblob + lay.ecol);
-        const double *eval = reinterpret_cast<const double *>(sblob + lay.eval);
-        const int C = stab[0];
-        const int *cl = stab + 1, *xp = cl + (C + 1), *gp = xp + (C + 1), *gates = gp + (C + 1);
-        for (int s0 = 0; s0 < nrows; s0 += 256) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int s = s0 + u * 32 + lane;
-                v[u] = (s < nrows) ? __ldg(a.rhs + sperm[s]) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int s = s0 + u * 32 + lane;
-                if (s < nrows) sx[s] = v[u];
-            }
-        }
-        if (lane == 0) sx[nrows + d.next] = 0.0;
-        for (int c = 0; c < C; c++) {
-            // gate: one lane per (predecessor box, chunk) polls the operand of it that is stored last
-            for (int q = gp[c] + lane; q < gp[c + 1]; q += 32) {
-                const double *f = a.x + gates[q];
-                int spins = 0;
-                while ((unsigned long long)__double_as_longlong(ldx_relaxed(f)) == kSentinelBitsT) {
-                    if (++spins > 16) __nanosleep(40);
-                    if (spins > (1 << 21)) { *a.err = 1; break; }
-                }
-            }
-            __syncwarp();
-            for (int q0 = xp[c]; q0 < xp[c + 1]; q0 += 256) {
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int q = q0 + u * 32 + lane;
-                    v[u] = (q < xp[c + 1]) ? ldx_relaxed(a.x + sext[q]) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int q = q0 + u * 32 + lane;
-                    if (q < xp[c + 1]) {
-                        int spins = 0;
-                        while ((unsigned long long)__double_as_longlong(v[u]) == kSentinelBitsT) {
-                            v[u] = ldx_relaxed(a.x + sext[q]);
-                            if (++spins > (1 << 21)) { *a.err = 1; break; }
-                        }
-                        sx[nrows + q] = v[u];
-                    }
-                }
-            }
-            __syncwarp();
-            const int *clev = slev + cl[c];
-            const int cn = cl[c + 1] - cl[c];
-            switch (w) {
-                case 1: box_levels<1, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
-                case 2: box_levels<2, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
-                case 3: box_levels<3, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
-                case 4: box_levels<4, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
-                case 5: box_levels<5, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
-                case 6: box_levels<6, 2>(clev, cn, nrows, nrows + d.next + 1, ecol, eval, sdiag, sx, lane); break;
-                default:
-                    for (int L = 0; L < cn; L++) {
-                        const int sa = clev[L], sb = clev[L + 1];
-                        for (int slot = sa + lane; slot < sb; slot += 32) {
-                            double r = sx[slot];
-                            for (int k = 0; k < w; k++) r = r - eval[k * nrows + slot] * sx[ecol[k * nrows + slot]];
-                            const double dg = sdiag[slot];
-                            if (dg != 1.0) r = r / dg;
-                            sx[slot] = r;
-                        }
-                        __syncwarp();
-                    }
-            }
-            // publish the rows of this chunk (the values are their own ready flags)
-            for (int s = slev[cl[c]] + lane; s < slev[cl[c + 1]]; s += 32)
-                asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(a.x + sperm[s]), "d"(sx[s]) : "memory");
-        }
-    }
-}
-
 int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs, bool guarded)
 {
     double sentinel;
@@ -1032,13 +714,12 @@ int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double
     a.blob = T->t_blob; a.desc = (const BoxDesc *)T->t_desc;
     a.counter = T->d_counter; a.num_tiles = T->num_tiles; a.blob_cap = T->blob_cap; a.max_tile_rows = T->max_tile_rows;
     a.max_ext = T->max_ext;
-    a.flags = T->box_flags ? T->t_flags : nullptr;
+    a.flags = nullptr;
     a.epoch = ++const_cast<lsspg_tri *>(T)->epoch;
     a.x = dx; a.rhs = drhs;
     a.stop = guarded ? ctx->d_flags + FLAG_STOP : nullptr;
     a.err = ctx->d_flags + FLAG_TRI_TIMEOUT;
-    const size_t smem = T->box_flags ? 16 + (size_t)T->blob_cap + 8 * ((size_t)T->max_tile_rows + T->max_ext + 2)
-                                     : 16 + (size_t)T->blob_cap + 16 * (size_t)T->max_tile_rows + 8 * (size_t)T->max_ext;
+    const size_t smem = 16 + (size_t)T->blob_cap + 8 * ((size_t)T->max_tile_rows + T->max_ext + 2);
     static int env_cap = -1;
     if (env_cap < 0) {
         const char *e = getenv("LSSPG_TRI_TILED_CTAS_PER_SM");
@@ -1056,17 +737,14 @@ int tri_tiled_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double
         if (prof_on) { cudaMalloc(&d_prof, 64); cudaMemset(d_prof, 0, 64); }
     }
     a.prof = prof_on ? d_prof : nullptr;
-    if (T->box_flags && T->box_chunks > 1) LSSPG_LAUNCH(ctx, tri_box_chunk_kernel, grid, 32, smem, a);
-    else if (T->box_flags) LSSPG_LAUNCH(ctx, tri_box_ell_kernel, grid, 32, smem, a);
-    else LSSPG_LAUNCH(ctx, tri_box_kernel, grid, 32, smem, a);
+    LSSPG_LAUNCH(ctx, tri_box_ell_kernel, grid, 32, smem, a);
     if (prof_on) {
         unsigned long long h[8];
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, d_prof, 64, cudaMemcpyDeviceToHost);
         cudaMemset(d_prof, 0, 64);
         if (h[5])
-            fprintf(stderr, T->box_flags ? "[tri_box_ell] boxes=%llu grid=%d cycles/box: fetch %.0f wait %.0f operands %.0f levels %.0f publish %.0f\n"
-                                         : "[tri_box] boxes=%llu grid=%d cycles/box: ticket %.0f blob %.0f gather %.0f compute %.0f (of which polling %.0f)\n",
+            fprintf(stderr, "[tri_box_ell] boxes=%llu grid=%d cycles/box: fetch %.0f wait %.0f operands %.0f levels %.0f publish %.0f\n",
                     h[5], grid, (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5]);
     }
     return 0;
@@ -1078,13 +756,11 @@ static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const
     const std::vector<unsigned char> &desc = P.desc_bytes;
     const size_t cap = P.cap;
     const int max_ext = P.max_ext;
-    const bool flags = P.flags;
     T->tiled = true;
     T->num_tiles = H.num_tiles; T->max_tile_rows = H.max_tile_rows; T->num_tile_levels = H.num_tile_levels;
     T->blob_cap = (int)cap;
     T->max_ext = max_ext;
-    T->box_flags = flags;
-    T->box_chunks = P.chunks;
+    T->box_flags = true;
     LSSPG_CUDA(cudaMalloc(&T->t_flags, sizeof(unsigned int) * std::max(H.num_tiles, 1)));
     LSSPG_CUDA(cudaMemsetAsync(T->t_flags, 0, sizeof(unsigned int) * std::max(H.num_tiles, 1), ctx->stream));
     for (int k = 0; k < 3; k++) { T->tile_dims[k] = H.tile_dims[k]; T->grid_dims[k] = H.grid_dims[k]; }
@@ -1095,9 +771,7 @@ static int upload_common(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T, const
         LSSPG_CUDA(cudaMemcpyAsync(T->t_desc, desc.data(), desc.size(), cudaMemcpyHostToDevice, ctx->stream));
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(tri_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(tri_box_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(tri_box_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
     LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1110,55 +784,10 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
 {
     const int nb = H.num_tiles;
     std::vector<BoxDesc> desc(nb);
-    // experimental chunked hand-off (tri_box_chunk_kernel): LSSPG_TRI_CHUNKS = 2..8
-    int chunks = 1;
-    if (const char *e = getenv("LSSPG_TRI_CHUNKS")) chunks = std::max(1, std::min(atoi(e), 8));
     IVec pos_of_row((size_t)H.n);   // row -> position in box-major order
     parallel_ranges(H.n, [&](long long a, long long b, int) {
         for (int s = (int)a; s < (int)b; s++) pos_of_row[H.perm[s]] = s;
     });
-    // chunk table of box k: [C][cl: C+1][xp: C+1][gp: C+1][gate rows] (see tri_box_chunk_kernel)
-    std::vector<std::vector<int>> tables(chunks > 1 ? nb : 0);
-    auto chunk_table = [&](int k, std::vector<int> &tab) {
-        const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
-        const int nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
-        const int C = std::max(1, std::min(chunks, nlev));
-        std::vector<int> cl(C + 1), xp(C + 1, 0), gp(C + 1, 0), gates;
-        for (int c = 0; c <= C; c++) cl[c] = (int)((long long)c * nlev / C);
-        std::vector<std::pair<int, int>> best;   // (predecessor ticket, latest position read from it) of the current chunk
-        int L = 0, c = 0, q = 0;
-        auto close_chunk = [&] {
-            for (auto &pb : best) gates.push_back(H.perm[pb.second]);
-            best.clear();
-        };
-        for (int s = s0; s < s1; s++) {
-            while (L + 1 < nlev && s >= H.lev_ptr[H.lev_off[k] + L + 1]) L++;
-            while (c + 1 < C && L >= cl[c + 1]) {
-                close_chunk();
-                c++;
-                xp[c] = q;
-                gp[c] = (int)gates.size();
-            }
-            for (int e = H.ptr[s]; e < H.ptr[s + 1]; e++) {
-                if (H.col[e] < 0) continue;
-                const int pos = pos_of_row[H.col[e]];
-                const int p = (int)(std::upper_bound(H.tile_ptr.begin(), H.tile_ptr.end(), pos) - H.tile_ptr.begin()) - 1;
-                size_t m = 0;
-                for (; m < best.size() && best[m].first != p; m++) {}
-                if (m == best.size()) best.emplace_back(p, pos);
-                else if (pos > best[m].second) best[m].second = pos;
-                q++;
-            }
-        }
-        close_chunk();
-        for (int cc = c + 1; cc <= C; cc++) { xp[cc] = q; gp[cc] = (int)gates.size(); }
-        tab.clear();
-        tab.push_back(C);
-        tab.insert(tab.end(), cl.begin(), cl.end());
-        tab.insert(tab.end(), xp.begin(), xp.end());
-        tab.insert(tab.end(), gp.begin(), gp.end());
-        tab.insert(tab.end(), gates.begin(), gates.end());
-    };
     parallel_ranges(nb, [&](long long k0, long long k1, int) {
         for (int k = (int)k0; k < (int)k1; k++) {
             const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
@@ -1166,10 +795,6 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
             d.nrows = s1 - s0;
             d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
             d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
-            if (chunks > 1) {
-                chunk_table(k, tables[k]);
-                d.npred = (int)tables[k].size();
-            }
             d.next = 0;
             int w = 0;
             for (int s = s0; s < s1; s++) w = std::max(w, H.ptr[s + 1] - H.ptr[s]);
@@ -1204,9 +829,8 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
             int *ecol = (int *)(b + lay.ecol);
             double *diag = (double *)(b + lay.diag), *eval = (double *)(b + lay.eval);
             for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
-            if (chunks > 1) std::copy(tables[k].begin(), tables[k].end(), pred);
             // gate operand per predecessor box: of the rows this box reads from it, the one that box stores last
-            for (int q = 0; chunks <= 1 && q < d.npred; q++) {
+            for (int q = 0; q < d.npred; q++) {
                 const int p = H.pred[H.pred_ptr[k] + q];
                 int best = -1;
                 for (int e = H.ptr[s0]; e < H.ptr[s0 + nr]; e++) {
@@ -1241,82 +865,22 @@ static int pack_ell_host(const TiledHost &H, PackedBoxes &P)
     for (char b : bad)
         if (b) return 1;
     P.desc_bytes.assign((const unsigned char *)desc.data(), (const unsigned char *)(desc.data() + desc.size()));
-    P.cap = cap; P.max_ext = max_ext; P.flags = true; P.chunks = chunks;
+    P.cap = cap; P.max_ext = max_ext; P.flags = true;
     return 0;
 }
 
+// 0: packed; 2: not applicable (a box would not fit into shared memory, or the box graph is cyclic): slice schedule
 int tri_tiled_pack_host(const TiledHost &H, PackedBoxes &P)
 {
-    {
-        const char *e = getenv("LSSPG_TRI_BOX_FLAGS");
-        if (H.acyclic && !(e && atoi(e) == 0)) {
-            const int rc = pack_ell_host(H, P);
-            if (rc != 2) return rc;
-        }
-    }
-    // pack the boxes (CSR blobs for tri_box_kernel)
-    const int nb = H.num_tiles;
-    std::vector<BoxDesc> desc(nb);
-    parallel_ranges(nb, [&](long long k0, long long k1, int) {
-        for (int k = (int)k0; k < (int)k1; k++) {
-            const int s0 = H.tile_ptr[k], s1 = H.tile_ptr[k + 1];
-            BoxDesc &d = desc[k];
-            d.nrows = s1 - s0;
-            d.nent = H.ptr[s1] - H.ptr[s0];
-            d.nlev = H.lev_off[k + 1] - H.lev_off[k] - 1;
-            d.next = 0;
-            d.npred = H.pred_ptr[k + 1] - H.pred_ptr[k];
-            for (int e = H.ptr[s0]; e < H.ptr[s1]; e++) d.next += (H.col[e] >= 0);
-            d.bytes = (int)box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred).total;
-        }
-    }, 0, 64);
-    size_t total = 0, cap = 0;
-    int max_ext = 0;
-    for (int k = 0; k < nb; k++) {
-        desc[k].off = (long long)total;
-        total += (size_t)desc[k].bytes;
-        cap = std::max(cap, (size_t)desc[k].bytes);
-        max_ext = std::max(max_ext, desc[k].next);
-    }
-    if (16 + cap + 16 * (size_t)H.max_tile_rows + 8 * (size_t)max_ext > (size_t)200 * 1024) {
-        set_error("tri_tiled: a box needs more shared memory than one SM has");
-        return 1;
-    }
-    P.blob.resize(std::max<size_t>(total, 16));
-    if (total < 16) memset(P.blob.data(), 0, 16);
-    unsigned char *blob = P.blob.data();
-    parallel_ranges(nb, [&](long long k0, long long k1, int) {
-        for (int k = (int)k0; k < (int)k1; k++) {
-            const int s0 = H.tile_ptr[k];
-            const BoxDesc &d = desc[k];
-            const BoxLayout lay = box_layout(d.nrows, d.nent, d.nlev, d.next, d.npred);
-            unsigned char *b = blob + d.off;
-            memset(b, 0, (size_t)d.bytes);
-            int *lev = (int *)(b + lay.lev), *ptr = (int *)(b + lay.ptr), *perm = (int *)(b + lay.perm), *col = (int *)(b + lay.col);
-            int *ext = (int *)(b + lay.ext), *pred = (int *)(b + lay.pred);
-            for (int q = 0; q < d.npred; q++) pred[q] = H.pred[H.pred_ptr[k] + q];
-            double *diag = (double *)(b + lay.diag), *val = (double *)(b + lay.val);
-            for (int L = 0; L <= d.nlev; L++) lev[L] = H.lev_ptr[H.lev_off[k] + L] - s0;
-            const int e0 = H.ptr[s0];
-            for (int s = 0; s <= d.nrows; s++) ptr[s] = H.ptr[s0 + s] - e0;
-            for (int s = 0; s < d.nrows; s++) { perm[s] = H.perm[s0 + s]; diag[s] = H.diag[s0 + s]; }
-            for (int e = 0, q = 0; e < d.nent; e++) {
-                const int c = H.col[e0 + e];
-                if (c >= 0) { ext[q] = c; col[e] = q++; }
-                else col[e] = c;
-                val[e] = H.val[e0 + e];
-            }
-        }
-    }, 0, 64);
-    P.desc_bytes.assign((const unsigned char *)desc.data(), (const unsigned char *)(desc.data() + desc.size()));
-    P.cap = cap; P.max_ext = max_ext; P.flags = false; P.chunks = 1;
-    return 0;
+    if (!H.acyclic) return 2;
+    return pack_ell_host(H, P);
 }
 
 int tri_tiled_upload(lsspg_ctx *ctx, const TiledHost &H, lsspg_tri *T)
 {
     PackedBoxes P;
-    LSSPG_TRY(tri_tiled_pack_host(H, P));
+    const int rc = tri_tiled_pack_host(H, P);
+    if (rc) return rc;
     return upload_common(ctx, H, T, P);
 }
 
@@ -1417,8 +981,11 @@ int lsspg_debug_tri_walk_packed_host(int which, int n, const int *hTp, const int
     if (rc == 1) return 1;
     if (rc == 2) return 0;
     PackedBoxes P;
-    LSSPG_TRY(tri_tiled_pack_host(H, P));
-    if (!P.flags) return 0;   // CSR blobs of the polling kernel: not emulated here
+    {
+        const int prc = tri_tiled_pack_host(H, P);
+        if (prc == 1) return 1;
+        if (prc == 2) return 0;
+    }
     if (applicable) *applicable = 1;
     const BoxDesc *desc = (const BoxDesc *)P.desc_bytes.data();
     const double poison = strtod("nan", nullptr);
@@ -1442,13 +1009,6 @@ int lsspg_debug_tri_walk_packed_host(int which, int n, const int *hTp, const int
             int C = 1;
             std::vector<int> cl = {0, d.nlev}, xp = {0, d.next}, gp = {0, d.npred};
             const int *gates = tab;
-            if (P.chunks > 1) {
-                C = tab[0];
-                cl.assign(tab + 1, tab + 2 + C);
-                xp.assign(tab + 2 + C, tab + 3 + 2 * C);
-                gp.assign(tab + 3 + 2 * C, tab + 4 + 3 * C);
-                gates = tab + 4 + 3 * C;
-            }
             max_chunks = std::max(max_chunks, C);
             const int c = next_chunk[tk];
             if (c >= C) continue;

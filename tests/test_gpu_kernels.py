@@ -253,47 +253,47 @@ def test_trisolve_and_ilu_apply_bit_exact(ctx, golden, checker, name, tag, kw):
     assert np.array_equal(pc.apply_host(rhs), x)
 
 
-def test_both_tri_schedules_are_exercised(ctx, checker):
-    """Stencil factors take the box schedule, everything else the slice schedule; with the box
-    schedule disabled (LSSPG_TRI_TILED=0 at analysis time) the same factor must give the same bits."""
+def test_all_tri_schedules_are_exercised(ctx, checker):
+    """Stencil (lattice) factors take the pencil schedule; with it disabled (LSSPG_TRI_PENCIL=0 at analysis time) the box
+    schedule, and with that disabled too (LSSPG_TRI_TILED=0) the slice schedule: the same factor must give the same bits
+    on all three, in every variant of the pencil kernel (hole masks on, own-line operand through the ring)."""
     import os
+
+    def tri_with(env, which, T):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            return api.Tri(ctx, which, T)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
     A = matrix("lap3d_32")
     n = len(A[0]) - 1
-    for level in (0, 1):
+    for level in (0, 1, 2):
         L, U = api.ilu_factor(A, "iluk", level=level)
         rhs = tvec(n, 4)
-        want = checker.tri_lower(L, rhs)
-        # ILU(0): the plain 8x8x8 box grid is acyclic -> box schedule.  ILU(1): axis-aligned boxes depend on each other
-        # both ways; by default the boxes are skewed (acyclic again, completion-flag kernel); with LSSPG_TRI_SKEW=0
-        # the factor takes the slice schedule, or the polling box kernel on request (LSSPG_TRI_TILED_CYCLIC=1).
-        os.environ["LSSPG_TRI_TILED_CYCLIC"] = "1"
-        os.environ["LSSPG_TRI_SKEW"] = "0"
-        try:
-            T = api.Tri(ctx, 0, L)
-            del os.environ["LSSPG_TRI_TILED_CYCLIC"]
-            Tn = api.Tri(ctx, 0, L)
-        finally:
-            os.environ.pop("LSSPG_TRI_TILED_CYCLIC", None)
-            del os.environ["LSSPG_TRI_SKEW"]
-        assert T.schedule()["tiled"] and T.schedule()["boxes"] == 64
-        assert Tn.schedule()["tiled"] == (level == 0)
-        Td = api.Tri(ctx, 0, L)
-        assert Td.schedule()["tiled"] and Td.schedule()["boxes"] == api.tri_walk_tiled_host(0, L, rhs)[1]["boxes"]
-        assert (Td.schedule()["boxes"] == 64) == (level == 0)     # skewed boxes: more (partial) boxes than the plain grid
-        os.environ["LSSPG_TRI_TILED"] = "0"
-        try:
-            T0 = api.Tri(ctx, 0, L)
-        finally:
-            del os.environ["LSSPG_TRI_TILED"]
-        assert not T0.schedule()["tiled"]
-        drhs, dx = ctx.upload(rhs), ctx.empty(n)
-        for t in (T, Tn, Td, T0):
-            t.solve(dx, drhs)
-            assert np.array_equal(dx.get(), want)
-            t.solve(dx, drhs)      # a second sweep reuses flags / counters (epoch bump, ticket wrap)
-            assert np.array_equal(dx.get(), want)
+        for which, F, serial in ((0, L, checker.tri_lower), (1, U, checker.tri_upper)):
+            want = serial(F, rhs)
+            variants = [tri_with({}, which, F), tri_with({"LSSPG_TRI_PENCIL": "0"}, which, F),
+                        tri_with({"LSSPG_TRI_PENCIL": "0", "LSSPG_TRI_TILED": "0"}, which, F),
+                        tri_with({"LSSPG_TRI_PENCIL_HOLES": "1"}, which, F), tri_with({"LSSPG_TRI_PENCIL_OWNLAST": "0"}, which, F),
+                        tri_with({"LSSPG_TRI_PENCIL": "16,16"}, which, F), tri_with({"LSSPG_TRI_PENCIL": "16,8"}, which, F)]
+            kinds = [t.schedule()["kind"] for t in variants]
+            # ILU(2) rows (12 off-diagonals) are wider than the pencil kernel's 8 slots: box schedule (skewed boxes)
+            assert kinds[:3] == ([2, 1, 0] if level < 2 else [1, 1, 0]), kinds
+            drhs, dx = ctx.upload(rhs), ctx.empty(n)
+            for t in variants:
+                t.solve(dx, drhs)
+                assert np.array_equal(dx.get(), want)
+                t.solve(dx, drhs)      # a second sweep reuses mailboxes / counters (ticket wrap)
+                assert np.array_equal(dx.get(), want)
+                t.free()
     Tp = api.Tri(ctx, 0, api.ilu_factor(matrix("powerlaw_4000"), "iluk", level=0)[0])
-    assert not Tp.schedule()["tiled"]
+    assert Tp.schedule()["kind"] == 0
 
 
 def test_trisolve_single_chain_and_diagonal(ctx, checker):

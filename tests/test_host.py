@@ -124,11 +124,10 @@ def test_box_schedule_reproduces_reference_sweeps(golden, monkeypatch, name, tag
     L, U = api.ilu_factor(A, **kw)
     e = golden["factors"][name + "/" + tag]
     if tag != "iluk0":
-        # the plain box grid is cyclic for fill factors; such box graphs are opt-in (they need per-operand polling,
-        # measured slower than slices).  The default -- skewed boxes -- is covered by tests/test_setup_threads.py.
+        # the plain box grid is cyclic for fill factors: no box schedule; the default -- skewed boxes -- is acyclic
         monkeypatch.setenv("LSSPG_TRI_SKEW", "0")
         assert api.tri_walk_tiled_host(0, L, tvec(n))[1] is None
-        monkeypatch.setenv("LSSPG_TRI_TILED_CYCLIC", "1")
+        monkeypatch.delenv("LSSPG_TRI_SKEW")
     y, info = api.tri_walk_tiled_host(0, L, tvec(n))
     assert info is not None, "expected a box schedule for a stencil factor"
     assert info["nx"] * info["ny"] * info["nz"] == n and info["max_box_rows"] <= 512

@@ -106,10 +106,7 @@ def test_skewed_boxes_give_fill_factors_an_acyclic_box_schedule(case, port, monk
     monkeypatch.setenv("LSSPG_TRI_SKEW", "0")
     assert api.tri_pack_host(0, L)["kind"] == 0 and api.tri_walk_tiled_host(0, L, rhs)[1] is None
     monkeypatch.delenv("LSSPG_TRI_SKEW")
-    if kw["level"] >= 2:
-        # rows wider than 6 entries (ILU(2)) only take skewed boxes on request until that path has run on a GPU
-        assert api.tri_pack_host(0, L)["kind"] == 0
-        monkeypatch.setenv("LSSPG_TRI_SKEW", "2")
+    # (rows wider than 6 entries, ILU(2), take skewed boxes too since that path ran bit-exact on a B200 in round 2)
     assert api.tri_pack_host(0, L)["kind"] == 2 and api.tri_pack_host(1, U)["kind"] == 2
     y, info = api.tri_walk_tiled_host(0, L, rhs)
     x, info_u = api.tri_walk_tiled_host(1, U, y)
@@ -122,28 +119,19 @@ def test_skewed_boxes_give_fill_factors_an_acyclic_box_schedule(case, port, monk
     assert "%016x" % r["fingerprint"] == PACK["lap3d_32/iluk0/L"]["fingerprint"]
 
 
-@pytest.mark.parametrize("case,chunks", [("lap3d_32/iluk0", 1), ("lap3d_32/iluk0", 3), ("lap2d_300/iluk0", 4), ("cd3d_32/iluk1", 3),
-                                         ("lap3d_48/iluk0_bj3", 6)])
-def test_packed_box_blobs_replay_to_the_serial_sweeps(case, chunks, port, monkeypatch):
-    """lsspg_debug_tri_walk_packed_host replays the BYTES the box kernels read (blob sections, ELL columns, operand lists,
-    gate rows), boxes advancing round-robin: the sweeps must be reproduced bit for bit.  chunks > 1 is the experimental
-    progressive hand-off (LSSPG_TRI_CHUNKS, tri_box_chunk_kernel; opt-in): a box publishes its rows chunk by chunk, so
-    the longest chain of hand-offs, measured in whole boxes, gets shorter."""
+@pytest.mark.parametrize("case", ["lap3d_32/iluk0", "lap2d_300/iluk0", "cd3d_32/iluk1", "lap3d_48/iluk0_bj3"])
+def test_packed_box_blobs_replay_to_the_serial_sweeps(case, port):
+    """lsspg_debug_tri_walk_packed_host replays the BYTES the box kernel reads (blob sections, ELL columns, operand lists,
+    gate rows), boxes advancing round-robin: the sweeps must be reproduced bit for bit, one hand-off per box level."""
     make, kw = mpg.CASES[case][:2]
     A = make()
     n = len(A[0]) - 1
     L, U = api.ilu_factor(A, **kw)
     rhs = np.sin(np.arange(n) * 0.37) + 0.3
     want = port.ilu_apply(L, U, rhs)
-    y1, base = api.tri_walk_packed_host(0, L, rhs)
-    assert base["chunks"] == 1 and base["rounds"] == base["box_levels"]      # whole boxes: one hand-off per box level
-    monkeypatch.setenv("LSSPG_TRI_CHUNKS", str(chunks))
     y, info = api.tri_walk_packed_host(0, L, rhs)
     x, info_u = api.tri_walk_packed_host(1, U, y)
-    assert np.array_equal(x, want) and np.array_equal(y, y1)
-    assert info["chunks"] == chunks and info["boxes"] == base["boxes"]
-    if chunks >= 3 and case == "lap3d_32/iluk0":
-        assert info["rounds"] / chunks <= 0.75 * base["rounds"]              # 8x8x8 boxes, 3 chunks: 2/3 of the chain
-    monkeypatch.delenv("LSSPG_TRI_CHUNKS")
+    assert np.array_equal(x, want)
+    assert info["chunks"] == 1 and info["rounds"] == info["box_levels"]
     r = api.tri_pack_host(0, L)                                                # and the default image is untouched
     assert "%016x" % r["fingerprint"] == PACK[case + "/L"]["fingerprint"]
