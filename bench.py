@@ -306,19 +306,36 @@ def main():
     value = its / (total_ms / 1e3)
     nits, residual = r["nits"], r["residual"]
 
-    # ---- e2e: reference-facing host call, pinned host buffers, copies inside the timed region
+    # ---- e2e: the reference-facing call, lssp_solver_solve(LSSP_SOLVER &, LSSP_PC &) of liblssp.so (through the extern "C"
+    # handle of liblssp_e2e.so, ctypes cannot call C++), with the caller's HOST vectors: the library copies b and x0 to the
+    # device and x back inside the timed call.  The vectors live in pinned host memory.
     hb, hx = C.c_void_p(), C.c_void_p()
     check(L.lsspg_host_alloc(C.c_size_t(8 * n), C.byref(hb)))
     check(L.lsspg_host_alloc(C.c_size_t(8 * n), C.byref(hx)))
     b_host = np.ctypeslib.as_array(C.cast(hb, C.POINTER(C.c_double)), shape=(n,))
     x_host = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_double)), shape=(n,))
     b_host[:] = 1.0
+    x_host[:] = 0.0
+    facade = None
+    if pckind in ("iluk", "non"):
+        E = C.CDLL(os.path.join(ROOT, "lssp_b200", "liblssp_e2e.so"))
+        E.lssp_e2e_create.restype = C.c_void_p
+        E.lssp_e2e_solve.restype = C.c_int
+        C.c_int.in_dll(C.CDLL(os.path.join(ROOT, "lssp_b200", "liblssp.so")), "lssp_verbosity").value = 0
+        LSSP_SOLVER = {"cg": 7, "bicgstab": 4, "gmres": 0, "idrs": 18}[solver]     # include/lssp/type-defs.h
+        facade = C.c_void_p(E.lssp_e2e_create(LSSP_SOLVER, 1 if pckind == "iluk" else 0, n, A[0].ctypes.data_as(C.c_void_p),
+                                              A[1].ctypes.data_as(C.c_void_p), A[2].ctypes.data_as(C.c_void_p), hx, hb, 0, 3000, 50,
+                                              C.c_double(-1.0)))
     e2e_its, e2e_s = 0, 0.0
     for step in range(1 + args.steps):
         x_host[:] = 0.0
         ctx.sync()
         t0 = time.perf_counter()
-        re = api.lssp_solver_solve(ctx, solver, dA, pc, b_host, x_host, maxit=3000)
+        if facade is not None:
+            res = C.c_double()
+            re = {"nits": E.lssp_e2e_solve(facade, C.byref(res)), "residual": res.value}
+        else:
+            re = api.lssp_solver_solve(ctx, solver, dA, pc, b_host, x_host, maxit=3000)
         checksum = float(x_host[n // 2])          # the caller reads its answer from its own x
         dt = time.perf_counter() - t0
         if step >= 1:
@@ -326,7 +343,10 @@ def main():
             e2e_s += dt
     clocks = sampler.finish()
     e2e = {"value": e2e_its / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n,
-           "x_mid": checksum}
+           "x_mid": checksum, "iterations_per_solve": re["nits"], "residual": re["residual"],
+           "through": "liblssp.so lssp_solver_solve(LSSP_SOLVER&, LSSP_PC&)" if facade is not None else "lssp_b200.api.lssp_solver_solve"}
+    if facade is not None:
+        E.lssp_e2e_destroy(facade)
 
     # ---- per-kernel roofline numbers, timed live on the library's stream
     peak, peak_kind = measured_peak()

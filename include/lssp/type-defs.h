@@ -1,7 +1,8 @@
 /* type-defs.h -- containers and handles of the LSSP API (same names, fields and enumerator order
  * as the reference's include/type-defs.h with every USE_* = 0), written fresh for the B200 build.
- * Vectors and matrices stay HOST objects, exactly as callers of the reference see them; the
- * device images live behind the opaque `gpu` members, created by assemble and freed by destroy. */
+ * Vectors and matrices stay HOST objects, exactly as callers of the reference see them.  The structs are
+ * binary-identical to the reference's for the same USE_* switches (tests/cxx/struct_layout_check.cpp): device
+ * images hang off pc.data (built-in preconditioners) or a side table inside liblssp.so (lssp_facade.cpp). */
 #ifndef LSSP_TYPES_H
 #define LSSP_TYPES_H
 
@@ -88,8 +89,6 @@ typedef struct LSSP_PC_ {
     FILE *log;
     int verb;
     bool assembled;
-
-    void *gpu;                   /* device-side application object (lsspg_pc) */
 } LSSP_PC;
 
 typedef enum LSSP_SOLVER_TYPE_ {
@@ -121,6 +120,10 @@ typedef struct LSSP_SOLVER_ {
     double tol_rel, tol_abs, tol_rb;
     int maxit, restart, aug_k, bgsl, idrs;
 
+#if USE_SXAMG
+    struct SXAMG_DATA_ *sxamg;   /* reference include/type-defs.h:280-282 (before the matrix, as there) */
+#endif
+
     lssp_mat_csr A;              /* host deep copy, columns sorted (as the reference keeps it) */
     lssp_mat_bcsr Ab;
     int num_blks;
@@ -132,15 +135,9 @@ typedef struct LSSP_SOLVER_ {
     double residual;
     int nits;
 
-#if USE_SXAMG
-    struct SXAMG_DATA_ *sxamg;   /* reference include/type-defs.h:280-282 */
-#endif
-
     int verb;
     FILE *log;
     bool assembled;
-
-    void *gpu;                   /* device-resident matrix (lsspg_csr) */
 } LSSP_SOLVER;
 
 #endif

@@ -44,6 +44,9 @@ int lsspg_sync(lsspg_ctx *ctx);
 /* the CUDA stream (cudaStream_t) every kernel of this context is launched on */
 void *lsspg_ctx_stream(lsspg_ctx *ctx);
 /* CUDA-event timer on that stream (slot 0..3): milliseconds between start and stop */
+/* Where driver messages go (per-iteration residual lines, breakdown notices): the facade registers the reference's
+ * lssp_printf (src/utils.cxx:93-112), so that lssp_solver_set_log files receive them.  NULL: stdout, flushed. */
+void lsspg_set_printer(void (*fn)(const char *msg));
 int lsspg_timer_start(lsspg_ctx *ctx, int slot);
 int lsspg_timer_stop(lsspg_ctx *ctx, int slot, double *ms);
 /* number of kernels this context has launched so far (bench.py: gpu_launches) */
@@ -125,6 +128,9 @@ int lsspg_tri_analyse(lsspg_ctx *ctx, int which, int n, const int *hTp,
 int lsspg_tri_destroy(lsspg_ctx *ctx, lsspg_tri *T);
 int lsspg_tri_info(const lsspg_tri *T, int *num_levels, int *num_slices, long long *padded_nnz);
 /* x = T^-1 rhs (device operands; x and rhs must not alias) */
+/* Synchronises the stream and returns non-zero (lsspg_last_error) when a sweep since the last check was aborted by
+ * the watchdog; the flag is cleared.  The *_host entry points and the Krylov drivers check by themselves. */
+int lsspg_check_flags(lsspg_ctx *ctx);
 int lsspg_tri_solve(lsspg_ctx *ctx, const lsspg_tri *T, double *dx, const double *drhs);
 /* host-side schedule for tests: level of every row (length n) */
 int lsspg_tri_levels_host(int which, int n, const int *hTp, const int *hTj,

@@ -591,7 +591,7 @@ int lsspg_amg_solve(lsspg_ctx *ctx, lsspg_pc *amg, const double *db, double *dx,
         if (!rc) rc = spmv_launch(ctx, LSSPG_MV_AMXPBYZ, L0.A, minus, dx, one, db, r, nullptr);
         if (!rc) rc = lsspg_vec_norm(ctx, n, r, &res);
         it++;
-        if (!rc && M->pars.verb > 0) printf("amg: cycle %3d, residual %.8e, relative %.8e\n", it, res, res / denom);
+        if (!rc && M->pars.verb > 0) log_printf("amg: cycle %3d, residual %.8e, relative %.8e\n", it, res, res / denom);
     }
     cudaFree(r);
     if (rc) return rc;

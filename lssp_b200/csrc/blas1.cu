@@ -454,6 +454,9 @@ using namespace lsspg;
 
 extern "C" {
 
+// synchronises the stream, reads the device status flags and reports (and clears) a sweep aborted by the watchdog
+int lsspg_check_flags(lsspg_ctx *ctx) { return read_scalars(ctx, 0, 1, true); }
+
 int lsspg_vec_set(lsspg_ctx *ctx, int n, double *dx, double val) { return vec_set(ctx, n, dx, val, false); }
 int lsspg_vec_copy(lsspg_ctx *ctx, int n, double *ddst, const double *dsrc) { return vec_copy(ctx, n, ddst, dsrc); }
 int lsspg_vec_axy(lsspg_ctx *ctx, int n, double a, const double *dx, double *dy)

@@ -15,6 +15,7 @@
 namespace lsspg {
 
 void set_error(const char *fmt, ...);
+void log_printf(const char *fmt, ...);   // driver output: the registered printer (lssp_printf of the facade) or stdout
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 #define LSSPG_CUDA(call)                                                             \

@@ -14,6 +14,25 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+// Driver messages (per-iteration lines, breakdown notices): the reference prints them with lssp_printf, which flushes and
+// mirrors into the file given to lssp_solver_set_log (src/utils.cxx:93-112, src/solver-cg.cxx:108-112).  The library
+// above this one registers its lssp_printf here; without a printer the text goes to stdout, flushed.
+static void (*g_printer)(const char *) = nullptr;
+
+void log_printf(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (g_printer) g_printer(buf);
+    else {
+        fputs(buf, stdout);
+        fflush(stdout);
+    }
+}
+
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 {
     set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
@@ -23,6 +42,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 int ensure_stage(lsspg_ctx *ctx, size_t n)
 {
     if (n <= ctx->stage_len) return 0;
+    ctx->stage_len = 0;   // a failed allocation below must not leave a length that vouches for NULL buffers
     for (int i = 0; i < 3; i++) {
         if (ctx->stage[i]) LSSPG_CUDA(cudaFree(ctx->stage[i]));
         ctx->stage[i] = nullptr;
@@ -47,6 +67,9 @@ int ensure_seq(lsspg_ctx *ctx, size_t n)
 using namespace lsspg;
 
 extern "C" {
+
+void lsspg_set_printer(void (*fn)(const char *msg)) { lsspg::g_printer = fn; }
+
 
 const char *lsspg_last_error(void) { return g_err; }
 const char *lsspg_version(void) { return "lsspg 0.1 (sm_100a)"; }

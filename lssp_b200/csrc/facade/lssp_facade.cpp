@@ -15,6 +15,37 @@
 #include "lssp.h"
 #include "lsspg.h"
 
+// ---- device handles without touching the reference's struct layout ------------------------------------------------
+// LSSP_PC / LSSP_SOLVER are binary-identical to the reference's (include/type-defs.h:107-151, 225-304; checked by
+// tests/cxx/struct_layout_check.cpp).  A built-in preconditioner keeps its device object in pc.data, which the reference
+// sets to NULL in lssp_pc_create (src/pc.cxx:46) and never uses for its own preconditioners; a USER preconditioner owns
+// pc.data, so its trampoline object lives in a side table keyed by the address of the LSSP_PC.  The solver's device matrix
+// is keyed by the host deep copy's row-pointer array (s.A.Ap), which survives the by-value copies of LSSP_SOLVER that
+// lssp_pc_assemble(LSSP_PC &, LSSP_SOLVER) makes.
+#include <unordered_map>
+static std::unordered_map<const void *, void *> &side_table()
+{
+    static std::unordered_map<const void *, void *> t;
+    return t;
+}
+static void *side_get(const void *key)
+{
+    auto it = side_table().find(key);
+    return it == side_table().end() ? NULL : it->second;
+}
+static void side_set(const void *key, void *v)
+{
+    if (v) side_table()[key] = v;
+    else side_table().erase(key);
+}
+static inline void *pc_dev(const LSSP_PC *pc) { return pc->type == LSSP_PC_USER ? side_get(pc) : pc->data; }
+static inline void pc_dev_set(LSSP_PC *pc, void *d)
+{
+    if (pc->type == LSSP_PC_USER) side_set(pc, d);
+    else pc->data = d;
+}
+static inline void *solver_dev(const LSSP_SOLVER &s) { return s.A.Ap ? side_get(s.A.Ap) : NULL; }
+
 // ---- globals: defaults of the reference (src/lssp.cxx:5-14, src/pc.cxx:3-7, src/utils.cxx:19-22) ----
 int LSSP_RESTART = 50;
 int LSSP_AUG_K = 3;
@@ -94,11 +125,14 @@ void lssp_warning(const char *fmt, ...)
 // ---- device context ------------------------------------------------------------------------------
 static lsspg_ctx *g_ctx = NULL;
 
+static void driver_print(const char *msg) { lssp_printf("%s", msg); }
+
 static lsspg_ctx *ctx()
 {
     if (!g_ctx) {
         const char *e = getenv("LSSP_GPU");
         if (lsspg_ctx_create(e ? atoi(e) : 0, &g_ctx)) lssp_error(1, "lssp: %s\n", lsspg_last_error());
+        lsspg_set_printer(driver_print);   // per-iteration lines of the drivers go where lssp_printf sends them (log file too)
     }
     return g_ctx;
 }
@@ -377,9 +411,9 @@ lssp_mat_csr lssp_mat_transpose(const lssp_mat_csr A)   // :700-765: rows of the
 lssp_vec lssp_vec_create(int n)
 {
     lssp_vec v;
-    assert(n > 0);
+    assert(n >= 0);            // n == 0 gives an empty vector, as the reference (src/vector.cxx:8-17)
     v.n = n;
-    v.d = lssp_malloc<double>(n);
+    v.d = n > 0 ? lssp_malloc<double>(n) : NULL;
     return v;
 }
 
@@ -493,6 +527,7 @@ static void tri_host(int which, const lssp_mat_csr &T, double *x, const double *
     GPU(lsspg_malloc(ctx(), nb, (void **)&dr));
     GPU(lsspg_h2d(ctx(), dr, rhs, nb));
     GPU(lsspg_tri_solve(ctx(), dT, dx, dr));
+    GPU(lsspg_check_flags(ctx()));   // a sweep aborted by the watchdog is an error here, not a silently wrong x
     GPU(lsspg_d2h(ctx(), x, dx, nb));
     lsspg_free(ctx(), dx);
     lsspg_free(ctx(), dr);
@@ -512,8 +547,8 @@ void lssp_pc_ilu_solve_lu_matrix(lssp_mat_csr L, lssp_mat_csr U, double *x, doub
 // pc.solve of ILUK / ILUT (reference src/solver-tri.cxx:57-60): the factors are resident on the device
 void lssp_pc_ilu_solve(LSSP_PC *pc, lssp_vec x, lssp_vec rhs)
 {
-    assert(pc->gpu != NULL);
-    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc->gpu, x.d, rhs.d));
+    assert(pc_dev(pc) != NULL);
+    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc_dev(pc), x.d, rhs.d));
 }
 
 // ---- preconditioners (reference src/pc.cxx, src/pc-iluk.cxx:554-592, src/pc-ilut.cxx:423-466) ----------
@@ -527,7 +562,7 @@ void lssp_pc_create(LSSP_PC &pc, LSSP_PC_TYPE type)
     pc.solve = NULL;
     pc.destroy = NULL;
     pc.data = NULL;
-    pc.gpu = NULL;
+    side_set(&pc, NULL);
     lssp_mat_init(pc.L);
     lssp_mat_init(pc.U);
     lssp_mat_init(pc.D);
@@ -624,14 +659,14 @@ static void lssp_pc_sxamg_destroy(LSSP_PC *pc)   // src/pc-sxamg.cxx:27-40
 // pc.solve: one cycle from the incoming x (src/pc-sxamg.cxx:42-73)
 static void amg_solve(LSSP_PC *pc, lssp_vec x, lssp_vec rhs)
 {
-    assert(pc != NULL && pc->gpu != NULL);
-    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc->gpu, x.d, rhs.d));
+    assert(pc != NULL && pc_dev(pc) != NULL);
+    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc_dev(pc), x.d, rhs.d));
 }
 
 void lssp_pc_sxamg_assemble(LSSP_PC &pc, LSSP_SOLVER s)   // src/pc-sxamg.cxx:75-126
 {
     assert(pc.sxamg != NULL);
-    pc.gpu = build_device_amg(s.A, (const lsspg_csr *)s.gpu, pc.sxamg->pars);
+    pc.data = build_device_amg(s.A, (const lsspg_csr *)solver_dev(s), pc.sxamg->pars);
     pc.solve = amg_solve;
     pc.destroy = lssp_pc_sxamg_destroy;
 }
@@ -661,7 +696,7 @@ int lssp_solver_sxamg(LSSP_SOLVER *solver)
     solver->sxamg->pars.maxit = solver->maxit;
     solver->sxamg->pars.verb = solver->verb;
     solver->sxamg->pars.tol = solver->tol_rel;
-    lsspg_pc *d = build_device_amg(solver->A, (const lsspg_csr *)solver->gpu, solver->sxamg->pars);
+    lsspg_pc *d = build_device_amg(solver->A, (const lsspg_csr *)solver_dev(*solver), solver->sxamg->pars);
     int nits = 0;
     double ares = 0.;
     GPU(lsspg_amg_solve_host(ctx(), d, solver->rhs.d, solver->x.d, solver->tol_rel, solver->maxit, &nits, &ares));
@@ -679,8 +714,8 @@ void lssp_solver_sxamg_set_pars(LSSP_SOLVER *solver, SX_AMG_PARS *pars)   // src
 
 static void release_device_pc(LSSP_PC *pc)
 {
-    if (pc->gpu) lsspg_pc_destroy(ctx(), (lsspg_pc *)pc->gpu);
-    pc->gpu = NULL;
+    if (pc_dev(pc)) lsspg_pc_destroy(ctx(), (lsspg_pc *)pc_dev(pc));
+    pc_dev_set(pc, NULL);
 }
 
 void lssp_pc_destroy(LSSP_PC &pc)
@@ -706,7 +741,7 @@ static void adopt_factors(LSSP_PC &pc, lsspg_factors *F)
     lsspg_factors_destroy(F);
     lsspg_pc *d = NULL;
     GPU(lsspg_pc_create_ilu(ctx(), n, pc.L.Ap, pc.L.Aj, pc.L.Ax, pc.U.Ap, pc.U.Aj, pc.U.Ax, &d));
-    pc.gpu = d;
+    pc_dev_set(&pc, d);
     pc.cache = lssp_malloc<double>(n);
     pc.solve = lssp_pc_ilu_solve;
 }
@@ -760,8 +795,8 @@ void lssp_pc_ilut_set_p(LSSP_PC &pc, int p) { pc.ilut_p = p; }
 // pc.solve: x = U^-1 D L^-1 rhs (src/pc-biluk.cxx:22-60) with the factors resident on the device
 void lssp_pc_bilu_solve(LSSP_PC *pc, lssp_vec x, lssp_vec rhs)
 {
-    assert(pc->gpu != NULL);
-    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc->gpu, x.d, rhs.d));
+    assert(pc_dev(pc) != NULL);
+    GPU(lsspg_pc_apply_host(ctx(), (lsspg_pc *)pc_dev(pc), x.d, rhs.d));
 }
 
 void lssp_pc_biluk_destroy(LSSP_PC *pc)   // src/pc-biluk.cxx:303-313
@@ -792,7 +827,7 @@ static void adopt_block_factors(LSSP_PC &pc, lsspg_bfactors *F)
     lsspg_bfactors_destroy(F);
     lsspg_pc *d = NULL;
     GPU(lsspg_pc_create_bilu(ctx(), n, pc.L.Ap, pc.L.Aj, pc.L.Ax, pc.D.Ap, pc.D.Aj, pc.D.Ax, pc.U.Ap, pc.U.Aj, pc.U.Ax, &d));
-    pc.gpu = d;
+    pc_dev_set(&pc, d);
     pc.cache = lssp_malloc<double>(2 * n);   // src/pc-biluk.cxx:406
     pc.solve = lssp_pc_bilu_solve;
     pc.destroy = lssp_pc_biluk_destroy;
@@ -863,7 +898,7 @@ void lssp_pc_assemble(LSSP_PC &pc, LSSP_SOLVER s)
     lssp_mat_init(pc.U);
     lssp_mat_init(pc.D);
     pc.A = s.A;
-    pc.gpu = NULL;
+    if (pc.type != LSSP_PC_USER) pc.data = NULL;
     switch (pc.type) {
         case LSSP_PC_NON: {
             pc.cache = NULL;
@@ -871,7 +906,7 @@ void lssp_pc_assemble(LSSP_PC &pc, LSSP_SOLVER s)
             pc.destroy = NULL;
             lsspg_pc *d = NULL;
             GPU(lsspg_pc_create_non(ctx(), s.A.num_rows, &d));
-            pc.gpu = d;
+            pc_dev_set(&pc, d);
             break;
         }
         case LSSP_PC_ILUK:
@@ -899,7 +934,7 @@ void lssp_pc_assemble(LSSP_PC &pc, LSSP_SOLVER s)
             assert(pc.solve != NULL);
             lsspg_pc *d = NULL;
             GPU(lsspg_pc_create_user(ctx(), s.A.num_rows, user_pc_trampoline, &pc, &d));
-            pc.gpu = d;
+            pc_dev_set(&pc, d);
             break;
         }
         default:
@@ -963,7 +998,7 @@ void lssp_solver_assemble(LSSP_SOLVER &s, lssp_mat_csr &Ax, lssp_vec x, lssp_vec
     s.A = A;
     lsspg_csr *dA = NULL;
     GPU(lsspg_csr_upload(ctx(), A.num_rows, A.num_cols, A.Ap, A.Aj, A.Ax, &dA));
-    s.gpu = dA;
+    side_set(s.A.Ap, dA);
     if (s.verb > 1) lssp_printf("solver: assemble time: %g\n", lssp_get_time() - t);
     s.assembled = true;
     lssp_pc_assemble(pc, s);
@@ -977,8 +1012,10 @@ void lssp_solver_destroy(LSSP_SOLVER &s, LSSP_PC &pc)
     if (s.type == LSSP_SOLVER_SXAMG) lssp_solver_sxamg_destroy(s);   // src/lssp.cxx:240-244
 #endif
     lssp_pc_destroy(pc);   // before the matrix: an AMG preconditioner shares the device copy of A
-    if (s.gpu) lsspg_csr_destroy(ctx(), (lsspg_csr *)s.gpu);
-    s.gpu = NULL;
+    if (solver_dev(s)) {
+        lsspg_csr_destroy(ctx(), (lsspg_csr *)solver_dev(s));
+        side_set(s.A.Ap, NULL);
+    }
     s.assembled = false;
 }
 
@@ -1033,7 +1070,7 @@ static int drive(LSSP_SOLVER &solver, LSSP_PC &pc, int kind, const char *name)
         lssp_printf("%s: tolerance rbn: %g\n", name, solver.tol_rb);
     }
     lsspg_solve_info info;
-    GPU(lsspg_krylov_solve_host(ctx(), kind, (lsspg_csr *)solver.gpu, (lsspg_pc *)pc.gpu, solver.rhs.d, solver.x.d, &o, &info));
+    GPU(lsspg_krylov_solve_host(ctx(), kind, (lsspg_csr *)solver_dev(solver), (lsspg_pc *)pc_dev(&pc), solver.rhs.d, solver.x.d, &o, &info));
     solver.residual = info.residual;
     solver.nits = info.nits;
     if (solver.verb >= 2) {

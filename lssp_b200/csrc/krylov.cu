@@ -84,7 +84,7 @@ int krylov_cg(KrylovArgs &k)
             residual = ctx->h_scal[S_HIST + j];
             record(k, it + j, residual);
             if (k.verb >= 1)
-                printf("cg: itr: %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", it + j, residual,
+                log_printf("cg: itr: %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", it + j, residual,
                        (err_rel == 0 ? 0 : residual / err_rel), (b_norm == 0 ? 0 : residual / b_norm));
             if (residual <= tol) {
                 converged = true;
@@ -182,7 +182,7 @@ int krylov_bicgstab(KrylovArgs &k)
         for (; j < nb; j++) {
             if (brk == j + 1) {   // ||s|| <= LSSP_BREAKDOWN  (:117-128)
                 LSSPG_TRY(read_scalars(ctx, S_SN, 1, false));
-                printf("bicgstab: ||s|| is too small: %f, terminated.\n", ctx->h_scal[S_SN]);
+                log_printf("bicgstab: ||s|| is too small: %f, terminated.\n", ctx->h_scal[S_SN]);
                 LSSPG_TRY(clear_flags(ctx));
                 LSSPG_TRY(vec_xpay_inplace(ctx, n, coef_slot(S_ALPHA), ph, k.x));
                 SpmvDots d; d.ndot = 1; d.out_slot = S_XR;
@@ -196,7 +196,7 @@ int krylov_bicgstab(KrylovArgs &k)
             residual = ctx->h_scal[S_HIST + j];
             record(k, it + j, residual);
             if (k.verb >= 1)
-                printf("bicgstab: itr: %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", it + j, residual,
+                log_printf("bicgstab: itr: %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", it + j, residual,
                        (err_rel == 0 ? 0 : residual / err_rel), (b_norm == 0 ? 0 : residual / b_norm));
             if (residual <= tol) {
                 done = true;
@@ -204,7 +204,7 @@ int krylov_bicgstab(KrylovArgs &k)
             }
             if (aux == j + 1) {   // rho1 == 0 at the top of the next iteration (:89-92)
                 if (it + j + 1 < k.maxit) {
-                    printf("bicgstab: method failed.!\n");
+                    log_printf("bicgstab: method failed.!\n");
                     k.info->breakdown = 1;
                     j++;          // the loop counter had already advanced when the reference breaks
                     done = true;
@@ -307,11 +307,17 @@ int lsspg_krylov_solve_host(lsspg_ctx *ctx, int solver, const lsspg_csr *A, lssp
 {
     LSSPG_CHECK(ctx && A && hb && hx, "lsspg_krylov_solve_host: NULL argument");
     const size_t n = A->num_rows;
-    LSSPG_TRY(ensure_stage(ctx, (size_t)(A->num_cols > A->num_rows ? A->num_cols : A->num_rows)));
-    LSSPG_CUDA(cudaMemcpyAsync(ctx->stage[0], hx, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    LSSPG_CUDA(cudaMemcpyAsync(ctx->stage[1], hb, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    LSSPG_TRY(lsspg_krylov_solve(ctx, solver, A, pc, ctx->stage[1], ctx->stage[0], opts, info));
-    LSSPG_CUDA(cudaMemcpyAsync(hx, ctx->stage[0], n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // x and b of the running solve get vectors of their OWN (from the work-vector pool), not the context's staging
+    // buffers: a user preconditioner runs on the host inside the solve (pc.cu: LSSPG_PC_USER) and may call lssp_mv_*,
+    // lssp_pc_ilu_solve, amg_solve -- all of which stage through ctx->stage[] (the reference allows such calls from
+    // pc.solve, include/type-defs.h:104).
+    Workspace ws(ctx, (long long)(A->num_cols > A->num_rows ? A->num_cols : A->num_rows));
+    double *dx = ws.vec(), *db = ws.vec();
+    LSSPG_CHECK(dx && db, "lsspg_krylov_solve_host: out of device memory");
+    LSSPG_CUDA(cudaMemcpyAsync(dx, hx, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LSSPG_CUDA(cudaMemcpyAsync(db, hb, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LSSPG_TRY(lsspg_krylov_solve(ctx, solver, A, pc, db, dx, opts, info));
+    LSSPG_CUDA(cudaMemcpyAsync(hx, dx, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -229,7 +229,7 @@ int krylov_gmres(KrylovArgs &k)
         LSSPG_TRY(op.norm(rg, &beta));
         record(k, cycle++, beta);
         if (k.verb >= 1)
-            printf("gmres: itr: %4d / %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_inner, itr_inner, beta,
+            log_printf("gmres: itr: %4d / %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_inner, itr_inner, beta,
                    (err_rel == 0 ? 0 : beta / err_rel), (b_norm == 0 ? 0 : beta / b_norm));
         if (beta <= tol) break;
         gstol = rtol * gs_norm / (beta / err_rel) * 0.5;              // :220
@@ -414,7 +414,7 @@ int krylov_idrs(KrylovArgs &k, const lsspg_solver_opts *raw)
             iter++;
             LSSPG_TRY(op.norm(r, &nrm2));
             record(k, iter - s - 1, nrm2);
-            if (k.verb >= 1) printf("idrs: itr: %5d, abs res: %.6e, rel res: %.6e\n", iter, nrm2, nrm2 / ires);
+            if (k.verb >= 1) log_printf("idrs: itr: %5d, abs res: %.6e, rel res: %.6e\n", iter, nrm2, nrm2 / ires);
             if (tol >= nrm2) break;
             std::vector<const double *> px(s), py(s);
             std::vector<double> hh(s);
@@ -544,7 +544,7 @@ int krylov_rgmres(KrylovArgs &k)
             beta = h.rotate(i);
             record(k, itr_inner - 1, beta);
             if (k.verb >= 1)
-                printf("rgmres: itr: %4d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_inner, beta,
+                log_printf("rgmres: itr: %4d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_inner, beta,
                        (err_rel == 0 ? 0 : beta / err_rel), (b_norm == 0 ? 0 : beta / b_norm));
             if (beta <= tol) break;
         }
@@ -650,7 +650,7 @@ int krylov_lgmres(KrylovArgs &k)
         LSSPG_TRY(op.norm(rg, &beta));
         record(k, itr_outer, beta);
         if (k.verb >= 1)
-            printf("lgmres: itr: %4d / %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_outer, itr_inner, beta,
+            log_printf("lgmres: itr: %4d / %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_outer, itr_inner, beta,
                    (err_rel == 0 ? 0 : beta / err_rel), (b_norm == 0 ? 0 : beta / b_norm));
         if (beta <= tol) break;
         gstol = rtol * gs_norm / (beta / err_rel) * 0.5;
@@ -717,7 +717,7 @@ int krylov_rlgmres(KrylovArgs &k)
             beta = h.rotate(i);
             record(k, itr_inner - 1, beta);
             if (k.verb >= 1)
-                printf("rlgmres: itr: %4d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_inner, beta,
+                log_printf("rlgmres: itr: %4d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", itr_inner, beta,
                        (err_rel == 0 ? 0 : beta / err_rel), (b_norm == 0 ? 0 : beta / b_norm));
             if (beta <= tol) break;
         }

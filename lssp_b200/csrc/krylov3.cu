@@ -346,7 +346,7 @@ int krylov_qmrcgstab(KrylovArgs &k)
         LSSPG_TRY(d.norm(rk, &t1));
         rerror = t1 / ires;
         record(k, it, rerror);
-        if (k.verb >= 1) printf("qmrcgstab: itr: %4d, rel res: %.6e\n", it, rerror);
+        if (k.verb >= 1) log_printf("qmrcgstab: itr: %4d, rel res: %.6e\n", it, rerror);
         if (rerror <= tol) {
             LSSPG_TRY(d.resid(xk, tk));
             LSSPG_TRY(d.norm(tk, &residual));

@@ -98,7 +98,7 @@ int krylov_orthomin(KrylovArgs &k)
         LSSPG_TRY(d.norm(z, &beta));
         record(k, it, beta);
         if (k.verb >= 1)
-            printf("orthomin: itr: %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", it, beta,
+            log_printf("orthomin: itr: %5d, abs res: %.6e, rel res: %.6e, rbn: %.6e\n", it, beta,
                    (err_rel == 0 ? 0 : beta / err_rel), (b_norm == 0 ? 0 : beta / b_norm));
         if (beta <= tol) break;
     }
@@ -276,7 +276,7 @@ static int gpbic(KrylovArgs &k, const lsspg_solver_opts *raw, bool cr, const cha
         LSSPG_TRY(d.axpby(-1, r, 1, y));
         LSSPG_TRY(d.axpbyz(-alpha, ap, 1, r, t));
         LSSPG_TRY(d.norm(t, &nrm2));
-        if (k.verb >= 1) printf("%s: itr: %5d, abs res: %.6e, rel res: %.6e\n", name, iter, nrm2, nrm2 / ires);
+        if (k.verb >= 1) log_printf("%s: itr: %5d, abs res: %.6e, rel res: %.6e\n", name, iter, nrm2, nrm2 / ires);
         if (nrm2 <= tol) {
             LSSPG_TRY(d.axpby(alpha, p, 1, x));
             break;
@@ -410,7 +410,7 @@ int krylov_bicgstabl(KrylovArgs &k, const lsspg_solver_opts *raw)
             LSSPG_TRY(d.axpby(-gamma1[j], r[j], 1, r[0]));
         }
         LSSPG_TRY(d.norm(r[0], &nrm2));
-        if (k.verb >= 1) printf("bicgstabl: itr: %5d, abs res: %.6e, rel res: %.6e\n", iter, nrm2, nrm2 / ires);
+        if (k.verb >= 1) log_printf("bicgstabl: itr: %5d, abs res: %.6e, rel res: %.6e\n", iter, nrm2, nrm2 / ires);
         if (nrm2 < tol) { LSSPG_TRY(back()); break; }
     }
     return d.finish(iter, nrm2);

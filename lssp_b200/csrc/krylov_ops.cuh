@@ -52,7 +52,7 @@ struct Drv : Ops {
     void report(const char *name, int iter, double nrm2, double ires, int minverb)
     {
         record(k, iter > 0 ? iter - 1 : 0, nrm2);
-        if (k.verb >= minverb) printf("%s: itr: %5d, abs res: %.6e, rel res: %.6e\n", name, iter, nrm2, nrm2 / ires);
+        if (k.verb >= minverb) log_printf("%s: itr: %5d, abs res: %.6e, rel res: %.6e\n", name, iter, nrm2, nrm2 / ires);
     }
     int finish(int nits, double residual)
     {

@@ -28,6 +28,7 @@
 #include "blas1.cuh"
 #include "comm.cuh"
 #include "spmv.cuh"
+#include "host_par.h"
 
 namespace lsspg {
 
@@ -569,6 +570,15 @@ int lsspg_csr_upload(lsspg_ctx *ctx, int num_rows, int num_cols, const int *hAp,
     LSSPG_CHECK(nnz >= 0 && hAp[0] == 0, "lsspg_csr_upload: malformed Ap");
     LSSPG_CHECK(nnz == 0 || (hAj && hAx), "lsspg_csr_upload: NULL Aj/Ax");
     A->num_nnzs = nnz;
+    {   // a column index outside [0, num_cols) would become an out-of-bounds gather on the device
+        const int np = host_threads();
+        std::vector<char> bad(np, 0);
+        parallel_ranges(nnz, [&](long long e0, long long e1, int p) {
+            for (long long e = e0; e < e1; e++)
+                if (hAj[e] < 0 || hAj[e] >= num_cols) { bad[p] = 1; return; }
+        }, np);
+        for (char b : bad) LSSPG_CHECK(!b, "lsspg_csr_upload: column index out of range");
+    }
     std::vector<int> rows;
     std::vector<unsigned char> kinds;
     build_tiles(num_rows, hAp, ctx->opt_spmv_exact != 0, rows, kinds, A->max_tile_nnz, A->num_stream_tiles);

@@ -60,8 +60,9 @@ def test_facade_exports_the_reference_cxx_symbols():
 
 
 def test_facade_symbols_are_link_compatible_with_the_reference():
-    """Same MANGLED names as the reference build for every hot-path function, so an object file
-    compiled against the reference headers would also resolve against liblssp.so."""
+    """Same MANGLED names as the reference build for every hot-path function, so an object file compiled against the
+    reference headers resolves against liblssp.so -- and works, because the structs are binary-identical
+    (test_structs_are_binary_identical_to_the_reference, test_unmodified_reference_example_runs_against_the_library)."""
     if not os.path.exists(REF):
         pytest.skip("oracle/_ref not built")
     ours, ref_dem, ref_m = mangled(LIB), exported(REF), mangled(REF)
@@ -94,6 +95,62 @@ def test_block_ilu_symbols_are_link_compatible_with_a_blas_build_of_the_referenc
     want = {m for m in mangled(refb) if re.match(r"_Z\d+lssp_pc_bilu", m)}
     assert len(want) == 4, want     # bilu_solve, biluk_destroy, biluk_assemble_mat, biluk_assemble
     assert not (want - mangled(LIB)), sorted(want - mangled(LIB))
+
+
+def test_structs_are_binary_identical_to_the_reference(tmp_path):
+    """tests/cxx/struct_layout_check.cpp compiled against the reference's headers (config.h generated with the USE_*
+    switches of include/lssp/config.h: BLAS, LAPACK, SXAMG on) and against include/lssp must print the same sizes,
+    member offsets and enumerator values: LSSP_PC / LSSP_SOLVER cross the API by reference AND by value
+    (lssp_pc_assemble(LSSP_PC &, LSSP_SOLVER), reference include/pc.h:15)."""
+    refinc = "/root/reference/include"
+    if not os.path.exists(refinc):
+        pytest.skip("/root/reference not present")
+    cfg = tmp_path / "cfg"
+    cfg.mkdir()
+    text = open(os.path.join(refinc, "config.h.in")).read()
+    for name in ("HAVE_SYS_TIME_H", "USE_BLAS", "USE_LAPACK", "USE_SXAMG"):
+        text = re.sub(r"(#define\s+%s\s+)0" % name, r"\g<1>1", text)
+    (cfg / "config.h").write_text(text)
+    src = os.path.join(ROOT, "tests", "cxx", "struct_layout_check.cpp")
+    outs = []
+    for tag, inc in (("ref", ["-I" + str(cfg), "-I" + refinc]), ("ours", ["-I" + os.path.join(ROOT, "include", "lssp")])):
+        exe = str(tmp_path / tag)
+        subprocess.run(["g++", "-std=c++17"] + inc + [src, "-o", exe], check=True)
+        outs.append(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1] and "LSSP_SOLVER.assembled" in outs[0]
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_example_runs_against_the_library():
+    """examples/exam_ref = /root/reference/example/exam.cxx, UNMODIFIED, compiled against the REFERENCE's own headers
+    (lssp_b200/csrc/Makefile, in the build container) and linked against liblssp.so: the drop-in claim of SURVEY.md 8b.
+    The reference's run of this program prints 49 iterations, residual 8.18058783e-06, ||x|| = 4.25082937e+04."""
+    exe = os.path.join(ROOT, "examples", "exam_ref")
+    if not os.path.exists(exe):
+        pytest.skip("examples/exam_ref not built (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"solution L2 norm: (\S+) residual: (\S+)", out.stdout)
+    v = re.search(r"verification, residual: (\S+)", out.stdout)
+    its = re.findall(r"gmres: itr:\s*\d+ /\s*(\d+)", out.stdout)
+    assert m and v and its, out.stdout
+    assert abs(int(its[-1]) - 49) <= 1, out.stdout
+    assert abs(float(m.group(1)) - 4.25082937e+04) <= 1e-6 * 4.25082937e+04
+    assert float(m.group(2)) <= 1.0e-5 and abs(float(v.group(1)) - float(m.group(2))) <= 1e-3 * float(m.group(2)) + 1e-9
+    if int(its[-1]) == 49:
+        assert abs(float(m.group(2)) - 8.18058783e-06) <= 1e-5 * 8.18058783e-06
+
+
+@pytest.mark.gpu
+def test_user_preconditioner_may_call_the_library_and_log_files_get_the_iteration_lines(tmp_path):
+    """tests/cxx/user_pc_and_log.cpp: a LSSP_PC_USER preconditioner that calls lssp_mv_mxy and an inner ILU's pc.solve
+    from inside the running solve must give the solve of the built-in ILUK bit for bit (the Krylov x / b must not
+    share the context's staging buffers); and lssp_solver_set_log files receive the per-iteration lines."""
+    exe = os.path.join(ROOT, "examples", "user_pc_and_log")
+    out = subprocess.run([exe, str(tmp_path / "solve.log")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "reentrant user preconditioner: OK" in out.stdout, out.stdout
+    assert re.search(r"log file: \d+ iteration lines for \d+ iterations: OK", out.stdout), out.stdout
 
 
 @pytest.mark.gpu
