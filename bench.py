@@ -251,6 +251,14 @@ def main():
     ap.add_argument("--amg-order", type=int, default=1, help="cf_order of the AMG smoother (cg_amg): 1 C/F by index, 2 multicolour")
     ap.add_argument("--ref-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="--gpus > 1: weak = a grid^3 block per GPU (default, the driver's curve); strong = ONE grid^3 problem "
+                         "cut into z-slabs over the GPUs")
+    ap.add_argument("--shape", default="slab", choices=["slab", "cubic"],
+                    help="--gpus > 1, weak scaling: slab = grid x grid x (grid n_gpus); cubic = the most cubic global grid with "
+                         "grid^3 rows per GPU (8 GPUs, grid 256: 512^3, 2 MiB halo planes)")
+    ap.add_argument("--operator", default=None, choices=[None, "lap", "cd"],
+                    help="--gpus > 1: lap = 7-point Laplacian, cd = convection-diffusion (default: cd for bicgstab_ilu0, else lap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -302,6 +302,12 @@ int lsspg_amg_solve_host(lsspg_ctx *ctx, lsspg_pc *amg, const double *hb, double
 typedef struct lsspg_halo lsspg_halo;
 int lsspg_comm_unique_id(void *out128);                       /* rank 0: 128-byte NCCL id to broadcast */
 int lsspg_comm_init(lsspg_ctx *ctx, int rank, int nranks, const void *id128);
+/* One-shot peer-to-peer all-reduce for the dot products (k_p2p_allreduce_fin, comm.cu) instead of ncclAllReduce:
+ * (1) every rank allocates its mailbox and returns its 64-byte CUDA IPC handle; (2) after the launcher has all-gathered
+ * the handles (rank order) and passed a barrier, every rank maps its peers' mailboxes.  Optional: without it the sums
+ * travel through NCCL. */
+int lsspg_comm_p2p_local(lsspg_ctx *ctx, void *handle64);
+int lsspg_comm_p2p_connect(lsspg_ctx *ctx, const void *handles);
 int lsspg_comm_destroy(lsspg_ctx *ctx);
 int lsspg_comm_size(lsspg_ctx *ctx, int *rank, int *nranks);
 int lsspg_allreduce_sum(lsspg_ctx *ctx, double *d_buf, int count);   /* in place */

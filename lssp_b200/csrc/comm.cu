@@ -68,9 +68,18 @@ static int nccl_bind()
         }                                                                                  \
     } while (0)
 
+constexpr int kP2PMaxRanks = 64;
+constexpr int kP2PSlot = kMaxRedK + 1;   // K sums + the sequence number that announces them
+
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // one-shot peer-to-peer all-reduce (see k_p2p_allreduce_fin): this rank's mailbox and the peers' mailboxes,
+    // mapped with CUDA IPC
+    double *mail = nullptr;               // [2][kP2PMaxRanks][kP2PSlot]
+    double **d_peer_mail = nullptr;       // device array of nranks mailbox pointers (own one included)
+    std::vector<void *> opened;
+    unsigned long long seq = 0;
 };
 
 int comm_allreduce(lsspg_ctx *ctx, double *d_buf, int count)
@@ -87,9 +96,57 @@ __global__ void k_fin(FinProg fin, double *scal, int *flags, const int *stop)
     fin_run(fin, scal, flags);
 }
 
+// One-shot all-reduce of K <= 8 doubles over NVLink, fused with the FinProg that derives alpha / beta / omega from the
+// global sums: ONE launch of one CTA instead of ncclAllReduce (8 bytes: ~12 us of launch + protocol latency) followed by
+// a one-thread kernel.  Every rank stores its partial sums and then the sequence number of this reduction into slot
+// [seq & 1][rank] of EVERY rank's mailbox (peer stores through the IPC mappings), waits until its own mailbox shows the
+// sequence number in all P slots, and adds the P contributions in rank order -- the same order on every rank, so all
+// ranks hold bit-identical sums, run to run.  Two slot generations suffice: a rank can only be one reduction ahead of
+// the slowest one, because finishing reduction s needs everybody's contribution to s.
+__global__ void __launch_bounds__(64) k_p2p_allreduce_fin(double *const *peer_mail, int rank, int nranks, unsigned long long seq, int K,
+                                                          int slot, FinProg fin, double *scal, int *flags, const int *stop, int *err)
+{
+    const int t = threadIdx.x;
+    const size_t gen = (size_t)(seq & 1) * kP2PMaxRanks * kP2PSlot;
+    if (t < nranks) {
+        double *dst = peer_mail[t] + gen + (size_t)rank * kP2PSlot;
+        for (int k = 0; k < K; k++) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + k), "d"(scal[slot + k]) : "memory");
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + kMaxRedK), "l"(seq) : "memory");
+        const double *src = peer_mail[rank] + gen + (size_t)t * kP2PSlot;
+        unsigned long long got = 0;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src + kMaxRedK) : "memory");
+            if (++spins > (1ll << 26)) { *err = 1; break; }
+        } while (got != seq);
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double *mine = peer_mail[rank] + gen;
+        for (int k = 0; k < K; k++) {
+            double s = 0.0;
+            for (int r = 0; r < nranks; r++) {
+                double v;
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(mine + (size_t)r * kP2PSlot + k) : "memory");
+                s += v;
+            }
+            scal[slot + k] = s;
+        }
+        if (fin.n > 0 && !(stop && *stop)) fin_run(fin, scal, flags);
+    }
+}
+
 // after a reducing kernel that deferred its FinProg: combine the ranks' partial sums, then derive
 int red_post(lsspg_ctx *ctx, int slot, int K, const FinProg &fin, bool guarded)
 {
+    Comm *c = (Comm *)ctx->comm;
+    if (c && c->nranks > 1 && c->d_peer_mail && K <= kMaxRedK) {
+        c->seq++;
+        LSSPG_LAUNCH(ctx, k_p2p_allreduce_fin, 1, 64, 0, c->d_peer_mail, c->rank, c->nranks, c->seq, K, slot, fin, ctx->d_scal,
+                     ctx->d_flags, guarded ? ctx->d_flags + FLAG_STOP : (const int *)nullptr, ctx->d_flags + FLAG_TRI_TIMEOUT);
+        return 0;
+    }
     LSSPG_TRY(comm_allreduce(ctx, ctx->d_scal + slot, K));
     if (fin.n > 0)
         LSSPG_LAUNCH(ctx, k_fin, 1, 1, 0, fin, ctx->d_scal, ctx->d_flags,
@@ -149,11 +206,56 @@ int lsspg_comm_init(lsspg_ctx *ctx, int rank, int nranks, const void *id128)
     return 0;
 }
 
+// Peer-to-peer all-reduce, step 1: allocate this rank's mailbox and hand out its CUDA IPC handle (64 bytes), to be
+// all-gathered by the launcher (torch.distributed in lssp_b200/dist.py).
+int lsspg_comm_p2p_local(lsspg_ctx *ctx, void *handle64)
+{
+    Comm *c = (Comm *)ctx->comm;
+    LSSPG_CHECK(c && handle64, "lsspg_comm_p2p_local: no communicator");
+    LSSPG_CHECK(c->nranks <= kP2PMaxRanks, "lsspg_comm_p2p_local: more than %d ranks", kP2PMaxRanks);
+    LSSPG_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(double) * 2 * kP2PMaxRanks * kP2PSlot;
+    if (!c->mail) {
+        LSSPG_CUDA(cudaMalloc(&c->mail, bytes));
+        LSSPG_CUDA(cudaMemset(c->mail, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    LSSPG_CUDA(cudaIpcGetMemHandle(&h, c->mail));
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+// step 2: map every peer's mailbox (handles[r] = rank r's 64-byte handle).  After this, dot products and norms are
+// combined by k_p2p_allreduce_fin instead of ncclAllReduce.  Call on all ranks, after a barrier that follows step 1.
+int lsspg_comm_p2p_connect(lsspg_ctx *ctx, const void *handles)
+{
+    Comm *c = (Comm *)ctx->comm;
+    LSSPG_CHECK(c && c->mail && handles, "lsspg_comm_p2p_connect: call lsspg_comm_p2p_local first");
+    LSSPG_CUDA(cudaSetDevice(ctx->device));
+    std::vector<double *> ptrs(c->nranks, nullptr);
+    for (int r = 0; r < c->nranks; r++) {
+        if (r == c->rank) { ptrs[r] = c->mail; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)r, sizeof(h));
+        void *p = nullptr;
+        LSSPG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->opened.push_back(p);
+        ptrs[r] = (double *)p;
+    }
+    LSSPG_CUDA(cudaMalloc(&c->d_peer_mail, sizeof(double *) * c->nranks));
+    LSSPG_CUDA(cudaMemcpy(c->d_peer_mail, ptrs.data(), sizeof(double *) * c->nranks, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 int lsspg_comm_destroy(lsspg_ctx *ctx)
 {
     Comm *c = (Comm *)ctx->comm;
     if (!c) return 0;
     cudaStreamSynchronize(ctx->stream);
+    for (void *p : c->opened) cudaIpcCloseMemHandle(p);
+    cudaFree(c->d_peer_mail);
+    cudaFree(c->mail);
     if (c->comm) nccl.CommDestroy(c->comm);
     delete c;
     ctx->comm = nullptr;

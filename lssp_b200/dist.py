@@ -140,6 +140,7 @@ class DeviceShard:
         if self.owns_comm:
             buf = (C.c_char * 128).from_buffer_copy(id_bytes)
             check(L.lsspg_comm_init(ctx.h, shard.rank, shard.P, buf))
+            self._connect_p2p()
         self.A = api.Csr(ctx, (shard.Ap, shard.Aj, shard.Ax), num_cols=shard.n_owned + shard.n_ghost)
         self.halo = C.c_void_p()
         np_ = len(shard.peers)
@@ -150,6 +151,30 @@ class DeviceShard:
         check(L.lsspg_halo_create(ctx.h, shard.n_owned, np_, peers, sc, si.ctypes.data_as(C.c_void_p), rc,
                                   C.byref(self.halo)))
         check(L.lsspg_csr_set_halo(self.A.h, self.halo))
+
+    def _connect_p2p(self):
+        """Peer-to-peer mailboxes for the one-shot all-reduce of the dot products (comm.cu): CUDA IPC handles exchanged
+        with torch.distributed; LSSPG_P2P_ALLREDUCE=0 keeps ncclAllReduce."""
+        import os
+        if os.environ.get("LSSPG_P2P_ALLREDUCE", "1") == "0" or self.shard.P < 2:
+            return
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        L = lib()
+        mine = (C.c_char * 64)()
+        ok = L.lsspg_comm_p2p_local(self.ctx.h, mine) == 0
+        handles = [None] * self.shard.P
+        dist.all_gather_object(handles, bytes(mine) if ok else None)
+        if any(h is None for h in handles):
+            return
+        blob = (C.c_char * (64 * self.shard.P)).from_buffer_copy(b"".join(handles))
+        ok = L.lsspg_comm_p2p_connect(self.ctx.h, blob) == 0
+        flags = [None] * self.shard.P
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            raise RuntimeError("peer-to-peer all-reduce: a rank could not map its peers (%s); set LSSPG_P2P_ALLREDUCE=0"
+                               % lib().lsspg_last_error().decode())
 
     @staticmethod
     def unique_id():

@@ -35,10 +35,23 @@ def main(args, rank, world, local_rank):
     L = lib()
     N = args.grid
     powerlaw = args.workload == "idrs_powerlaw"
-    dims = (N, N, N * world)
+    strong = getattr(args, "scaling", "weak") == "strong"
+    if strong:
+        dims = (N, N, N)                      # ONE grid^3 problem, z-slabs of N / world planes
+    elif getattr(args, "shape", "slab") == "cubic":
+        f = [1, 1, 1]                         # the most cubic factorisation of the GPU count (8 -> 2 x 2 x 2)
+        w = world
+        while w > 1:
+            p = next(q for q in (2, 3, 5, 7, w) if w % q == 0)
+            f[f.index(min(f))] *= p
+            w //= p
+        dims = (N * f[0], N * f[1], N * f[2])
+    else:
+        dims = (N, N, N * world)
     n = args.pl_rows * world if powerlaw else dims[0] * dims[1] * dims[2]
     blk, r0, r1 = dist.block_rows(n, world, rank)
-    conv = (0.3, 0.2, 0.1) if args.workload == "bicgstab_ilu0" else (0.0, 0.0, 0.0)
+    op = getattr(args, "operator", None) or ("cd" if args.workload == "bicgstab_ilu0" else "lap")
+    conv = (0.3, 0.2, 0.1) if op == "cd" else (0.0, 0.0, 0.0)
     solver = "idrs" if powerlaw else "bicgstab" if args.workload == "bicgstab_ilu0" else "cg"
     t0 = time.perf_counter()
     # BASELINE.json configs[4] (power-law CSR, IDRS(4)): --pl-rows rows per GPU, every rank generates its own block
@@ -128,33 +141,62 @@ def main(args, rank, world, local_rank):
     tmax = torch.tensor([tm.value / 20], dtype=torch.float64, device="cuda")
     td.all_reduce(tmax, op=td.ReduceOp.MAX)
     ms_spmv = float(tmax[0])
+    # the preconditioner application (local to the rank: block-Jacobi), the dominant kernel of the iteration as at N = 1
+    ms_pc = None
+    if pcname != "no preconditioner":
+        z = ctx.empty(nc)
+        pc.apply(z, b)
+        ctx.sync()
+        td.barrier()
+        check(L.lsspg_timer_start(ctx.h, 1))
+        for _ in range(10):
+            pc.apply(z, b)
+        check(L.lsspg_timer_stop(ctx.h, 1, C.byref(tm)))
+        tmax = torch.tensor([tm.value / 10], dtype=torch.float64, device="cuda")
+        td.all_reduce(tmax, op=td.ReduceOp.MAX)
+        ms_pc = float(tmax[0])
     if rank == 0:
         from bench import measured_peak
         peak, peak_kind = measured_peak()
         gbs = D.A.spmv_bytes / ms_spmv / 1e6
-        roof = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
-                "kernel": "spmv_tiles_kernel on one rank's row block, halo exchange (NCCL send/recv) included",
-                "ms": ms_spmv, "bytes": D.A.spmv_bytes, "peak_kind": peak_kind, "per_gpu": True}
-        value = world * its / (total_ms / 1e3)
-        line = {"metric": "%s_iterations_per_second" % args.workload, "value": value, "unit": "iter/s x n_gpus",
+        roof_spmv = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                     "kernel": "SpMV on one rank's row block, halo exchange (pack kernel + NCCL send/recv) included",
+                     "ms": ms_spmv, "bytes": D.A.spmv_bytes, "peak_kind": peak_kind, "per_gpu": True}
+        ms_it = total_ms / its
+        if ms_pc is not None and args.workload != "cg_amg":
+            pgbs = pc.bytes / ms_pc / 1e6
+            roof = {"bound": "hbm", "achieved": pgbs, "peak": peak, "unit": "GB/s", "frac": pgbs / peak, "traffic": None,
+                    "kernel": "triangular sweep of the rank's block-Jacobi ILU (tri_pencil_kernel; 2 launches per application, "
+                              "average of the two), the same kernel bench.py reports at N = 1",
+                    "ms": ms_pc / 2, "bytes": pc.bytes / 2, "share_of_iteration": ms_pc * (2 if solver == "bicgstab" else 1) / ms_it,
+                    "peak_kind": peak_kind, "per_gpu": True}
+        else:
+            roof = dict(roof_spmv)
+        per_s = its / (total_ms / 1e3)
+        value = per_s if strong else world * per_s
+        line = {"metric": "%s_iterations_per_second" % args.workload, "value": value, "unit": "iter/s" if strong else "iter/s x n_gpus",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": ("power-law CSR n=%d (nnz %d on rank 0) IDRS(4), %s, row-sharded over %d GPUs "
                                         "(%d rows per GPU)" % (n, int(rows[0][-1]), pcname, world, args.pl_rows)) if powerlaw else
-                                       "lap3d %dx%dx%d %s + %s, row-sharded over %d GPUs "
-                                       "(%d^3 rows per GPU)" % (dims[0], dims[1], dims[2], solver.upper(), pcname, world, N),
+                                       "%s %dx%dx%d %s + %s, row-sharded (z-slabs) over %d GPUs "
+                                       "(%d rows per GPU)" % ("lap3d" if op == "lap" else "cd3d", dims[0], dims[1], dims[2], solver.upper(),
+                                                              pcname, world, no),
                            "n": n, "rows_per_gpu": no, "ghost_per_gpu": shard.n_ghost, "tol_rel": 1e-7,
                            "iterations_per_solve": r["nits"], "residual": r["residual"],
                            "iterations_per_second": its / (total_ms / 1e3),
-                           "value_definition": "n_gpus x iterations/s (each iteration advances n_gpus shards of the 1-GPU size)",
+                           "value_definition": "iterations/s of the one fixed-size problem" if strong else
+                                               "n_gpus x iterations/s (each iteration advances n_gpus shards of the 1-GPU size)",
+                           "allreduce": "one-shot peer-to-peer kernel (k_p2p_allreduce_fin)" if os.environ.get("LSSPG_P2P_ALLREDUCE", "1") != "0"
+                                        else "ncclAllReduce + k_fin",
                            "preconditioner": "block-Jacobi (triangular sweeps / AMG hierarchy local to each GPU's row block, "
                                              "= reference blocked ILU with blk_size=ceil(n/P)); iteration counts depend on P "
                                              "(SURVEY.md App. A.5)",
                            "l2": "per-GPU working set (1.7 GB CSR + factors) far exceeds the 126 MB L2"},
                 "ms_per_iteration": total_ms / its, "gpu_launches": int(launches), "clocks": clocks,
-                "e2e": {"value": world * e2e_its / e2e_s, "unit": "iter/s x n_gpus", "h2d_bytes_per_step": 16 * no * world,
-                        "d2h_bytes_per_step": 8 * no * world},
-                "roofline": roof,
+                "e2e": {"value": (1 if strong else world) * e2e_its / e2e_s, "unit": "iter/s" if strong else "iter/s x n_gpus",
+                        "h2d_bytes_per_step": 16 * no * world, "d2h_bytes_per_step": 8 * no * world},
+                "roofline": roof, "roofline_spmv": roof_spmv,
                 "setup_s": {"generate_and_shard": t_gen, "pc_host_setup_and_upload": t_pc}}
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
