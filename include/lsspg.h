@@ -63,6 +63,7 @@ int lsspg_ctx_set_option(lsspg_ctx *ctx, int option, int value);
 #define LSSPG_OPT_REDUCE_SEQUENTIAL 4 /* 1: every dot/norm is summed in the reference's sequential order
                                        (src/vector.cxx:129) -> whole solves become bit-identical to the
                                        CPU reference; verification mode, one thread does the adds */
+#define LSSPG_OPT_GRAPHS 5            /* 1 (default): CG replays the launch train of a batch of iterations as a CUDA graph */
 
 int lsspg_malloc(lsspg_ctx *ctx, size_t bytes, void **dptr);
 int lsspg_free(lsspg_ctx *ctx, void *dptr);

@@ -16,7 +16,7 @@ SOLVERS = {"gmres": 0, "lgmres": 1, "rgmres": 2, "rlgmres": 3, "bicgstab": 4, "b
            "bicgsafe": 6, "cg": 7, "cgs": 8, "gpbicg": 9, "cr": 10, "crs": 11, "bicrstab": 12,
            "bicrsafe": 13, "gpbicr": 14, "qmrcgstab": 15, "tfqmr": 16, "orthomin": 17, "idrs": 18}
 MV_MXY, MV_AMXY, MV_AMXPBY, MV_AMXPBYZ = 0, 1, 2, 3
-OPT_SPMV_KERNEL, OPT_SPMV_EXACT, OPT_CHECK_EVERY, OPT_REDUCE_SEQUENTIAL = 1, 2, 3, 4
+OPT_SPMV_KERNEL, OPT_SPMV_EXACT, OPT_CHECK_EVERY, OPT_REDUCE_SEQUENTIAL, OPT_GRAPHS = 1, 2, 3, 4, 5
 
 
 def _p(a):

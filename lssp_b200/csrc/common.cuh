@@ -68,6 +68,7 @@ struct lsspg_ctx {
     int opt_spmv_kernel = 0;
     int opt_spmv_exact = 0;
     int opt_check_every = 8;   // CG / BiCGStab: host reads the residuals every 8 iterations (device-side stop flag)
+    int opt_graphs = 1;              // CG: replay the steady-state launch train as a CUDA graph
     int opt_reduce_sequential = 0;   // verification mode: sums in the reference's sequential order
     double *d_seq = nullptr;         // [kMaxRedK][seq_len] per-element terms of the sums (sequential mode)
     size_t seq_len = 0;

@@ -1,5 +1,6 @@
 // ctx.cu -- device context, memory plumbing and error reporting of liblsspg.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace lsspg {
@@ -103,6 +104,7 @@ int lsspg_ctx_create(int device, lsspg_ctx **out)
     LSSPG_CUDA(cudaMallocHost(&c->h_flags, sizeof(int) * 16));
     LSSPG_CUDA(cudaEventCreate(&c->ev0));
     LSSPG_CUDA(cudaEventCreate(&c->ev1));
+    if (const char *g = getenv("LSSPG_GRAPHS")) c->opt_graphs = atoi(g) != 0;   // 0: no CUDA-graph replay in the drivers
     LSSPG_CUDA(cudaDeviceSynchronize());
     *out = c;
     return 0;
@@ -170,6 +172,7 @@ int lsspg_ctx_set_option(lsspg_ctx *ctx, int option, int value)
         case LSSPG_OPT_SPMV_EXACT: ctx->opt_spmv_exact = value; return 0;
         case LSSPG_OPT_CHECK_EVERY: ctx->opt_check_every = value < 1 ? 1 : value; return 0;
         case LSSPG_OPT_REDUCE_SEQUENTIAL: ctx->opt_reduce_sequential = value; return 0;
+        case LSSPG_OPT_GRAPHS: ctx->opt_graphs = value; return 0;
     }
     set_error("lsspg_ctx_set_option: unknown option %d", option);
     return 1;

@@ -10,6 +10,7 @@
 // iteration counts stay exactly those of the reference.
 #include <algorithm>
 #include "krylov.cuh"
+#include "comm.cuh"
 #include "krylov_ops.cuh"
 
 namespace lsspg {
@@ -54,10 +55,10 @@ int krylov_cg(KrylovArgs &k)
     LSSPG_TRY(write_scalar(ctx, S_TOL, tol));
     const int batch = std::max(1, std::min(ctx->opt_check_every, kMaxBatch));
 
-    while (it < k.maxit && !converged) {
-        const int nb = std::min(batch, k.maxit - it);
+    // one batch of iterations [it0, it0 + nb): the launch train between two read-backs of the residuals
+    auto launch_batch = [&](int it0, int nb) -> int {
         for (int j = 0; j < nb; j++) {
-            const int i = it + j, cur = i & 1, nxt = cur ^ 1;
+            const int i = it0 + j, cur = i & 1, nxt = cur ^ 1;
             if (!non) {
                 LSSPG_TRY(pc_apply(ctx, k.pc, z, r, true));                        // :79
                 const double *xs[1] = {z}, *ys[1] = {r};
@@ -78,6 +79,42 @@ int krylov_cg(KrylovArgs &k)
             o.fin.add(FIN_FLAG_LE, FLAG_STOP, S_HIST + j, S_TOL);                 // :114
             LSSPG_TRY(cg_update_xr(ctx, n, coef_slot(S_ALPHA), p, q, k.x, r, o));
         }
+        return 0;
+    };
+    // CUDA graph of the steady-state batch: with an even batch length every batch after the
+    // first launches the same kernels with the same arguments -- coefficients are slot numbers, the scalars stay on the
+    // device -- so the train is captured once and replayed; small problems are launch-bound (1000^2 CG: 3 launches per
+    // 40 us iteration).  Not on several GPUs (the all-reduce kernel carries a sequence number) and not with a user
+    // preconditioner (host callback).  LSSPG_OPT_GRAPHS = 0 turns it off.
+    const bool use_graph = ctx->opt_graphs && !distributed(ctx) && batch % 2 == 0 && k.pc->kind != LSSPG_PC_USER &&
+                           k.pc->kind != LSSPG_PC_AMG && !ctx->opt_reduce_sequential;
+    cudaGraphExec_t gexec = nullptr;
+    long long graph_launches = 0;
+    struct GraphGuard {
+        cudaGraphExec_t &g;
+        ~GraphGuard() { if (g) cudaGraphExecDestroy(g); }
+    } guard{gexec};
+
+    while (it < k.maxit && !converged) {
+        const int nb = std::min(batch, k.maxit - it);
+        if (use_graph && it >= batch && nb == batch) {
+            if (!gexec) {
+                cudaGraph_t graph = nullptr;
+                const long long l0 = ctx->launches;
+                LSSPG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                const int rc = launch_batch(it, nb);
+                const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                LSSPG_CUDA(ce);
+                graph_launches = ctx->launches - l0;
+                ctx->launches = l0;
+                LSSPG_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+                cudaGraphDestroy(graph);
+            }
+            LSSPG_CUDA(cudaGraphLaunch(gexec, ctx->stream));
+            ctx->launches += graph_launches;
+        }
+        else LSSPG_TRY(launch_batch(it, nb));
         LSSPG_TRY(read_scalars(ctx, S_HIST, nb, true));
         int j = 0;
         for (; j < nb; j++) {

@@ -484,7 +484,7 @@ struct PencilArgs {
     double *mail;
     unsigned int *counter;
     int num_pencils, T, RS, dir;
-    int nb, vr;                 // rhs tiles and steps of values kept in shared memory
+    int nb, vr, l2ahead;        // rhs tiles and steps of values kept in shared memory; steps the value stream is prefetched into L2
     double *x;
     const double *rhs;
     const int *stop;
@@ -517,20 +517,21 @@ __device__ __forceinline__ double pen_ld_stream(const double *p)
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-// Progress words in shared memory.  Deliberately NOT ld.acquire / st.release: those carry a fence that waits for the
-// thread's outstanding global loads -- the value stream fetched P steps ahead -- and would expose the HBM latency in
-// every step (measured: 0.95 ms per sweep with acquire/release).  Shared-memory accesses of one warp are performed in
-// program order, so a volatile flag written after the data (writer) and read before the data (reader) is enough;
-// the "memory" clobbers keep the compiler from moving the accesses.
+// Progress words in shared memory, written by one role and polled by another (compute warps, stagers, valuers, mailer,
+// helper).  They are release / acquire at CTA scope: the data they announce (ring rows, tiles, value ring) is written by
+// OTHER threads of the announcing role, ordered before the announcement by that role's barrier -- release is cumulative
+// over it.  (An earlier version used plain volatile accesses: intermittently wrong sweeps at 256^3, 50 000 of 16.8 M rows,
+// scripts/dist_pc_check.py.  The very first version's acquire loads were slow only because the compute threads then had
+// global loads in flight, which the fence drained; they have none any more.)
 __device__ __forceinline__ int pen_ld_flag(const int *p)
 {
     int v;
-    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned int)__cvta_generic_to_shared(p)) : "memory");
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned int)__cvta_generic_to_shared(p)) : "memory");
     return v;
 }
 __device__ __forceinline__ void pen_st_flag(int *p, int v)
 {
-    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(kPenMaxThreads + kPenExtra, 2) tri_pencil_kern
             bool aborted = false;
             const char *vbase = reinterpret_cast<const char *>(a.vals + h.val_off);
             const long long step_bytes = (long long)NV * T * 8, vend = step_bytes * h.nsteps;
-            for (long long b = (long long)lane * 128; b < step_bytes * kPenL2Ahead && b < vend; b += 32 * 128)
+            for (long long b = (long long)lane * 128; b < step_bytes * a.l2ahead && b < vend; b += 32 * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + b));
             for (int g = kPenG0; g < h.kgend; g += kPenBatch) {
                 // a ghost slot is reused every RD virtual steps and read up to kPenMaxDk steps after it was written
@@ -832,7 +833,7 @@ __global__ void __launch_bounds__(kPenMaxThreads + kPenExtra, 2) tri_pencil_kern
                     }
                 }
                 if (g >= 0) {   // the values of steps [g + kPenL2Ahead, + kPenBatch) on their way to L2
-                    const long long b0 = step_bytes * (g + kPenL2Ahead), b1 = min(b0 + step_bytes * kPenBatch, vend);
+                    const long long b0 = step_bytes * (g + a.l2ahead), b1 = min(b0 + step_bytes * kPenBatch, vend);
                     for (long long b = b0 + (long long)lane * 128; b < b1; b += 32 * 128)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + b));
                 }
@@ -883,7 +884,19 @@ static int pencil_launch(lsspg_ctx *ctx, const lsspg_tri *Tr, const PencilArgs &
     // SLOWER, 0.69 / 0.84 ms instead of 0.49 / 0.55 -- the shallow value ring stalls every step; off by default.
     static int env_lean = -1;
     if (env_lean < 0) env_lean = getenv("LSSPG_TRI_PENCIL_LEAN") ? atoi(getenv("LSSPG_TRI_PENCIL_LEAN")) : 0;
-    a.nb = kPenNB; a.vr = kPenVRing;
+    a.nb = kPenNB; a.vr = kPenVRing; a.l2ahead = kPenL2Ahead;
+    {   // tuning knobs (even VR >= 4, NB >= 2); defaults are the measured optimum at 256^3
+        static int env_vr = -1, env_nb = -1, env_l2 = -1;
+        if (env_vr < 0) {
+            env_vr = getenv("LSSPG_TRI_PENCIL_VR") ? atoi(getenv("LSSPG_TRI_PENCIL_VR")) : 0;
+            env_nb = getenv("LSSPG_TRI_PENCIL_NB") ? atoi(getenv("LSSPG_TRI_PENCIL_NB")) : 0;
+            env_l2 = getenv("LSSPG_TRI_PENCIL_L2") ? atoi(getenv("LSSPG_TRI_PENCIL_L2")) : 0;
+        }
+        if (env_vr >= 4 && env_vr % 2 == 0 && env_vr <= 64) a.vr = env_vr;
+        if (env_nb >= 2 && env_nb <= 8) a.nb = env_nb;
+        if (env_l2 > 0) a.l2ahead = env_l2;
+        while (a.vr > 4 && pencil_smem_bytes(a.T, a.RS, W + DIAG, a.nb, a.vr) > (size_t)226 * 1024) a.vr -= 2;
+    }
     if (env_lean && pencil_smem_bytes(a.T, a.RS, W + DIAG, 2, 4) <= (size_t)112 * 1024 &&
         pencil_smem_bytes(a.T, a.RS, W + DIAG) > (size_t)112 * 1024 && Tr->num_tiles > ctx->num_sms) { a.nb = 2; a.vr = 4; }
     const size_t smem = pencil_smem_bytes(a.T, a.RS, W + DIAG, a.nb, a.vr);
