@@ -544,8 +544,8 @@ __device__ __forceinline__ void pen_st_flag(int *p, int v)
 //     cycles (128 B/clk), an exposed poll of a progress word ~80, a mailbox store by two lanes of a warp ~40.
 // Hence WARP SPECIALISATION with as few shared-memory accesses as possible on the compute warps, which keep only
 //     LDS operands -> products -> subtractions (-> divide) -> STS -> bar.sync
-// while everything that moves data runs beside them, synchronised through progress words in shared memory (polled one
-// step ahead of their use, so that no poll latency is exposed):
+// while everything that moves data runs beside them, synchronised through release / acquire progress words in shared
+// memory (polled one step ahead of their use, so that no poll latency is exposed):
 //   * stagers (4 warps): rhs tiles in ([line][8 + 1] doubles, cp.async, consecutive threads along x = 64-byte pieces of
 //     a line); x out, read straight from the ring of hyperplanes;
 //   * valuers (2 warps): the value stream [step][slot][thread] into a ring of kPenVRing steps, 16-byte cp.async;
