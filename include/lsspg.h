@@ -60,9 +60,11 @@ int lsspg_ctx_set_option(lsspg_ctx *ctx, int option, int value);
 #define LSSPG_OPT_CHECK_EVERY   3   /* CG / BiCGStab: the host reads the residuals back every k iterations (default 8;
                                        a device-side stop flag freezes the state at convergence, so the iteration
                                        count, history and solution do not depend on k) */
-#define LSSPG_OPT_REDUCE_SEQUENTIAL 4 /* 1: every dot/norm is summed in the reference's sequential order
-                                       (src/vector.cxx:129) -> whole solves become bit-identical to the
-                                       CPU reference; verification mode, one thread does the adds */
+#define LSSPG_OPT_REDUCE_SEQUENTIAL 4 /* every dot/norm equals the reference's sequential sum (src/vector.cxx:129)
+                                       bit for bit -> whole solves become bit-identical to the CPU reference.
+                                       1: one thread does the adds (verification only, ~4 ns per term);
+                                       2: the same result computed in parallel (exact_sum.cu: binade-wise exact
+                                          integer sums, term-by-term only across binade crossings and ties) */
 #define LSSPG_OPT_GRAPHS 5            /* 1 (default): CG replays the launch train of a batch of iterations as a CUDA graph */
 
 int lsspg_malloc(lsspg_ctx *ctx, size_t bytes, void **dptr);
@@ -168,6 +170,10 @@ int lsspg_debug_tri_walk_pencil_host(int which, int n, const int *hTp, const int
 /* LSSPG_TRI_PROF=1: per-pencil timers of the last sweep (8 words per pencil, ticket order: start ns, end ns, cycles
  * total / waiting for ghost lanes / in the step barrier, steps, CTA, SM); returns the number of pencils copied */
 int lsspg_debug_tri_pencil_prof(lsspg_ctx *ctx, const lsspg_tri *T, unsigned long long *out, int max_pencils);
+/* CPU replay of the parallel reference-order summation (exact_sum.cu, LSSPG_OPT_REDUCE_SEQUENTIAL = 2): *out must equal
+ * `s = 0; for (i = 0; i < n; i++) s += t[i];` bit for bit.  stats[4]: blocks, rounds of the walk, blocks not advanced as a
+ * whole, 32-term pieces added term by term.  Test-suite only. */
+int lsspg_debug_exact_seq_sum_host(long long n, const double *t, double *out, long long *stats);
 /* schedule of a device-resident factor: tiled = 2 pencil schedule, 1 box schedule, 0 slice schedule */
 int lsspg_tri_schedule(const lsspg_tri *T, int *tiled, int *num_tiles, int *num_tile_levels,
                        int *max_tile_rows);

@@ -93,7 +93,8 @@ int seq_prepare(lsspg_ctx *ctx, long long n)
 // several GPUs, the cross-rank combination of the sums followed by the deferred FinProg
 int seq_finish(lsspg_ctx *ctx, long long n, int K, const RedOut &o)
 {
-    if (ctx->opt_reduce_sequential) LSSPG_LAUNCH(ctx, k_seq_sum, 1, 32, 0, n, K, red_args(ctx, o));
+    if (ctx->opt_reduce_sequential == 2) LSSPG_TRY(exact_seq_sum(ctx, n, K, o));   // the same sums, computed in parallel
+    else if (ctx->opt_reduce_sequential) LSSPG_LAUNCH(ctx, k_seq_sum, 1, 32, 0, n, K, red_args(ctx, o));
     if (distributed(ctx)) return red_post(ctx, o.out_slot, K, o.fin, o.guarded);
     return 0;
 }

@@ -49,6 +49,8 @@ int vec_xpay_inplace(lsspg_ctx *ctx, int n, Coef a, const double *p, double *x);
 // sequential-order verification mode helpers (LSSPG_OPT_REDUCE_SEQUENTIAL)
 int seq_prepare(lsspg_ctx *ctx, long long n);
 int seq_finish(lsspg_ctx *ctx, long long n, int K, const RedOut &o);
+// LSSPG_OPT_REDUCE_SEQUENTIAL = 2 (exact_sum.cu): the K sequential sums of the parked terms, computed in parallel
+int exact_seq_sum(lsspg_ctx *ctx, long long n, int K, const RedOut &o);
 
 // read scalars / flags back to the pinned mirrors (one sync)
 int read_scalars(lsspg_ctx *ctx, int first, int count, bool with_flags);

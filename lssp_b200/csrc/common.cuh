@@ -69,9 +69,11 @@ struct lsspg_ctx {
     int opt_spmv_exact = 0;
     int opt_check_every = 8;   // CG / BiCGStab: host reads the residuals every 8 iterations (device-side stop flag)
     int opt_graphs = 1;              // CG: replay the steady-state launch train as a CUDA graph
-    int opt_reduce_sequential = 0;   // verification mode: sums in the reference's sequential order
+    int opt_reduce_sequential = 0;   // sums in the reference's sequential order: 1 = one thread adds (verification), 2 = the same result in parallel (exact_sum.cu)
     double *d_seq = nullptr;         // [kMaxRedK][seq_len] per-element terms of the sums (sequential mode)
     size_t seq_len = 0;
+    void *d_xs = nullptr;            // scratch of the parallel reference-order sum (exact_sum.cu), xs_blocks blocks per sum
+    size_t xs_blocks = 0;
     // grow-only device staging for the *_host entry points
     double *stage[3] = {nullptr, nullptr, nullptr};
     size_t stage_len = 0;

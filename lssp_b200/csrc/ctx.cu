@@ -119,6 +119,7 @@ int lsspg_ctx_destroy(lsspg_ctx *c)
         if (c->stage[i]) cudaFree(c->stage[i]);
     for (auto &pr : c->pool) cudaFree(pr.first);
     if (c->d_seq) cudaFree(c->d_seq);
+    if (c->d_xs) cudaFree(c->d_xs);
     cudaFree(c->d_partials);
     cudaFree(c->d_ticket);
     cudaFree(c->d_scal);

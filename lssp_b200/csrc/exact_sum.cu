@@ -1,0 +1,425 @@
+// exact_sum.cu -- kernels K1..K4 of exact_sum.cuh (LSSPG_OPT_REDUCE_SEQUENTIAL = 2: every dot product / norm equals the
+// reference's sequential sum bit for bit, at the cost of two more passes over the parked terms instead of an n-step
+// chain) and their host replay for the CPU test-suite.
+#include "exact_sum.cuh"
+#include <algorithm>
+#include <vector>
+#include "blas1.cuh"
+#include "comm.cuh"
+
+namespace lsspg {
+
+// scratch per sum (ctx->d_xs, [kMaxRedK] slices of `stride` blocks): approximate block sums, sums of |t|, largest |prefix|, predicted
+// binades, D and its inclusive wrap-around scan
+struct XsScratch {
+    double *approx, *absb, *xmax;
+    unsigned long long *D, *scan;
+    int *e;
+    unsigned int *ticket;
+    long long stride;
+};
+
+static XsScratch xs_scratch(lsspg_ctx *ctx)
+{
+    XsScratch sc;
+    const size_t nb = ctx->xs_blocks;
+    char *p = reinterpret_cast<char *>(ctx->d_xs);
+    sc.approx = reinterpret_cast<double *>(p); p += sizeof(double) * kMaxRedK * nb;
+    sc.absb = reinterpret_cast<double *>(p); p += sizeof(double) * kMaxRedK * nb;
+    sc.xmax = reinterpret_cast<double *>(p); p += sizeof(double) * kMaxRedK * nb;
+    sc.D = reinterpret_cast<unsigned long long *>(p); p += sizeof(unsigned long long) * kMaxRedK * nb;
+    sc.scan = reinterpret_cast<unsigned long long *>(p); p += sizeof(unsigned long long) * kMaxRedK * nb;
+    sc.e = reinterpret_cast<int *>(p); p += sizeof(int) * kMaxRedK * nb;
+    sc.ticket = reinterpret_cast<unsigned int *>(p);
+    sc.stride = (long long)nb;
+    return sc;
+}
+
+size_t xs_scratch_bytes(size_t nb) { return (size_t)kMaxRedK * nb * (8 + 8 + 8 + 8 + 8 + 4) + 64; }
+
+LSSPG_HD long long xs_min(long long a, long long b) { return a < b ? a : b; }
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_scan(double v, int lane)   // inclusive
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double w = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += w;
+    }
+    return v;
+}
+
+// K1: one warp per block of kXsB terms (lane l holds terms l, l + 32, ...: coalesced)
+__global__ void __launch_bounds__(256) k_xs_blocks(long long n, long long nb, const double *__restrict__ terms, long long seq_n,
+                                                   XsScratch sc, const int *stop)
+{
+    if (stop && *stop) return;
+    const int lane = threadIdx.x & 31, k = blockIdx.y;
+    const double *t = terms + (size_t)k * seq_n;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nb; b += warps) {
+        double v[kXsB / 32];
+#pragma unroll
+        for (int j = 0; j < kXsB / 32; j++) {
+            const long long i = b * kXsB + j * 32 + lane;
+            v[j] = (i < n) ? t[i] : 0.0;
+        }
+        double carry = 0.0, a = 0.0, x = 0.0;   // prefix sums in index order: 32 terms per warp scan
+#pragma unroll
+        for (int j = 0; j < kXsB / 32; j++) {
+            const double inc = carry + warp_scan(v[j], lane);
+            x = fmax(x, fabs(inc));
+            a += fabs(v[j]);
+            carry = __shfl_sync(0xffffffffu, inc, 31);
+        }
+        a = warp_sum(a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+        if (lane == 0) {
+            sc.approx[k * sc.stride + b] = carry;
+            sc.absb[k * sc.stride + b] = a;
+            sc.xmax[k * sc.stride + b] = x;
+        }
+    }
+}
+
+// K2: one CTA of 1024 threads per sum: exclusive prefix of the approximate block sums -> predicted binades
+__global__ void __launch_bounds__(1024) k_xs_predict(long long nb, XsScratch sc, const int *stop)
+{
+    if (stop && *stop) return;
+    __shared__ double s_w[32];
+    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double *ap = sc.approx + k * sc.stride;
+    int *eb = sc.e + k * sc.stride;
+    const long long per = (nb + 1023) / 1024, b0 = xs_min(nb, tid * per), b1 = xs_min(nb, b0 + per);
+    double loc = 0.0;
+    for (long long b = b0; b < b1; b++) loc += ap[b];
+    double inc = loc;   // inclusive scan over the warp, then over the warps
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        double w = s_w[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        s_w[lane] = wi - w;   // exclusive
+    }
+    __syncthreads();
+    double run = s_w[wid] + (inc - loc);
+    for (long long b = b0; b < b1; b++) {
+        eb[b] = xs_exponent(run);
+        run += ap[b];
+    }
+}
+
+// K3: one warp per block: D_b = sum_i rn_u(t_i) / u for the predicted binade; a tie makes the block unclean
+__global__ void __launch_bounds__(256) k_xs_round(long long n, long long nb, const double *__restrict__ terms, long long seq_n,
+                                                  XsScratch sc, const int *stop)
+{
+    if (stop && *stop) return;
+    const int lane = threadIdx.x & 31, k = blockIdx.y;
+    const double *t = terms + (size_t)k * seq_n;
+    int *eb = sc.e + k * sc.stride;
+    unsigned long long *D = sc.D + k * sc.stride;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nb; b += warps) {
+        const int e = eb[b];
+        long long d = 0;
+        bool tie = false;
+        if (e != kXsUnclean) {
+#pragma unroll
+            for (int j = 0; j < kXsB / 32; j++) {
+                const long long i = b * kXsB + j * 32 + lane;
+                const double v = (i < n) ? t[i] : 0.0;
+                d += xs_round(v, e, &tie);
+            }
+        }
+        d = warp_sum_ll(d);
+        tie = __any_sync(0xffffffffu, tie);
+        if (lane == 0) {
+            if (tie) eb[b] = kXsUnclean;
+            D[b] = (tie || e == kXsUnclean) ? 0ull : (unsigned long long)d;
+        }
+    }
+}
+
+// K4: the walk (one CTA of kXsChunk threads per sum)
+__global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb, int K, const double *__restrict__ terms,
+                                                      long long seq_n, XsScratch sc, double *scal, int *flags, int out_slot,
+                                                      int defer_fin, FinProg fin, const int *stop)
+{
+    if (stop && *stop) return;
+    __shared__ unsigned long long s_w[32];
+    __shared__ double s_terms[kXsB], s_fabs[kXsB / kXsFine], s_fmax[kXsB / kXsFine];
+    __shared__ long long s_fD[kXsB / kXsFine];
+    __shared__ int s_ftie[kXsB / kXsFine];
+    __shared__ double s_s;
+    __shared__ long long s_pos, s_bad;
+    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double *t = terms + (size_t)k * seq_n;
+    const double *absb = sc.absb + k * sc.stride, *xmax = sc.xmax + k * sc.stride;
+    const int *eb = sc.e + k * sc.stride;
+    const unsigned long long *D = sc.D + k * sc.stride;
+    unsigned long long *scan = sc.scan + k * sc.stride;
+    {   // inclusive wrap-around scan of D: only differences inside a run of equal binades are ever used
+        const long long per = (nb + kXsChunk - 1) / kXsChunk, b0 = xs_min(nb, tid * per), b1 = xs_min(nb, b0 + per);
+        unsigned long long loc = 0;
+        for (long long b = b0; b < b1; b++) loc += D[b];
+        unsigned long long inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w = s_w[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        unsigned long long run = s_w[wid] + (inc - loc);
+        for (long long b = b0; b < b1; b++) {
+            run += D[b];
+            scan[b] = run;
+        }
+    }
+    if (tid == 0) { s_s = 0.0; s_pos = 0; }   // src/vector.cxx:127: the sum starts at +0.0
+    for (;;) {
+        __syncthreads();   // s_s, s_pos (and, the first time, scan[]) are visible
+        const long long pos = s_pos;
+        const double s = s_s;
+        if (pos >= nb) break;
+        const int e = eb[pos];
+        bool seq = (e == kXsUnclean) || xs_exponent(s) != e;
+        if (tid == 0) s_bad = xs_min(nb, pos + (long long)kXsChunk * kXsPer);
+        __syncthreads();
+        if (!seq) {
+            const long long m0 = xs_to_int(s, e);
+            const unsigned long long base = pos > 0 ? scan[pos - 1] : 0ull;
+            long long mine = nb;
+#pragma unroll
+            for (int q = 0; q < kXsPer; q++) {   // independent loads: their L2 latencies overlap
+                const long long b = pos + (long long)q * kXsChunk + tid;
+                if (b < nb) {
+                    bool ok = (eb[b] == e);
+                    if (ok) {
+                        const long long m = m0 + (long long)((b > 0 ? scan[b - 1] : 0ull) - base);
+                        ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, xmax[b], absb[b]);
+                    }
+                    if (!ok) mine = xs_min(mine, b);
+                }
+            }
+            if (mine < nb) atomicMin(&s_bad, mine);
+            __syncthreads();
+            const long long bad = s_bad;
+            if (bad == pos) seq = true;   // (uniform: every thread reads the same s_bad)
+            else {
+                if (tid == 0) {
+                    s_s = xs_from_int(m0 + (long long)(scan[bad - 1] - base), e);
+                    s_pos = bad;
+                }
+                continue;
+            }
+        }
+        // The block cannot be advanced as a whole.  Second level: its kXsFine-term pieces, rounded for the binade s is in
+        // NOW (8 warps, one piece each); thread 0 then advances piece by piece, and only pieces that fail the same
+        // verification -- the one with the binade crossing or the tie -- are added term by term, as the reference does.
+        const long long i0 = pos * kXsB;
+        const int cnt = (int)xs_min(kXsB, n - i0);
+        if (tid < kXsB) s_terms[tid] = (tid < cnt) ? t[i0 + tid] : 0.0;
+        __syncthreads();
+        const int es = xs_exponent(s);
+        if (tid < kXsB && es != kXsUnclean) {
+            bool tie = false;
+            const double v = s_terms[tid];
+            long long d = xs_round(v, es, &tie);
+            double a = fabs(v), x = fabs(warp_scan(v, lane));
+            d = warp_sum_ll(d);
+            a = warp_sum(a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+            tie = __any_sync(0xffffffffu, tie);
+            if (lane == 0) { s_fD[wid] = d; s_fabs[wid] = a; s_fmax[wid] = x; s_ftie[wid] = tie ? 1 : 0; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double acc = s;
+            for (int j = 0; j * kXsFine < cnt; j++) {
+                if (es != kXsUnclean && !s_ftie[j] && xs_exponent(acc) == es && xs_verify(acc, es, s_fmax[j], s_fabs[j])) {
+                    const long long m = xs_to_int(acc, es) + s_fD[j];
+                    if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
+                }
+                const int i1 = (j + 1) * kXsFine < cnt ? (j + 1) * kXsFine : cnt;
+                for (int i = j * kXsFine; i < i1; i++) acc += s_terms[i];
+            }
+            s_s = acc;
+            s_pos = pos + 1;
+        }
+    }
+    if (tid == 0) {
+        scal[out_slot + k] = s_s;
+        __threadfence();
+        const unsigned int tk = atomicInc(sc.ticket, (unsigned int)K - 1);
+        if (tk == (unsigned int)K - 1 && !defer_fin) {
+            __threadfence();
+            fin_run(fin, scal, flags);
+        }
+    }
+}
+
+int ensure_xs(lsspg_ctx *ctx, size_t n)
+{
+    const size_t nb = (n + kXsB - 1) / kXsB + 1;
+    if (nb <= ctx->xs_blocks) return 0;
+    if (ctx->d_xs) LSSPG_CUDA(cudaFree(ctx->d_xs));
+    ctx->d_xs = nullptr;
+    ctx->xs_blocks = 0;
+    LSSPG_CUDA(cudaMalloc(&ctx->d_xs, xs_scratch_bytes(nb)));
+    LSSPG_CUDA(cudaMemsetAsync(ctx->d_xs, 0, xs_scratch_bytes(nb), ctx->stream));
+    ctx->xs_blocks = nb;
+    return 0;
+}
+
+// K sums of the n parked terms each (ctx->d_seq), in the reference's order, into scal[out_slot ..]; then the FinProg
+int exact_seq_sum(lsspg_ctx *ctx, long long n, int K, const RedOut &o)
+{
+    LSSPG_TRY(ensure_xs(ctx, (size_t)std::max<long long>(n, 1)));
+    const XsScratch sc = xs_scratch(ctx);
+    const long long nb = (n + kXsB - 1) / kXsB;
+    const int *stop = o.guarded ? ctx->d_flags + FLAG_STOP : nullptr;
+    const long long seq_n = (long long)ctx->seq_len;
+    if (nb > 0) {
+        const dim3 grid((unsigned int)std::max<long long>(1, std::min<long long>((nb + 7) / 8, (long long)ctx->num_sms * 8)), (unsigned int)K);
+        LSSPG_LAUNCH(ctx, k_xs_blocks, grid, 256, 0, n, nb, ctx->d_seq, seq_n, sc, stop);
+        LSSPG_LAUNCH(ctx, k_xs_predict, K, 1024, 0, nb, sc, stop);
+        LSSPG_LAUNCH(ctx, k_xs_round, grid, 256, 0, n, nb, ctx->d_seq, seq_n, sc, stop);
+    }
+    LSSPG_LAUNCH(ctx, k_xs_walk, K, kXsChunk, 0, n, nb, K, ctx->d_seq, seq_n, sc, ctx->d_scal, ctx->d_flags, o.out_slot,
+                 distributed(ctx) ? 1 : 0, o.fin, stop);
+    return 0;
+}
+
+// ---- host replay: the same four phases with the same shared functions (CPU test-suite) -------------------------------
+static double xs_host(long long n, const double *t, long long *stats)
+{
+    const long long nb = (n + kXsB - 1) / kXsB;
+    std::vector<double> approx(nb), absb(nb), xmax(nb);
+    std::vector<int> eb(nb);
+    std::vector<unsigned long long> D(nb), scan(nb);
+    for (long long b = 0; b < nb; b++) {   // K1 (pairwise order inside a block; any order will do)
+        double s = 0.0, a = 0.0, x = 0.0;
+        for (long long i = b * kXsB; i < std::min(n, (b + 1) * kXsB); i++) { s += t[i]; a += fabs(t[i]); x = std::max(x, fabs(s)); }
+        approx[b] = s; absb[b] = a; xmax[b] = x;
+    }
+    {   // K2
+        double run = 0.0;
+        for (long long b = 0; b < nb; b++) { eb[b] = xs_exponent(run); run += approx[b]; }
+    }
+    for (long long b = 0; b < nb; b++) {   // K3
+        const int e = eb[b];
+        long long d = 0;
+        bool tie = false;
+        if (e != kXsUnclean)
+            for (long long i = b * kXsB; i < std::min(n, (b + 1) * kXsB); i++) d += xs_round(t[i], e, &tie);
+        if (tie) eb[b] = kXsUnclean;
+        D[b] = (tie || e == kXsUnclean) ? 0ull : (unsigned long long)d;
+    }
+    {
+        unsigned long long run = 0;
+        for (long long b = 0; b < nb; b++) { run += D[b]; scan[b] = run; }
+    }
+    double s = 0.0;   // K4
+    long long pos = 0, rounds = 0, seq_blocks = 0, seq_pieces = 0;
+    while (pos < nb) {
+        rounds++;
+        const int e = eb[pos];
+        bool seq = (e == kXsUnclean) || xs_exponent(s) != e;
+        if (!seq) {
+            const long long m0 = xs_to_int(s, e);
+            const unsigned long long base = pos > 0 ? scan[pos - 1] : 0ull;
+            long long bad = std::min<long long>(nb, pos + (long long)kXsChunk * kXsPer);
+            for (long long b = pos; b < std::min<long long>(nb, pos + (long long)kXsChunk * kXsPer); b++) {
+                bool ok = (eb[b] == e);
+                if (ok) {
+                    const long long m = m0 + (long long)((b > 0 ? scan[b - 1] : 0ull) - base);
+                    ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, xmax[b], absb[b]);
+                }
+                if (!ok) { bad = b; break; }
+            }
+            if (bad == pos) seq = true;
+            else {
+                s = xs_from_int(m0 + (long long)(scan[bad - 1] - base), e);
+                pos = bad;
+                continue;
+            }
+        }
+        {   // second level, as in k_xs_walk
+            const long long i0 = pos * kXsB;
+            const int cnt = (int)std::min<long long>(kXsB, n - i0);
+            const int es = xs_exponent(s);
+            double acc = s;
+            for (int j = 0; j * kXsFine < cnt; j++) {
+                const int i1 = std::min((j + 1) * kXsFine, cnt);
+                if (es != kXsUnclean && xs_exponent(acc) == es) {
+                    bool tie = false;
+                    long long d = 0;
+                    double a = 0.0, x = 0.0, pre = 0.0;
+                    for (int i = j * kXsFine; i < i1; i++) {
+                        d += xs_round(t[i0 + i], es, &tie);
+                        a += fabs(t[i0 + i]);
+                        pre += t[i0 + i];
+                        x = std::max(x, fabs(pre));
+                    }
+                    if (!tie && xs_verify(acc, es, x, a)) {
+                        const long long m = xs_to_int(acc, es) + d;
+                        if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
+                    }
+                }
+                for (int i = j * kXsFine; i < i1; i++) acc += t[i0 + i];
+                seq_pieces++;
+            }
+            s = acc;
+        }
+        seq_blocks++;
+        pos++;
+    }
+    if (stats) { stats[0] = nb; stats[1] = rounds; stats[2] = seq_blocks; stats[3] = seq_pieces; }
+    return s;
+}
+
+}  // namespace lsspg
+
+using namespace lsspg;
+
+extern "C" {
+
+// CPU self-check for the test-suite (never called by a product path): the reference-order sum of t[0..n) by the host
+// replay of the kernels above.  stats[4]: blocks, rounds of the walk, blocks not advanced as a whole, pieces (32 terms) added term by term.
+int lsspg_debug_exact_seq_sum_host(long long n, const double *t, double *out, long long *stats)
+{
+    if (n < 0 || !out) return 1;
+    *out = xs_host(n, t, stats);
+    return 0;
+}
+
+}  // extern "C"

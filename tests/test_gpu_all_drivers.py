@@ -23,11 +23,11 @@ _state = {}
 
 
 def setup(seq):
-    key = "seq" if seq else "fast"
+    key = {0: "fast", 1: "seq", 2: "exact"}[int(seq)]
     if key not in _state:
         c = api.Context(0)
         if seq:
-            c.set_option(api.OPT_REDUCE_SEQUENTIAL, 1)
+            c.set_option(api.OPT_REDUCE_SEQUENTIAL, int(seq))
         A = matrix("lap2d_100")
         n = len(A[0]) - 1
         pcs = {"non": api.Preconditioner.non(c, n)}
@@ -52,6 +52,16 @@ def test_every_driver_equals_reference_in_sequential_mode(golden, s, tag):
     assert r["nits"] == e["nits"], (r["nits"], e["nits"])
     assert r["residual"] == e["residual"], (r["residual"], e["residual"])
     assert abs(np.linalg.norm(r["x"]) - e["xnorm"]) <= 1e-13 * e["xnorm"]
+
+
+@pytest.mark.parametrize("tag", [p[0] for p in PCS])
+@pytest.mark.parametrize("s", SOLVERS)
+def test_every_driver_equals_reference_with_parallel_reference_order_sums(golden, s, tag):
+    """LSSPG_OPT_REDUCE_SEQUENTIAL = 2 (exact_sum.cu): the reference's sequential sums computed in parallel"""
+    e = golden["solves"]["lap2d_100/%s/%s" % (s, tag)]
+    r = solve(2, s, tag)
+    assert r["nits"] == e["nits"], (r["nits"], e["nits"])
+    assert r["residual"] == e["residual"], (r["residual"], e["residual"])
 
 
 @pytest.mark.parametrize("tag", [p[0] for p in PCS])

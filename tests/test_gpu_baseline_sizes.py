@@ -129,6 +129,38 @@ def test_solves_match_the_reference_at_256(ctx, gold, lap, cd, case, record_prop
     dA.free()
 
 
+@pytest.mark.parametrize("case", list(CASES))
+def test_solves_EQUAL_the_reference_at_256_with_reference_order_sums(gold, lap, cd, case):
+    """LSSPG_OPT_REDUCE_SEQUENTIAL = 2 (exact_sum.cu): every dot product is the reference's sequential sum, computed in
+    parallel.  Then nothing differs from the CPU arithmetic and the whole solve is bit-identical at the BASELINE size:
+    iterations to tolerance, final residual and the first 20 residuals EQUAL the unmodified reference's -- the bars of
+    BASELINE.json north_star (1e-10, +-1) are met with margin zero, BiCGStab included."""
+    if case not in gold:
+        pytest.skip("no golden values for " + case)
+    which, solver, pckw, skw = CASES[case]
+    A = lap if which == "lap" else cd
+    e = gold[case]
+    n = N ** 3
+    c = api.Context(0)
+    c.set_option(api.OPT_REDUCE_SEQUENTIAL, 2)
+    dA = api.Csr(c, A)
+    L, U = api.ilu_factor(A, **pckw)
+    pc = api.Preconditioner(c, "ilu", n, L, U)
+    x = np.zeros(n)
+    r = api.lssp_solver_solve(c, solver, dA, pc, np.ones(n), x, nhist=20, maxit=3000, **skw)
+    print("%s: nits %d (reference %d) residual %.17g (reference %.17g) %.1f ms" %
+          (case, r["nits"], e["nits"], r["residual"], e["residual"], r.get("solve_ms", -1.0)))
+    assert r["nits"] == e["nits"]
+    assert r["residual"] == e["residual"]
+    want = np.array(e["history"])
+    if len(set(want.tolist())) > 2:      # (GMRES: the reference's history is one repeated number, see above)
+        assert list(r["hist"][:len(want)]) == list(want)
+    assert abs(np.linalg.norm(x) - e["x_norm"]) <= 1e-13 * e["x_norm"]
+    pc.free()
+    dA.free()
+    c.close()
+
+
 def test_pencil_sweeps_are_repeatable_at_256(ctx, gold, lap):
     """256 pencils on 148 SMs, 286 steps each, five roles per CTA synchronised through progress words: every application
     must give the same bits, for several right-hand sides, and the bits of the box schedule (which shares no code with
