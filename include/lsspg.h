@@ -33,6 +33,7 @@ typedef struct lsspg_ctx lsspg_ctx;   /* one device, one stream, reduction scrat
 typedef struct lsspg_csr lsspg_csr;   /* device-resident CSR matrix + SpMV row-tile schedule */
 typedef struct lsspg_tri lsspg_tri;   /* device-resident triangular factor, level-ordered  */
 typedef struct lsspg_pc  lsspg_pc;    /* preconditioner application object                 */
+typedef struct lsspg_dmat lsspg_dmat; /* device-resident CSR / BCSR matrix of the set-up path (no SpMV schedule) */
 
 const char *lsspg_last_error(void);
 const char *lsspg_version(void);
@@ -90,6 +91,30 @@ int lsspg_csr_schedule_info(const lsspg_csr *A, int *num_tiles, int *num_stream_
                             int *max_tile_nnz);
 /* algorithmic bytes of one y = A x: 12 nnz + 4 (n+1) + 16 n */
 double lsspg_csr_spmv_bytes(const lsspg_csr *A);
+
+/* ---- device-side ingest & matrix utilities (matops_gpu.cu) ---------------------------------
+ * What lssp_solver_assemble and the preconditioner set-up do to the caller's matrix, on matrices that live in device
+ * memory: results are byte-identical to the host utilities of liblssp.so (include/lssp/matrix-utils.h), which are
+ * pinned against the reference. */
+int lsspg_dmat_upload(lsspg_ctx *ctx, int num_rows, int num_cols, const int *hAp, const int *hAj, const double *hAx,
+                      lsspg_dmat **out);
+int lsspg_dmat_download(lsspg_ctx *ctx, const lsspg_dmat *M, int *hAp, int *hAj, double *hAx);   /* NULL: skip that array */
+int lsspg_dmat_dims(const lsspg_dmat *M, int *num_rows, int *num_cols, long long *num_nnzs, int *blk_size);
+int lsspg_dmat_destroy(lsspg_ctx *ctx, lsspg_dmat *M);
+int lsspg_dmat_copy(lsspg_ctx *ctx, const lsspg_dmat *A, lsspg_dmat **out);            /* deep copy, src/lssp.cxx:169-171 */
+int lsspg_dmat_is_sorted(lsspg_ctx *ctx, const lsspg_dmat *A, int *sorted);           /* lssp_mat_csr_is_sorted, src/matrix-utils.cxx:249-279 */
+int lsspg_dmat_sort_columns(lsspg_ctx *ctx, lsspg_dmat *A);                           /* lssp_mat_sort_column, :387-481 (stable) */
+int lsspg_dmat_adjust_zero_diag(lsspg_ctx *ctx, const lsspg_dmat *A, double tol, lsspg_dmat **out);   /* :483-587 */
+int lsspg_dmat_get_block_diag(lsspg_ctx *ctx, const lsspg_dmat *A, int blk_size, lsspg_dmat **out);   /* :589-698 */
+int lsspg_dmat_to_bcsr(lsspg_ctx *ctx, const lsspg_dmat *A, int blk_size, lsspg_dmat **out);          /* lssp_mat_csr_to_bcsr, :62-162 */
+/* rows [r0, r1) of the 7-point operator on an nx x ny x nz grid in natural order (nz == 1: the 5-point operator of
+ * example/exam.cxx:4-59), columns ascending, minus col_shift; stencil[7] = the values at -nx ny, -nx, -1, 0, +1, +nx,
+ * +nx ny (byte-identical to lssp_b200/generators.py) */
+int lsspg_dmat_gen_stencil(lsspg_ctx *ctx, int nx, int ny, int nz, long long r0, long long r1, long long col_shift,
+                           const double *stencil, lsspg_dmat **out);
+/* the SpMV matrix of a device-resident CSR: only the row pointer visits the host (row-tile schedule); take != 0 adopts
+ * M's arrays (M is left empty), else they are copied device to device */
+int lsspg_csr_from_dmat(lsspg_ctx *ctx, lsspg_dmat *M, int take, lsspg_csr **out);
 
 /* ---- mvops (replaces include/mvops.h:8-19, src/mvops.cxx) ------------------ */
 #define LSSPG_MV_MXY      0   /* z = A x                  lssp_mv_mxy      src/mvops.cxx:118-150 */
@@ -188,11 +213,15 @@ typedef struct lsspg_factors lsspg_factors;   /* host L and U in the reference's
  * (the reference's blocked driver, src/pc-iluk.cxx:411-552). */
 int lsspg_ilu_factor(int kind, int n, const int *hAp, const int *hAj, const double *hAx,
                      int level, int p, double tol, int blk_size, lsspg_factors **out);
-/* ILU(k) with the NUMERIC phase on the GPU (src/pc-iluk.cxx:347-409): rows are
- * factored level by level of the dependency graph of L, one thread per row, same operations in the
- * same order as the host loop -> bit-identical factors.  Symbolic phase and L/U split stay on the host. */
+/* ILU(k) set-up ON THE GPU (ilu_gpu.cu): ingest (column sort, missing diagonals), the symbolic
+ * level-of-fill phase (src/pc-iluk.cxx:22-135, :279-345, level-raising rule :101), the block restriction (:441-446), the
+ * numeric IKJ phase (:347-409) and the L / U split (:501-532) run on the device -- one persistent kernel per phase, a
+ * thread per row, rows wait for the finished rows of their lower columns; same operations in the same order as the host
+ * loops -> bit-identical factors.  Only the finished factors come back to the host. */
 int lsspg_ilu_factor_device(lsspg_ctx *ctx, int n, const int *hAp, const int *hAj, const double *hAx,
                             int level, int blk_size, lsspg_factors **out);
+/* the same from a matrix that is already in device memory (see "device-side ingest" below) */
+int lsspg_ilu_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A, int level, int blk_size, lsspg_factors **out);
 int lsspg_factors_sizes(const lsspg_factors *F, int *n, int *nnzL, int *nnzU);
 int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int *Up, int *Uj,
                       double *Ux);

@@ -159,6 +159,115 @@ class Csr:
             pass
 
 
+class DMat:
+    """Device-resident CSR / BCSR matrix of the set-up path (lsspg_dmat; matops_gpu.cu): generated,
+    sorted, repaired, restricted and factorised on the GPU without a host copy of Aj / Ax."""
+
+    def __init__(self, ctx, A=None, handle=None):
+        self.ctx = ctx
+        self.h = C.c_void_p() if handle is None else handle
+        if A is not None:
+            Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
+            n = len(Ap) - 1
+            check(lib().lsspg_dmat_upload(ctx.h, n, n, _p(Ap), _p(Aj), _p(Ax), C.byref(self.h)))
+
+    @classmethod
+    def stencil(cls, ctx, dims, stencil, r0=0, r1=None, col_shift=0):
+        """rows [r0, r1) of the 7-point operator on an nx x ny x nz grid (generators.stencil_7pt / laplacian_5pt)"""
+        nx, ny, nz = dims
+        r1 = nx * ny * nz if r1 is None else r1
+        st = _f64(np.asarray(stencil, dtype=np.float64))
+        h = C.c_void_p()
+        check(lib().lsspg_dmat_gen_stencil(ctx.h, nx, ny, nz, C.c_longlong(r0), C.c_longlong(r1), C.c_longlong(col_shift),
+                                           _p(st), C.byref(h)))
+        return cls(ctx, handle=h)
+
+    @classmethod
+    def lap3d(cls, ctx, N):
+        return cls.stencil(ctx, (N, N, N), [-1.0, -1.0, -1.0, 6.0, -1.0, -1.0, -1.0])
+
+    @classmethod
+    def cd3d(cls, ctx, N, conv=(0.3, 0.2, 0.1)):
+        cx, cy, cz = conv
+        return cls.stencil(ctx, (N, N, N), [-1.0 - cz, -1.0 - cy, -1.0 - cx, 6.0, -1.0 + cx, -1.0 + cy, -1.0 + cz])
+
+    @classmethod
+    def laplacian_5pt(cls, ctx, N):
+        return cls.stencil(ctx, (N, N, 1), [0.0, -1.0, -1.0, 4.0, -1.0, -1.0, 0.0])
+
+    def dims(self):
+        n, m, nnz, bs = C.c_int(), C.c_int(), C.c_longlong(), C.c_int()
+        check(lib().lsspg_dmat_dims(self.h, C.byref(n), C.byref(m), C.byref(nnz), C.byref(bs)))
+        return n.value, m.value, nnz.value, bs.value
+
+    def download(self):
+        n, m, nnz, bs = self.dims()
+        Ap, Aj, Ax = np.empty(n + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz * bs * bs)
+        check(lib().lsspg_dmat_download(self.ctx.h, self.h, _p(Ap), _p(Aj), _p(Ax)))
+        return Ap, Aj, Ax
+
+    def _derive(self, fn, *args):
+        h = C.c_void_p()
+        check(fn(self.ctx.h, self.h, *args, C.byref(h)))
+        return DMat(self.ctx, handle=h)
+
+    def copy(self):
+        return self._derive(lib().lsspg_dmat_copy)
+
+    def is_sorted(self):
+        r = C.c_int()
+        check(lib().lsspg_dmat_is_sorted(self.ctx.h, self.h, C.byref(r)))
+        return bool(r.value)
+
+    def sort_columns(self):
+        check(lib().lsspg_dmat_sort_columns(self.ctx.h, self.h))
+        return self
+
+    def adjust_zero_diag(self, tol=1e-10):
+        return self._derive(lib().lsspg_dmat_adjust_zero_diag, C.c_double(tol))
+
+    def get_block_diag(self, blk_size):
+        return self._derive(lib().lsspg_dmat_get_block_diag, int(blk_size))
+
+    def to_bcsr(self, blk_size):
+        return self._derive(lib().lsspg_dmat_to_bcsr, int(blk_size))
+
+    def to_csr(self, take=False):
+        """the SpMV-ready matrix (Csr) of this device matrix; take=True hands the arrays over"""
+        n, m, nnz, bs = self.dims()
+        out = Csr.__new__(Csr)
+        out.ctx, out.h, out.n, out.nnz = self.ctx, C.c_void_p(), n, nnz
+        check(lib().lsspg_csr_from_dmat(self.ctx.h, self.h, 1 if take else 0, C.byref(out.h)))
+        return out
+
+    def ilu_factor(self, level=0, blk_size=0):
+        """ILU(k) on the device (lsspg_ilu_factor_dmat): (L, U) in the reference's layout, on the host"""
+        h = C.c_void_p()
+        check(lib().lsspg_ilu_factor_dmat(self.ctx.h, self.h, int(level), int(blk_size), C.byref(h)))
+        return _factors_out(h, self.dims()[0])
+
+    def free(self):
+        if self.h and self.ctx.h:
+            lib().lsspg_dmat_destroy(self.ctx.h, self.h)
+        self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _factors_out(h, n):
+    nn, nl, nu = C.c_int(), C.c_int(), C.c_int()
+    lib().lsspg_factors_sizes(h, C.byref(nn), C.byref(nl), C.byref(nu))
+    Lp, Lj, Lx = np.empty(n + 1, np.int32), np.empty(nl.value, np.int32), np.empty(nl.value)
+    Up, Uj, Ux = np.empty(n + 1, np.int32), np.empty(nu.value, np.int32), np.empty(nu.value)
+    lib().lsspg_factors_get(h, _p(Lp), _p(Lj), _p(Lx), _p(Up), _p(Uj), _p(Ux))
+    lib().lsspg_factors_destroy(h)
+    return (Lp, Lj, Lx), (Up, Uj, Ux)
+
+
 # ---- reference-named entry points (host vectors in, host vectors out) ------------
 def lssp_mv_mxy(A, x):
     """y = A x   (reference src/mvops.cxx:118-150)"""
@@ -337,8 +446,9 @@ class Tri:
 
 def ilu_factor(A, kind="iluk", level=0, p=-1, tol=1e-3, blk_size=0, ctx=None):
     """ILU(k) / ILUT set-up (reference src/pc-iluk.cxx, src/pc-ilut.cxx).  Returns (L, U) CSR
-    triples in the reference's layout.  ctx given (ILU(k) only): the numeric phase runs on the GPU
-    (lsspg_ilu_factor_device), with bit-identical factors."""
+    triples in the reference's layout.  ctx given (ILU(k) only): the whole set-up -- ingest, symbolic and
+    numeric phases, block restriction, L / U split -- runs on the GPU (lsspg_ilu_factor_device, ilu_gpu.cu),
+    with bit-identical factors."""
     Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
     n = len(Ap) - 1
     h = C.c_void_p()
@@ -347,13 +457,7 @@ def ilu_factor(A, kind="iluk", level=0, p=-1, tol=1e-3, blk_size=0, ctx=None):
     else:
         check(lib().lsspg_ilu_factor(0 if kind == "iluk" else 1, n, _p(Ap), _p(Aj), _p(Ax), int(level), int(p),
                                      C.c_double(tol), int(blk_size), C.byref(h)))
-    nn, nl, nu = C.c_int(), C.c_int(), C.c_int()
-    lib().lsspg_factors_sizes(h, C.byref(nn), C.byref(nl), C.byref(nu))
-    Lp, Lj, Lx = np.empty(n + 1, np.int32), np.empty(nl.value, np.int32), np.empty(nl.value)
-    Up, Uj, Ux = np.empty(n + 1, np.int32), np.empty(nu.value, np.int32), np.empty(nu.value)
-    lib().lsspg_factors_get(h, _p(Lp), _p(Lj), _p(Lx), _p(Up), _p(Uj), _p(Ux))
-    lib().lsspg_factors_destroy(h)
-    return (Lp, Lj, Lx), (Up, Uj, Ux)
+    return _factors_out(h, n)
 
 
 def bilu_factor(A, num_blks, level=0):

@@ -7,7 +7,7 @@
 namespace lsspg {
 
 // flag slots in ctx->d_flags
-enum { FLAG_STOP = 0, FLAG_AUX = 1, FLAG_TRI_TIMEOUT = 8 };
+enum { FLAG_STOP = 0, FLAG_AUX = 1, FLAG_TRI_TIMEOUT = 8, FLAG_SETUP = 9 /* set-up kernels: unsorted row, overflow, bad index */ };
 
 // Reduction target: sums -> d_scal[out_slot + k], then `fin` runs on the device.
 struct RedOut {

@@ -164,6 +164,30 @@ __device__ __forceinline__ void grid_sum(double (&v)[K], double *partials, unsig
     }
 }
 
+// inclusive scan of one value per thread over a CTA of 1024 threads (32 warps); s_w: 32 words of shared memory.
+// Returns the inclusive prefix; *total = the sum over the CTA.  Two barriers.
+template <class T>
+__device__ __forceinline__ T cta_scan_1024(T v, T *s_w, T *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T w = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += w;
+    }
+    __syncthreads();   // s_w may still be read from the previous call
+    if (lane == 31) s_w[wid] = v;
+    __syncthreads();
+    T w = s_w[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T x = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += x;
+    }
+    *total = __shfl_sync(0xffffffffu, wi, 31);
+    return v + __shfl_sync(0xffffffffu, wi - w, wid);
+}
+
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 #endif
 

@@ -91,38 +91,22 @@ __global__ void __launch_bounds__(256) k_xs_blocks(long long n, long long nb, co
 }
 
 // K2: one CTA of 1024 threads per sum: exclusive prefix of the approximate block sums -> predicted binades
+// (1024 consecutive blocks per round: coalesced)
 __global__ void __launch_bounds__(1024) k_xs_predict(long long nb, XsScratch sc, const int *stop)
 {
     if (stop && *stop) return;
     __shared__ double s_w[32];
-    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = blockIdx.x, tid = threadIdx.x;
     const double *ap = sc.approx + k * sc.stride;
     int *eb = sc.e + k * sc.stride;
-    const long long per = (nb + 1023) / 1024, b0 = xs_min(nb, tid * per), b1 = xs_min(nb, b0 + per);
-    double loc = 0.0;
-    for (long long b = b0; b < b1; b++) loc += ap[b];
-    double inc = loc;   // inclusive scan over the warp, then over the warps
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    if (lane == 31) s_w[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        double w = s_w[lane], wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
-        }
-        s_w[lane] = wi - w;   // exclusive
-    }
-    __syncthreads();
-    double run = s_w[wid] + (inc - loc);
-    for (long long b = b0; b < b1; b++) {
-        eb[b] = xs_exponent(run);
-        run += ap[b];
+    double carry = 0.0;
+    for (long long b0 = 0; b0 < nb; b0 += 1024) {
+        const long long b = b0 + tid;
+        const double v = (b < nb) ? ap[b] : 0.0;
+        double total;
+        const double inc = cta_scan_1024<double>(v, s_w, &total);
+        if (b < nb) eb[b] = xs_exponent(carry + (inc - v));
+        carry += total;
     }
 }
 
@@ -157,125 +141,148 @@ __global__ void __launch_bounds__(256) k_xs_round(long long n, long long nb, con
     }
 }
 
-// K4: the walk (one CTA of kXsChunk threads per sum)
+// K4: the walk (one CTA of kXsChunk threads per sum).  The blocks are taken in windows of kXsWin; a window's binades,
+// excursion bounds and the inclusive wrap-around scan of its D are staged in shared memory, so that the rounds of a window
+// -- one per run of verified blocks, one more per block that has to be taken apart -- cost barriers, not L2 round trips.
+constexpr int kXsWin = kXsChunk * kXsPer;
+struct XsWindow {
+    unsigned long long scan[kXsWin];
+    double xmax[kXsWin], absb[kXsWin];
+    int e[kXsWin];
+};
+
 __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb, int K, const double *__restrict__ terms,
                                                       long long seq_n, XsScratch sc, double *scal, int *flags, int out_slot,
                                                       int defer_fin, FinProg fin, const int *stop)
 {
     if (stop && *stop) return;
+    extern __shared__ __align__(16) unsigned char xs_smem[];
+    XsWindow &W = *reinterpret_cast<XsWindow *>(xs_smem);
     __shared__ unsigned long long s_w[32];
     __shared__ double s_terms[kXsB], s_fabs[kXsB / kXsFine], s_fmax[kXsB / kXsFine];
     __shared__ long long s_fD[kXsB / kXsFine];
     __shared__ int s_ftie[kXsB / kXsFine];
     __shared__ double s_s;
-    __shared__ long long s_pos, s_bad;
+    __shared__ int s_pos, s_bad;
     const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double *t = terms + (size_t)k * seq_n;
     const double *absb = sc.absb + k * sc.stride, *xmax = sc.xmax + k * sc.stride;
     const int *eb = sc.e + k * sc.stride;
     const unsigned long long *D = sc.D + k * sc.stride;
-    unsigned long long *scan = sc.scan + k * sc.stride;
-    {   // inclusive wrap-around scan of D: only differences inside a run of equal binades are ever used
-        const long long per = (nb + kXsChunk - 1) / kXsChunk, b0 = xs_min(nb, tid * per), b1 = xs_min(nb, b0 + per);
-        unsigned long long loc = 0;
-        for (long long b = b0; b < b1; b++) loc += D[b];
-        unsigned long long inc = loc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) s_w[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned long long w = s_w[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += v;
+    if (tid == 0) s_s = 0.0;   // src/vector.cxx:127: the sum starts at +0.0
+    for (long long w0 = 0; w0 < nb; w0 += kXsWin) {
+        const int wlen = (int)xs_min(kXsWin, nb - w0);
+        __syncthreads();   // the previous window is done with W
+        {   // stage the window; thread tid scans blocks kXsPer tid .. + kXsPer - 1 (only differences inside a run of equal
+            // binades are ever used, so the scan may wrap around and restart with every window)
+            for (int r = tid; r < wlen; r += kXsChunk) {
+                W.scan[r] = D[w0 + r];
+                W.xmax[r] = xmax[w0 + r];
+                W.absb[r] = absb[w0 + r];
+                W.e[r] = eb[w0 + r];
             }
-            s_w[lane] = wi - w;
-        }
-        __syncthreads();
-        unsigned long long run = s_w[wid] + (inc - loc);
-        for (long long b = b0; b < b1; b++) {
-            run += D[b];
-            scan[b] = run;
-        }
-    }
-    if (tid == 0) { s_s = 0.0; s_pos = 0; }   // src/vector.cxx:127: the sum starts at +0.0
-    for (;;) {
-        __syncthreads();   // s_s, s_pos (and, the first time, scan[]) are visible
-        const long long pos = s_pos;
-        const double s = s_s;
-        if (pos >= nb) break;
-        const int e = eb[pos];
-        bool seq = (e == kXsUnclean) || xs_exponent(s) != e;
-        if (tid == 0) s_bad = xs_min(nb, pos + (long long)kXsChunk * kXsPer);
-        __syncthreads();
-        if (!seq) {
-            const long long m0 = xs_to_int(s, e);
-            const unsigned long long base = pos > 0 ? scan[pos - 1] : 0ull;
-            long long mine = nb;
-#pragma unroll
-            for (int q = 0; q < kXsPer; q++) {   // independent loads: their L2 latencies overlap
-                const long long b = pos + (long long)q * kXsChunk + tid;
-                if (b < nb) {
-                    bool ok = (eb[b] == e);
-                    if (ok) {
-                        const long long m = m0 + (long long)((b > 0 ? scan[b - 1] : 0ull) - base);
-                        ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, xmax[b], absb[b]);
-                    }
-                    if (!ok) mine = xs_min(mine, b);
-                }
-            }
-            if (mine < nb) atomicMin(&s_bad, mine);
             __syncthreads();
-            const long long bad = s_bad;
-            if (bad == pos) seq = true;   // (uniform: every thread reads the same s_bad)
-            else {
-                if (tid == 0) {
-                    s_s = xs_from_int(m0 + (long long)(scan[bad - 1] - base), e);
-                    s_pos = bad;
-                }
-                continue;
-            }
-        }
-        // The block cannot be advanced as a whole.  Second level: its kXsFine-term pieces, rounded for the binade s is in
-        // NOW (8 warps, one piece each); thread 0 then advances piece by piece, and only pieces that fail the same
-        // verification -- the one with the binade crossing or the tie -- are added term by term, as the reference does.
-        const long long i0 = pos * kXsB;
-        const int cnt = (int)xs_min(kXsB, n - i0);
-        if (tid < kXsB) s_terms[tid] = (tid < cnt) ? t[i0 + tid] : 0.0;
-        __syncthreads();
-        const int es = xs_exponent(s);
-        if (tid < kXsB && es != kXsUnclean) {
-            bool tie = false;
-            const double v = s_terms[tid];
-            long long d = xs_round(v, es, &tie);
-            double a = fabs(v), x = fabs(warp_scan(v, lane));
-            d = warp_sum_ll(d);
-            a = warp_sum(a);
+            unsigned long long loc[kXsPer], sum = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
-            tie = __any_sync(0xffffffffu, tie);
-            if (lane == 0) { s_fD[wid] = d; s_fabs[wid] = a; s_fmax[wid] = x; s_ftie[wid] = tie ? 1 : 0; }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double acc = s;
-            for (int j = 0; j * kXsFine < cnt; j++) {
-                if (es != kXsUnclean && !s_ftie[j] && xs_exponent(acc) == es && xs_verify(acc, es, s_fmax[j], s_fabs[j])) {
-                    const long long m = xs_to_int(acc, es) + s_fD[j];
-                    if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
-                }
-                const int i1 = (j + 1) * kXsFine < cnt ? (j + 1) * kXsFine : cnt;
-                for (int i = j * kXsFine; i < i1; i++) acc += s_terms[i];
+            for (int q = 0; q < kXsPer; q++) {
+                const int r = tid * kXsPer + q;
+                loc[q] = (r < wlen) ? W.scan[r] : 0ull;
+                sum += loc[q];
             }
-            s_s = acc;
-            s_pos = pos + 1;
+            unsigned long long total;
+            unsigned long long run = cta_scan_1024<unsigned long long>(sum, s_w, &total) - sum;
+#pragma unroll
+            for (int q = 0; q < kXsPer; q++) {
+                const int r = tid * kXsPer + q;
+                run += loc[q];
+                if (r < wlen) W.scan[r] = run;
+            }
+            // blocks that will most likely be taken apart (no binade, or the binade changes after them): their terms on
+            // the way to L2
+            for (int r = tid; r < wlen; r += kXsChunk) {
+                const int e = W.e[r];
+                if (e == kXsUnclean || (r + 1 < wlen && W.e[r + 1] != e)) {
+                    const char *pf = reinterpret_cast<const char *>(t + (w0 + r) * kXsB);
+                    const long long lim = (n - (w0 + r) * kXsB) * 8;
+                    for (int o = 0; o < kXsB * 8 && o < lim; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + o));
+                }
+            }
+        }
+        if (tid == 0) s_pos = 0;
+        for (;;) {
+            __syncthreads();   // s_s, s_pos (and, the first time, W) are visible
+            const int pos = s_pos;
+            const double s = s_s;
+            if (pos >= wlen) break;
+            const int e = W.e[pos];
+            bool seq = (e == kXsUnclean) || xs_exponent(s) != e;
+            if (tid == 0) s_bad = wlen;
+            __syncthreads();
+            if (!seq) {
+                const long long m0 = xs_to_int(s, e);
+                const unsigned long long base = pos > 0 ? W.scan[pos - 1] : 0ull;
+                int mine = wlen;
+#pragma unroll
+                for (int q = 0; q < kXsPer; q++) {
+                    const int r = pos + q * kXsChunk + tid;
+                    if (r < wlen) {
+                        bool ok = (W.e[r] == e);
+                        if (ok) {
+                            const long long m = m0 + (long long)((r > 0 ? W.scan[r - 1] : 0ull) - base);
+                            ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, W.xmax[r], W.absb[r]);
+                        }
+                        if (!ok && r < mine) mine = r;
+                    }
+                }
+                if (mine < wlen) atomicMin(&s_bad, mine);
+                __syncthreads();
+                const int bad = s_bad;
+                if (bad == pos) seq = true;   // (uniform: every thread reads the same s_bad)
+                else {
+                    if (tid == 0) {
+                        s_s = xs_from_int(m0 + (long long)(W.scan[bad - 1] - base), e);
+                        s_pos = bad;
+                    }
+                    continue;
+                }
+            }
+            // The block cannot be advanced as a whole.  Second level: its kXsFine-term pieces, rounded for the binade s is
+            // in NOW (8 warps, one piece each); thread 0 then advances piece by piece, and only pieces that fail the same
+            // verification -- the one with the binade crossing or the tie -- are added term by term, as the reference does.
+            const long long i0 = (w0 + pos) * kXsB;
+            const int cnt = (int)xs_min(kXsB, n - i0);
+            if (tid < kXsB) s_terms[tid] = (tid < cnt) ? t[i0 + tid] : 0.0;
+            __syncthreads();
+            const int es = xs_exponent(s);
+            if (tid < kXsB && es != kXsUnclean) {
+                bool tie = false;
+                const double v = s_terms[tid];
+                long long d = xs_round(v, es, &tie);
+                double a = fabs(v), x = fabs(warp_scan(v, lane));
+                d = warp_sum_ll(d);
+                a = warp_sum(a);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+                tie = __any_sync(0xffffffffu, tie);
+                if (lane == 0) { s_fD[wid] = d; s_fabs[wid] = a; s_fmax[wid] = x; s_ftie[wid] = tie ? 1 : 0; }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double acc = s;
+                for (int j = 0; j * kXsFine < cnt; j++) {
+                    if (es != kXsUnclean && !s_ftie[j] && xs_exponent(acc) == es && xs_verify(acc, es, s_fmax[j], s_fabs[j])) {
+                        const long long m = xs_to_int(acc, es) + s_fD[j];
+                        if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
+                    }
+                    const int i1 = (j + 1) * kXsFine < cnt ? (j + 1) * kXsFine : cnt;
+                    for (int i = j * kXsFine; i < i1; i++) acc += s_terms[i];
+                }
+                s_s = acc;
+                s_pos = pos + 1;
+            }
         }
     }
+    __syncthreads();
     if (tid == 0) {
         scal[out_slot + k] = s_s;
         __threadfence();
@@ -314,7 +321,12 @@ int exact_seq_sum(lsspg_ctx *ctx, long long n, int K, const RedOut &o)
         LSSPG_LAUNCH(ctx, k_xs_predict, K, 1024, 0, nb, sc, stop);
         LSSPG_LAUNCH(ctx, k_xs_round, grid, 256, 0, n, nb, ctx->d_seq, seq_n, sc, stop);
     }
-    LSSPG_LAUNCH(ctx, k_xs_walk, K, kXsChunk, 0, n, nb, K, ctx->d_seq, seq_n, sc, ctx->d_scal, ctx->d_flags, o.out_slot,
+    static bool attr_done = false;
+    if (!attr_done) {
+        LSSPG_CUDA(cudaFuncSetAttribute(k_xs_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XsWindow)));
+        attr_done = true;
+    }
+    LSSPG_LAUNCH(ctx, k_xs_walk, K, kXsChunk, sizeof(XsWindow), n, nb, K, ctx->d_seq, seq_n, sc, ctx->d_scal, ctx->d_flags, o.out_slot,
                  distributed(ctx) ? 1 : 0, o.fin, stop);
     return 0;
 }
@@ -344,64 +356,73 @@ static double xs_host(long long n, const double *t, long long *stats)
         if (tie) eb[b] = kXsUnclean;
         D[b] = (tie || e == kXsUnclean) ? 0ull : (unsigned long long)d;
     }
-    {
+    {   // the scan restarts with every window (wrap-around arithmetic: only differences inside a run are used)
         unsigned long long run = 0;
-        for (long long b = 0; b < nb; b++) { run += D[b]; scan[b] = run; }
+        for (long long b = 0; b < nb; b++) {
+            if (b % kXsWin == 0) run = 0;
+            run += D[b];
+            scan[b] = run;
+        }
     }
-    double s = 0.0;   // K4
-    long long pos = 0, rounds = 0, seq_blocks = 0, seq_pieces = 0;
-    while (pos < nb) {
-        rounds++;
-        const int e = eb[pos];
-        bool seq = (e == kXsUnclean) || xs_exponent(s) != e;
-        if (!seq) {
-            const long long m0 = xs_to_int(s, e);
-            const unsigned long long base = pos > 0 ? scan[pos - 1] : 0ull;
-            long long bad = std::min<long long>(nb, pos + (long long)kXsChunk * kXsPer);
-            for (long long b = pos; b < std::min<long long>(nb, pos + (long long)kXsChunk * kXsPer); b++) {
-                bool ok = (eb[b] == e);
-                if (ok) {
-                    const long long m = m0 + (long long)((b > 0 ? scan[b - 1] : 0ull) - base);
-                    ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, xmax[b], absb[b]);
-                }
-                if (!ok) { bad = b; break; }
-            }
-            if (bad == pos) seq = true;
-            else {
-                s = xs_from_int(m0 + (long long)(scan[bad - 1] - base), e);
-                pos = bad;
-                continue;
-            }
-        }
-        {   // second level, as in k_xs_walk
-            const long long i0 = pos * kXsB;
-            const int cnt = (int)std::min<long long>(kXsB, n - i0);
-            const int es = xs_exponent(s);
-            double acc = s;
-            for (int j = 0; j * kXsFine < cnt; j++) {
-                const int i1 = std::min((j + 1) * kXsFine, cnt);
-                if (es != kXsUnclean && xs_exponent(acc) == es) {
-                    bool tie = false;
-                    long long d = 0;
-                    double a = 0.0, x = 0.0, pre = 0.0;
-                    for (int i = j * kXsFine; i < i1; i++) {
-                        d += xs_round(t[i0 + i], es, &tie);
-                        a += fabs(t[i0 + i]);
-                        pre += t[i0 + i];
-                        x = std::max(x, fabs(pre));
+    auto scan_before = [](long long) { return 0ull; };   // the scan value "before" the first block of a window
+    double s = 0.0;   // K4: windows of kXsWin blocks, as k_xs_walk
+    long long rounds = 0, seq_blocks = 0, seq_pieces = 0;
+    for (long long w0 = 0; w0 < nb; w0 += kXsWin) {
+        const long long wend = std::min<long long>(nb, w0 + kXsWin);
+        long long pos = w0;
+        while (pos < wend) {
+            rounds++;
+            const int e = eb[pos];
+            bool seq = (e == kXsUnclean) || xs_exponent(s) != e;
+            if (!seq) {
+                const long long m0 = xs_to_int(s, e);
+                const unsigned long long base = pos > w0 ? scan[pos - 1] : scan_before(w0);
+                long long bad = wend;
+                for (long long b = pos; b < wend; b++) {
+                    bool ok = (eb[b] == e);
+                    if (ok) {
+                        const long long m = m0 + (long long)((b > w0 ? scan[b - 1] : scan_before(w0)) - base);
+                        ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, xmax[b], absb[b]);
                     }
-                    if (!tie && xs_verify(acc, es, x, a)) {
-                        const long long m = xs_to_int(acc, es) + d;
-                        if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
-                    }
+                    if (!ok) { bad = b; break; }
                 }
-                for (int i = j * kXsFine; i < i1; i++) acc += t[i0 + i];
-                seq_pieces++;
+                if (bad == pos) seq = true;
+                else {
+                    s = xs_from_int(m0 + (long long)(scan[bad - 1] - base), e);
+                    pos = bad;
+                    continue;
+                }
             }
-            s = acc;
+            {   // second level, as in k_xs_walk
+                const long long i0 = pos * kXsB;
+                const int cnt = (int)std::min<long long>(kXsB, n - i0);
+                const int es = xs_exponent(s);
+                double acc = s;
+                for (int j = 0; j * kXsFine < cnt; j++) {
+                    const int i1 = std::min((j + 1) * kXsFine, cnt);
+                    if (es != kXsUnclean && xs_exponent(acc) == es) {
+                        bool tie = false;
+                        long long d = 0;
+                        double a = 0.0, x = 0.0, pre = 0.0;
+                        for (int i = j * kXsFine; i < i1; i++) {
+                            d += xs_round(t[i0 + i], es, &tie);
+                            a += fabs(t[i0 + i]);
+                            pre += t[i0 + i];
+                            x = std::max(x, fabs(pre));
+                        }
+                        if (!tie && xs_verify(acc, es, x, a)) {
+                            const long long m = xs_to_int(acc, es) + d;
+                            if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
+                        }
+                    }
+                    for (int i = j * kXsFine; i < i1; i++) acc += t[i0 + i];
+                    seq_pieces++;
+                }
+                s = acc;
+            }
+            seq_blocks++;
+            pos++;
         }
-        seq_blocks++;
-        pos++;
     }
     if (stats) { stats[0] = nb; stats[1] = rounds; stats[2] = seq_blocks; stats[3] = seq_pieces; }
     return s;

@@ -1156,28 +1156,17 @@ struct lsspg_bfactors {
 
 namespace lsspg {
 
-// Host half of the GPU factorisation (ilu_gpu.cu): the matrix the numeric phase works on -- A with
-// its diagonal repaired, scattered into the ILU(level) pattern, restricted to the diagonal blocks.
-int ilu_prepare(int n, const int *Ap, const int *Aj, const double *Ax, int level, int bs, IVec &Mp, IVec &Mj, DVec &Mx)
-{
-    Csr Ad = ingest(n, Ap, Aj, Ax);
-    Csr M = (level > 0) ? block_diagonal(iluk_pattern(Ad, level), bs) : block_diagonal(std::move(Ad), bs);
-    Mp.swap(M.p);
-    Mj.swap(M.j);
-    Mx.swap(M.x);
-    return 0;
-}
-
-// ... and the split of the factored rows into L (unit diagonal last) and U (diagonal first)
-lsspg_factors *ilu_split(int n, IVec &Mp, IVec &Mj, DVec &Mx)
+// an empty factor pair of the given sizes for the device set-up (ilu_gpu.cu), which downloads into the arrays
+lsspg_factors *factors_new(int n, size_t nnzL, size_t nnzU, int **Lp, int **Lj, double **Lx, int **Up, int **Uj, double **Ux)
 {
     lsspg_factors *F = new lsspg_factors();
     F->f.n = n;
-    Csr M;
-    M.n = n;
-    M.p.swap(Mp); M.j.swap(Mj); M.x.swap(Mx);
-    split_all(M, F->f.L, F->f.U);
-    M.p.swap(Mp); M.j.swap(Mj); M.x.swap(Mx);
+    Csr &L = F->f.L, &U = F->f.U;
+    L.n = U.n = n;
+    L.p.resize((size_t)n + 1); L.j.resize(nnzL); L.x.resize(nnzL);
+    U.p.resize((size_t)n + 1); U.j.resize(nnzU); U.x.resize(nnzU);
+    *Lp = L.p.data(); *Lj = L.j.data(); *Lx = L.x.data();
+    *Up = U.p.data(); *Uj = U.j.data(); *Ux = U.x.data();
     return F;
 }
 

@@ -28,6 +28,7 @@
 #include "blas1.cuh"
 #include "comm.cuh"
 #include "spmv.cuh"
+#include "setup_gpu.cuh"
 #include "host_par.h"
 
 namespace lsspg {
@@ -546,6 +547,12 @@ static void build_tiles(int n, const int *Ap, bool exact, std::vector<int> &rows
     rows.push_back(n);
 }
 
+__global__ void __launch_bounds__(256) k_check_cols(long long nnz, const int *__restrict__ j, int m, int *bad)
+{
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x)
+        if (j[e] < 0 || j[e] >= m) *bad = 1;
+}
+
 }  // namespace lsspg
 
 using namespace lsspg;
@@ -601,6 +608,58 @@ int lsspg_csr_upload(lsspg_ctx *ctx, int num_rows, int num_cols, const int *hAp,
         LSSPG_CUDA(cudaMemcpyAsync(A->d_tile_kind, kinds.data(), kinds.size(), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<int> e0(rows.size());
     for (size_t t = 0; t < rows.size(); t++) e0[t] = hAp[rows[t]];
+    LSSPG_CUDA(cudaMalloc(&A->d_tile_e0, sizeof(int) * e0.size()));
+    LSSPG_CUDA(cudaMemcpyAsync(A->d_tile_e0, e0.data(), sizeof(int) * e0.size(), cudaMemcpyHostToDevice, ctx->stream));
+    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (unsigned char k : kinds) A->irregular |= (k == TILE_MIXED || k == TILE_BALANCED || k == TILE_BLOCK);
+    *out = A;
+    return 0;
+}
+
+/* The SpMV matrix of a device-resident CSR (setup_gpu.cuh): only the row pointer visits the host (the row-tile schedule is
+ * built there, 4 (n + 1) bytes); Aj / Ax stay where they are -- adopted when take != 0 (M is emptied), copied device to
+ * device otherwise.  Column indices are range-checked by a kernel. */
+int lsspg_csr_from_dmat(lsspg_ctx *ctx, lsspg_dmat *M, int take, lsspg_csr **out)
+{
+    LSSPG_CHECK(ctx && M && out && M->bs == 1 && M->p, "lsspg_csr_from_dmat: needs a device CSR matrix");
+    LSSPG_CUDA(cudaSetDevice(ctx->device));
+    const int n = M->n;
+    const long long nnz = M->nnz;
+    std::vector<int> hp((size_t)n + 1);
+    int *flag = ctx->d_flags + FLAG_SETUP;
+    LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    if (nnz > 0) LSSPG_LAUNCH(ctx, k_check_cols, stream_grid(ctx, nnz, 256), 256, 0, nnz, M->j, M->m, flag);
+    int bad = 0;
+    LSSPG_CUDA(cudaMemcpyAsync(hp.data(), M->p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    LSSPG_CHECK(!bad, "lsspg_csr_from_dmat: column index out of range");
+    LSSPG_CHECK(hp[0] == 0 && hp[n] == nnz, "lsspg_csr_from_dmat: malformed row pointer");
+    lsspg_csr *A = new lsspg_csr();
+    A->num_rows = n; A->num_cols = M->m; A->num_nnzs = (int)nnz;
+    std::vector<int> rows;
+    std::vector<unsigned char> kinds;
+    build_tiles(n, hp.data(), ctx->opt_spmv_exact != 0, rows, kinds, A->max_tile_nnz, A->num_stream_tiles);
+    A->num_tiles = (int)kinds.size();
+    if (take) {
+        A->dAp = M->p; A->dAj = M->j; A->dAx = M->x;   // allocated with the slack the kernels expect (dmat_alloc)
+        M->p = nullptr; M->j = nullptr; M->x = nullptr; M->nnz = 0; M->n = 0;
+    }
+    else {
+        LSSPG_CUDA(cudaMalloc(&A->dAp, sizeof(int) * ((size_t)n + 1 + 8)));
+        LSSPG_CUDA(cudaMalloc(&A->dAj, sizeof(int) * ((size_t)nnz + 16)));
+        LSSPG_CUDA(cudaMalloc(&A->dAx, sizeof(double) * ((size_t)nnz + 16)));
+        LSSPG_CUDA(cudaMemcpyAsync(A->dAp, M->p, sizeof(int) * ((size_t)n + 1 + 8), cudaMemcpyDeviceToDevice, ctx->stream));
+        LSSPG_CUDA(cudaMemcpyAsync(A->dAj, M->j, sizeof(int) * ((size_t)nnz + 16), cudaMemcpyDeviceToDevice, ctx->stream));
+        LSSPG_CUDA(cudaMemcpyAsync(A->dAx, M->x, sizeof(double) * ((size_t)nnz + 16), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    LSSPG_CUDA(cudaMalloc(&A->d_tile_row, sizeof(int) * rows.size()));
+    LSSPG_CUDA(cudaMalloc(&A->d_tile_kind, std::max<size_t>(kinds.size(), 1)));
+    LSSPG_CUDA(cudaMemcpyAsync(A->d_tile_row, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!kinds.empty())
+        LSSPG_CUDA(cudaMemcpyAsync(A->d_tile_kind, kinds.data(), kinds.size(), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int> e0(rows.size());
+    for (size_t t = 0; t < rows.size(); t++) e0[t] = hp[rows[t]];
     LSSPG_CUDA(cudaMalloc(&A->d_tile_e0, sizeof(int) * e0.size()));
     LSSPG_CUDA(cudaMemcpyAsync(A->d_tile_e0, e0.data(), sizeof(int) * e0.size(), cudaMemcpyHostToDevice, ctx->stream));
     LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,219 @@
+"""Set-up on the device: matrix utilities and generators (matops_gpu.cu) and the ILU(k)
+factorisation (ilu_gpu.cu) on matrices that live in GPU memory.  Every result must be byte-identical to the host path,
+which is pinned against the unmodified reference (tests/test_host.py, tests/cxx/mat_utils_abi_check.cpp,
+tests/golden/*.json) -- including the BASELINE-size factors of tests/golden/baseline_256.json."""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+from lssp_b200 import api
+from lssp_b200 import generators as g
+from util import matrix, sha, tvec
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def same(A, B):
+    return all(np.array_equal(a, b) for a, b in zip(A, B)) and all(a.dtype == b.dtype for a, b in zip(A, B))
+
+
+def shuffled(A, seed=0, drop_diag_every=0):
+    """the rows of A with their entries in random order (and some diagonals removed): what a caller may hand to
+    lssp_solver_assemble before lssp_mat_sort_column / lssp_mat_adjust_zero_diag"""
+    rng = np.random.default_rng(seed)
+    Ap, Aj, Ax = A
+    n = len(Ap) - 1
+    cols, vals, p = [], [], [0]
+    for i in range(n):
+        c, v = Aj[Ap[i]:Ap[i + 1]].copy(), Ax[Ap[i]:Ap[i + 1]].copy()
+        if drop_diag_every and i % drop_diag_every == 0:
+            keep = c != i
+            c, v = c[keep], v[keep]
+        o = rng.permutation(len(c))
+        cols.append(c[o]); vals.append(v[o]); p.append(p[-1] + len(c))
+    return np.array(p, np.int32), np.concatenate(cols).astype(np.int32), np.concatenate(vals)
+
+
+# ---- host restatements of the facade's utilities (lssp_facade.cpp), small sizes ------------------------------------
+def host_sort(A):
+    Ap, Aj, Ax = A
+    Aj, Ax = Aj.copy(), Ax.copy()
+    for i in range(len(Ap) - 1):
+        b, e = Ap[i], Ap[i + 1]
+        o = np.argsort(Aj[b:e], kind="stable")
+        Aj[b:e], Ax[b:e] = Aj[b:e][o], Ax[b:e][o]
+    return Ap, Aj, Ax
+
+
+def host_adjust(A, tol):
+    Ap, Aj, Ax = A
+    p, cols, vals = [0], [], []
+    for i in range(len(Ap) - 1):
+        c, v = list(Aj[Ap[i]:Ap[i + 1]]), list(Ax[Ap[i]:Ap[i + 1]])
+        if i not in c:
+            c.append(i); v.append(1 * tol)
+            q = len(c) - 1
+            while q > 0 and c[q - 1] > c[q]:
+                c[q - 1], c[q] = c[q], c[q - 1]
+                v[q - 1], v[q] = v[q], v[q - 1]
+                q -= 1
+        cols += c; vals += v; p.append(len(cols))
+    return np.array(p, np.int32), np.array(cols, np.int32), np.array(vals, np.float64)
+
+
+def host_block_diag(A, bs):
+    Ap, Aj, Ax = A
+    n = len(Ap) - 1
+    p, cols, vals = [0], [], []
+    for i in range(n):
+        lo = (i // bs) * bs
+        hi = min(n, lo + bs)
+        c, v = Aj[Ap[i]:Ap[i + 1]], Ax[Ap[i]:Ap[i + 1]]
+        keep = (c >= lo) & (c < hi)
+        if keep.any():
+            cols += list(c[keep]); vals += list(v[keep])
+        else:
+            cols.append(i); vals.append(1.0)
+        p.append(len(cols))
+    return np.array(p, np.int32), np.array(cols, np.int32), np.array(vals, np.float64)
+
+
+def host_bcsr(A, bs):
+    Ap, Aj, Ax = A
+    nb = (len(Ap) - 1) // bs
+    Bp, Bj = [0], []
+    for i in range(nb):
+        Bj += sorted(set(int(c) // bs for c in Aj[Ap[i * bs]:Ap[(i + 1) * bs]]))
+        Bp.append(len(Bj))
+    Bx = np.zeros(len(Bj) * bs * bs)
+    for i in range(nb):
+        where = {Bj[k]: k for k in range(Bp[i], Bp[i + 1])}
+        for r in range(i * bs, (i + 1) * bs):
+            for k in range(Ap[r], Ap[r + 1]):
+                c = int(Aj[k])
+                Bx[where[c // bs] * bs * bs + (c % bs) * bs + (r % bs)] = Ax[k]
+    return np.array(Bp, np.int32), np.array(Bj, np.int32), Bx
+
+
+# ---- utilities ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["random_600", "powerlaw_4000", "cd3d_12", "lap2d_100"])
+def test_upload_copy_sort_adjust_block_diag(ctx, name):
+    A = matrix(name)
+    d = api.DMat(ctx, A)
+    assert same(d.download(), A) and d.is_sorted()
+    assert same(d.copy().download(), A)
+    S = shuffled(A, seed=3, drop_diag_every=7)
+    ds = api.DMat(ctx, S)
+    assert not ds.is_sorted()
+    ds.sort_columns()
+    want = host_sort(S)
+    assert same(ds.download(), want) and ds.is_sorted()
+    assert same(ds.adjust_zero_diag(1e-10).download(), host_adjust(want, 1e-10))
+    # the diagonal slides in front of the trailing run of larger columns of an UNSORTED row as well
+    assert same(api.DMat(ctx, S).adjust_zero_diag(0.5).download(), host_adjust(S, 0.5))
+    n = len(A[0]) - 1
+    for bs in (1, 7, (n + 2) // 3, n):
+        assert same(d.get_block_diag(bs).download(), host_block_diag(A, bs)), bs
+
+
+def test_sort_is_stable_for_repeated_columns(ctx):
+    Ap = np.array([0, 6, 6, 9], np.int32)
+    Aj = np.array([2, 0, 2, 1, 0, 2, 1, 1, 0], np.int32)
+    Ax = np.arange(9, dtype=np.float64)
+    d = api.DMat(ctx, (Ap, Aj, Ax)).sort_columns()
+    assert same(d.download(), host_sort((Ap, Aj, Ax)))
+
+
+@pytest.mark.parametrize("name,bs", [("cd3d_12", 2), ("cd3d_12", 3), ("lap2d_100", 4), ("powerlaw_4000", 5), ("random_600", 6)])
+def test_csr_to_bcsr(ctx, name, bs):
+    A = matrix(name)
+    assert (len(A[0]) - 1) % bs == 0
+    B = api.DMat(ctx, A).to_bcsr(bs)
+    assert B.dims()[3] == bs
+    assert same(B.download(), host_bcsr(A, bs))
+    assert same(api.DMat(ctx, shuffled(A, seed=1)).to_bcsr(bs).download(), host_bcsr(shuffled(A, seed=1), bs))
+
+
+def test_generators_on_the_device(ctx):
+    assert same(api.DMat.lap3d(ctx, 20).download(), g.lap3d(20))
+    assert same(api.DMat.cd3d(ctx, 17).download(), g.cd3d(17))
+    assert same(api.DMat.laplacian_5pt(ctx, 100).download(), g.laplacian_5pt(100))
+    dims, r0, r1 = (9, 7, 11), 123, 600      # a rank's row block of an anisotropic grid, global columns
+    Ap, Aj, Ax = g.stencil_7pt_rows(dims, r0, r1, conv=(0.3, 0.2, 0.1))
+    got = api.DMat.stencil(ctx, dims, [-1.0 - 0.1, -1.0 - 0.2, -1.0 - 0.3, 6.0, -1.0 + 0.3, -1.0 + 0.2, -1.0 + 0.1], r0=r0, r1=r1).download()
+    assert np.array_equal(got[0], Ap) and np.array_equal(got[1], Aj.astype(np.int32)) and np.array_equal(got[2], Ax)
+
+
+def test_spmv_matrix_from_a_device_matrix(ctx):
+    for A, d in ((g.lap3d(24), api.DMat.lap3d(ctx, 24)), (matrix("powerlaw_4000"), api.DMat(ctx, matrix("powerlaw_4000")))):
+        n = len(A[0]) - 1
+        x = tvec(n)
+        want = api.Csr(ctx, A).mv_host(0, x)
+        assert np.array_equal(d.to_csr().mv_host(0, x), want)            # copied
+        assert np.array_equal(d.to_csr(take=True).mv_host(0, x), want)   # adopted
+        assert d.dims()[2] == 0
+
+
+# ---- ILU(k) on the device -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["lap2d_100", "lap3d_32", "cd3d_32", "cd3d_12", "powerlaw_4000", "random_600"])
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_iluk_on_the_device_is_bit_identical(ctx, name, level):
+    if name == "powerlaw_4000" and level > 1:
+        pytest.skip("near-dense factors (rows of 2000+ entries): a thread per row is the wrong tool; host set-up")
+    # (powerlaw_4000 at level 1 has pattern rows of 1200 entries: the first pool of 1024 per row overflows and is regrown)
+    A = matrix(name)
+    want = api.ilu_factor(A, "iluk", level=level)
+    got = api.DMat(ctx, A).ilu_factor(level=level)
+    assert all(same(a, b) for a, b in zip(got, want)), (name, level)
+    assert all(same(a, b) for a, b in zip(api.ilu_factor(A, "iluk", level=level, ctx=ctx), want))
+
+
+@pytest.mark.parametrize("name", ["cd3d_12", "powerlaw_4000", "random_600"])
+def test_iluk_on_the_device_blocks_and_unsorted_input(ctx, name):
+    A = matrix(name)
+    n = len(A[0]) - 1
+    for level, bs in ((0, (n + 3) // 4), (1, (n + 2) // 3), (1, 97)):
+        want = api.ilu_factor(A, "iluk", level=level, blk_size=bs)
+        got = api.DMat(ctx, A).ilu_factor(level=level, blk_size=bs)
+        assert all(same(a, b) for a, b in zip(got, want)), (name, level, bs)
+    S = shuffled(A, seed=5, drop_diag_every=11)          # ingest on the device: sort + missing diagonals
+    want = api.ilu_factor(S, "iluk", level=1)
+    got = api.DMat(ctx, S).ilu_factor(level=1)
+    assert all(same(a, b) for a, b in zip(got, want)), name
+
+
+@pytest.mark.parametrize("case", ["lap3d/ilu0", "cd3d/iluk1"])
+def test_device_factorisation_at_the_baseline_size(ctx, case, record_property):
+    """256^3: matrix generated on the device, factorised on the device; factors == the unmodified reference's
+    (tests/golden/baseline_256.json)"""
+    path = os.path.join(HERE, "golden", "baseline_256.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/baseline_256.json not generated")
+    with open(path) as f:
+        gold = json.load(f)
+    N = 256
+    t0 = time.perf_counter()
+    d = api.DMat.lap3d(ctx, N) if case == "lap3d/ilu0" else api.DMat.cd3d(ctx, N)
+    ctx.sync()
+    t1 = time.perf_counter()
+    tag, level = ("ilu0", 0) if case == "lap3d/ilu0" else ("iluk1", 1)
+    L, U = d.ilu_factor(level=level)
+    t2 = time.perf_counter()
+    e = gold[case.split("/")[0] + "/kernels"]
+    A = g.lap3d(N) if case == "lap3d/ilu0" else g.cd3d(N)
+    t3 = time.perf_counter()
+    Lh, Uh = api.ilu_factor(A, "iluk", level=level)
+    t4 = time.perf_counter()
+    print("%s: generate on the device %.3f s, factorise on the device + download %.3f s (host threads: %.3f s)" % (case, t1 - t0, t2 - t1, t4 - t3))
+    record_property("host_setup_s", t4 - t3)
+    assert same(L, Lh) and same(U, Uh)
+    record_property("device_setup_s", t2 - t1)
+    assert [int(L[0][-1]), int(U[0][-1])] == e[tag + "_nnz"]
+    assert sha(np.concatenate([L[2], U[2]])) == e[tag + "_factor_sha"]
+    # and the SpMV matrix straight from the device arrays
+    x = tvec(N ** 3)
+    assert sha(d.to_csr(take=True).mv_host(0, x)) == (e["mxy_sha"] if case == "lap3d/ilu0" else sha(api.Csr(ctx, g.cd3d(N)).mv_host(0, x)))
