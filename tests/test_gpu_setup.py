@@ -18,7 +18,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def same(A, B):
-    return all(np.array_equal(a, b) for a, b in zip(A, B)) and all(a.dtype == b.dtype for a, b in zip(A, B))
+    """arrays equal entry by entry (NaN == NaN: a factorisation that overflows does so on both sides) and of the same type"""
+    return all(np.array_equal(a, b, equal_nan=(a.dtype == np.float64)) for a, b in zip(A, B)) and \
+        all(a.dtype == b.dtype for a, b in zip(A, B))
 
 
 def shuffled(A, seed=0, drop_diag_every=0):
