@@ -222,6 +222,12 @@ int lsspg_ilu_factor_device(lsspg_ctx *ctx, int n, const int *hAp, const int *hA
                             int level, int blk_size, lsspg_factors **out);
 /* the same from a matrix that is already in device memory (see "device-side ingest" below) */
 int lsspg_ilu_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A, int level, int blk_size, lsspg_factors **out);
+/* ILUT(p, tol) set-up on the GPU (src/pc-ilut.cxx:51-286, :429-456): the dual-threshold row recurrence incl. the
+ * reference's quick-select (:7-49, the stored order of the kept entries is part of the result), one thread per row in a
+ * persistent kernel as above; p <= 0 and tol < 0 select the reference's defaults (:436-442).  Bit-identical factors. */
+int lsspg_ilut_factor_device(lsspg_ctx *ctx, int n, const int *hAp, const int *hAj, const double *hAx, int p, double tol,
+                             int blk_size, lsspg_factors **out);
+int lsspg_ilut_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A, int p, double tol, int blk_size, lsspg_factors **out);
 int lsspg_factors_sizes(const lsspg_factors *F, int *n, int *nnzL, int *nnzU);
 int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int *Up, int *Uj,
                       double *Ux);

@@ -246,6 +246,12 @@ class DMat:
         check(lib().lsspg_ilu_factor_dmat(self.ctx.h, self.h, int(level), int(blk_size), C.byref(h)))
         return _factors_out(h, self.dims()[0])
 
+    def ilut_factor(self, p=-1, tol=1e-3, blk_size=0):
+        """ILUT(p, tol) on the device (lsspg_ilut_factor_dmat)"""
+        h = C.c_void_p()
+        check(lib().lsspg_ilut_factor_dmat(self.ctx.h, self.h, int(p), C.c_double(tol), int(blk_size), C.byref(h)))
+        return _factors_out(h, self.dims()[0])
+
     def free(self):
         if self.h and self.ctx.h:
             lib().lsspg_dmat_destroy(self.ctx.h, self.h)
@@ -446,14 +452,16 @@ class Tri:
 
 def ilu_factor(A, kind="iluk", level=0, p=-1, tol=1e-3, blk_size=0, ctx=None):
     """ILU(k) / ILUT set-up (reference src/pc-iluk.cxx, src/pc-ilut.cxx).  Returns (L, U) CSR
-    triples in the reference's layout.  ctx given (ILU(k) only): the whole set-up -- ingest, symbolic and
-    numeric phases, block restriction, L / U split -- runs on the GPU (lsspg_ilu_factor_device, ilu_gpu.cu),
+    triples in the reference's layout.  ctx given: the whole set-up -- ingest, symbolic and
+    numeric phases (ILUT: the dual-threshold row recurrence), block restriction, L / U split -- runs on the GPU (ilu_gpu.cu),
     with bit-identical factors."""
     Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
     n = len(Ap) - 1
     h = C.c_void_p()
     if ctx is not None and kind == "iluk":
         check(lib().lsspg_ilu_factor_device(ctx.h, n, _p(Ap), _p(Aj), _p(Ax), int(level), int(blk_size), C.byref(h)))
+    elif ctx is not None:
+        check(lib().lsspg_ilut_factor_device(ctx.h, n, _p(Ap), _p(Aj), _p(Ax), int(p), C.c_double(tol), int(blk_size), C.byref(h)))
     else:
         check(lib().lsspg_ilu_factor(0 if kind == "iluk" else 1, n, _p(Ap), _p(Aj), _p(Ax), int(level), int(p),
                                      C.c_double(tol), int(blk_size), C.byref(h)))

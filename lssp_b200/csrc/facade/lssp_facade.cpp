@@ -133,6 +133,13 @@ static lsspg_ctx *ctx()
         const char *e = getenv("LSSP_GPU");
         if (lsspg_ctx_create(e ? atoi(e) : 0, &g_ctx)) lssp_error(1, "lssp: %s\n", lsspg_last_error());
         lsspg_set_printer(driver_print);   // per-iteration lines of the drivers go where lssp_printf sends them (log file too)
+        // LSSP_REDUCE=reference: every dot product / norm is the reference's sequential sum (src/vector.cxx:127-131), bit
+        // for bit, computed in parallel -> whole solves are bit-identical to the CPU library (exact_sum.cu); default: fixed
+        // tree reductions (faster, more accurate, different in the last bits)
+        if (const char *r = getenv("LSSP_REDUCE")) {
+            const int mode = !strcmp(r, "reference") ? 2 : !strcmp(r, "sequential") ? 1 : 0;
+            if (lsspg_ctx_set_option(g_ctx, LSSPG_OPT_REDUCE_SEQUENTIAL, mode)) lssp_error(1, "lssp: %s\n", lsspg_last_error());
+        }
     }
     return g_ctx;
 }

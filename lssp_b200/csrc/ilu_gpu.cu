@@ -12,6 +12,7 @@
 // (t / kStride) 32 kStride + l kStride + t % kStride): chains run ACROSS warps and 32 chains advance per warp.
 // No FMA, same operations in the same order: the factors are bit-identical to ilu_host.cpp's and hence to the
 // reference's (tests/test_gpu_setup.py, tests/test_gpu_kernels.py).
+#include <time.h>
 #include <algorithm>
 #include <vector>
 #include "blas1.cuh"
@@ -33,6 +34,29 @@ int lsspg_dmat_get_block_diag(lsspg_ctx *ctx, const lsspg_dmat *A, int blk_size,
 namespace lsspg {
 
 lsspg_factors *factors_new(int n, size_t nnzL, size_t nnzU, int **Lp, int **Lj, double **Lx, int **Up, int **Uj, double **Ux);
+
+// LSSPG_SETUP_PROF=1: phase times of the device set-up on stderr (each phase is synchronised first)
+static double gprof_now()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+static bool gprof_on()
+{
+    static const bool on = getenv("LSSPG_SETUP_PROF") && atoi(getenv("LSSPG_SETUP_PROF")) != 0;
+    return on;
+}
+#define GPROF_T0 double gprof_t = gprof_now()
+#define GPROF(ctx, what)                                                              \
+    do {                                                                              \
+        if (gprof_on()) {                                                             \
+            cudaStreamSynchronize((ctx)->stream);                                     \
+            const double t_ = gprof_now();                                            \
+            fprintf(stderr, "[setup/gpu] %-26s %.3f s\n", what, t_ - gprof_t);        \
+            gprof_t = t_;                                                             \
+        }                                                                             \
+    } while (0)
 
 constexpr double kPivotTolG = 1e-10;    // mat_zero_diag_tol,   reference src/pc.cxx:7
 constexpr double kPivotValueG = 1e-3;   // mat_zero_diag_value, reference src/pc.cxx:6
@@ -257,17 +281,196 @@ __global__ void __launch_bounds__(256) k_split_fill(int n, const int *__restrict
     }
 }
 
+
+// ---- ILUT (src/pc-ilut.cxx:51-286) ---------------------------------------------------------------------------------------
+// The row recurrence of ilu_host.cpp: factor_ilut_rows, statement for statement, one thread per row: work row as two
+// compact arrays (lower part / upper part) in the thread's scratch, `present?` answered by a linear search of the part
+// the column belongs to instead of the host's column map (processed pivots are smaller than every candidate, so only
+// the live entries are searched), quick-select with the reference's exact sequence of exchanges (:7-49) because the kept
+// entries are stored -- and later summed by the sweeps -- in the order it leaves them.  Finished rows live in a pool
+// ([kept lower | diagonal | kept upper], rcap entries each) and are published like the ILU(k) rows.
+__device__ __forceinline__ void select_largest_dev(double *a, int *ind, int n, int ncut)
+{
+    int lo = 0, hi = n - 1;
+    if (ncut < lo || ncut >= hi) return;
+    for (;;) {
+        int mid = lo;
+        const double key = fabs(a[mid]);
+        for (int q = lo + 1; q <= hi; q++) {
+            if (fabs(a[q]) > key) {
+                ++mid;
+                const double ta = a[mid]; a[mid] = a[q]; a[q] = ta;
+                const int ti = ind[mid]; ind[mid] = ind[q]; ind[q] = ti;
+            }
+        }
+        const double ta = a[mid]; a[mid] = a[lo]; a[lo] = ta;
+        const int ti = ind[mid]; ind[mid] = ind[lo]; ind[lo] = ti;
+        if (mid == ncut) return;
+        if (mid > ncut) hi = mid - 1;
+        else lo = mid + 1;
+    }
+}
+
+__device__ __forceinline__ double repaired_pivot_dev(double d)
+{
+    return (fabs(d) < kPivotTolG) ? (d > 0 ? kPivotValueG : -kPivotValueG) : d;
+}
+
+__global__ void __launch_bounds__(kFacBlock) k_ilut_rows(int n, int bs, int p, double tau, const int *__restrict__ Bp,
+                                                        const int *__restrict__ Bj, const double *__restrict__ Bx, int rcap,
+                                                        int *rc, double *rv, int *rlen, double *diag, int wcap, int *wj,
+                                                        double *wx, int *done, unsigned int *ticket, int *flags)
+{
+    const int lane = threadIdx.x & 31;
+    int *abort_flag = flags + FLAG_SETUP;
+    const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int *jwl = wj + gt * 2 * wcap, *jwu = jwl + wcap;
+    double *wl = wx + gt * 2 * wcap, *wu = wl + wcap;
+    for (;;) {
+        bool more;
+        const long long row = fac_next_row(ticket, lane, n, &more);
+        if (!more) break;
+        if (row >= n) continue;
+        const int i = (int)row;
+        const int b = Bp[i], e = Bp[i + 1];
+        int *c_ = rc + (size_t)i * rcap;
+        double *v_ = rv + (size_t)i * rcap;
+        bool ok = true;
+        if (i % bs == 0) {
+            // first row of a block: copied verbatim; its leading entry is the pivot
+            if (e - b > rcap) ok = false;
+            for (int k = b; ok && k < e; k++) { c_[k - b] = Bj[k]; v_[k - b] = Bx[k]; }
+            rlen[i] = ok ? e - b : 0;
+            __stcg(diag + i, repaired_pivot_dev(Bx[b]));
+        }
+        else {
+            double norm = 0.0;
+            for (int k = b; k < e; k++) norm += fabs(Bx[k]);
+            norm /= (double)(e - b);
+            const double drop = tau * norm;
+            int nl = 0, nu = 0;
+            double wd = 0.0;
+            for (int k = b; k < e && ok; k++) {
+                const int c = Bj[k];
+                if (c < i) { if (nl == wcap) { ok = false; break; } jwl[nl] = c; wl[nl] = Bx[k]; nl++; }
+                else if (c == i) wd = Bx[k];
+                else { if (nu == wcap) { ok = false; break; } jwu[nu] = c; wu[nu] = Bx[k]; nu++; }
+            }
+            for (int tt = 0; ok && tt < nl; tt++) {
+                int piv = jwl[tt], at = tt;
+                for (int q = tt + 1; q < nl; q++)
+                    if (jwl[q] < piv) { piv = jwl[q]; at = q; }
+                if (at != tt) {
+                    const int c = jwl[tt];
+                    jwl[tt] = jwl[at];
+                    jwl[at] = c;
+                    const double tw = wl[tt]; wl[tt] = wl[at]; wl[at] = tw;
+                }
+                if (!fac_wait(done, piv, abort_flag)) { ok = false; break; }
+                const double a_ik = wl[tt] / __ldcg(diag + piv);
+                wl[tt] = a_ik;
+                const int *pc = rc + (size_t)piv * rcap;
+                const double *pv = rv + (size_t)piv * rcap;
+                for (int q = 0, qe = __ldcg(rlen + piv); q < qe; q++) {
+                    const int c = __ldcg(pc + q);
+                    if (c <= piv) continue;
+                    const double mx = -a_ik * __ldcg(pv + q);
+                    if (c == i) { wd += mx; continue; }
+                    if (c < i) {
+                        int at2 = -1;
+                        for (int z = tt + 1; z < nl; z++)
+                            if (jwl[z] == c) { at2 = z; break; }
+                        if (at2 >= 0) wl[at2] += mx;
+                        else if (!(fabs(mx) < drop)) {   // only NEW fill is dropped
+                            if (nl == wcap) { ok = false; break; }
+                            jwl[nl] = c; wl[nl] = mx; nl++;
+                        }
+                    }
+                    else {
+                        int at2 = -1;
+                        for (int z = 0; z < nu; z++)
+                            if (jwu[z] == c) { at2 = z; break; }
+                        if (at2 >= 0) wu[at2] += mx;
+                        else if (!(fabs(mx) < drop)) {
+                            if (nu == wcap) { ok = false; break; }
+                            jwu[nu] = c; wu[nu] = mx; nu++;
+                        }
+                    }
+                }
+            }
+            const double d = repaired_pivot_dev(wd);
+            const int keepl = min(nl, p), keepu = min(nu, p);
+            if (ok && keepl + 1 + keepu > rcap) ok = false;
+            if (ok) {
+                select_largest_dev(wl, jwl, nl, keepl);
+                select_largest_dev(wu, jwu, nu, keepu);
+                for (int q = 0; q < keepl; q++) { c_[q] = jwl[q]; v_[q] = wl[q]; }
+                c_[keepl] = i;
+                v_[keepl] = d;
+                for (int q = 0; q < keepu; q++) { c_[keepl + 1 + q] = jwu[q]; v_[keepl + 1 + q] = wu[q]; }
+            }
+            rlen[i] = ok ? keepl + 1 + keepu : 0;
+            __stcg(diag + i, d);
+        }
+        if (!ok) atomicExch(abort_flag, 1);
+        __threadfence();
+        st_flag(done + i, 1);
+    }
+}
+
+// split of the pool rows (stored order kept: the sweeps add in this order, src/pc-ilut.cxx:253-274)
+__global__ void __launch_bounds__(256) k_pool_split_count(int n, int rcap, const int *__restrict__ rc, const int *__restrict__ rlen,
+                                                         int *nl, int *nu)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int *c_ = rc + (size_t)i * rcap;
+    int a = 0, b = 0;
+    for (int q = 0; q < rlen[i]; q++) {
+        a += (c_[q] <= i);
+        b += (c_[q] >= i);
+    }
+    nl[i] = a;
+    nu[i] = b;
+}
+
+__global__ void __launch_bounds__(256) k_pool_split_fill(int n, int rcap, const int *__restrict__ rc, const double *__restrict__ rv,
+                                                        const int *__restrict__ rlen, const int *__restrict__ Lp,
+                                                        int *__restrict__ Lj, double *__restrict__ Lx, const int *__restrict__ Up,
+                                                        int *__restrict__ Uj, double *__restrict__ Ux)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int *c_ = rc + (size_t)i * rcap;
+    const double *v_ = rv + (size_t)i * rcap;
+    int ol = Lp[i], ou = Up[i];
+    for (int q = 0; q < rlen[i]; q++) {
+        const int c = c_[q];
+        const double v = v_[q];
+        if (c < i) { Lj[ol] = c; Lx[ol] = v; ol++; }
+        else if (c == i) {
+            Lj[ol] = i; Lx[ol] = 1; ol++;
+            Uj[ou] = i; Ux[ou] = v; ou++;
+        }
+        else { Uj[ou] = c; Ux[ou] = v; ou++; }
+    }
+}
+
 static inline unsigned int rows_grid(long long n) { return (unsigned int)std::max<long long>(1, (n + 255) / 256); }
 
-// grid of a persistent factorisation kernel: every CTA resident, at least kStride + 32 warps in flight
+// grid of a persistent factorisation kernel: every CTA resident, at least kStride + 32 warps in flight (the row
+// interleave needs them, see the header), no more CTAs than there are warp tickets
 template <class K>
-static int fac_grid(lsspg_ctx *ctx, K kernel, int *grid)
+static int fac_grid(lsspg_ctx *ctx, K kernel, long long n, int *grid)
 {
     int occ = 0;
     LSSPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kFacBlock, 0));
     LSSPG_CHECK(occ >= 1, "ilu_gpu: the factorisation kernel does not fit on an SM");
-    *grid = ctx->num_sms * std::min(occ, 16);
-    LSSPG_CHECK((long long)*grid * (kFacBlock / 32) >= kStride + 32, "ilu_gpu: %d resident warps are too few for the row interleave", *grid * (kFacBlock / 32));
+    const long long resident = (long long)ctx->num_sms * std::min(occ, 16), warps_per_cta = kFacBlock / 32;
+    const long long tickets = ((n + 32ll * kStride - 1) / (32ll * kStride)) * kStride;
+    const long long need = std::max<long long>((kStride + 32 + warps_per_cta - 1) / warps_per_cta, (tickets + warps_per_cta - 1) / warps_per_cta);
+    *grid = (int)std::min(resident, need);
+    LSSPG_CHECK((long long)*grid * warps_per_cta >= kStride + 32, "ilu_gpu: %lld resident warps are too few for the row interleave", (long long)*grid * warps_per_cta);
     return 0;
 }
 
@@ -284,7 +487,7 @@ static int iluk_symbolic_gpu(lsspg_ctx *ctx, const lsspg_dmat *A, int level, lss
     long long cap = std::min<long long>(1024, (long long)std::max(hmax, 1) * (level + 1) * (level + 1));
     cap = std::max<long long>(32, (cap + 31) / 32 * 32);
     int grid = 0;
-    LSSPG_TRY(fac_grid(ctx, k_iluk_symbolic, &grid));
+    LSSPG_TRY(fac_grid(ctx, k_iluk_symbolic, n, &grid));
     for (;; cap *= 2) {
         LSSPG_CHECK(cap <= 4096, "ilu_gpu: pattern rows longer than 4096 entries (level %d): use the host set-up", level);
         int *pc = nullptr, *pl = nullptr, *meta = nullptr;
@@ -327,6 +530,52 @@ static int iluk_symbolic_gpu(lsspg_ctx *ctx, const lsspg_dmat *A, int level, lss
     }
 }
 
+
+// download a device L / U pair into a host factor object
+static int factors_download(lsspg_ctx *ctx, int n, const lsspg_dmat *L, const lsspg_dmat *U, lsspg_factors **out)
+{
+    int *Lp, *Lj, *Up, *Uj;
+    double *Lx, *Ux;
+    lsspg_factors *F = factors_new(n, (size_t)L->nnz, (size_t)U->nnz, &Lp, &Lj, &Lx, &Up, &Uj, &Ux);
+    LSSPG_CUDA(cudaMemcpyAsync(Lp, L->p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaMemcpyAsync(Lj, L->j, sizeof(int) * (size_t)L->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaMemcpyAsync(Lx, L->x, sizeof(double) * (size_t)L->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaMemcpyAsync(Up, U->p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaMemcpyAsync(Uj, U->j, sizeof(int) * (size_t)U->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaMemcpyAsync(Ux, U->x, sizeof(double) * (size_t)U->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = F;
+    return 0;
+}
+
+// ingest of ilu_host.cpp on the device: strictly ascending columns with the diagonal stored.  *owned receives a repaired
+// copy when A_in needed one (else NULL and A_in itself is used).
+static int ingest_gpu(lsspg_ctx *ctx, const lsspg_dmat *A_in, lsspg_dmat **owned, const char *who)
+{
+    const int n = A_in->n;
+    int *flag = ctx->d_flags + FLAG_SETUP;
+    int bad = 0;
+    *owned = nullptr;
+    LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    LSSPG_LAUNCH(ctx, k_check_rows, rows_grid(n), 256, 0, n, A_in->p, A_in->j, flag);
+    LSSPG_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!bad) return 0;
+    lsspg_dmat *S = nullptr;
+    LSSPG_TRY(lsspg_dmat_copy(ctx, A_in, &S));
+    int rc = lsspg_dmat_sort_columns(ctx, S);
+    if (!rc) rc = lsspg_dmat_adjust_zero_diag(ctx, S, kPivotTolG, owned);
+    dmat_free(S);
+    LSSPG_TRY(rc);
+    LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    LSSPG_LAUNCH(ctx, k_check_rows, rows_grid(n), 256, 0, n, (*owned)->p, (*owned)->j, flag);
+    LSSPG_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    LSSPG_CHECK(!bad, "%s: rows with repeated columns are not supported on the device (use lsspg_ilu_factor)", who);
+    return 0;
+}
+
 }  // namespace lsspg
 
 using namespace lsspg;
@@ -349,43 +598,29 @@ int lsspg_ilu_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A_in, int level, int
     double *inv = nullptr;
     lsspg_dmat *L = nullptr, *U = nullptr;
     auto body = [&]() -> int {
-        // ingest: strictly ascending columns with the diagonal stored (ilu_host.cpp: ingest)
-        int bad = 0;
-        LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
-        LSSPG_LAUNCH(ctx, k_check_rows, rows_grid(n), 256, 0, n, A_in->p, A_in->j, flag);
-        LSSPG_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
-        const lsspg_dmat *Ad = A_in;
-        if (bad) {
-            lsspg_dmat *S = nullptr;
-            LSSPG_TRY(lsspg_dmat_copy(ctx, A_in, &S));
-            int rc = lsspg_dmat_sort_columns(ctx, S);
-            if (!rc) rc = lsspg_dmat_adjust_zero_diag(ctx, S, kPivotTolG, &A);
-            dmat_free(S);
-            LSSPG_TRY(rc);
-            LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
-            LSSPG_LAUNCH(ctx, k_check_rows, rows_grid(n), 256, 0, n, A->p, A->j, flag);
-            LSSPG_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
-            LSSPG_CHECK(!bad, "lsspg_ilu_factor_dmat: rows with repeated columns are not supported on the device (use lsspg_ilu_factor)");
-            Ad = A;
-        }
+        GPROF_T0;
+        LSSPG_TRY(ingest_gpu(ctx, A_in, &A, "lsspg_ilu_factor_dmat"));
+        const lsspg_dmat *Ad = A ? A : A_in;
+        GPROF(ctx, "ingest");
         // symbolic phase, then the block restriction (src/pc-iluk.cxx:432-446: in this order)
         const lsspg_dmat *Mfull = Ad;
         if (level > 0) {
             LSSPG_TRY(iluk_symbolic_gpu(ctx, Ad, level, &M));
             Mfull = M;
         }
+        GPROF(ctx, "symbolic");
         if (bs < n) LSSPG_TRY(lsspg_dmat_get_block_diag(ctx, Mfull, bs, &B));
         else LSSPG_TRY(lsspg_dmat_copy(ctx, Mfull, &B));
+        GPROF(ctx, "block restriction / copy");
         // numeric phase, in place on B
         int grid = 0;
-        LSSPG_TRY(fac_grid(ctx, k_ilu_numeric, &grid));
+        LSSPG_TRY(fac_grid(ctx, k_ilu_numeric, n, &grid));
         LSSPG_CUDA(cudaMalloc(&done, sizeof(int) * ((size_t)n + 4)));
         LSSPG_CUDA(cudaMalloc(&inv, sizeof(double) * (size_t)n));
         LSSPG_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * ((size_t)n + 4), ctx->stream));
         LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
         LSSPG_LAUNCH(ctx, k_ilu_numeric, grid, kFacBlock, 0, n, bs, B->p, B->j, B->x, inv, done, reinterpret_cast<unsigned int *>(done + n), ctx->d_flags);
+        GPROF(ctx, "numeric");
         // split
         LSSPG_CUDA(cudaMalloc(&cl, sizeof(int) * ((size_t)n + 1 + 8)));
         LSSPG_CUDA(cudaMalloc(&cu, sizeof(int) * ((size_t)n + 1 + 8)));
@@ -400,17 +635,9 @@ int lsspg_ilu_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A_in, int level, int
         L->p = cl; cl = nullptr;
         U->p = cu; cu = nullptr;
         LSSPG_LAUNCH(ctx, k_split_fill, rows_grid(n), 256, 0, n, B->p, B->j, B->x, L->p, L->j, L->x, U->p, U->j, U->x);
-        int *Lp, *Lj, *Up, *Uj;
-        double *Lx, *Ux;
-        lsspg_factors *F = factors_new(n, (size_t)tl, (size_t)tu, &Lp, &Lj, &Lx, &Up, &Uj, &Ux);
-        LSSPG_CUDA(cudaMemcpyAsync(Lp, L->p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        LSSPG_CUDA(cudaMemcpyAsync(Lj, L->j, sizeof(int) * (size_t)tl, cudaMemcpyDeviceToHost, ctx->stream));
-        LSSPG_CUDA(cudaMemcpyAsync(Lx, L->x, sizeof(double) * (size_t)tl, cudaMemcpyDeviceToHost, ctx->stream));
-        LSSPG_CUDA(cudaMemcpyAsync(Up, U->p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        LSSPG_CUDA(cudaMemcpyAsync(Uj, U->j, sizeof(int) * (size_t)tu, cudaMemcpyDeviceToHost, ctx->stream));
-        LSSPG_CUDA(cudaMemcpyAsync(Ux, U->x, sizeof(double) * (size_t)tu, cudaMemcpyDeviceToHost, ctx->stream));
-        LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
-        *out = F;
+        GPROF(ctx, "split");
+        LSSPG_TRY(factors_download(ctx, n, L, U, out));
+        GPROF(ctx, "download of L, U");
         return 0;
     };
     const int rc = body();
@@ -429,6 +656,98 @@ int lsspg_ilu_factor_device(lsspg_ctx *ctx, int n, const int *hAp, const int *hA
     lsspg_dmat *A = nullptr;
     LSSPG_TRY(lsspg_dmat_upload(ctx, n, n, hAp, hAj, hAx, &A));
     const int rc = lsspg_ilu_factor_dmat(ctx, A, level, blk_size, out);
+    lsspg_dmat_destroy(ctx, A);
+    return rc;
+}
+
+/* ILUT(p, tol) of a device-resident matrix (src/pc-ilut.cxx:51-286, :429-456): p <= 0 -> ceil(nnz / n) (:436-438), tol < 0 ->
+ * 1e-3 (:440-442); blk_size as lsspg_ilu_factor_dmat.  Rows keep the reference's unsorted storage order. */
+int lsspg_ilut_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A_in, int p, double tol, int blk_size, lsspg_factors **out)
+{
+    LSSPG_CHECK(ctx && A_in && out && A_in->bs == 1 && A_in->n > 0 && A_in->n == A_in->m && A_in->nnz > 0, "lsspg_ilut_factor_dmat: needs a square CSR matrix on the device");
+    LSSPG_CUDA(cudaSetDevice(ctx->device));
+    const int n = A_in->n;
+    if (p <= 0) p = (int)((A_in->nnz + n - 1) / n);
+    if (tol < 0) tol = 1e-3;
+    const int bs = (blk_size <= 0 || blk_size > n) ? n : blk_size;
+    int *flag = ctx->d_flags + FLAG_SETUP;
+    lsspg_dmat *A = nullptr, *B = nullptr, *L = nullptr, *U = nullptr;
+    int *rc_ = nullptr, *meta = nullptr, *wj = nullptr, *cl = nullptr, *cu = nullptr;
+    double *rv = nullptr, *diag = nullptr, *wx = nullptr;
+    auto body = [&]() -> int {
+        GPROF_T0;
+        LSSPG_TRY(ingest_gpu(ctx, A_in, &A, "lsspg_ilut_factor_dmat"));
+        const lsspg_dmat *Ad = A ? A : A_in;
+        if (bs < n) LSSPG_TRY(lsspg_dmat_get_block_diag(ctx, Ad, bs, &B));
+        const lsspg_dmat *Bd = B ? B : Ad;
+        int hmax = 0;
+        LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+        LSSPG_LAUNCH(ctx, k_max_row, rows_grid(n), 256, 0, n, Bd->p, flag);
+        LSSPG_CUDA(cudaMemcpyAsync(&hmax, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+        const int rcap = std::max(2 * p + 1, hmax);
+        int grid = 0;
+        LSSPG_TRY(fac_grid(ctx, k_ilut_rows, n, &grid));
+        const size_t threads = (size_t)grid * kFacBlock, pool = (size_t)n * rcap;
+        LSSPG_CUDA(cudaMalloc(&rc_, sizeof(int) * pool));
+        LSSPG_CUDA(cudaMalloc(&rv, sizeof(double) * pool));
+        LSSPG_CUDA(cudaMalloc(&diag, sizeof(double) * (size_t)n));
+        LSSPG_CUDA(cudaMalloc(&meta, sizeof(int) * ((size_t)n * 2 + 4)));   // rlen, done, ticket
+        int *rlen = meta, *done = meta + n;
+        for (int wcap = std::max(64, 4 * (hmax + p));; wcap *= 2) {
+            LSSPG_CHECK(wcap <= 16384, "lsspg_ilut_factor_dmat: work rows longer than 16384 entries: use the host set-up");
+            {
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                LSSPG_CHECK(threads * 2 * wcap * 12 < free_b, "lsspg_ilut_factor_dmat: work rows of %d entries need %zu MB of device memory", wcap, threads * 2 * wcap * 12 >> 20);
+            }
+            LSSPG_CUDA(cudaMalloc(&wj, sizeof(int) * threads * 2 * wcap));
+            LSSPG_CUDA(cudaMalloc(&wx, sizeof(double) * threads * 2 * wcap));
+            LSSPG_CUDA(cudaMemsetAsync(meta, 0, sizeof(int) * ((size_t)n * 2 + 4), ctx->stream));
+            LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+            LSSPG_LAUNCH(ctx, k_ilut_rows, grid, kFacBlock, 0, n, bs, p, tol, Bd->p, Bd->j, Bd->x, rcap, rc_, rv, rlen, diag, wcap, wj, wx, done,
+                         reinterpret_cast<unsigned int *>(done + n), ctx->d_flags);
+            int hflag = 0;
+            LSSPG_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(wj); cudaFree(wx);
+            wj = nullptr; wx = nullptr;
+            LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+            if (!hflag) break;
+        }
+        GPROF(ctx, "ilut rows");
+        LSSPG_CUDA(cudaMalloc(&cl, sizeof(int) * ((size_t)n + 1 + 8)));
+        LSSPG_CUDA(cudaMalloc(&cu, sizeof(int) * ((size_t)n + 1 + 8)));
+        LSSPG_CUDA(cudaMemsetAsync(cl + n, 0, sizeof(int) * 9, ctx->stream));
+        LSSPG_CUDA(cudaMemsetAsync(cu + n, 0, sizeof(int) * 9, ctx->stream));
+        LSSPG_LAUNCH(ctx, k_pool_split_count, rows_grid(n), 256, 0, n, rcap, rc_, rlen, cl, cu);
+        long long tl = 0, tu = 0;
+        LSSPG_TRY(dev_exclusive_scan(ctx, cl, n, &tl));
+        LSSPG_TRY(dev_exclusive_scan(ctx, cu, n, &tu));
+        LSSPG_TRY(dmat_alloc(ctx, n, n, tl, 1, false, &L));
+        LSSPG_TRY(dmat_alloc(ctx, n, n, tu, 1, false, &U));
+        L->p = cl; cl = nullptr;
+        U->p = cu; cu = nullptr;
+        LSSPG_LAUNCH(ctx, k_pool_split_fill, rows_grid(n), 256, 0, n, rcap, rc_, rv, rlen, L->p, L->j, L->x, U->p, U->j, U->x);
+        GPROF(ctx, "split");
+        LSSPG_TRY(factors_download(ctx, n, L, U, out));
+        GPROF(ctx, "download of L, U");
+        return 0;
+    };
+    const int rc = body();
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(rc_); cudaFree(rv); cudaFree(diag); cudaFree(meta); cudaFree(wj); cudaFree(wx); cudaFree(cl); cudaFree(cu);
+    dmat_free(A); dmat_free(B); dmat_free(L); dmat_free(U);
+    return rc;
+}
+
+int lsspg_ilut_factor_device(lsspg_ctx *ctx, int n, const int *hAp, const int *hAj, const double *hAx, int p, double tol,
+                             int blk_size, lsspg_factors **out)
+{
+    LSSPG_CHECK(ctx && out && hAp && hAj && hAx && n > 0, "lsspg_ilut_factor_device: bad argument");
+    lsspg_dmat *A = nullptr;
+    LSSPG_TRY(lsspg_dmat_upload(ctx, n, n, hAp, hAj, hAx, &A));
+    const int rc = lsspg_ilut_factor_dmat(ctx, A, p, tol, blk_size, out);
     lsspg_dmat_destroy(ctx, A);
     return rc;
 }

@@ -188,6 +188,20 @@ def test_iluk_on_the_device_blocks_and_unsorted_input(ctx, name):
     assert all(same(a, b) for a, b in zip(got, want)), name
 
 
+@pytest.mark.parametrize("name", ["lap2d_100", "lap3d_32", "cd3d_32", "cd3d_12", "powerlaw_4000", "random_600"])
+def test_ilut_on_the_device_is_bit_identical(ctx, name):
+    """the kept entries, their values AND their (unsorted) stored order: src/pc-ilut.cxx:7-49, :253-274"""
+    A = matrix(name)
+    n = len(A[0]) - 1
+    for kw in (dict(), dict(p=9, tol=1e-4), dict(p=3, tol=1e-2), dict(p=4, tol=1e-2, blk_size=(n + 4) // 5), dict(p=50, tol=0.0)):
+        want = api.ilu_factor(A, "ilut", **kw)
+        got = api.DMat(ctx, A).ilut_factor(**kw)
+        assert all(same(a, b) for a, b in zip(got, want)), (name, kw)
+    assert all(same(a, b) for a, b in zip(api.ilu_factor(A, "ilut", ctx=ctx), api.ilu_factor(A, "ilut")))
+    S = shuffled(A, seed=2)
+    assert all(same(a, b) for a, b in zip(api.DMat(ctx, S).ilut_factor(), api.ilu_factor(S, "ilut")))
+
+
 @pytest.mark.parametrize("case", ["lap3d/ilu0", "cd3d/iluk1"])
 def test_device_factorisation_at_the_baseline_size(ctx, case, record_property):
     """256^3: matrix generated on the device, factorised on the device; factors == the unmodified reference's
@@ -216,6 +230,13 @@ def test_device_factorisation_at_the_baseline_size(ctx, case, record_property):
     record_property("device_setup_s", t2 - t1)
     assert [int(L[0][-1]), int(U[0][-1])] == e[tag + "_nnz"]
     assert sha(np.concatenate([L[2], U[2]])) == e[tag + "_factor_sha"]
+    if case == "cd3d/iluk1":     # ILUT of the same matrix (GMRES(30) + ILUT of BASELINE.json configs[2])
+        t5 = time.perf_counter()
+        Lt, Ut = d.ilut_factor(p=-1, tol=1e-3)
+        t6 = time.perf_counter()
+        print("cd3d/ilut: factorise on the device + download %.3f s" % (t6 - t5))
+        assert [int(Lt[0][-1]), int(Ut[0][-1])] == e["ilut_nnz"]
+        assert sha(np.concatenate([Lt[2], Ut[2]])) == e["ilut_factor_sha"]
     # and the SpMV matrix straight from the device arrays
     x = tvec(N ** 3)
     assert sha(d.to_csr(take=True).mv_host(0, x)) == (e["mxy_sha"] if case == "lap3d/ilu0" else sha(api.Csr(ctx, g.cd3d(N)).mv_host(0, x)))
