@@ -9,10 +9,10 @@
 
 namespace lsspg {
 
-// scratch per sum (ctx->d_xs, [kMaxRedK] slices of `stride` blocks): approximate block sums, sums of |t|, largest |prefix|, predicted
+// scratch per sum (ctx->d_xs, [kMaxRedK] slices of `stride` blocks): approximate block sums, excursion bounds (xs_dev), predicted
 // binades, D and its inclusive wrap-around scan
 struct XsScratch {
-    double *approx, *absb, *xmax;
+    double *approx, *dev;
     unsigned long long *D, *scan;
     int *e;
     unsigned int *ticket;
@@ -25,8 +25,7 @@ static XsScratch xs_scratch(lsspg_ctx *ctx)
     const size_t nb = ctx->xs_blocks;
     char *p = reinterpret_cast<char *>(ctx->d_xs);
     sc.approx = reinterpret_cast<double *>(p); p += sizeof(double) * kMaxRedK * nb;
-    sc.absb = reinterpret_cast<double *>(p); p += sizeof(double) * kMaxRedK * nb;
-    sc.xmax = reinterpret_cast<double *>(p); p += sizeof(double) * kMaxRedK * nb;
+    sc.dev = reinterpret_cast<double *>(p); p += sizeof(double) * kMaxRedK * nb;
     sc.D = reinterpret_cast<unsigned long long *>(p); p += sizeof(unsigned long long) * kMaxRedK * nb;
     sc.scan = reinterpret_cast<unsigned long long *>(p); p += sizeof(unsigned long long) * kMaxRedK * nb;
     sc.e = reinterpret_cast<int *>(p); p += sizeof(int) * kMaxRedK * nb;
@@ -35,7 +34,7 @@ static XsScratch xs_scratch(lsspg_ctx *ctx)
     return sc;
 }
 
-size_t xs_scratch_bytes(size_t nb) { return (size_t)kMaxRedK * nb * (8 + 8 + 8 + 8 + 8 + 4) + 64; }
+size_t xs_scratch_bytes(size_t nb) { return (size_t)kMaxRedK * nb * (8 + 8 + 8 + 8 + 4) + 64; }
 
 LSSPG_HD long long xs_min(long long a, long long b) { return a < b ? a : b; }
 
@@ -84,8 +83,7 @@ __global__ void __launch_bounds__(256) k_xs_blocks(long long n, long long nb, co
         for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
         if (lane == 0) {
             sc.approx[k * sc.stride + b] = carry;
-            sc.absb[k * sc.stride + b] = a;
-            sc.xmax[k * sc.stride + b] = x;
+            sc.dev[k * sc.stride + b] = xs_dev(x, a);
         }
     }
 }
@@ -100,13 +98,22 @@ __global__ void __launch_bounds__(1024) k_xs_predict(long long nb, XsScratch sc,
     const double *ap = sc.approx + k * sc.stride;
     int *eb = sc.e + k * sc.stride;
     double carry = 0.0;
-    for (long long b0 = 0; b0 < nb; b0 += 1024) {
-        const long long b = b0 + tid;
-        const double v = (b < nb) ? ap[b] : 0.0;
-        double total;
-        const double inc = cta_scan_1024<double>(v, s_w, &total);
-        if (b < nb) eb[b] = xs_exponent(carry + (inc - v));
-        carry += total;
+    constexpr int kBatch = 8;   // chunks loaded together: their L2 latencies overlap
+    for (long long b0 = 0; b0 < nb; b0 += 1024 * kBatch) {
+        double v[kBatch];
+#pragma unroll
+        for (int r = 0; r < kBatch; r++) {
+            const long long b = b0 + r * 1024 + tid;
+            v[r] = (b < nb) ? ap[b] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < kBatch; r++) {
+            const long long b = b0 + r * 1024 + tid;
+            double total;
+            const double inc = cta_scan_1024<double>(v[r], s_w, &total);
+            if (b < nb) eb[b] = xs_exponent(carry + (inc - v[r]));
+            carry += total;
+        }
     }
 }
 
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(256) k_xs_round(long long n, long long nb, con
 constexpr int kXsWin = kXsChunk * kXsPer;
 struct XsWindow {
     unsigned long long scan[kXsWin];
-    double xmax[kXsWin], absb[kXsWin];
+    double dev[kXsWin];
     int e[kXsWin];
 };
 
@@ -159,14 +166,14 @@ __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb,
     extern __shared__ __align__(16) unsigned char xs_smem[];
     XsWindow &W = *reinterpret_cast<XsWindow *>(xs_smem);
     __shared__ unsigned long long s_w[32];
-    __shared__ double s_terms[kXsB], s_fabs[kXsB / kXsFine], s_fmax[kXsB / kXsFine];
+    __shared__ double s_terms[kXsB], s_fdev[kXsB / kXsFine];
     __shared__ long long s_fD[kXsB / kXsFine];
     __shared__ int s_ftie[kXsB / kXsFine];
     __shared__ double s_s;
     __shared__ int s_pos, s_bad;
     const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double *t = terms + (size_t)k * seq_n;
-    const double *absb = sc.absb + k * sc.stride, *xmax = sc.xmax + k * sc.stride;
+    const double *dev = sc.dev + k * sc.stride;
     const int *eb = sc.e + k * sc.stride;
     const unsigned long long *D = sc.D + k * sc.stride;
     if (tid == 0) s_s = 0.0;   // src/vector.cxx:127: the sum starts at +0.0
@@ -177,8 +184,7 @@ __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb,
             // binades are ever used, so the scan may wrap around and restart with every window)
             for (int r = tid; r < wlen; r += kXsChunk) {
                 W.scan[r] = D[w0 + r];
-                W.xmax[r] = xmax[w0 + r];
-                W.absb[r] = absb[w0 + r];
+                W.dev[r] = dev[w0 + r];
                 W.e[r] = eb[w0 + r];
             }
             __syncthreads();
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb,
                         bool ok = (W.e[r] == e);
                         if (ok) {
                             const long long m = m0 + (long long)((r > 0 ? W.scan[r - 1] : 0ull) - base);
-                            ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, W.xmax[r], W.absb[r]);
+                            ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, W.dev[r]);
                         }
                         if (!ok && r < mine) mine = r;
                     }
@@ -264,13 +270,13 @@ __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb,
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
                 tie = __any_sync(0xffffffffu, tie);
-                if (lane == 0) { s_fD[wid] = d; s_fabs[wid] = a; s_fmax[wid] = x; s_ftie[wid] = tie ? 1 : 0; }
+                if (lane == 0) { s_fD[wid] = d; s_fdev[wid] = xs_dev(x, a); s_ftie[wid] = tie ? 1 : 0; }
             }
             __syncthreads();
             if (tid == 0) {
                 double acc = s;
                 for (int j = 0; j * kXsFine < cnt; j++) {
-                    if (es != kXsUnclean && !s_ftie[j] && xs_exponent(acc) == es && xs_verify(acc, es, s_fmax[j], s_fabs[j])) {
+                    if (es != kXsUnclean && !s_ftie[j] && xs_exponent(acc) == es && xs_verify(acc, es, s_fdev[j])) {
                         const long long m = xs_to_int(acc, es) + s_fD[j];
                         if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
                     }
@@ -335,13 +341,13 @@ int exact_seq_sum(lsspg_ctx *ctx, long long n, int K, const RedOut &o)
 static double xs_host(long long n, const double *t, long long *stats)
 {
     const long long nb = (n + kXsB - 1) / kXsB;
-    std::vector<double> approx(nb), absb(nb), xmax(nb);
+    std::vector<double> approx(nb), dev(nb);
     std::vector<int> eb(nb);
     std::vector<unsigned long long> D(nb), scan(nb);
     for (long long b = 0; b < nb; b++) {   // K1 (pairwise order inside a block; any order will do)
         double s = 0.0, a = 0.0, x = 0.0;
         for (long long i = b * kXsB; i < std::min(n, (b + 1) * kXsB); i++) { s += t[i]; a += fabs(t[i]); x = std::max(x, fabs(s)); }
-        approx[b] = s; absb[b] = a; xmax[b] = x;
+        approx[b] = s; dev[b] = xs_dev(x, a);
     }
     {   // K2
         double run = 0.0;
@@ -382,7 +388,7 @@ static double xs_host(long long n, const double *t, long long *stats)
                     bool ok = (eb[b] == e);
                     if (ok) {
                         const long long m = m0 + (long long)((b > w0 ? scan[b - 1] : scan_before(w0)) - base);
-                        ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, xmax[b], absb[b]);
+                        ok = xs_int_in_binade(m) && xs_verify(xs_from_int(m, e), e, dev[b]);
                     }
                     if (!ok) { bad = b; break; }
                 }
@@ -410,7 +416,7 @@ static double xs_host(long long n, const double *t, long long *stats)
                             pre += t[i0 + i];
                             x = std::max(x, fabs(pre));
                         }
-                        if (!tie && xs_verify(acc, es, x, a)) {
+                        if (!tie && xs_verify(acc, es, xs_dev(x, a))) {
                             const long long m = xs_to_int(acc, es) + d;
                             if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
                         }

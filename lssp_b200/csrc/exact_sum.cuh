@@ -86,15 +86,17 @@ LSSPG_HD long long xs_round(double t, int e, bool *tie)
     return (long long)r;
 }
 
-// K4: may a block be advanced as one integer addition from the exact sum s?  `xmax` is the largest |t_0 + .. + t_i| over
-// the block's prefixes and `absb` the sum of the |t_i|, both as computed in floating point (any order).  dev bounds every
-// |partial sum - s| of the SEQUENTIAL additions: the real prefixes are within kXsB 2^-53 absb of the computed ones, each of
-// the kXsB additions rounds by at most u / 2, and the comparisons below round once more.  dev < 2^(e-2) is not needed
-// for the lattice argument but keeps every |t_i| <= 2 dev far inside the range of the int64 sums.
-LSSPG_HD bool xs_verify(double s, int e, double xmax, double absb)
+// Excursion bound of a block: `xmax` is the largest |t_0 + .. + t_i| over the block's prefixes and `absb` the sum of the
+// |t_i|, both as computed in floating point (any order).  The real prefixes are within kXsB 2^-53 absb of the computed ones.
+LSSPG_HD double xs_dev(double xmax, double absb) { return xmax * (1.0 + 9.5367431640625e-07) + absb * 9.094947017729282e-13; }
+
+// K4: may a block be advanced as one integer addition from the exact sum s?  dev = xs_dev(..) + the roundings of the
+// SEQUENTIAL additions (u / 2 each) + the rounding of the comparisons below bounds every |partial sum - s|.
+// dev < 2^(e-2) is not needed for the lattice argument but keeps every |t_i| <= 2 dev far inside the range of the int64 sums.
+LSSPG_HD bool xs_verify(double s, int e, double dev0)
 {
     const double lo = xs_pow2(e), hi = xs_pow2(e + 1), u = xs_pow2(e - 52);
-    const double dev = xmax * (1.0 + 9.5367431640625e-07) + absb * 9.094947017729282e-13 + (double)(kXsB + 8) * u;
+    const double dev = dev0 + (double)(kXsB + 8) * u;
     const double as = fabs(s);
     return (as - dev >= lo) && (as + dev < hi) && (dev < 0.25 * lo);   // false for NaN / inf
 }

@@ -316,16 +316,34 @@ __device__ __forceinline__ double repaired_pivot_dev(double d)
     return (fabs(d) < kPivotTolG) ? (d > 0 ? kPivotValueG : -kPivotValueG) : d;
 }
 
+// column -> position map of the work row: open addressing, H slots (power of two, >= 4 wcap) of {column, row stamp,
+// position}; a slot whose stamp is not the current row is empty, so nothing is ever cleared (and nothing is deleted inside
+// a row: processed pivots are smaller than every later candidate and are never looked up again)
+struct IlutSlot {
+    int key, stamp, pos;
+};
+__device__ __forceinline__ IlutSlot *ilut_find(IlutSlot *tab, int hmask, int row, int c)
+{
+    unsigned int h = ((unsigned int)c * 2654435761u) >> 7;
+    for (;; h++) {
+        IlutSlot *s = tab + (h & (unsigned int)hmask);
+        if (s->stamp != row || s->key == c) return s;
+    }
+}
+
 __global__ void __launch_bounds__(kFacBlock) k_ilut_rows(int n, int bs, int p, double tau, const int *__restrict__ Bp,
                                                         const int *__restrict__ Bj, const double *__restrict__ Bx, int rcap,
                                                         int *rc, double *rv, int *rlen, double *diag, int wcap, int *wj,
-                                                        double *wx, int *done, unsigned int *ticket, int *flags)
+                                                        double *wx, IlutSlot *tabs, int hmask, int *done, unsigned int *ticket,
+                                                        int *flags)
 {
     const int lane = threadIdx.x & 31;
     int *abort_flag = flags + FLAG_SETUP;
     const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int *jwl = wj + gt * 2 * wcap, *jwu = jwl + wcap;
     double *wl = wx + gt * 2 * wcap, *wu = wl + wcap;
+    IlutSlot *tab = tabs + gt * ((size_t)hmask + 1);
+    constexpr int kUp = 1 << 30;   // positions >= kUp: upper part
     for (;;) {
         bool more;
         const long long row = fac_next_row(ticket, lane, n, &more);
@@ -350,11 +368,15 @@ __global__ void __launch_bounds__(kFacBlock) k_ilut_rows(int n, int bs, int p, d
             const double drop = tau * norm;
             int nl = 0, nu = 0;
             double wd = 0.0;
+            auto put = [&](int c, int pos) {
+                IlutSlot *s = ilut_find(tab, hmask, i, c);
+                s->key = c; s->stamp = i; s->pos = pos;
+            };
             for (int k = b; k < e && ok; k++) {
                 const int c = Bj[k];
-                if (c < i) { if (nl == wcap) { ok = false; break; } jwl[nl] = c; wl[nl] = Bx[k]; nl++; }
+                if (c < i) { if (nl == wcap) { ok = false; break; } put(c, nl); jwl[nl] = c; wl[nl] = Bx[k]; nl++; }
                 else if (c == i) wd = Bx[k];
-                else { if (nu == wcap) { ok = false; break; } jwu[nu] = c; wu[nu] = Bx[k]; nu++; }
+                else { if (nu == wcap) { ok = false; break; } put(c, kUp + nu); jwu[nu] = c; wu[nu] = Bx[k]; nu++; }
             }
             for (int tt = 0; ok && tt < nl; tt++) {
                 int piv = jwl[tt], at = tt;
@@ -364,6 +386,7 @@ __global__ void __launch_bounds__(kFacBlock) k_ilut_rows(int n, int bs, int p, d
                     const int c = jwl[tt];
                     jwl[tt] = jwl[at];
                     jwl[at] = c;
+                    put(c, at);
                     const double tw = wl[tt]; wl[tt] = wl[at]; wl[at] = tw;
                 }
                 if (!fac_wait(done, piv, abort_flag)) { ok = false; break; }
@@ -376,23 +399,20 @@ __global__ void __launch_bounds__(kFacBlock) k_ilut_rows(int n, int bs, int p, d
                     if (c <= piv) continue;
                     const double mx = -a_ik * __ldcg(pv + q);
                     if (c == i) { wd += mx; continue; }
-                    if (c < i) {
-                        int at2 = -1;
-                        for (int z = tt + 1; z < nl; z++)
-                            if (jwl[z] == c) { at2 = z; break; }
-                        if (at2 >= 0) wl[at2] += mx;
-                        else if (!(fabs(mx) < drop)) {   // only NEW fill is dropped
+                    IlutSlot *sl = ilut_find(tab, hmask, i, c);
+                    if (sl->stamp == i) {   // present
+                        if (sl->pos >= kUp) wu[sl->pos - kUp] += mx;
+                        else wl[sl->pos] += mx;
+                    }
+                    else if (!(fabs(mx) < drop)) {   // only NEW fill is dropped
+                        if (c < i) {
                             if (nl == wcap) { ok = false; break; }
+                            sl->key = c; sl->stamp = i; sl->pos = nl;
                             jwl[nl] = c; wl[nl] = mx; nl++;
                         }
-                    }
-                    else {
-                        int at2 = -1;
-                        for (int z = 0; z < nu; z++)
-                            if (jwu[z] == c) { at2 = z; break; }
-                        if (at2 >= 0) wu[at2] += mx;
-                        else if (!(fabs(mx) < drop)) {
+                        else {
                             if (nu == wcap) { ok = false; break; }
+                            sl->key = c; sl->stamp = i; sl->pos = kUp + nu;
                             jwu[nu] = c; wu[nu] = mx; nu++;
                         }
                     }
@@ -674,6 +694,7 @@ int lsspg_ilut_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A_in, int p, double
     lsspg_dmat *A = nullptr, *B = nullptr, *L = nullptr, *U = nullptr;
     int *rc_ = nullptr, *meta = nullptr, *wj = nullptr, *cl = nullptr, *cu = nullptr;
     double *rv = nullptr, *diag = nullptr, *wx = nullptr;
+    IlutSlot *tabs = nullptr;
     auto body = [&]() -> int {
         GPROF_T0;
         LSSPG_TRY(ingest_gpu(ctx, A_in, &A, "lsspg_ilut_factor_dmat"));
@@ -688,30 +709,38 @@ int lsspg_ilut_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A_in, int p, double
         const int rcap = std::max(2 * p + 1, hmax);
         int grid = 0;
         LSSPG_TRY(fac_grid(ctx, k_ilut_rows, n, &grid));
-        const size_t threads = (size_t)grid * kFacBlock, pool = (size_t)n * rcap;
+        const size_t pool = (size_t)n * rcap;
         LSSPG_CUDA(cudaMalloc(&rc_, sizeof(int) * pool));
         LSSPG_CUDA(cudaMalloc(&rv, sizeof(double) * pool));
         LSSPG_CUDA(cudaMalloc(&diag, sizeof(double) * (size_t)n));
         LSSPG_CUDA(cudaMalloc(&meta, sizeof(int) * ((size_t)n * 2 + 4)));   // rlen, done, ticket
         int *rlen = meta, *done = meta + n;
         for (int wcap = std::max(64, 4 * (hmax + p));; wcap *= 2) {
-            LSSPG_CHECK(wcap <= 16384, "lsspg_ilut_factor_dmat: work rows longer than 16384 entries: use the host set-up");
-            {
-                size_t free_b = 0, total_b = 0;
-                cudaMemGetInfo(&free_b, &total_b);
-                LSSPG_CHECK(threads * 2 * wcap * 12 < free_b, "lsspg_ilut_factor_dmat: work rows of %d entries need %zu MB of device memory", wcap, threads * 2 * wcap * 12 >> 20);
-            }
+            LSSPG_CHECK(wcap <= 65536, "lsspg_ilut_factor_dmat: work rows longer than 65536 entries: use the host set-up");
+            int hsize = 256;
+            while (hsize < 4 * wcap) hsize *= 2;
+            // scratch per thread: two work arrays of wcap (column, value) and the column map; fewer CTAs when it does not fit
+            const size_t per_thread = (size_t)2 * wcap * 12 + (size_t)hsize * sizeof(IlutSlot);
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            int g = grid;
+            while (g > 1 && (size_t)g * kFacBlock * per_thread > free_b / 2) g = (g + 1) / 2;
+            LSSPG_CHECK((long long)g * (kFacBlock / 32) >= kStride + 32 && (size_t)g * kFacBlock * per_thread <= free_b / 2,
+                        "lsspg_ilut_factor_dmat: work rows of %d entries need more device memory than is free: use the host set-up", wcap);
+            const size_t threads = (size_t)g * kFacBlock;
             LSSPG_CUDA(cudaMalloc(&wj, sizeof(int) * threads * 2 * wcap));
             LSSPG_CUDA(cudaMalloc(&wx, sizeof(double) * threads * 2 * wcap));
+            LSSPG_CUDA(cudaMalloc(&tabs, sizeof(IlutSlot) * threads * hsize));
+            LSSPG_CUDA(cudaMemsetAsync(tabs, 0xff, sizeof(IlutSlot) * threads * hsize, ctx->stream));   // stamp -1: empty
             LSSPG_CUDA(cudaMemsetAsync(meta, 0, sizeof(int) * ((size_t)n * 2 + 4), ctx->stream));
             LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
-            LSSPG_LAUNCH(ctx, k_ilut_rows, grid, kFacBlock, 0, n, bs, p, tol, Bd->p, Bd->j, Bd->x, rcap, rc_, rv, rlen, diag, wcap, wj, wx, done,
-                         reinterpret_cast<unsigned int *>(done + n), ctx->d_flags);
+            LSSPG_LAUNCH(ctx, k_ilut_rows, g, kFacBlock, 0, n, bs, p, tol, Bd->p, Bd->j, Bd->x, rcap, rc_, rv, rlen, diag, wcap, wj, wx, tabs,
+                         hsize - 1, done, reinterpret_cast<unsigned int *>(done + n), ctx->d_flags);
             int hflag = 0;
             LSSPG_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
-            cudaFree(wj); cudaFree(wx);
-            wj = nullptr; wx = nullptr;
+            cudaFree(wj); cudaFree(wx); cudaFree(tabs);
+            wj = nullptr; wx = nullptr; tabs = nullptr;
             LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
             if (!hflag) break;
         }
@@ -736,7 +765,7 @@ int lsspg_ilut_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A_in, int p, double
     };
     const int rc = body();
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(rc_); cudaFree(rv); cudaFree(diag); cudaFree(meta); cudaFree(wj); cudaFree(wx); cudaFree(cl); cudaFree(cu);
+    cudaFree(rc_); cudaFree(rv); cudaFree(diag); cudaFree(meta); cudaFree(wj); cudaFree(wx); cudaFree(tabs); cudaFree(cl); cudaFree(cu);
     dmat_free(A); dmat_free(B); dmat_free(L); dmat_free(U);
     return rc;
 }
