@@ -238,6 +238,43 @@ def cpu_baseline(args, A, solver, pc, pcobj=None):
             "sample": "%d iterations of the same solve, oracle/oracle.c" % r["nits"], "host_cores_total": os.cpu_count()}
 
 
+def parity_block(args, ctx, api, solver, dA, pc, n):
+    """Outside the timed region: this run against the UNMODIFIED reference's numbers for the same problem
+    (tests/golden/baseline_<N>.json, generated by tests/golden/make_baseline_golden.py from oracle/_ref) -- iterations to
+    tolerance and the first 20 residuals in the shipped tree-reduction mode, and the same solve with the reference-order
+    reductions (exact_sum.cu), which must reproduce the reference bit for bit."""
+    key = {"cg_ilu0": "lap3d/cg+iluk0", "bicgstab_ilu0": "lap3d/bicgstab+iluk0"}.get(args.workload)
+    path = os.path.join(ROOT, "tests", "golden", "baseline_%d.json" % args.grid)
+    if key is None or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        gold = json.load(f).get(key)
+    if not gold:
+        return None
+    want = np.array(gold["history"])
+    out = {"reference_iterations": gold["nits"], "reference_residual": gold["residual"],
+           "reference_source": "tests/golden/baseline_%d.json (unmodified reference, oracle/_ref)" % args.grid}
+    x = np.zeros(n)
+    r = api.lssp_solver_solve(ctx, solver, dA, pc, np.ones(n), x, nhist=20, maxit=3000)
+    k = min(len(want), len(r["hist"]))
+    out["history_relerr"] = float(np.max(np.abs(r["hist"][:k] - want[:k]) / want[:k]))
+    ctx.set_option(api.OPT_REDUCE_SEQUENTIAL, 2)
+    try:
+        x = np.zeros(n)
+        api.lssp_solver_solve(ctx, solver, dA, pc, np.ones(n), x, nhist=20, maxit=3000)      # warm-up (scratch allocation)
+        x = np.zeros(n)
+        r2 = api.lssp_solver_solve(ctx, solver, dA, pc, np.ones(n), x, nhist=20, maxit=3000)
+    finally:
+        ctx.set_option(api.OPT_REDUCE_SEQUENTIAL, 0)
+    out["reference_order_mode"] = {
+        "what": "LSSPG_OPT_REDUCE_SEQUENTIAL = 2: dot products = the reference's sequential sums, computed in parallel",
+        "iterations": r2["nits"], "residual": r2["residual"],
+        "bit_identical_to_reference": bool(r2["nits"] == gold["nits"] and r2["residual"] == gold["residual"] and
+                                           list(r2["hist"][:len(want)]) == list(want)),
+        "iter_per_s": r2["nits"] / (r2["solve_ms"] / 1e3)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -414,6 +451,9 @@ def main():
             "ms_per_iteration": ms_per_it, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
             "roofline": roof, "roofline_spmv": roof_spmv,
             "setup_s": {"generate": t_gen, "pc_host_setup_and_upload": t_pc, "host_threads": int(L.lsspg_host_threads())}}
+    par = parity_block(args, ctx, api, solver, dA, pc, n)
+    if par:
+        line["config"].update(par)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, A, solver, pckind, pc)
     print(json.dumps(line))
