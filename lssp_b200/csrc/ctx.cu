@@ -56,6 +56,7 @@ int ensure_stage(lsspg_ctx *ctx, size_t n)
 int ensure_seq(lsspg_ctx *ctx, size_t n)
 {
     if (n <= ctx->seq_len) return 0;
+    n = (n + 31) / 32 * 32;   // every sum's slice starts 16-byte aligned (exact_sum.cu reads pairs)
     if (ctx->d_seq) LSSPG_CUDA(cudaFree(ctx->d_seq));
     ctx->d_seq = nullptr;
     LSSPG_CUDA(cudaMalloc(&ctx->d_seq, sizeof(double) * kMaxRedK * n));

@@ -55,34 +55,48 @@ __device__ __forceinline__ double warp_scan(double v, int lane)   // inclusive
     return v;
 }
 
-// K1: one warp per block of kXsB terms (lane l holds terms l, l + 32, ...: coalesced)
+// K1: one warp per block of kXsB terms; lane l holds the kXsB / 32 CONSECUTIVE terms l kXsB/32 ..: its prefix sums are
+// local additions and one warp scan of the lane totals does the rest (the terms array is 16-byte aligned: ensure_seq)
 __global__ void __launch_bounds__(256) k_xs_blocks(long long n, long long nb, const double *__restrict__ terms, long long seq_n,
                                                    XsScratch sc, const int *stop)
 {
     if (stop && *stop) return;
+    constexpr int PER = kXsB / 32;
     const int lane = threadIdx.x & 31, k = blockIdx.y;
     const double *t = terms + (size_t)k * seq_n;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nb; b += warps) {
-        double v[kXsB / 32];
+        double v[PER];
+        const long long i0 = b * kXsB + lane * PER;
+        if ((b + 1) * kXsB <= n) {
 #pragma unroll
-        for (int j = 0; j < kXsB / 32; j++) {
-            const long long i = b * kXsB + j * 32 + lane;
-            v[j] = (i < n) ? t[i] : 0.0;
+            for (int j = 0; j < PER; j += 2) {
+                const double2 w = *reinterpret_cast<const double2 *>(t + i0 + j);
+                v[j] = w.x;
+                v[j + 1] = w.y;
+            }
         }
-        double carry = 0.0, a = 0.0, x = 0.0;   // prefix sums in index order: 32 terms per warp scan
+        else {
 #pragma unroll
-        for (int j = 0; j < kXsB / 32; j++) {
-            const double inc = carry + warp_scan(v[j], lane);
-            x = fmax(x, fabs(inc));
+            for (int j = 0; j < PER; j++) v[j] = (i0 + j < n) ? t[i0 + j] : 0.0;
+        }
+        double run = 0.0, a = 0.0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            run += v[j];
             a += fabs(v[j]);
-            carry = __shfl_sync(0xffffffffu, inc, 31);
+            v[j] = run;          // the lane's own inclusive prefixes
         }
+        const double incl = warp_scan(run, lane), off = incl - run;   // lanes before this one
+        double x = 0.0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) x = fmax(x, fabs(off + v[j]));
         a = warp_sum(a);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+        const double total = __shfl_sync(0xffffffffu, incl, 31);
         if (lane == 0) {
-            sc.approx[k * sc.stride + b] = carry;
+            sc.approx[k * sc.stride + b] = total;
             sc.dev[k * sc.stride + b] = xs_dev(x, a);
         }
     }
@@ -152,10 +166,13 @@ __global__ void __launch_bounds__(256) k_xs_round(long long n, long long nb, con
 // excursion bounds and the inclusive wrap-around scan of its D are staged in shared memory, so that the rounds of a window
 // -- one per run of verified blocks, one more per block that has to be taken apart -- cost barriers, not L2 round trips.
 constexpr int kXsWin = kXsChunk * kXsPer;
+constexpr int kXsPre = 12;   // blocks of a window whose terms are fetched into shared memory ahead of the walk
 struct XsWindow {
     unsigned long long scan[kXsWin];
     double dev[kXsWin];
+    double pre[kXsPre][kXsB];   // terms of the blocks expected to be taken apart (no binade, or the binade changes after them)
     int e[kXsWin];
+    int pre_block[kXsPre];      // their window-relative numbers (any order); unused entries: -1
 };
 
 __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb, int K, const double *__restrict__ terms,
@@ -170,7 +187,7 @@ __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb,
     __shared__ long long s_fD[kXsB / kXsFine];
     __shared__ int s_ftie[kXsB / kXsFine];
     __shared__ double s_s;
-    __shared__ int s_pos, s_bad;
+    __shared__ int s_pos, s_bad, s_npre;
     const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double *t = terms + (size_t)k * seq_n;
     const double *dev = sc.dev + k * sc.stride;
@@ -203,14 +220,30 @@ __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb,
                 run += loc[q];
                 if (r < wlen) W.scan[r] = run;
             }
-            // blocks that will most likely be taken apart (no binade, or the binade changes after them): their terms on
-            // the way to L2
+            // blocks that will most likely be taken apart (no binade, or the binade changes after them): the first kXsPre of
+            // the window have their terms fetched into shared memory now (warp w fetches candidate w), the rest go to L2
+            if (tid < kXsPre) W.pre_block[tid] = -1;
+            if (tid == 0) s_npre = 0;
+            __syncthreads();
             for (int r = tid; r < wlen; r += kXsChunk) {
                 const int e = W.e[r];
                 if (e == kXsUnclean || (r + 1 < wlen && W.e[r + 1] != e)) {
-                    const char *pf = reinterpret_cast<const char *>(t + (w0 + r) * kXsB);
-                    const long long lim = (n - (w0 + r) * kXsB) * 8;
-                    for (int o = 0; o < kXsB * 8 && o < lim; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + o));
+                    const int slot = atomicAdd(&s_npre, 1);
+                    if (slot < kXsPre) W.pre_block[slot] = r;
+                    else {
+                        const char *pf = reinterpret_cast<const char *>(t + (w0 + r) * kXsB);
+                        const long long lim = (n - (w0 + r) * kXsB) * 8;
+                        for (int o = 0; o < kXsB * 8 && o < lim; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + o));
+                    }
+                }
+            }
+            __syncthreads();
+            if (wid < kXsPre && W.pre_block[wid] >= 0) {
+                const long long i0 = (w0 + W.pre_block[wid]) * kXsB;
+#pragma unroll
+                for (int q = 0; q < kXsB / 32; q++) {
+                    const long long i = i0 + q * 32 + lane;
+                    W.pre[wid][q * 32 + lane] = (i < n) ? t[i] : 0.0;
                 }
             }
         }
@@ -257,7 +290,11 @@ __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb,
             // verification -- the one with the binade crossing or the tie -- are added term by term, as the reference does.
             const long long i0 = (w0 + pos) * kXsB;
             const int cnt = (int)xs_min(kXsB, n - i0);
-            if (tid < kXsB) s_terms[tid] = (tid < cnt) ? t[i0 + tid] : 0.0;
+            int pre = -1;
+#pragma unroll
+            for (int q = 0; q < kXsPre; q++)
+                if (W.pre_block[q] == pos) pre = q;
+            if (tid < kXsB) s_terms[tid] = (pre >= 0) ? W.pre[pre][tid] : ((tid < cnt) ? t[i0 + tid] : 0.0);
             __syncthreads();
             const int es = xs_exponent(s);
             if (tid < kXsB && es != kXsUnclean) {
@@ -280,8 +317,13 @@ __global__ void __launch_bounds__(kXsChunk) k_xs_walk(long long n, long long nb,
                         const long long m = xs_to_int(acc, es) + s_fD[j];
                         if (xs_int_in_binade(m)) { acc = xs_from_int(m, es); continue; }
                     }
-                    const int i1 = (j + 1) * kXsFine < cnt ? (j + 1) * kXsFine : cnt;
-                    for (int i = j * kXsFine; i < i1; i++) acc += s_terms[i];
+                    // term by term (terms beyond the end of the data are +0.0: acc is never -0.0, so adding them changes
+                    // nothing); loaded first, then added: the chain is 32 dependent additions, not 32 load-add pairs
+                    double tv[kXsFine];
+#pragma unroll
+                    for (int i = 0; i < kXsFine; i++) tv[i] = s_terms[j * kXsFine + i];
+#pragma unroll
+                    for (int i = 0; i < kXsFine; i++) acc += tv[i];
                 }
                 s_s = acc;
                 s_pos = pos + 1;
