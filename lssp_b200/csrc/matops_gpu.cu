@@ -309,6 +309,34 @@ static int count_array(lsspg_ctx *ctx, long long n, int **cnt)
     return 0;
 }
 
+
+// The common shape of the utilities: count the entries of every output row, scan, allocate the result, fill it.
+// The row-count array becomes the result's row pointer; on any failure everything allocated here is released.
+template <class Count, class Fill>
+static int count_scan_fill(lsspg_ctx *ctx, long long rows, int n, int m, int bs, Count count, Fill fill, lsspg_dmat **out)
+{
+    int *cnt = nullptr;
+    LSSPG_TRY(count_array(ctx, rows, &cnt));
+    lsspg_dmat *M = nullptr;
+    auto body = [&]() -> int {
+        LSSPG_TRY(count(cnt));
+        long long total = 0;
+        LSSPG_TRY(dev_exclusive_scan(ctx, cnt, rows, &total));
+        LSSPG_TRY(dmat_alloc(ctx, n, m, total, bs, false, &M));
+        M->p = cnt;
+        cnt = nullptr;
+        return fill(M);
+    };
+    const int rc = body();
+    if (rc) {
+        cudaFree(cnt);
+        dmat_free(M);
+        return rc;
+    }
+    *out = M;
+    return 0;
+}
+
 static inline unsigned int grid_for(long long items, int block) { return (unsigned int)std::max<long long>(1, (items + block - 1) / block); }
 static inline unsigned int warp_grid(const lsspg_ctx *ctx, long long rows)
 {
@@ -373,9 +401,12 @@ int lsspg_dmat_copy(lsspg_ctx *ctx, const lsspg_dmat *A, lsspg_dmat **out)
     LSSPG_CHECK(ctx && A && out, "lsspg_dmat_copy: NULL argument");
     lsspg_dmat *M = nullptr;
     LSSPG_TRY(dmat_alloc(ctx, A->n, A->m, A->nnz, A->bs, true, &M));
-    cudaMemcpyAsync(M->p, A->p, sizeof(int) * ((size_t)A->n + 1), cudaMemcpyDeviceToDevice, ctx->stream);
-    cudaMemcpyAsync(M->j, A->j, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToDevice, ctx->stream);
-    cudaMemcpyAsync(M->x, A->x, sizeof(double) * (size_t)A->nnz * A->bs * A->bs, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (cudaMemcpyAsync(M->p, A->p, sizeof(int) * ((size_t)A->n + 1), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(M->j, A->j, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(M->x, A->x, sizeof(double) * (size_t)A->nnz * A->bs * A->bs, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+        dmat_free(M);
+        return cuda_fail(cudaGetLastError(), "lsspg_dmat_copy", __FILE__, __LINE__);
+    }
     *out = M;
     return 0;
 }
@@ -401,8 +432,13 @@ int lsspg_dmat_sort_columns(lsspg_ctx *ctx, lsspg_dmat *A)
     if (A->n == 0 || A->nnz == 0) return 0;
     lsspg_dmat *T = nullptr;
     LSSPG_TRY(dmat_alloc(ctx, A->n, A->m, A->nnz, 1, false, &T));
-    LSSPG_LAUNCH(ctx, k_sort_rows, warp_grid(ctx, A->n), 256, 0, A->n, A->p, A->j, A->x, T->j, T->x);
-    LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    k_sort_rows<<<warp_grid(ctx, A->n), 256, 0, ctx->stream>>>(A->n, A->p, A->j, A->x, T->j, T->x);
+    ctx->launches++;
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        dmat_free(T);
+        return cuda_fail(e, "k_sort_rows", __FILE__, __LINE__);
+    }
     std::swap(A->j, T->j);
     std::swap(A->x, T->x);
     dmat_free(T);
@@ -413,17 +449,17 @@ int lsspg_dmat_sort_columns(lsspg_ctx *ctx, lsspg_dmat *A)
 int lsspg_dmat_adjust_zero_diag(lsspg_ctx *ctx, const lsspg_dmat *A, double tol, lsspg_dmat **out)
 {
     LSSPG_CHECK(ctx && A && out && A->bs == 1 && A->n == A->m, "lsspg_dmat_adjust_zero_diag: needs a square CSR matrix");
-    int *cnt = nullptr;
-    LSSPG_TRY(count_array(ctx, A->n, &cnt));
-    LSSPG_LAUNCH(ctx, k_diag_count, grid_for(A->n, 256), 256, 0, A->n, A->p, A->j, cnt);
-    long long total = 0;
-    if (dev_exclusive_scan(ctx, cnt, A->n, &total)) { cudaFree(cnt); return 1; }
-    lsspg_dmat *M = nullptr;
-    if (dmat_alloc(ctx, A->n, A->m, total, 1, false, &M)) { cudaFree(cnt); return 1; }
-    M->p = cnt;
-    LSSPG_LAUNCH(ctx, k_diag_fill, grid_for(A->n, 256), 256, 0, A->n, A->p, A->j, A->x, M->p, M->j, M->x, tol);
-    *out = M;
-    return 0;
+    return count_scan_fill(
+        ctx, A->n, A->n, A->m, 1,
+        [&](int *cnt) -> int {
+            LSSPG_LAUNCH(ctx, k_diag_count, grid_for(A->n, 256), 256, 0, A->n, A->p, A->j, cnt);
+            return 0;
+        },
+        [&](lsspg_dmat *M) -> int {
+            LSSPG_LAUNCH(ctx, k_diag_fill, grid_for(A->n, 256), 256, 0, A->n, A->p, A->j, A->x, M->p, M->j, M->x, tol);
+            return 0;
+        },
+        out);
 }
 
 /* lssp_mat_get_block_diag (src/matrix-utils.cxx:589-698) */
@@ -431,17 +467,17 @@ int lsspg_dmat_get_block_diag(lsspg_ctx *ctx, const lsspg_dmat *A, int blk_size,
 {
     LSSPG_CHECK(ctx && A && out && A->bs == 1 && A->n == A->m && A->n > 0 && blk_size > 0, "lsspg_dmat_get_block_diag: bad argument");
     if (blk_size >= A->n) return lsspg_dmat_copy(ctx, A, out);
-    int *cnt = nullptr;
-    LSSPG_TRY(count_array(ctx, A->n, &cnt));
-    LSSPG_LAUNCH(ctx, k_blockdiag_count, grid_for(A->n, 256), 256, 0, A->n, blk_size, A->p, A->j, cnt);
-    long long total = 0;
-    if (dev_exclusive_scan(ctx, cnt, A->n, &total)) { cudaFree(cnt); return 1; }
-    lsspg_dmat *M = nullptr;
-    if (dmat_alloc(ctx, A->n, A->m, total, 1, false, &M)) { cudaFree(cnt); return 1; }
-    M->p = cnt;
-    LSSPG_LAUNCH(ctx, k_blockdiag_fill, grid_for(A->n, 256), 256, 0, A->n, blk_size, A->p, A->j, A->x, M->p, M->j, M->x);
-    *out = M;
-    return 0;
+    return count_scan_fill(
+        ctx, A->n, A->n, A->m, 1,
+        [&](int *cnt) -> int {
+            LSSPG_LAUNCH(ctx, k_blockdiag_count, grid_for(A->n, 256), 256, 0, A->n, blk_size, A->p, A->j, cnt);
+            return 0;
+        },
+        [&](lsspg_dmat *M) -> int {
+            LSSPG_LAUNCH(ctx, k_blockdiag_fill, grid_for(A->n, 256), 256, 0, A->n, blk_size, A->p, A->j, A->x, M->p, M->j, M->x);
+            return 0;
+        },
+        out);
 }
 
 /* lssp_mat_csr_to_bcsr (src/matrix-utils.cxx:62-162) */
@@ -450,28 +486,25 @@ int lsspg_dmat_to_bcsr(lsspg_ctx *ctx, const lsspg_dmat *A, int bs, lsspg_dmat *
     LSSPG_CHECK(ctx && A && out && A->bs == 1 && A->n == A->m && A->n > 0 && bs > 0, "lsspg_dmat_to_bcsr: bad argument");
     LSSPG_CHECK(A->n % bs == 0, "num_rows is not a multiple of block size: %d", bs);
     const int nb = A->n / bs;
-    int *cnt = nullptr, *firsts = nullptr;
-    LSSPG_TRY(count_array(ctx, nb, &cnt));
-    if (cudaMalloc(&firsts, sizeof(int) * (size_t)std::max<long long>(A->nnz, 1)) != cudaSuccess) { cudaFree(cnt); return cuda_fail(cudaGetLastError(), "lsspg_dmat_to_bcsr", __FILE__, __LINE__); }
-    int rc = 0;
-    lsspg_dmat *B = nullptr;
-    auto body = [&]() -> int {
-        LSSPG_LAUNCH(ctx, k_bcsr_count, warp_grid(ctx, nb), 256, 0, nb, bs, A->p, A->j, cnt, firsts);
-        long long total = 0;
-        LSSPG_TRY(dev_exclusive_scan(ctx, cnt, nb, &total));
-        LSSPG_TRY(dmat_alloc(ctx, nb, nb, total, bs, false, &B));
-        LSSPG_CUDA(cudaMemsetAsync(B->x, 0, sizeof(double) * (size_t)total * bs * bs, ctx->stream));
-        LSSPG_LAUNCH(ctx, k_bcsr_cols, warp_grid(ctx, nb), 256, 0, nb, bs, A->p, A->j, firsts, cnt, B->j);
-        LSSPG_LAUNCH(ctx, k_bcsr_vals, grid_for(A->n, 256), 256, 0, A->n, bs, A->p, A->j, A->x, cnt, B->j, B->x);
-        LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
-        return 0;
-    };
-    rc = body();
+    int *firsts = nullptr;
+    LSSPG_CUDA(cudaMalloc(&firsts, sizeof(int) * (size_t)std::max<long long>(A->nnz, 1)));
+    const int rc = count_scan_fill(
+        ctx, nb, nb, nb, bs,
+        [&](int *cnt) -> int {
+            LSSPG_LAUNCH(ctx, k_bcsr_count, warp_grid(ctx, nb), 256, 0, nb, bs, A->p, A->j, cnt, firsts);
+            return 0;
+        },
+        [&](lsspg_dmat *B) -> int {
+            LSSPG_CUDA(cudaMemsetAsync(B->x, 0, sizeof(double) * (size_t)B->nnz * bs * bs, ctx->stream));
+            LSSPG_LAUNCH(ctx, k_bcsr_cols, warp_grid(ctx, nb), 256, 0, nb, bs, A->p, A->j, firsts, B->p, B->j);
+            LSSPG_LAUNCH(ctx, k_bcsr_vals, grid_for(A->n, 256), 256, 0, A->n, bs, A->p, A->j, A->x, B->p, B->j, B->x);
+            LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));   // `firsts` is released below
+            return 0;
+        },
+        out);
+    cudaStreamSynchronize(ctx->stream);
     cudaFree(firsts);
-    if (rc) { cudaFree(cnt); dmat_free(B); return rc; }
-    B->p = cnt;
-    *out = B;
-    return 0;
+    return rc;
 }
 
 /* rows [r0, r1) of the 7-point operator on an nx x ny x nz grid (nz == 1: 5-point, 2-D); columns are global minus
@@ -484,19 +517,19 @@ int lsspg_dmat_gen_stencil(lsspg_ctx *ctx, int nx, int ny, int nz, long long r0,
     const long long n = (long long)nx * ny * nz, rows = r1 - r0;
     LSSPG_CHECK(r0 >= 0 && r1 <= n && rows > 0 && rows < (1ll << 31) && n - col_shift < (1ll << 31), "lsspg_dmat_gen_stencil: row range out of bounds");
     LSSPG_CUDA(cudaSetDevice(ctx->device));
-    int *cnt = nullptr;
-    LSSPG_TRY(count_array(ctx, rows, &cnt));
-    LSSPG_LAUNCH(ctx, k_stencil_count, grid_for(rows, 256), 256, 0, r0, rows, nx, ny, nz, cnt);
-    long long total = 0;
-    if (dev_exclusive_scan(ctx, cnt, rows, &total)) { cudaFree(cnt); return 1; }
-    lsspg_dmat *M = nullptr;
-    if (dmat_alloc(ctx, (int)rows, (int)std::min<long long>(n, (1ll << 31) - 1), total, 1, false, &M)) { cudaFree(cnt); return 1; }
-    M->p = cnt;
     Stencil7 s;
     for (int k = 0; k < 7; k++) s.v[k] = stencil[k];
-    LSSPG_LAUNCH(ctx, k_stencil_fill, grid_for(rows, 256), 256, 0, r0, rows, nx, ny, nz, s, col_shift, M->p, M->j, M->x);
-    *out = M;
-    return 0;
+    return count_scan_fill(
+        ctx, rows, (int)rows, (int)std::min<long long>(n, (1ll << 31) - 1), 1,
+        [&](int *cnt) -> int {
+            LSSPG_LAUNCH(ctx, k_stencil_count, grid_for(rows, 256), 256, 0, r0, rows, nx, ny, nz, cnt);
+            return 0;
+        },
+        [&](lsspg_dmat *M) -> int {
+            LSSPG_LAUNCH(ctx, k_stencil_fill, grid_for(rows, 256), 256, 0, r0, rows, nx, ny, nz, s, col_shift, M->p, M->j, M->x);
+            return 0;
+        },
+        out);
 }
 
 }  // extern "C"
