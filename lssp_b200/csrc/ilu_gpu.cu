@@ -84,14 +84,26 @@ __device__ __forceinline__ void st_flag(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// wait until row k has published itself; false when the kernel was aborted (overflow of a pattern row)
-__device__ __forceinline__ bool fac_wait(const int *done, int k, const int *abort_flag)
+// wait until row k has published itself; false when the kernel was aborted (a pattern row outgrew its pool slot, or
+// the watchdog fired: no row waits longer than a fraction of a second on a healthy run, so 20 s without progress mean
+// a dependency that will never be published -- the kernel then drains instead of hanging the device)
+__device__ __forceinline__ bool fac_wait(const int *done, int k, int *abort_flag)
 {
     int spins = 0;
+    unsigned long long t0 = 0;
     while (ld_flag(done + k) == 0) {
         if (++spins > 16) {
             __nanosleep(spins > 256 ? 400 : 60);
-            if ((spins & 63) == 0 && ld_flag(abort_flag)) return false;
+            if ((spins & 63) == 0) {
+                if (ld_flag(abort_flag)) return false;
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 20000000000ull) {
+                    atomicExch(abort_flag, 3);
+                    return false;
+                }
+            }
         }
     }
     return true;
@@ -149,7 +161,8 @@ __global__ void __launch_bounds__(kFacBlock) k_iluk_symbolic(int n, int level, i
             }
             t++;
         }
-        if (!ok || t >= len || c_[t] != i) atomicExch(overflow, (!ok) ? 1 : 2);   // 1: a row outgrew cap, 2: no diagonal
+        if (!ok) atomicCAS(overflow, 0, 1);                           // 1: a row outgrew cap (or the kernel is draining)
+        else if (t >= len || c_[t] != i) atomicExch(overflow, 2);     // 2: no diagonal
         plen[i] = len;
         dpos[i] = t;
         __threadfence();
@@ -174,9 +187,10 @@ __global__ void __launch_bounds__(256) k_check_rows(int n, const int *__restrict
     bool diag = false;
     for (int k = p[i]; k < p[i + 1]; k++) {
         diag |= (j[k] == i);
-        if (k > p[i] && j[k - 1] >= j[k]) { *bad = 1; return; }
+        if (j[k] < 0 || j[k] >= n) { *bad = 2; return; }          // out of range: nothing below may run
+        if (k > p[i] && j[k - 1] >= j[k]) atomicCAS(bad, 0, 1);
     }
-    if (!diag) *bad = 1;
+    if (!diag) atomicCAS(bad, 0, 1);
 }
 
 // pattern rows out of the pool, with A's values where present and 0 on fill (src/pc-iluk.cxx:318-343)
@@ -432,7 +446,7 @@ __global__ void __launch_bounds__(kFacBlock) k_ilut_rows(int n, int bs, int p, d
             rlen[i] = ok ? keepl + 1 + keepu : 0;
             __stcg(diag + i, d);
         }
-        if (!ok) atomicExch(abort_flag, 1);
+        if (!ok) atomicCAS(abort_flag, 0, 1);
         __threadfence();
         st_flag(done + i, 1);
     }
@@ -546,6 +560,7 @@ static int iluk_symbolic_gpu(lsspg_ctx *ctx, const lsspg_dmat *A, int level, lss
         LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
         if (rc) { dmat_free(M); return rc; }
         LSSPG_CHECK(hflag != 2, "ilu_gpu: a row without a stored diagonal reached the symbolic phase");
+        LSSPG_CHECK(hflag != 3, "ilu_gpu: the symbolic phase made no progress for 20 s (watchdog)");
         if (!hflag) { *out = M; return 0; }
     }
 }
@@ -581,6 +596,8 @@ static int ingest_gpu(lsspg_ctx *ctx, const lsspg_dmat *A_in, lsspg_dmat **owned
     LSSPG_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (!bad) return 0;
+    LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    LSSPG_CHECK(bad != 2, "%s: column index out of range", who);
     lsspg_dmat *S = nullptr;
     LSSPG_TRY(lsspg_dmat_copy(ctx, A_in, &S));
     int rc = lsspg_dmat_sort_columns(ctx, S);
@@ -640,6 +657,13 @@ int lsspg_ilu_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A_in, int level, int
         LSSPG_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * ((size_t)n + 4), ctx->stream));
         LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
         LSSPG_LAUNCH(ctx, k_ilu_numeric, grid, kFacBlock, 0, n, bs, B->p, B->j, B->x, inv, done, reinterpret_cast<unsigned int *>(done + n), ctx->d_flags);
+        {
+            int hflag = 0;
+            LSSPG_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            LSSPG_CUDA(cudaStreamSynchronize(ctx->stream));
+            LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+            LSSPG_CHECK(!hflag, "lsspg_ilu_factor_dmat: the numeric phase made no progress for 20 s (watchdog)");
+        }
         GPROF(ctx, "numeric");
         // split
         LSSPG_CUDA(cudaMalloc(&cl, sizeof(int) * ((size_t)n + 1 + 8)));
@@ -742,6 +766,7 @@ int lsspg_ilut_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A_in, int p, double
             cudaFree(wj); cudaFree(wx); cudaFree(tabs);
             wj = nullptr; wx = nullptr; tabs = nullptr;
             LSSPG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+            LSSPG_CHECK(hflag != 3, "lsspg_ilut_factor_dmat: no progress for 20 s (watchdog)");
             if (!hflag) break;
         }
         GPROF(ctx, "ilut rows");

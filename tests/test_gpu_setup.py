@@ -188,6 +188,20 @@ def test_iluk_on_the_device_blocks_and_unsorted_input(ctx, name):
     assert all(same(a, b) for a, b in zip(got, want)), name
 
 
+def test_malformed_input_is_rejected_not_factorised(ctx):
+    """a column index outside the matrix must end in an error, not in a row that waits for a pivot that never comes"""
+    from lssp_b200._lib import LsspgError
+    Ap, Aj, Ax = (a.copy() for a in matrix("cd3d_12"))
+    Aj[Ap[50]] = -3
+    with pytest.raises(LsspgError):
+        api.DMat(ctx, (Ap, Aj, Ax)).ilu_factor(level=1)
+    Aj[Ap[50]] = len(Ap) + 7
+    with pytest.raises(LsspgError):
+        api.DMat(ctx, (Ap, Aj, Ax)).ilut_factor()
+    with pytest.raises(LsspgError):
+        api.DMat(ctx, (Ap, Aj, Ax)).to_csr()
+
+
 @pytest.mark.parametrize("name", ["lap2d_100", "lap3d_32", "cd3d_32", "cd3d_12", "powerlaw_4000", "random_600"])
 def test_ilut_on_the_device_is_bit_identical(ctx, name):
     """the kept entries, their values AND their (unsorted) stored order: src/pc-ilut.cxx:7-49, :253-274"""
