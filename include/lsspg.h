@@ -228,6 +228,11 @@ int lsspg_ilu_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A, int level, int bl
 int lsspg_ilut_factor_device(lsspg_ctx *ctx, int n, const int *hAp, const int *hAj, const double *hAx, int p, double tol,
                              int blk_size, lsspg_factors **out);
 int lsspg_ilut_factor_dmat(lsspg_ctx *ctx, const lsspg_dmat *A, int p, double tol, int blk_size, lsspg_factors **out);
+/* CPU replay of the device factorisations (the row functions of ilu_rows.cuh that the kernels run, rows in ascending
+ * order): kind 0 ILU(k), 1 ILUT; *applicable = 0 when the input is not sorted / lacks diagonals (the device path repairs
+ * that first).  The factors must equal lsspg_ilu_factor's bit for bit.  Test-suite only. */
+int lsspg_debug_ilu_gpu_replay_host(int kind, int n, const int *hAp, const int *hAj, const double *hAx, int level, int p,
+                                    double tol, int blk_size, int *applicable, lsspg_factors **out);
 int lsspg_factors_sizes(const lsspg_factors *F, int *n, int *nnzL, int *nnzU);
 int lsspg_factors_get(const lsspg_factors *F, int *Lp, int *Lj, double *Lx, int *Up, int *Uj,
                       double *Ux);

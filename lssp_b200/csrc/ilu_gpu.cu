@@ -17,6 +17,7 @@
 #include <vector>
 #include "blas1.cuh"
 #include "host_par.h"
+#include "ilu_rows.cuh"
 #include "setup_gpu.cuh"
 
 struct lsspg_factors;
@@ -58,8 +59,6 @@ static bool gprof_on()
         }                                                                             \
     } while (0)
 
-constexpr double kPivotTolG = 1e-10;    // mat_zero_diag_tol,   reference src/pc.cxx:7
-constexpr double kPivotValueG = 1e-3;   // mat_zero_diag_value, reference src/pc.cxx:6
 constexpr int kStride = 257;            // distance between the rows of a warp (not a divisor of the usual grid offsets)
 constexpr int kFacBlock = 128;
 
@@ -109,62 +108,32 @@ __device__ __forceinline__ bool fac_wait(const int *done, int k, int *abort_flag
     return true;
 }
 
-// ---- symbolic phase ---------------------------------------------------------------------------------------------------
-// Row i starts as A's row (levels 0) in its slot of the pool, pc / pl [i cap ..), and stays sorted.  Pivots are the lower
-// columns in ascending order -- fill lands behind the current pivot, so "the smallest lower column not used yet"
-// (src/pc-iluk.cxx:62-75) is simply the next entry.  A candidate (c, lev(i,piv) + lev(piv,c) + 1) above `level` is
-// ignored, an absent column is inserted, a present one has its level RAISED to the candidate's when that is larger
-// (the reference's rule, :101); the diagonal is never a candidate.  dpos[i] = position of the diagonal.
+struct FacWaitDev {
+    const int *done;
+    int *abort_flag;
+    __device__ __forceinline__ bool operator()(int k) const { return fac_wait(done, k, abort_flag); }
+};
+struct FacWaitNone {   // host replay: rows run in ascending order
+    bool operator()(int) const { return true; }
+};
+
+// ---- symbolic phase (row recurrence: ilu_rows.cuh) --------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFacBlock) k_iluk_symbolic(int n, int level, int cap, const int *__restrict__ Ap,
                                                             const int *__restrict__ Aj, int *pc, int *pl, int *plen, int *dpos,
                                                             int *done, unsigned int *ticket, int *flags)
 {
     const int lane = threadIdx.x & 31;
     int *overflow = flags + FLAG_SETUP;
+    const FacWaitDev wait{done, overflow};
     for (;;) {
         bool more;
         const long long row = fac_next_row(ticket, lane, n, &more);
         if (!more) break;
         if (row >= n) continue;
         const int i = (int)row;
-        int *c_ = pc + (size_t)i * cap, *l_ = pl + (size_t)i * cap;
-        int len = 0;
-        bool ok = true;
-        for (int k = Ap[i]; k < Ap[i + 1]; k++) {
-            if (len == cap) { ok = false; break; }
-            c_[len] = Aj[k];
-            l_[len] = 0;
-            len++;
-        }
-        int t = 0;
-        while (ok && t < len && c_[t] < i) {
-            const int piv = c_[t], lt = l_[t];
-            if (!fac_wait(done, piv, overflow)) { ok = false; break; }
-            const int pn = __ldcg(plen + piv);
-            const int *qc = pc + (size_t)piv * cap, *ql = pl + (size_t)piv * cap;
-            int a = t + 1;
-            for (int q = __ldcg(dpos + piv) + 1; q < pn; q++) {
-                const int c = __ldcg(qc + q);
-                const int cand = __ldcg(ql + q) + lt + 1;
-                if (cand > level || c == i) continue;
-                while (a < len && c_[a] < c) a++;
-                if (a < len && c_[a] == c) {
-                    if (l_[a] < cand) l_[a] = cand;
-                }
-                else {
-                    if (len == cap) { ok = false; break; }
-                    for (int z = len; z > a; z--) { c_[z] = c_[z - 1]; l_[z] = l_[z - 1]; }
-                    c_[a] = c;
-                    l_[a] = cand;
-                    len++;
-                }
-            }
-            t++;
-        }
-        if (!ok) atomicCAS(overflow, 0, 1);                           // 1: a row outgrew cap (or the kernel is draining)
-        else if (t >= len || c_[t] != i) atomicExch(overflow, 2);     // 2: no diagonal
-        plen[i] = len;
-        dpos[i] = t;
+        const int st = iluk_symbolic_row(i, level, cap, Ap, Aj, pc, pl, plen, dpos, wait);
+        if (st == 1) atomicCAS(overflow, 0, 1);      // 1: a row outgrew cap (or the kernel is draining)
+        else if (st == 2) atomicExch(overflow, 2);   // 2: no diagonal
         __threadfence();
         st_flag(done + i, 1);
     }
@@ -193,87 +162,37 @@ __global__ void __launch_bounds__(256) k_check_rows(int n, const int *__restrict
     if (!diag) atomicCAS(bad, 0, 1);
 }
 
-// pattern rows out of the pool, with A's values where present and 0 on fill (src/pc-iluk.cxx:318-343)
 __global__ void __launch_bounds__(256) k_pattern_rows(int n, int cap, const int *__restrict__ pc, const int *__restrict__ Ap,
                                                      const int *__restrict__ Aj, const double *__restrict__ Ax,
                                                      const int *__restrict__ Mp, int *__restrict__ Mj, double *__restrict__ Mx)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int *c_ = pc + (size_t)i * cap;
-    int a = Ap[i];
-    const int ae = Ap[i + 1], o = Mp[i], len = Mp[i + 1] - o;
-    for (int k = 0; k < len; k++) {
-        const int c = c_[k];
-        while (a < ae && Aj[a] < c) a++;
-        Mj[o + k] = c;
-        Mx[o + k] = (a < ae && Aj[a] == c) ? Ax[a] : 0.0;
-    }
+    if (i < n) iluk_pattern_row(i, cap, pc, Ap, Aj, Ax, Mp, Mj, Mx);
 }
 
-// ---- numeric phase: the IKJ loop of src/pc-iluk.cxx:347-409 per block of bs rows, in place --------------------------------
+// ---- numeric phase (row recurrence: ilu_rows.cuh) ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFacBlock) k_ilu_numeric(int n, int bs, const int *__restrict__ P, const int *__restrict__ C,
                                                           double *X, double *inv, int *done, unsigned int *ticket, int *flags)
 {
     const int lane = threadIdx.x & 31;
-    int *abort_flag = flags + FLAG_SETUP;
+    const FacWaitDev wait{done, flags + FLAG_SETUP};
     for (;;) {
         bool more;
         const long long row = fac_next_row(ticket, lane, n, &more);
         if (!more) break;
         if (row >= n) continue;
         const int i = (int)row;
-        const int e = P[i + 1];
-        int k = P[i];
-        if (i % bs == 0) {
-            // first row of a block: its leading entry is the pivot; the repaired value only enters the inverse, the
-            // stored entry is left alone (as the host loop)
-            const double d = __ldcg(X + k);
-            __stcg(inv + i, 1. / (fabs(d) < kPivotTolG ? (d > 0 ? kPivotValueG : -kPivotValueG) : d));
-        }
-        else {
-            bool ok = true;
-            for (; ok && k < e && C[k] < i; k++) {
-                const int pr = C[k];
-                if (!fac_wait(done, pr, abort_flag)) { ok = false; break; }
-                const double a_ik = __ldcg(X + k) * __ldcg(inv + pr);
-                __stcg(X + k, a_ik);
-                int pq = P[pr];
-                const int pe = P[pr + 1];
-                for (int q = k + 1; q < e; q++) {
-                    const int c = C[q];
-                    while (pq < pe && C[pq] < c) pq++;
-                    if (pq < pe && C[pq] == c) {
-                        const double w = __ldcg(X + pq);
-                        if (w != 0.) __stcg(X + q, __ldcg(X + q) - a_ik * w);
-                    }
-                }
-            }
-            double d = kPivotValueG;
-            if (k < e && C[k] == i) {
-                double v = __ldcg(X + k);
-                if (fabs(v) < kPivotTolG) { v = kPivotValueG; __stcg(X + k, v); }
-                d = v;
-            }
-            __stcg(inv + i, 1. / d);
-        }
+        ilu_numeric_row(i, bs, P, C, X, inv, wait);   // (an aborted wait has raised the flag already)
         __threadfence();
         st_flag(done + i, 1);
     }
 }
 
-// ---- split: L = strict lower + unit diagonal LAST, U = diagonal FIRST + strict upper (src/pc-iluk.cxx:501-532) ----------------
+// ---- split (ilu_rows.cuh) ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_split_count(int n, const int *__restrict__ P, const int *__restrict__ C, int *nl, int *nu)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int a = 0, b = 0;
-    for (int k = P[i]; k < P[i + 1]; k++) {
-        a += (C[k] <= i);
-        b += (C[k] >= i);
-    }
-    nl[i] = a;
-    nu[i] = b;
+    if (i < n) split_count_row(i, C + P[i], P[i + 1] - P[i], nl, nu);
 }
 
 __global__ void __launch_bounds__(256) k_split_fill(int n, const int *__restrict__ P, const int *__restrict__ C,
@@ -282,69 +201,10 @@ __global__ void __launch_bounds__(256) k_split_fill(int n, const int *__restrict
                                                    double *__restrict__ Ux)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int ol = Lp[i], ou = Up[i];
-    for (int k = P[i]; k < P[i + 1]; k++) {
-        const int c = C[k];
-        if (c < i) { Lj[ol] = c; Lx[ol] = X[k]; ol++; }
-        else if (c == i) {
-            Lj[ol] = i; Lx[ol] = 1; ol++;
-            Uj[ou] = i; Ux[ou] = X[k]; ou++;
-        }
-        else { Uj[ou] = c; Ux[ou] = X[k]; ou++; }
-    }
+    if (i < n) split_fill_row(i, C + P[i], X + P[i], P[i + 1] - P[i], Lp, Lj, Lx, Up, Uj, Ux);
 }
 
-
-// ---- ILUT (src/pc-ilut.cxx:51-286) ---------------------------------------------------------------------------------------
-// The row recurrence of ilu_host.cpp: factor_ilut_rows, statement for statement, one thread per row: work row as two
-// compact arrays (lower part / upper part) in the thread's scratch, `present?` answered by a linear search of the part
-// the column belongs to instead of the host's column map (processed pivots are smaller than every candidate, so only
-// the live entries are searched), quick-select with the reference's exact sequence of exchanges (:7-49) because the kept
-// entries are stored -- and later summed by the sweeps -- in the order it leaves them.  Finished rows live in a pool
-// ([kept lower | diagonal | kept upper], rcap entries each) and are published like the ILU(k) rows.
-__device__ __forceinline__ void select_largest_dev(double *a, int *ind, int n, int ncut)
-{
-    int lo = 0, hi = n - 1;
-    if (ncut < lo || ncut >= hi) return;
-    for (;;) {
-        int mid = lo;
-        const double key = fabs(a[mid]);
-        for (int q = lo + 1; q <= hi; q++) {
-            if (fabs(a[q]) > key) {
-                ++mid;
-                const double ta = a[mid]; a[mid] = a[q]; a[q] = ta;
-                const int ti = ind[mid]; ind[mid] = ind[q]; ind[q] = ti;
-            }
-        }
-        const double ta = a[mid]; a[mid] = a[lo]; a[lo] = ta;
-        const int ti = ind[mid]; ind[mid] = ind[lo]; ind[lo] = ti;
-        if (mid == ncut) return;
-        if (mid > ncut) hi = mid - 1;
-        else lo = mid + 1;
-    }
-}
-
-__device__ __forceinline__ double repaired_pivot_dev(double d)
-{
-    return (fabs(d) < kPivotTolG) ? (d > 0 ? kPivotValueG : -kPivotValueG) : d;
-}
-
-// column -> position map of the work row: open addressing, H slots (power of two, >= 4 wcap) of {column, row stamp,
-// position}; a slot whose stamp is not the current row is empty, so nothing is ever cleared (and nothing is deleted inside
-// a row: processed pivots are smaller than every later candidate and are never looked up again)
-struct IlutSlot {
-    int key, stamp, pos;
-};
-__device__ __forceinline__ IlutSlot *ilut_find(IlutSlot *tab, int hmask, int row, int c)
-{
-    unsigned int h = ((unsigned int)c * 2654435761u) >> 7;
-    for (;; h++) {
-        IlutSlot *s = tab + (h & (unsigned int)hmask);
-        if (s->stamp != row || s->key == c) return s;
-    }
-}
-
+// ---- ILUT (row recurrence: ilu_rows.cuh) ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFacBlock) k_ilut_rows(int n, int bs, int p, double tau, const int *__restrict__ Bp,
                                                         const int *__restrict__ Bj, const double *__restrict__ Bx, int rcap,
                                                         int *rc, double *rv, int *rlen, double *diag, int wcap, int *wj,
@@ -353,100 +213,19 @@ __global__ void __launch_bounds__(kFacBlock) k_ilut_rows(int n, int bs, int p, d
 {
     const int lane = threadIdx.x & 31;
     int *abort_flag = flags + FLAG_SETUP;
+    const FacWaitDev wait{done, abort_flag};
     const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int *jwl = wj + gt * 2 * wcap, *jwu = jwl + wcap;
     double *wl = wx + gt * 2 * wcap, *wu = wl + wcap;
     IlutSlot *tab = tabs + gt * ((size_t)hmask + 1);
-    constexpr int kUp = 1 << 30;   // positions >= kUp: upper part
     for (;;) {
         bool more;
         const long long row = fac_next_row(ticket, lane, n, &more);
         if (!more) break;
         if (row >= n) continue;
         const int i = (int)row;
-        const int b = Bp[i], e = Bp[i + 1];
-        int *c_ = rc + (size_t)i * rcap;
-        double *v_ = rv + (size_t)i * rcap;
-        bool ok = true;
-        if (i % bs == 0) {
-            // first row of a block: copied verbatim; its leading entry is the pivot
-            if (e - b > rcap) ok = false;
-            for (int k = b; ok && k < e; k++) { c_[k - b] = Bj[k]; v_[k - b] = Bx[k]; }
-            rlen[i] = ok ? e - b : 0;
-            __stcg(diag + i, repaired_pivot_dev(Bx[b]));
-        }
-        else {
-            double norm = 0.0;
-            for (int k = b; k < e; k++) norm += fabs(Bx[k]);
-            norm /= (double)(e - b);
-            const double drop = tau * norm;
-            int nl = 0, nu = 0;
-            double wd = 0.0;
-            auto put = [&](int c, int pos) {
-                IlutSlot *s = ilut_find(tab, hmask, i, c);
-                s->key = c; s->stamp = i; s->pos = pos;
-            };
-            for (int k = b; k < e && ok; k++) {
-                const int c = Bj[k];
-                if (c < i) { if (nl == wcap) { ok = false; break; } put(c, nl); jwl[nl] = c; wl[nl] = Bx[k]; nl++; }
-                else if (c == i) wd = Bx[k];
-                else { if (nu == wcap) { ok = false; break; } put(c, kUp + nu); jwu[nu] = c; wu[nu] = Bx[k]; nu++; }
-            }
-            for (int tt = 0; ok && tt < nl; tt++) {
-                int piv = jwl[tt], at = tt;
-                for (int q = tt + 1; q < nl; q++)
-                    if (jwl[q] < piv) { piv = jwl[q]; at = q; }
-                if (at != tt) {
-                    const int c = jwl[tt];
-                    jwl[tt] = jwl[at];
-                    jwl[at] = c;
-                    put(c, at);
-                    const double tw = wl[tt]; wl[tt] = wl[at]; wl[at] = tw;
-                }
-                if (!fac_wait(done, piv, abort_flag)) { ok = false; break; }
-                const double a_ik = wl[tt] / __ldcg(diag + piv);
-                wl[tt] = a_ik;
-                const int *pc = rc + (size_t)piv * rcap;
-                const double *pv = rv + (size_t)piv * rcap;
-                for (int q = 0, qe = __ldcg(rlen + piv); q < qe; q++) {
-                    const int c = __ldcg(pc + q);
-                    if (c <= piv) continue;
-                    const double mx = -a_ik * __ldcg(pv + q);
-                    if (c == i) { wd += mx; continue; }
-                    IlutSlot *sl = ilut_find(tab, hmask, i, c);
-                    if (sl->stamp == i) {   // present
-                        if (sl->pos >= kUp) wu[sl->pos - kUp] += mx;
-                        else wl[sl->pos] += mx;
-                    }
-                    else if (!(fabs(mx) < drop)) {   // only NEW fill is dropped
-                        if (c < i) {
-                            if (nl == wcap) { ok = false; break; }
-                            sl->key = c; sl->stamp = i; sl->pos = nl;
-                            jwl[nl] = c; wl[nl] = mx; nl++;
-                        }
-                        else {
-                            if (nu == wcap) { ok = false; break; }
-                            sl->key = c; sl->stamp = i; sl->pos = kUp + nu;
-                            jwu[nu] = c; wu[nu] = mx; nu++;
-                        }
-                    }
-                }
-            }
-            const double d = repaired_pivot_dev(wd);
-            const int keepl = min(nl, p), keepu = min(nu, p);
-            if (ok && keepl + 1 + keepu > rcap) ok = false;
-            if (ok) {
-                select_largest_dev(wl, jwl, nl, keepl);
-                select_largest_dev(wu, jwu, nu, keepu);
-                for (int q = 0; q < keepl; q++) { c_[q] = jwl[q]; v_[q] = wl[q]; }
-                c_[keepl] = i;
-                v_[keepl] = d;
-                for (int q = 0; q < keepu; q++) { c_[keepl + 1 + q] = jwu[q]; v_[keepl + 1 + q] = wu[q]; }
-            }
-            rlen[i] = ok ? keepl + 1 + keepu : 0;
-            __stcg(diag + i, d);
-        }
-        if (!ok) atomicCAS(abort_flag, 0, 1);
+        if (!ilut_row(i, bs, p, tau, Bp, Bj, Bx, rcap, rc, rv, rlen, diag, wcap, jwl, jwu, wl, wu, tab, hmask, wait))
+            atomicCAS(abort_flag, 0, 1);
         __threadfence();
         st_flag(done + i, 1);
     }
@@ -457,15 +236,7 @@ __global__ void __launch_bounds__(256) k_pool_split_count(int n, int rcap, const
                                                          int *nl, int *nu)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int *c_ = rc + (size_t)i * rcap;
-    int a = 0, b = 0;
-    for (int q = 0; q < rlen[i]; q++) {
-        a += (c_[q] <= i);
-        b += (c_[q] >= i);
-    }
-    nl[i] = a;
-    nu[i] = b;
+    if (i < n) split_count_row(i, rc + (size_t)i * rcap, rlen[i], nl, nu);
 }
 
 __global__ void __launch_bounds__(256) k_pool_split_fill(int n, int rcap, const int *__restrict__ rc, const double *__restrict__ rv,
@@ -474,20 +245,7 @@ __global__ void __launch_bounds__(256) k_pool_split_fill(int n, int rcap, const 
                                                         int *__restrict__ Uj, double *__restrict__ Ux)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int *c_ = rc + (size_t)i * rcap;
-    const double *v_ = rv + (size_t)i * rcap;
-    int ol = Lp[i], ou = Up[i];
-    for (int q = 0; q < rlen[i]; q++) {
-        const int c = c_[q];
-        const double v = v_[q];
-        if (c < i) { Lj[ol] = c; Lx[ol] = v; ol++; }
-        else if (c == i) {
-            Lj[ol] = i; Lx[ol] = 1; ol++;
-            Uj[ou] = i; Ux[ou] = v; ou++;
-        }
-        else { Uj[ou] = c; Ux[ou] = v; ou++; }
-    }
+    if (i < n) split_fill_row(i, rc + (size_t)i * rcap, rv + (size_t)i * rcap, rlen[i], Lp, Lj, Lx, Up, Uj, Ux);
 }
 
 static inline unsigned int rows_grid(long long n) { return (unsigned int)std::max<long long>(1, (n + 255) / 256); }
@@ -804,6 +562,133 @@ int lsspg_ilut_factor_device(lsspg_ctx *ctx, int n, const int *hAp, const int *h
     const int rc = lsspg_ilut_factor_dmat(ctx, A, p, tol, blk_size, out);
     lsspg_dmat_destroy(ctx, A);
     return rc;
+}
+
+/* CPU replay of the device factorisations for the test-suite (never called by a product path): the SAME row functions
+ * the kernels run (ilu_rows.cuh), rows in ascending order, no device.  kind 0: ILU(k) (symbolic with a growing pool,
+ * pattern with A's values, block restriction, numeric, split), kind 1: ILUT.  The input must have strictly ascending
+ * columns and stored diagonals (the device path sorts and repairs first); otherwise *applicable = 0.  The factors must
+ * equal lsspg_ilu_factor's bit for bit. */
+int lsspg_debug_ilu_gpu_replay_host(int kind, int n, const int *Ap, const int *Aj, const double *Ax, int level, int p, double tol,
+                                    int blk_size, int *applicable, lsspg_factors **out)
+{
+    LSSPG_CHECK(n > 0 && Ap && Aj && Ax && out && applicable, "lsspg_debug_ilu_gpu_replay_host: bad argument");
+    *applicable = 0;
+    for (int i = 0; i < n; i++) {
+        bool diag = false;
+        for (int k = Ap[i]; k < Ap[i + 1]; k++) {
+            if (Aj[k] < 0 || Aj[k] >= n || (k > Ap[i] && Aj[k - 1] >= Aj[k])) return 0;
+            diag |= (Aj[k] == i);
+        }
+        if (!diag) return 0;
+    }
+    *applicable = 1;
+    const int bs = (blk_size <= 0 || blk_size > n) ? n : blk_size;
+    const FacWaitNone wait;
+    // block restriction of a sorted matrix with diagonals (k_blockdiag_count / k_blockdiag_fill)
+    auto restrict_blocks = [&](const std::vector<int> &Mp, const std::vector<int> &Mj, const std::vector<double> &Mx, std::vector<int> &Bp,
+                               std::vector<int> &Bj, std::vector<double> &Bx) {
+        Bp.assign((size_t)n + 1, 0);
+        Bj.clear();
+        Bx.clear();
+        for (int i = 0; i < n; i++) {
+            const int lo = (i / bs) * bs, hi = std::min(n, lo + bs);
+            const size_t before = Bj.size();
+            for (int k = Mp[i]; k < Mp[i + 1]; k++)
+                if (Mj[k] >= lo && Mj[k] < hi) { Bj.push_back(Mj[k]); Bx.push_back(Mx[k]); }
+            if (Bj.size() == before) { Bj.push_back(i); Bx.push_back(1.0); }
+            Bp[i + 1] = (int)Bj.size();
+        }
+    };
+    std::vector<int> nl((size_t)n + 1, 0), nu((size_t)n + 1, 0);
+    auto scan = [&](std::vector<int> &v) {
+        int run = 0;
+        for (int i = 0; i < n; i++) { const int c = v[i]; v[i] = run; run += c; }
+        v[n] = run;
+    };
+    int *Lp, *Lj, *Up, *Uj;
+    double *Lx, *Ux;
+    if (kind == 0) {
+        if (level < 0) level = 0;
+        std::vector<int> Mp(Ap, Ap + n + 1), Mj(Aj, Aj + Ap[n]);
+        std::vector<double> Mx(Ax, Ax + Ap[n]);
+        if (level > 0) {
+            int hmax = 1;
+            for (int i = 0; i < n; i++) hmax = std::max(hmax, Ap[i + 1] - Ap[i]);
+            long long cap = std::max<long long>(32, (std::min<long long>(1024, (long long)hmax * (level + 1) * (level + 1)) + 31) / 32 * 32);
+            std::vector<int> pc, pl, plen((size_t)n + 1), dpos((size_t)n);
+            for (;; cap *= 2) {
+                LSSPG_CHECK(cap <= 4096, "replay: pattern rows longer than 4096 entries");
+                pc.assign((size_t)n * cap, 0);
+                pl.assign((size_t)n * cap, 0);
+                int st = 0;
+                for (int i = 0; i < n && st == 0; i++)
+                    st = iluk_symbolic_row(i, level, (int)cap, Ap, Aj, pc.data(), pl.data(), plen.data(), dpos.data(), wait);
+                LSSPG_CHECK(st != 2, "replay: a row without a stored diagonal");
+                if (st == 0) break;
+            }
+            Mp.assign(plen.begin(), plen.end());
+            scan(Mp);
+            Mj.resize((size_t)Mp[n]);
+            Mx.resize((size_t)Mp[n]);
+            for (int i = 0; i < n; i++) iluk_pattern_row(i, (int)cap, pc.data(), Ap, Aj, Ax, Mp.data(), Mj.data(), Mx.data());
+        }
+        if (bs < n) {
+            std::vector<int> Bp, Bj;
+            std::vector<double> Bx;
+            restrict_blocks(Mp, Mj, Mx, Bp, Bj, Bx);
+            Mp.swap(Bp); Mj.swap(Bj); Mx.swap(Bx);
+        }
+        std::vector<double> inv((size_t)n);
+        for (int i = 0; i < n; i++) ilu_numeric_row(i, bs, Mp.data(), Mj.data(), Mx.data(), inv.data(), wait);
+        for (int i = 0; i < n; i++) split_count_row(i, Mj.data() + Mp[i], Mp[i + 1] - Mp[i], nl.data(), nu.data());
+        scan(nl);
+        scan(nu);
+        lsspg_factors *F = factors_new(n, (size_t)nl[n], (size_t)nu[n], &Lp, &Lj, &Lx, &Up, &Uj, &Ux);
+        std::copy(nl.begin(), nl.end(), Lp);
+        std::copy(nu.begin(), nu.end(), Up);
+        for (int i = 0; i < n; i++) split_fill_row(i, Mj.data() + Mp[i], Mx.data() + Mp[i], Mp[i + 1] - Mp[i], Lp, Lj, Lx, Up, Uj, Ux);
+        *out = F;
+        return 0;
+    }
+    // ILUT
+    if (p <= 0) p = (int)(((long long)Ap[n] + n - 1) / n);
+    if (tol < 0) tol = 1e-3;
+    std::vector<int> Bp(Ap, Ap + n + 1), Bj(Aj, Aj + Ap[n]);
+    std::vector<double> Bx(Ax, Ax + Ap[n]);
+    if (bs < n) {
+        std::vector<int> Mp(Bp), Mj(Bj);
+        std::vector<double> Mx(Bx);
+        restrict_blocks(Mp, Mj, Mx, Bp, Bj, Bx);
+    }
+    int hmax = 1;
+    for (int i = 0; i < n; i++) hmax = std::max(hmax, Bp[i + 1] - Bp[i]);
+    const int rcap = std::max(2 * p + 1, hmax);
+    std::vector<int> rc((size_t)n * rcap), rlen((size_t)n);
+    std::vector<double> rv((size_t)n * rcap), diag((size_t)n);
+    for (int wcap = std::max(64, 4 * (hmax + p));; wcap *= 2) {
+        LSSPG_CHECK(wcap <= 65536, "replay: work rows longer than 65536 entries");
+        int hsize = 256;
+        while (hsize < 4 * wcap) hsize *= 2;
+        std::vector<int> wj((size_t)2 * wcap);
+        std::vector<double> wx((size_t)2 * wcap);
+        std::vector<IlutSlot> tab((size_t)hsize, IlutSlot{-1, -1, -1});
+        bool ok = true;
+        for (int i = 0; i < n && ok; i++)
+            ok = ilut_row(i, bs, p, tol, Bp.data(), Bj.data(), Bx.data(), rcap, rc.data(), rv.data(), rlen.data(), diag.data(), wcap, wj.data(),
+                          wj.data() + wcap, wx.data(), wx.data() + wcap, tab.data(), hsize - 1, wait);
+        if (ok) break;
+    }
+    for (int i = 0; i < n; i++) split_count_row(i, rc.data() + (size_t)i * rcap, rlen[i], nl.data(), nu.data());
+    scan(nl);
+    scan(nu);
+    lsspg_factors *F = factors_new(n, (size_t)nl[n], (size_t)nu[n], &Lp, &Lj, &Lx, &Up, &Uj, &Ux);
+    std::copy(nl.begin(), nl.end(), Lp);
+    std::copy(nu.begin(), nu.end(), Up);
+    for (int i = 0; i < n; i++)
+        split_fill_row(i, rc.data() + (size_t)i * rcap, rv.data() + (size_t)i * rcap, rlen[i], Lp, Lj, Lx, Up, Uj, Ux);
+    *out = F;
+    return 0;
 }
 
 }  // extern "C"
