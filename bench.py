@@ -93,6 +93,7 @@ class ClockSampler(threading.Thread):
 def build_problem(args):
     from lssp_b200 import generators as g
     N = args.grid
+    args.ilu_level = 0
     if args.workload == "cg_ilu0":
         A = g.lap3d(N)
         name = "lap3d_%d CG+ILU(0) (BASELINE.json configs[1])" % N
@@ -101,6 +102,11 @@ def build_problem(args):
         A = g.cd3d(N)
         name = "cd3d_%d BiCGStab+ILU(0)" % N
         solver, pc = "bicgstab", "iluk"
+    elif args.workload == "bicgstab_iluk1":
+        A = g.cd3d(N)
+        name = "cd3d_%d BiCGStab+ILUK(1) (BASELINE.json configs[2])" % N
+        solver, pc = "bicgstab", "iluk"
+        args.ilu_level = 1
     elif args.workload == "cg_amg":
         A = g.lap3d(N)
         name = "lap3d_%d CG+SXAMG-style V-cycle, zero initial guess, %s Gauss-Seidel (BASELINE.json configs[3] operator)" % (
@@ -133,7 +139,7 @@ def reference_arm(args, rank):
             H = api.AmgHierarchy(A, cf_order=args.amg_order)
             kw["amg"] = P.amg(H.levels, coarse_inv=H.coarse_inv, zero_guess=1, cf_order=args.amg_order)
         elif pc == "iluk":
-            kw["LU"] = api.ilu_factor(A, "iluk", level=0)
+            kw["LU"] = api.ilu_factor(A, "iluk", level=args.ilu_level)
         its, secs = 0, 0.0
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
@@ -156,7 +162,7 @@ def reference_arm(args, rank):
     L = R.lib
     L.ref_session_create.restype = C.c_void_p
     L.ref_session_solve.restype = C.c_int
-    prm = oracle.ref_params(maxit=args.ref_iters, iluk_level=0)
+    prm = oracle.ref_params(maxit=args.ref_iters, iluk_level=args.ilu_level)
     tas = C.c_double()
     h = C.c_void_p(L.ref_session_create(oracle.SOLVERS[solver], oracle.PCS[pc], n, A[0].ctypes.data_as(C.c_void_p),
                                         A[1].ctypes.data_as(C.c_void_p), A[2].ctypes.data_as(C.c_void_p),
@@ -211,7 +217,7 @@ def cpu_baseline(args, A, solver, pc, pcobj=None):
         L.ref_session_solve.restype = C.c_int
         L.ref_session_time_mxy.restype = C.c_double
         L.ref_session_time_pc.restype = C.c_double
-        prm = oracle.ref_params(maxit=args.ref_iters, iluk_level=0)
+        prm = oracle.ref_params(maxit=args.ref_iters, iluk_level=args.ilu_level)
         tas = C.c_double()
         h = C.c_void_p(L.ref_session_create(oracle.SOLVERS[solver], oracle.PCS[pc], n, A[0].ctypes.data_as(C.c_void_p),
                                             A[1].ctypes.data_as(C.c_void_p), A[2].ctypes.data_as(C.c_void_p),
@@ -230,7 +236,7 @@ def cpu_baseline(args, A, solver, pc, pcobj=None):
                 "pc_apply_ms": 1e3 * t_pc, "host_cores_total": os.cpu_count()}
     P = oracle.Port()
     from lssp_b200 import api
-    LU = api.ilu_factor(A, "iluk", level=0) if pc == "iluk" else None
+    LU = api.ilu_factor(A, "iluk", level=args.ilu_level) if pc == "iluk" else None
     t0 = time.perf_counter()
     r = P.solve(solver, A, np.ones(n), LU=LU, maxit=args.ref_iters)
     t = time.perf_counter() - t0
@@ -243,7 +249,7 @@ def parity_block(args, ctx, api, solver, dA, pc, n):
     (tests/golden/baseline_<N>.json, generated by tests/golden/make_baseline_golden.py from oracle/_ref) -- iterations to
     tolerance and the first 20 residuals in the shipped tree-reduction mode, and the same solve with the reference-order
     reductions (exact_sum.cu), which must reproduce the reference bit for bit."""
-    key = {"cg_ilu0": "lap3d/cg+iluk0", "bicgstab_ilu0": "lap3d/bicgstab+iluk0"}.get(args.workload)
+    key = {"cg_ilu0": "lap3d/cg+iluk0", "bicgstab_iluk1": "cd3d/bicgstab+iluk1"}.get(args.workload)
     path = os.path.join(ROOT, "tests", "golden", "baseline_%d.json" % args.grid)
     if key is None or not os.path.exists(path):
         return None
@@ -318,8 +324,9 @@ def main():
     ctx.set_option(api.OPT_CHECK_EVERY, args.check_every)
     dA = api.Csr(ctx, A)
     t0 = time.perf_counter()
+    ilu_level = args.ilu_level
     if pckind == "iluk":
-        pc = api.Preconditioner.iluk(ctx, A, level=0)
+        pc = api.Preconditioner.iluk(ctx, A, level=ilu_level)
     elif pckind == "amg":
         pc = api.Preconditioner.sxamg(ctx, A, share=dA, zero_guess=1, cf_order=args.amg_order)
     else:
@@ -369,7 +376,7 @@ def main():
         C.c_int.in_dll(C.CDLL(os.path.join(ROOT, "lssp_b200", "liblssp.so")), "lssp_verbosity").value = 0
         LSSP_SOLVER = {"cg": 7, "bicgstab": 4, "gmres": 0, "idrs": 18}[solver]     # include/lssp/type-defs.h
         facade = C.c_void_p(E.lssp_e2e_create(LSSP_SOLVER, 1 if pckind == "iluk" else 0, n, A[0].ctypes.data_as(C.c_void_p),
-                                              A[1].ctypes.data_as(C.c_void_p), A[2].ctypes.data_as(C.c_void_p), hx, hb, 0, 3000, 50,
+                                              A[1].ctypes.data_as(C.c_void_p), A[2].ctypes.data_as(C.c_void_p), hx, hb, ilu_level, 3000, 50,
                                               C.c_double(-1.0)))
     e2e_its, e2e_s = 0, 0.0
     for step in range(1 + args.steps):

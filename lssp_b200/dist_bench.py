@@ -50,9 +50,10 @@ def main(args, rank, world, local_rank):
         dims = (N, N, N * world)
     n = args.pl_rows * world if powerlaw else dims[0] * dims[1] * dims[2]
     blk, r0, r1 = dist.block_rows(n, world, rank)
-    op = getattr(args, "operator", None) or ("cd" if args.workload == "bicgstab_ilu0" else "lap")
+    bicg = args.workload in ("bicgstab_ilu0", "bicgstab_iluk1")   # iluk1: BASELINE.json configs[2] (C3), block-Jacobi ILU(1)
+    op = getattr(args, "operator", None) or ("cd" if bicg else "lap")
     conv = (0.3, 0.2, 0.1) if op == "cd" else (0.0, 0.0, 0.0)
-    solver = "idrs" if powerlaw else "bicgstab" if args.workload == "bicgstab_ilu0" else "cg"
+    solver = "idrs" if powerlaw else "bicgstab" if bicg else "cg"
     t0 = time.perf_counter()
     # BASELINE.json configs[4] (power-law CSR, IDRS(4)): --pl-rows rows per GPU, every rank generates its own block
     rows = g.powerlaw_rows(n, r0, r1) if powerlaw else g.stencil_7pt_rows(dims, r0, r1, conv=conv)
@@ -72,7 +73,9 @@ def main(args, rank, world, local_rank):
         pc = api.Preconditioner.sxamg(ctx, shard.diag_block(), zero_guess=1, cf_order=args.amg_order)
         pcname = "block-Jacobi SX-AMG-style V-cycle (zero initial guess, cf_order %d)" % args.amg_order
     else:
-        Lf, Uf = api.ilu_factor(shard.diag_block(), "iluk", level=0)
+        lvl = 1 if args.workload == "bicgstab_iluk1" else 0
+        pcname = "block-Jacobi ILU(%d)" % lvl
+        Lf, Uf = api.ilu_factor(shard.diag_block(), "iluk", level=lvl)
         pc = api.Preconditioner(ctx, "ilu", shard.n_owned, Lf, Uf)
     t_pc = time.perf_counter() - t0
     no, nc = shard.n_owned, shard.n_owned + shard.n_ghost

@@ -23,5 +23,6 @@ case $t in
  bicgstab) run weak_bicgstab_ilu0_lap --workload bicgstab_ilu0 --operator lap ;;
  amg) run cubic_cg_amg --workload cg_amg --shape cubic --amg-order 2 ;;
  strongcd) run strong_bicgstab_ilu0_cd --scaling strong --workload bicgstab_ilu0 ;;
+ c3) run strong_bicgstab_iluk1_cd --scaling strong --workload bicgstab_iluk1 ;;
 esac
 done
