@@ -1,17 +1,19 @@
-// ilu_gpu.cu -- ILU(k) set-up on the GPU: symbolic level-of-fill phase (src/pc-iluk.cxx:22-135,
-// :279-345), block restriction (:441-446), numeric IKJ phase (:347-409) and the split into L / U (:501-532), all on a
-// matrix that lives in device memory (setup_gpu.cuh).  Only the finished factors travel to the host, where the
-// triangular-sweep schedules are analysed.
+// ilu_gpu.cu -- ILU(k) and ILUT set-up on the GPU: symbolic level-of-fill phase
+// (src/pc-iluk.cxx:22-135, :279-345), block restriction (:441-446), numeric IKJ phase (:347-409), the dual-threshold ILUT
+// recurrence (src/pc-ilut.cxx:51-286) and the split into L / U (:501-532), all on a matrix that lives in device memory
+// (setup_gpu.cuh).  Only the finished factors travel to the host, where the triangular-sweep schedules are analysed.
 //
-// Both factorisation phases have the dependency graph of the forward sweep: row i needs the FINISHED rows of its
-// strictly lower columns.  They run as ONE persistent kernel each: a thread owns a row, executes the reference's serial
-// row recurrence statement for statement, and before it uses pivot row k it waits for done[k] (the row publishes itself
-// with a fence + flag).  Rows are handed out in ascending order (warp tickets), so a waiting thread only ever waits for
-// rows that are finished, running or about to be issued: deadlock-free on a grid of resident CTAs.  Consecutive rows
-// almost always depend on each other, so the 32 rows of a warp are kStride apart (lane l of warp ticket t owns row
-// (t / kStride) 32 kStride + l kStride + t % kStride): chains run ACROSS warps and 32 chains advance per warp.
+// The factorisation phases have the dependency graph of the forward sweep: row i needs the FINISHED rows of its strictly
+// lower columns.  Each runs as ONE persistent kernel: a thread owns a row, executes the reference's serial row
+// recurrence statement for statement (ilu_rows.cuh -- the same functions the CPU replay at the end of this file runs),
+// and before it uses pivot row k it waits for done[k] (the row publishes itself with a fence + flag).  Rows are handed
+// out in ascending order (warp tickets), so a waiting thread only ever waits for rows that are finished, running or about
+// to be issued: deadlock-free on a grid of resident CTAs.  Consecutive rows almost always depend on each other, so the
+// 32 rows of a warp are kStride apart (lane l of warp ticket t owns row (t / kStride) 32 kStride + l kStride +
+// t % kStride): chains run ACROSS warps and 32 chains advance per warp.  A watchdog turns a dependency that is never
+// published into an error instead of a hung device.
 // No FMA, same operations in the same order: the factors are bit-identical to ilu_host.cpp's and hence to the
-// reference's (tests/test_gpu_setup.py, tests/test_gpu_kernels.py).
+// reference's (tests/test_gpu_setup.py on the device, tests/test_ilu_rows.py for the row functions on the CPU).
 #include <time.h>
 #include <algorithm>
 #include <vector>
