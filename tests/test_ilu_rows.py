@@ -74,3 +74,22 @@ def test_unsorted_input_is_left_to_the_device_ingest():
     Ap = np.array([0, 2, 4], np.int32)
     Aj = np.array([1, 0, 0, 1], np.int32)
     assert replay((Ap, Aj, np.ones(4)), "iluk") is None
+
+
+def test_fuzz_random_matrices_weak_pivots_blocks():
+    """random patterns, repaired pivots (|d| < 1e-10 -> +-1e-3, src/pc-iluk.cxx:367-375), blocks, all levels / thresholds"""
+    from lssp_b200 import generators as g
+    rng = np.random.default_rng(31)
+    for trial in range(80):
+        n = int(rng.integers(5, 300))
+        Ap, Aj, Ax = g.random_csr(n, avg=int(rng.integers(2, 9)), seed=int(rng.integers(0, 1 << 30)))
+        if trial % 3 == 0:
+            Ax = Ax.copy()
+            for i in rng.integers(0, n, 3):
+                k = Ap[i] + int(np.where(Aj[Ap[i]:Ap[i + 1]] == i)[0][0])
+                Ax[k] = rng.choice([0.0, 1e-12, -1e-12, 1e-3])
+        A = (Ap, Aj, Ax)
+        lvl, bs = int(rng.integers(0, 4)), int(rng.choice([0, max(1, n // 3), 7]))
+        assert same(replay(A, "iluk", level=lvl, blk_size=bs), api.ilu_factor(A, "iluk", level=lvl, blk_size=bs)), (trial, n, lvl, bs)
+        p, tol = int(rng.choice([-1, 1, 2, 5, 20])), float(rng.choice([1e-3, 0.0, 1e-1, 1e-6]))
+        assert same(replay(A, "ilut", p=p, tol=tol, blk_size=bs), api.ilu_factor(A, "ilut", p=p, tol=tol, blk_size=bs)), (trial, n, p, tol, bs)
