@@ -310,6 +310,11 @@ typedef struct lsspg_amg_host lsspg_amg_host;   /* host image of the hierarchy *
 /* Setup (host; GPU setup is SURVEY.md 8f row 2).  Columns of A must be sorted. */
 int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hAx,
                          const lsspg_amg_pars *pars, lsspg_amg_host **out);
+/* CPU replay of the device set-up (amg_gpu.cu): the per-row phases (strong couplings, interpolation, restriction, Galerkin
+ * products) through the row functions of amg_rows.cuh, row after row; the hierarchy must equal lsspg_amg_setup_host's array
+ * by array.  Test-suite only. */
+int lsspg_debug_amg_setup_replay_host(int n, const int *hAp, const int *hAj, const double *hAx, const lsspg_amg_pars *pars,
+                                      lsspg_amg_host **out);
 int lsspg_amg_host_levels(const lsspg_amg_host *H, int *num_levels, int *coarse_dense);
 /* level l: unknowns, C points, nnz of A_l, of P_l (n_l x n_{l+1}) and of R_l = P_l^T; the last
  * level has nc = nnzP = nnzR = 0 */

@@ -589,7 +589,10 @@ class AmgHierarchy:
     """Host image of the SX-AMG-style hierarchy (lsspg_amg_setup_host; the role of sx_amg_setup,
     reference src/pc-sxamg.cxx:107-110).  `levels[l]` holds n, nc, A, P, R (CSR triples) and cf."""
 
-    def __init__(self, A, **pars):
+    def __init__(self, A, ctx=None, replay=False, **pars):
+        """ctx given: the per-row phases of the set-up (strong couplings, interpolation, restriction, Galerkin products) run
+        on the GPU (lsspg_amg_setup_device, amg_gpu.cu), the C/F splitting on the host; replay=True: the same row functions
+        on the CPU (test-suite).  The hierarchy is the same in every variant, array by array."""
         Ap, Aj, Ax = _i32(A[0]), _i32(A[1]), _f64(A[2])
         p = AmgPars()
         check(lib().lsspg_amg_pars_default(C.byref(p)))
@@ -599,7 +602,12 @@ class AmgHierarchy:
             setattr(p, k, v)
         self.pars = p
         self.h = C.c_void_p()
-        check(lib().lsspg_amg_setup_host(len(Ap) - 1, _p(Ap), _p(Aj), _p(Ax), C.byref(p), C.byref(self.h)))
+        if ctx is not None:
+            check(lib().lsspg_amg_setup_device(ctx.h, len(Ap) - 1, _p(Ap), _p(Aj), _p(Ax), C.byref(p), C.byref(self.h)))
+        elif replay:
+            check(lib().lsspg_debug_amg_setup_replay_host(len(Ap) - 1, _p(Ap), _p(Aj), _p(Ax), C.byref(p), C.byref(self.h)))
+        else:
+            check(lib().lsspg_amg_setup_host(len(Ap) - 1, _p(Ap), _p(Aj), _p(Ax), C.byref(p), C.byref(self.h)))
         nl, dense = C.c_int(), C.c_int()
         check(lib().lsspg_amg_host_levels(self.h, C.byref(nl), C.byref(dense)))
         self.coarse_dense = bool(dense.value)

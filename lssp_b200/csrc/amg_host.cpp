@@ -23,6 +23,7 @@
 #include <thread>
 #include <vector>
 #include "amg_host.h"
+#include "amg_rows.cuh"
 
 namespace lsspg {
 void set_error(const char *fmt, ...);
@@ -39,9 +40,7 @@ using namespace lsspg;
 
 namespace {
 
-struct Graph {
-    std::vector<int> p, j;
-};
+using Graph = AmgGraph;
 
 // strong couplings of every row, in the row's column order
 void strong_couplings(const AmgLevelHost &L, const lsspg_amg_pars &pr, Graph &S)
@@ -461,7 +460,224 @@ int dense_inverse(const AmgLevelHost &L, std::vector<double> &inv)
 
 }  // namespace
 
+// ---- the set-up loop and its providers ----------------------------------------------------------------------------------
+namespace {
+
+struct HostPhases : AmgPhases {
+    int strength(const AmgLevelHost &L, const lsspg_amg_pars &pr, AmgGraph &S) override
+    {
+        strong_couplings(L, pr, S);
+        return 0;
+    }
+    int interpolation(AmgLevelHost &L, const AmgGraph &S, const AmgGraph &, const lsspg_amg_pars &pr) override
+    {
+        direct_interpolation(L, S, pr);
+        return 0;
+    }
+    int restriction(AmgLevelHost &L, const AmgGraph &) override
+    {
+        transpose_csr(L.n, L.nc, L.Pp, L.Pj, L.Px, L.Rp, L.Rj, L.Rx);
+        return 0;
+    }
+    int galerkin(const AmgLevelHost &L, AmgLevelHost &C) override
+    {
+        std::vector<int> Tp, Tj;
+        std::vector<double> Tx;
+        int rc = spgemm(L.n, L.nc, L.Ap, L.Aj, L.Ax, L.Pp, L.Pj, L.Px, Tp, Tj, Tx);
+        if (!rc) rc = spgemm(L.nc, L.nc, L.Rp, L.Rj, L.Rx, Tp, Tj, Tx, C.Ap, C.Aj, C.Ax);
+        return rc;
+    }
+    const char *name() const override { return "host"; }
+};
+
+// the row functions of amg_rows.cuh, one row after the other: count, scan, fill -- as the device kernels do
+struct ReplayPhases : AmgPhases {
+    static void scan(std::vector<int> &p)
+    {
+        int run = 0;
+        for (size_t i = 0; i + 1 < p.size(); i++) { const int c = p[i]; p[i] = run; run += c; }
+        p.back() = run;
+    }
+    int strength(const AmgLevelHost &L, const lsspg_amg_pars &pr, AmgGraph &S) override
+    {
+        S.p.assign((size_t)L.n + 1, 0);
+        for (int i = 0; i < L.n; i++) S.p[i] = amg_strong_row(i, L.Ap.data(), L.Aj.data(), L.Ax.data(), pr.strong_threshold, pr.max_row_sum, nullptr);
+        scan(S.p);
+        S.j.resize((size_t)S.p[L.n]);
+        for (int i = 0; i < L.n; i++)
+            amg_strong_row(i, L.Ap.data(), L.Aj.data(), L.Ax.data(), pr.strong_threshold, pr.max_row_sum, S.j.data() + S.p[i]);
+        return 0;
+    }
+    int interpolation(AmgLevelHost &L, const AmgGraph &S, const AmgGraph &, const lsspg_amg_pars &pr) override
+    {
+        const int n = L.n;
+        std::vector<int> cidx((size_t)n + 1, 0);
+        for (int i = 0; i < n; i++) cidx[i] = (L.cf[i] == kAmgCPT);
+        scan(cidx);
+        L.nc = cidx[n];
+        L.Pp.assign((size_t)n + 1, 0);
+        for (int i = 0; i < n; i++)
+            L.Pp[i] = amg_interp_row(i, L.Ap.data(), L.Aj.data(), L.Ax.data(), S.p.data(), S.j.data(), L.cf.data(), cidx.data(), pr.trunc_threshold,
+                                     nullptr, nullptr);
+        scan(L.Pp);
+        L.Pj.resize((size_t)L.Pp[n]);
+        L.Px.resize((size_t)L.Pp[n]);
+        for (int i = 0; i < n; i++)
+            amg_interp_row(i, L.Ap.data(), L.Aj.data(), L.Ax.data(), S.p.data(), S.j.data(), L.cf.data(), cidx.data(), pr.trunc_threshold,
+                           L.Pj.data() + L.Pp[i], L.Px.data() + L.Pp[i]);
+        return 0;
+    }
+    int restriction(AmgLevelHost &L, const AmgGraph &T) override
+    {
+        const int n = L.n, nc = L.nc;
+        std::vector<int> cpoint((size_t)nc);
+        for (int i = 0, c = 0; i < n; i++)
+            if (L.cf[i] == kAmgCPT) cpoint[c++] = i;
+        L.Rp.assign((size_t)nc + 1, 0);
+        for (int c = 0; c < nc; c++)
+            L.Rp[c] = amg_restrict_row(c, cpoint[c], T.p.data(), T.j.data(), L.Pp.data(), L.Pj.data(), L.Px.data(), nullptr, nullptr);
+        scan(L.Rp);
+        L.Rj.resize((size_t)L.Rp[nc]);
+        L.Rx.resize((size_t)L.Rp[nc]);
+        for (int c = 0; c < nc; c++)
+            amg_restrict_row(c, cpoint[c], T.p.data(), T.j.data(), L.Pp.data(), L.Pj.data(), L.Px.data(), L.Rj.data() + L.Rp[c], L.Rx.data() + L.Rp[c]);
+        return 0;
+    }
+    static int product(int nrows, const std::vector<int> &Ap, const std::vector<int> &Aj, const std::vector<double> &Ax,
+                       const std::vector<int> &Bp, const std::vector<int> &Bj, const std::vector<double> &Bx, std::vector<int> &Cp,
+                       std::vector<int> &Cj, std::vector<double> &Cx)
+    {
+        int bound = 1;
+        for (int i = 0; i < nrows; i++) bound = std::max(bound, amg_spgemm_bound(i, Ap.data(), Aj.data(), Bp.data()));
+        int hsize = 64;
+        while (hsize < 2 * bound) hsize *= 2;
+        std::vector<AmgSlot> tab((size_t)hsize, AmgSlot{-1, -1, 0.0});
+        std::vector<int> cols((size_t)bound);
+        Cp.assign((size_t)nrows + 1, 0);
+        for (int i = 0; i < nrows; i++) {
+            Cp[i] = amg_spgemm_row(i, 2 * i, Ap.data(), Aj.data(), Ax.data(), Bp.data(), Bj.data(), Bx.data(), tab.data(), hsize - 1, cols.data(),
+                                   bound, nullptr, nullptr);
+            AMG_CHECK(Cp[i] >= 0, "amg replay: accumulator overflow in row %d", i);
+        }
+        scan(Cp);
+        Cj.resize((size_t)Cp[nrows]);
+        Cx.resize((size_t)Cp[nrows]);
+        for (int i = 0; i < nrows; i++)
+            amg_spgemm_row(i, 2 * i + 1, Ap.data(), Aj.data(), Ax.data(), Bp.data(), Bj.data(), Bx.data(), tab.data(), hsize - 1, cols.data(), bound,
+                           Cj.data() + Cp[i], Cx.data() + Cp[i]);
+        return 0;
+    }
+    int galerkin(const AmgLevelHost &L, AmgLevelHost &C) override
+    {
+        std::vector<int> Tp, Tj;
+        std::vector<double> Tx;
+        int rc = product(L.n, L.Ap, L.Aj, L.Ax, L.Pp, L.Pj, L.Px, Tp, Tj, Tx);
+        if (!rc) rc = product(L.nc, L.Rp, L.Rj, L.Rx, Tp, Tj, Tx, C.Ap, C.Aj, C.Ax);
+        return rc;
+    }
+    const char *name() const override { return "row functions (CPU replay)"; }
+};
+
+}  // namespace
+
 namespace lsspg {
+
+// the C/F splitting of a strength graph for the device set-up (amg_gpu.cu), which has S on the host at that point
+int amg_cf_split_host(int n, const AmgGraph &S, AmgGraph &T, std::vector<int> &cf)
+{
+    transpose_graph(n, S, T);
+    return cf_split(n, S, T, cf);
+}
+
+int amg_setup_with(AmgPhases &ph, int n, const int *hAp, const int *hAj, const double *hAx, const lsspg_amg_pars *pars,
+                   lsspg_amg_host **out)
+{
+    AMG_CHECK(out && n > 0 && hAp && hAj && hAx, "lsspg_amg_setup: bad argument");
+    lsspg_amg_pars pr;
+    if (pars) pr = *pars;
+    else lsspg_amg_pars_default(&pr);
+    AMG_CHECK(pr.max_levels >= 1 && pr.coarse_dof >= 1 && pr.pre_iter >= 0 && pr.post_iter >= 0,
+              "lsspg_amg_setup: bad parameters");
+    for (int i = 0; i < n; i++)
+        for (int k = hAp[i] + 1; k < hAp[i + 1]; k++)
+            AMG_CHECK(hAj[k - 1] < hAj[k], "lsspg_amg_setup: columns of row %d are not sorted", i);
+    lsspg_amg_host *H = new lsspg_amg_host();
+    H->pars = pr;
+    H->levels.emplace_back();
+    {
+        AmgLevelHost &L = H->levels[0];
+        L.n = n;
+        L.Ap.assign(hAp, hAp + n + 1);
+        L.Aj.assign(hAj, hAj + hAp[n]);
+        L.Ax.assign(hAx, hAx + hAp[n]);
+    }
+    int rc = ph.begin(H->levels[0]);
+    const bool prof = getenv("LSSPG_SETUP_PROF") && atoi(getenv("LSSPG_SETUP_PROF")) != 0;
+    auto now = [] {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    };
+    double tp = now();
+    auto PROF = [&](const char *what) {
+        if (!prof) return;
+        const double t = now();
+        fprintf(stderr, "[amg setup, %s] level %d %-22s %.3f s\n", ph.name(), (int)H->levels.size() - 1, what, t - tp);
+        tp = t;
+    };
+    while (!rc && (int)H->levels.size() < pr.max_levels && H->levels.back().n > pr.coarse_dof) {
+        AmgLevelHost &L = H->levels.back();
+        Graph S, T;
+        rc = ph.strength(L, pr, S);
+        if (rc) break;
+        PROF("strong couplings");
+        transpose_graph(L.n, S, T);
+        PROF("transpose graph");
+        const int nc = cf_split(L.n, S, T, L.cf);
+        PROF("C/F split");
+        if (nc == 0 || nc >= L.n) {   // coarsening stalled: this level is the last one
+            L.cf.clear();
+            break;
+        }
+        rc = ph.interpolation(L, S, T, pr);
+        if (rc) break;
+        PROF("interpolation");
+        visiting_ranks(L, pr.cf_order);
+        PROF("visiting ranks");
+        rc = ph.restriction(L, T);
+        if (rc) break;
+        PROF("restriction");
+        AmgLevelHost C;
+        C.n = L.nc;
+        rc = ph.galerkin(L, C);
+        if (rc) break;
+        PROF("Galerkin products");
+        if (pr.verb > 0)
+            printf("amg: level %d: n = %d, nnz = %d, C points = %d\n", (int)H->levels.size() - 1, L.n, L.Ap[L.n], L.nc);
+        H->levels.push_back(std::move(C));
+    }
+    if (!rc) {
+        AmgLevelHost &L = H->levels.back();
+        L.nc = 0;
+        L.cf.assign(L.n, 1);
+        visiting_ranks(L, 0);   // the last level is swept in natural order (when it is swept at all)
+        L.Pp.clear();
+        L.Rp.clear();
+        if (L.n <= pr.coarse_dense_max) {
+            rc = dense_inverse(L, H->coarse_inv);
+            H->coarse_dense = (rc == 0);
+        }
+        if (pr.verb > 0)
+            printf("amg: level %d (last): n = %d, nnz = %d, %s\n", (int)H->levels.size() - 1, L.n, L.Ap[L.n],
+                   H->coarse_dense ? "dense inverse" : "Gauss-Seidel sweeps");
+    }
+    if (rc) {
+        delete H;
+        return rc;
+    }
+    *out = H;
+    return 0;
+}
 
 int gs_build_host(int n, const int *Ap, const int *Aj, const double *Ax, const int *cf, const int *rank, GsHost &G,
                   int mode)
@@ -639,91 +855,17 @@ int lsspg_amg_pars_default(lsspg_amg_pars *p)
 int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hAx, const lsspg_amg_pars *pars,
                          lsspg_amg_host **out)
 {
-    AMG_CHECK(out && n > 0 && hAp && hAj && hAx, "lsspg_amg_setup_host: bad argument");
-    lsspg_amg_pars pr;
-    if (pars) pr = *pars;
-    else lsspg_amg_pars_default(&pr);
-    AMG_CHECK(pr.max_levels >= 1 && pr.coarse_dof >= 1 && pr.pre_iter >= 0 && pr.post_iter >= 0,
-              "lsspg_amg_setup_host: bad parameters");
-    for (int i = 0; i < n; i++)
-        for (int k = hAp[i] + 1; k < hAp[i + 1]; k++)
-            AMG_CHECK(hAj[k - 1] < hAj[k], "lsspg_amg_setup_host: columns of row %d are not sorted", i);
-    lsspg_amg_host *H = new lsspg_amg_host();
-    H->pars = pr;
-    H->levels.emplace_back();
-    {
-        AmgLevelHost &L = H->levels[0];
-        L.n = n;
-        L.Ap.assign(hAp, hAp + n + 1);
-        L.Aj.assign(hAj, hAj + hAp[n]);
-        L.Ax.assign(hAx, hAx + hAp[n]);
-    }
-    int rc = 0;
-    const bool prof = getenv("LSSPG_SETUP_PROF") && atoi(getenv("LSSPG_SETUP_PROF")) != 0;
-    auto now = [] {
-        timespec ts;
-        clock_gettime(CLOCK_MONOTONIC, &ts);
-        return ts.tv_sec + 1e-9 * ts.tv_nsec;
-    };
-    double tp = now();
-    auto PROF = [&](const char *what) {
-        if (!prof) return;
-        const double t = now();
-        fprintf(stderr, "[amg setup] level %d %-22s %.3f s\n", (int)H->levels.size() - 1, what, t - tp);
-        tp = t;
-    };
-    while ((int)H->levels.size() < pr.max_levels && H->levels.back().n > pr.coarse_dof) {
-        AmgLevelHost &L = H->levels.back();
-        Graph S, T;
-        strong_couplings(L, pr, S);
-        PROF("strong couplings");
-        transpose_graph(L.n, S, T);
-        PROF("transpose graph");
-        const int nc = cf_split(L.n, S, T, L.cf);
-        PROF("C/F split");
-        if (nc == 0 || nc >= L.n) {   // coarsening stalled: this level is the last one
-            L.cf.clear();
-            break;
-        }
-        direct_interpolation(L, S, pr);
-        PROF("interpolation");
-        visiting_ranks(L, pr.cf_order);
-        PROF("visiting ranks");
-        transpose_csr(L.n, L.nc, L.Pp, L.Pj, L.Px, L.Rp, L.Rj, L.Rx);
-        PROF("restriction");
-        std::vector<int> Tp, Tj;
-        std::vector<double> Tx;
-        AmgLevelHost C;
-        C.n = L.nc;
-        rc = spgemm(L.n, L.nc, L.Ap, L.Aj, L.Ax, L.Pp, L.Pj, L.Px, Tp, Tj, Tx);
-        if (!rc) rc = spgemm(L.nc, L.nc, L.Rp, L.Rj, L.Rx, Tp, Tj, Tx, C.Ap, C.Aj, C.Ax);
-        if (rc) break;
-        PROF("Galerkin products");
-        if (pr.verb > 0)
-            printf("amg: level %d: n = %d, nnz = %d, C points = %d\n", (int)H->levels.size() - 1, L.n, L.Ap[L.n], L.nc);
-        H->levels.push_back(std::move(C));
-    }
-    if (!rc) {
-        AmgLevelHost &L = H->levels.back();
-        L.nc = 0;
-        L.cf.assign(L.n, 1);
-        visiting_ranks(L, 0);   // the last level is swept in natural order (when it is swept at all)
-        L.Pp.clear();
-        L.Rp.clear();
-        if (L.n <= pr.coarse_dense_max) {
-            rc = dense_inverse(L, H->coarse_inv);
-            H->coarse_dense = (rc == 0);
-        }
-        if (pr.verb > 0)
-            printf("amg: level %d (last): n = %d, nnz = %d, %s\n", (int)H->levels.size() - 1, L.n, L.Ap[L.n],
-                   H->coarse_dense ? "dense inverse" : "Gauss-Seidel sweeps");
-    }
-    if (rc) {
-        delete H;
-        return rc;
-    }
-    *out = H;
-    return 0;
+    HostPhases ph;
+    return amg_setup_with(ph, n, hAp, hAj, hAx, pars, out);
+}
+
+/* CPU replay of the device set-up (amg_gpu.cu) for the test-suite: the SAME row functions (amg_rows.cuh), row after row.
+ * The hierarchy must equal lsspg_amg_setup_host's array by array. */
+int lsspg_debug_amg_setup_replay_host(int n, const int *hAp, const int *hAj, const double *hAx, const lsspg_amg_pars *pars,
+                                      lsspg_amg_host **out)
+{
+    ReplayPhases ph;
+    return amg_setup_with(ph, n, hAp, hAj, hAx, pars, out);
 }
 
 int lsspg_amg_host_levels(const lsspg_amg_host *H, int *num_levels, int *coarse_dense)

@@ -19,6 +19,29 @@ struct AmgLevelHost {
                                         // cf_order 2: colour by colour, see amg_host.cpp)
 };
 
+// strength graph (no values): row i lists the points that strongly influence i, in the row's column order
+struct AmgGraph {
+    std::vector<int> p, j;
+};
+
+// The phases of one coarsening step that are independent per row.  Three providers share the set-up loop
+// (amg_setup_with, amg_host.cpp): the host code of amg_host.cpp (lsspg_amg_setup_host), the row functions of
+// amg_rows.cuh replayed on the CPU (lsspg_debug_amg_setup_replay_host) and the same row functions one row per thread on
+// the device (amg_gpu.cu, lsspg_amg_setup_device).  The serial phases -- transposed strength graph, Ruge-Stueben C/F
+// splitting, visiting ranks, dense inverse of the last level -- are the loop's own.
+struct AmgPhases {
+    virtual ~AmgPhases() {}
+    virtual int begin(const AmgLevelHost &L0) { (void)L0; return 0; }                       // level 0 is ready on the host
+    virtual int strength(const AmgLevelHost &L, const lsspg_amg_pars &pr, AmgGraph &S) = 0;
+    // L.cf is set; fills L.nc, L.Pp / Pj / Px
+    virtual int interpolation(AmgLevelHost &L, const AmgGraph &S, const AmgGraph &T, const lsspg_amg_pars &pr) = 0;
+    virtual int restriction(AmgLevelHost &L, const AmgGraph &T) = 0;                        // fills L.Rp / Rj / Rx
+    virtual int galerkin(const AmgLevelHost &L, AmgLevelHost &C) = 0;                       // C.Ap / Aj / Ax = R A P
+    virtual const char *name() const = 0;
+};
+int amg_setup_with(AmgPhases &ph, int n, const int *hAp, const int *hAj, const double *hAx, const lsspg_amg_pars *pars,
+                   lsspg_amg_host **out);
+
 // One Gauss-Seidel sweep as a dependency schedule.  Rows are split into the C block and the F
 // block; inside a block they are grouped by dependency level (row i waits for the rows j < i of
 // its own block that it references) and packed into 32-row slices, C slices first.  Entry k of
