@@ -310,6 +310,10 @@ typedef struct lsspg_amg_host lsspg_amg_host;   /* host image of the hierarchy *
 /* Setup (host; GPU setup is SURVEY.md 8f row 2).  Columns of A must be sorted. */
 int lsspg_amg_setup_host(int n, const int *hAp, const int *hAj, const double *hAx,
                          const lsspg_amg_pars *pars, lsspg_amg_host **out);
+/* The same set-up with its per-row phases -- strong couplings, interpolation, restriction, Galerkin products -- on the GPU
+ * (amg_gpu.cu); the Ruge-Stueben C/F splitting stays on the host.  Same hierarchy, array by array. */
+int lsspg_amg_setup_device(lsspg_ctx *ctx, int n, const int *hAp, const int *hAj, const double *hAx, const lsspg_amg_pars *pars,
+                           lsspg_amg_host **out);
 /* CPU replay of the device set-up (amg_gpu.cu): the per-row phases (strong couplings, interpolation, restriction, Galerkin
  * products) through the row functions of amg_rows.cuh, row after row; the hierarchy must equal lsspg_amg_setup_host's array
  * by array.  Test-suite only. */
