@@ -6,6 +6,9 @@
 // host) and what the hierarchy object keeps (A, P, R of every level: the smoother layouts are built from them) is copied
 // back.  The set-up loop itself is amg_setup_with (amg_host.cpp), shared with the host and replay variants, so the
 // hierarchy is the same array by array (tests/test_gpu_amg_setup.py).
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <algorithm>
 #include <vector>
 #include "amg_host.h"
@@ -281,16 +284,31 @@ struct DevicePhases : AmgPhases {
     {
         const int n = L.n, nc = L.nc;
         int *dTp = nullptr, *dTj = nullptr;
+        const bool prof = getenv("LSSPG_SETUP_PROF") && atoi(getenv("LSSPG_SETUP_PROF")) > 1;
+        auto stamp = [&](const char *what) {
+            if (!prof) return;
+            cudaStreamSynchronize(ctx->stream);
+            timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            static double last = 0.0;
+            const double t = ts.tv_sec + 1e-9 * ts.tv_nsec;
+            fprintf(stderr, "[amg restriction] %-18s %.3f s\n", what, last > 0.0 ? t - last : 0.0);
+            last = t;
+        };
+        stamp("start");
         int rc = upload_ints(ctx, T.p, &dTp);
         if (!rc) rc = upload_ints(ctx, T.j, &dTj);
+        stamp("upload of T");
         if (!rc && cudaMalloc(&d_cpoint, sizeof(int) * std::max<size_t>((size_t)nc, 1)) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "amg restriction", __FILE__, __LINE__);
         if (!rc) {
             auto body = [&]() -> int {
                 LSSPG_LAUNCH(ctx, k_amg_cpoint, rows_grid(n), 256, 0, n, d_cf, d_cidx, d_cpoint);
+                stamp("cpoint");
                 LSSPG_TRY(csf(
                     ctx, nc, nc, n,
                     [&](int *cnt) -> int {
                         LSSPG_LAUNCH(ctx, k_amg_restrict_count, rows_grid(nc), 256, 0, nc, d_cpoint, dTp, dTj, dP->p, dP->j, dP->x, cnt);
+                        stamp("count kernel");
                         return 0;
                     },
                     [&](lsspg_dmat *R) -> int {
@@ -298,7 +316,10 @@ struct DevicePhases : AmgPhases {
                         return 0;
                     },
                     &dR));
-                return download(ctx, dR, L.Rp, L.Rj, &L.Rx);
+                stamp("scan + fill");
+                const int rd = download(ctx, dR, L.Rp, L.Rj, &L.Rx);
+                stamp("download of R");
+                return rd;
             };
             rc = body();
         }
